@@ -1,0 +1,149 @@
+/*
+ * tqsim.h -- C ABI of libtqsim: batched fp64 circuit simulation + energy evaluation on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the ONE hot path of Aqasch/TensorRL-QAS:
+ *   environments/VQAs/VQE_qulacs*.py : Parametric_Circuit.construct_ansatz / get_energy_qulacs / get_exp_val
+ * The reference has no FFI of its own (pure Python on top of the qulacs wheel); every entry point below
+ * names the reference call site(s) whose work it replaces.  All paths are relative to the reference tree.
+ *
+ * Conventions (qulacs semantics):
+ *   - little-endian basis: amplitude index i, qubit k  <->  bit (i >> k) & 1
+ *   - RX/RY/RZ(theta) = exp(+i * theta/2 * P)            (opposite sign to qiskit)
+ *   - CNOT: q0 = control, q1 = target
+ *   - complex128 is passed as interleaved (re, im) doubles
+ *
+ * Error model: every function returns 0 on success and a negative TQ_E* code on failure; nothing throws or
+ * aborts across the ABI.  tq_last_error(h) returns a human-readable message for the last failure on that
+ * handle (or, with h == NULL, for the last failed tq_create on the calling thread).
+ *
+ * Ownership: the caller owns every buffer it passes in.  The library owns only the scratch it allocates for a
+ * handle (state vectors, per-gate coefficient tables, partial sums) and frees it in tq_destroy.
+ * Threading: a handle is single-threaded; distinct handles may be driven from distinct host threads.
+ * Streams: *_dev entry points enqueue on the caller's stream (a cudaStream_t passed as void*, NULL = default
+ * stream) and return without synchronising; *_host entry points copy in, run and copy out, and return when
+ * the result is in the caller's host buffer.
+ * There is NO CPU fallback: without a CUDA device tq_create fails with TQ_ENODEV.
+ */
+#ifndef TQSIM_H
+#define TQSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQ_VERSION 100
+
+/* gate kinds for tq_set_circuit */
+enum {
+    TQ_RX = 0,     /* environments/VQAs/VQE_qulacs.py:36  add_parametric_RX_gate(q0, theta) */
+    TQ_RY = 1,     /* environments/VQAs/VQE_qulacs.py:38  add_parametric_RY_gate(q0, theta) */
+    TQ_RZ = 2,     /* environments/VQAs/VQE_qulacs.py:40  add_parametric_RZ_gate(q0, theta) */
+    TQ_CNOT = 3,   /* environments/VQAs/VQE_qulacs.py:25  add_gate(CNOT(ctrl=q0, targ=q1)) */
+    TQ_X = 4,      /* fixed Pauli gates (explicit noise insertions, state preparation in tests) */
+    TQ_Y = 5,
+    TQ_Z = 6,
+    TQ_DEPOL1 = 7, /* environments/VQAs/VQE_qulacs_noise.py:45-54  DepolarizingNoise(q0, p)  (p in `fixed`) */
+    TQ_DEPOL2 = 8  /* environments/VQAs/VQE_qulacs_noise.py:32-33  TwoQubitDepolarizingNoise(q0, q1, p) */
+};
+
+/* error codes */
+enum {
+    TQ_OK = 0,
+    TQ_EINVAL = -1,  /* bad argument */
+    TQ_ENODEV = -2,  /* no usable CUDA device / wrong architecture */
+    TQ_ECUDA = -3,   /* a CUDA runtime call failed (message has the CUDA error string) */
+    TQ_ENOMEM = -4,  /* device or host allocation failed */
+    TQ_ESTATE = -5   /* call sequence error (e.g. energy before a circuit/Hamiltonian was set) */
+};
+
+typedef struct tq_context* tq_handle;
+
+/* library/ABI version (TQ_VERSION of the build) */
+int tq_version(void);
+
+/* One handle per (n_qubits, device).  Replaces qulacs.QuantumState(n) + ParametricQuantumCircuit(n) construction:
+ * environments/VQAs/VQE_qulacs.py:8-10, :81. */
+int tq_create(int n_qubits, int device_id, tq_handle* out);
+int tq_destroy(tq_handle h);
+const char* tq_last_error(tq_handle h);
+
+/* Hamiltonian as a Pauli sum.  Term t = coeff[t] * prod_q P_q with P_q = X if only xmask bit q, Z if only zmask
+ * bit q, Y if both.  Bits are qubit indices of the little-endian state.  coeff_im may be NULL (all real).
+ * Data contract: dmrg-to-qc/mol_data/*.npz keys `paulis`/`weights` (dmrg-to-qc/heisenberg_model.py:21-72). */
+int tq_set_pauli_hamiltonian(tq_handle h, int n_terms, const uint64_t* xmask, const uint64_t* zmask,
+                             const double* coeff_re, const double* coeff_im);
+
+/* Hamiltonian as the dense 2^n x 2^n complex128 matrix the reference passes as `op`
+ * (environments/VQAs/VQE_qulacs.py:84-85, E = Re(conj(psi).T @ op @ psi)); row-major, n_qubits <= 13.
+ * The library keeps the non-zero entries and evaluates exactly that bilinear form over them. */
+int tq_set_dense_hamiltonian(tq_handle h, const double* h_matrix_host);
+
+/* Initial state: NULL = |0...0> (VQE_qulacs.py:81); otherwise 2^n complex128 copied from host
+ * (state.load(TN_state), environments/VQAs/VQE_qulacs_TN_notin_RL.py:82-83). */
+int tq_set_init_state(tq_handle h, const double* psi_host_or_null);
+
+/* The circuit shared by all elements of a batch: G gates in application order.
+ *   kind[g]       one of TQ_*
+ *   q0[g], q1[g]  qubits (q1 ignored for 1-qubit kinds; CNOT: q0 control, q1 target)
+ *   param_idx[g]  rotations: column of the parameter matrix that holds theta, or -1 to use fixed[g];
+ *                 TQ_DEPOL1/2: noise-slot index (column of the trajectory code matrix), or -1
+ *   fixed[g]      rotations with param_idx -1: theta; TQ_DEPOL1/2: probability p
+ * Replaces construct_ansatz's add_gate/add_parametric_* calls (VQE_qulacs.py:12-44) and the
+ * set_parameter loop (VQE_qulacs.py:73-74): parameters are bound per batch element at evaluation time. */
+int tq_set_circuit(tq_handle h, int n_gates, const int32_t* kind, const int32_t* q0, const int32_t* q1,
+                   const int32_t* param_idx, const double* fixed, int n_params);
+
+/* Energies of B parameter sets on the pure-state path: out[b] = <psi(params[b])| H |psi(params[b])>.
+ * params is [B][ld_params] row-major (ld_params >= n_params).  TQ_DEPOL* gates are skipped (noise-free).
+ * Replaces get_energy_qulacs + get_exp_val (VQE_qulacs.py:47-86), B calls at a time. */
+int tq_energy_batch(tq_handle h, int batch, const double* params_dev, int ld_params, double* out_dev,
+                    void* stream);
+int tq_energy_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* out_host);
+
+/* Pauli-trajectory noise on the pure-state path (what the reference's noise environments actually run:
+ * one sampled Pauli per noise gate and per evaluation, VQE_qulacs_noise.py:31-33,44-54).
+ * codes is [B][ld_codes] uint8: for a TQ_DEPOL1 gate with slot s, codes[b][s] in {0:I,1:X,2:Y,3:Z} acts on q0;
+ * for TQ_DEPOL2, codes[b][s] = pa + 4*pb with pa on q0 and pb on q1.  The caller samples the codes. */
+int tq_energy_traj_batch(tq_handle h, int batch, const double* params_dev, int ld_params,
+                         const uint8_t* codes_dev, int ld_codes, double* out_dev, void* stream);
+int tq_energy_traj_batch_host(tq_handle h, int batch, const double* params_host, int ld_params,
+                              const uint8_t* codes_host, int ld_codes, double* out_host);
+
+/* Exact density-matrix path: rho is evolved as a 2n-qubit vector, TQ_DEPOL* gates are the exact channels
+ * (mean of the reference's sampled trajectories); out[b] = Tr(rho H).  n_qubits <= 13. */
+int tq_energy_dm_batch(tq_handle h, int batch, const double* params_dev, int ld_params, double* out_dev,
+                       void* stream);
+int tq_energy_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* out_host);
+
+/* Final states psi(params[b]) for b in [0, B): states is [B][2^n] complex128 (debugging / parity;
+ * replaces state.get_vector(), VQE_qulacs.py:84). */
+int tq_state_batch(tq_handle h, int batch, const double* params_dev, int ld_params, double* states_dev,
+                   void* stream);
+int tq_state_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* states_host);
+/* Final density matrices, [B][4^n] complex128, entry rho[r][c] at index r + (c << n). */
+int tq_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* rho_host);
+
+/* Introspection of the compiled plan of the current circuit (for DESIGN/bench accounting):
+ *   info[0] gate passes over the state, info[1] expectation-only passes, info[2] tile qubits k,
+ *   info[3] kernel launches per energy call, info[4] Hamiltonian flip-mask groups M, info[5] non-zeros kept
+ *   of a dense Hamiltonian (0 if Pauli), info[6] unitary gates G, info[7] rotation gates.
+ * which: 0 = pure-state plan, 1 = density-matrix plan, 2 = pure-state plan with trajectory-noise slots. */
+int tq_plan_info(tq_handle h, int which, int64_t* info8);
+
+/* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+int64_t tq_launch_count(tq_handle h);
+
+/* Diagnostics -- planner dry run, needs no GPU: text dump ("PASS lead=.. local=a,b,.." / "OP op a b t flags fixed"
+ * lines) of the tile passes the circuit compiler produces for a gate list.  which as in tq_plan_info (2 =
+ * trajectory-noise plan).  The caller releases the string with tq_free. */
+char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t* q0, const int32_t* q1,
+                   const int32_t* param_idx, const double* fixed, int which, int tile_bits, int low_bits,
+                   int n_cover, const uint64_t* cover_masks);
+void tq_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TQSIM_H */

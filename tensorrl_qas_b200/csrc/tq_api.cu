@@ -1,0 +1,783 @@
+// tq_api.cu -- the C ABI of libtqsim (include/tqsim.h): handle, Hamiltonian/circuit compilation, launch sequencing.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/tqsim.h"
+#include "tq_kernels.cuh"
+#include "tq_plan.h"
+
+using namespace tq;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HamGroup {
+    uint64_t x;
+    std::vector<int> terms;
+};
+
+struct DevPass {
+    PassParams proto;  // geometry + device pointers filled at compile time
+    int threads = 0;
+    int n_tiles = 1;
+    int n_groups = 0;
+    bool gate_pass = true;
+};
+
+struct Plan {
+    bool valid = false;
+    int nbits = 0;
+    std::vector<DevPass> passes;  // gate passes first, then expectation-only passes
+    int n_gate_passes = 0;
+    int slots = 0;        // partial sums per element
+    int n_unitary = 0, n_rot = 0;
+    void* arena = nullptr;  // device blob holding ops / groups / terms of all passes
+    size_t arena_cap = 0;
+};
+
+}  // namespace
+
+struct tq_context {
+    int n = 0, device = 0;
+    std::string err;
+    PlanOptions opt;
+    size_t max_scratch = (size_t)16 << 30;
+
+    // Hamiltonian
+    bool have_pauli = false, have_dense = false;
+    std::vector<uint64_t> px, pz;
+    std::vector<double> pre, pim;  // already multiplied by i^{#Y}
+    std::vector<HamGroup> groups;
+    std::vector<HEntry> hent;
+    HEntry* d_hent = nullptr;
+    size_t d_hent_cap = 0;
+    bool hent_uploaded = false;
+
+    // initial state
+    bool have_init = false;
+    std::vector<double> init_host;
+    double2* d_init = nullptr;
+    double2* d_init_rho = nullptr;
+    bool init_rho_valid = false;
+
+    // circuit
+    bool have_circuit = false;
+    std::vector<Gate> gates;
+    int n_params = 0, n_slots = 0;
+    Plan plan_sv, plan_traj, plan_dm;
+
+    // scratch
+    double2* d_state = nullptr;
+    size_t state_cap = 0;  // bytes
+    double* d_partial = nullptr;
+    size_t partial_cap = 0;  // doubles
+
+    // host-call staging
+    cudaStream_t stream = nullptr;
+    cudaStream_t last_stream = nullptr;
+    void* h_pin = nullptr;
+    size_t h_pin_cap = 0;
+    void* d_stage = nullptr;
+    size_t d_stage_cap = 0;
+
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(tq_handle h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define TQ_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? TQ_ENOMEM : TQ_ECUDA,                      \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                            \
+    } while (0)
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+void invalidate_plans(tq_handle h) {
+    h->plan_sv.valid = h->plan_traj.valid = h->plan_dm.valid = false;
+}
+
+int grow(tq_handle h, void** ptr, size_t* cap, size_t need) {
+    if (need <= *cap) return TQ_OK;
+    if (*ptr) TQ_CUDA(cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    TQ_CUDA(cudaMalloc(ptr, need));
+    *cap = need;
+    return TQ_OK;
+}
+
+// ---------------------------------------------------------------- Hamiltonian -> groups / sparse entries -----
+void build_groups(tq_handle h) {
+    h->groups.clear();
+    std::map<uint64_t, int> index;
+    for (size_t t = 0; t < h->px.size(); ++t) {
+        auto it = index.find(h->px[t]);
+        if (it == index.end()) {
+            index[h->px[t]] = (int)h->groups.size();
+            h->groups.push_back({h->px[t], {}});
+            it = index.find(h->px[t]);
+        }
+        h->groups[it->second].terms.push_back((int)t);
+    }
+}
+
+// sparse upper-triangular entries of the symmetrised Pauli sum (n <= kMaxTileBits)
+void entries_from_pauli(tq_handle h) {
+    const int n = h->n;
+    const size_t dim = (size_t)1 << n;
+    h->hent.clear();
+    std::vector<double> fre(dim), fim(dim);
+    for (const HamGroup& g : h->groups) {
+        std::fill(fre.begin(), fre.end(), 0.0);
+        std::fill(fim.begin(), fim.end(), 0.0);
+        for (int t : g.terms) {
+            const uint64_t z = h->pz[t];
+            for (size_t i = 0; i < dim; ++i) {
+                const bool neg = __builtin_parityll(i & z);
+                fre[i] += neg ? -h->pre[t] : h->pre[t];
+                fim[i] += neg ? -h->pim[t] : h->pim[t];
+            }
+        }
+        // <i^x| H |i> = f(i)
+        for (size_t i = 0; i < dim; ++i) {
+            const size_t r = i ^ g.x, c = i;
+            if (r > c) continue;
+            HEntry e;
+            e.r = (uint32_t)r;
+            e.c = (uint32_t)c;
+            if (r == c) { e.re = fre[i]; e.im = 0.0; }
+            else { e.re = fre[c] + fre[r]; e.im = fim[c] - fim[r]; }  // H[r][c] + conj(H[c][r])
+            if (e.re != 0.0 || e.im != 0.0) h->hent.push_back(e);
+        }
+    }
+    std::sort(h->hent.begin(), h->hent.end(),
+              [](const HEntry& a, const HEntry& b) { return a.r != b.r ? a.r < b.r : a.c < b.c; });
+}
+
+void entries_from_dense(tq_handle h, const double* H) {
+    const size_t dim = (size_t)1 << h->n;
+    h->hent.clear();
+    for (size_t r = 0; r < dim; ++r)
+        for (size_t c = r; c < dim; ++c) {
+            const double* a = H + 2 * (r * dim + c);
+            const double* b = H + 2 * (c * dim + r);
+            HEntry e;
+            e.r = (uint32_t)r;
+            e.c = (uint32_t)c;
+            if (r == c) { e.re = a[0]; e.im = 0.0; }
+            else { e.re = a[0] + b[0]; e.im = a[1] - b[1]; }
+            if (e.re != 0.0 || e.im != 0.0) h->hent.push_back(e);
+        }
+}
+
+int upload_entries(tq_handle h) {
+    if (h->hent_uploaded) return TQ_OK;
+    if (h->last_stream) TQ_CUDA(cudaStreamSynchronize(h->last_stream));
+    const size_t bytes = std::max<size_t>(h->hent.size(), 1) * sizeof(HEntry);
+    int rc = grow(h, (void**)&h->d_hent, &h->d_hent_cap, bytes);
+    if (rc) return rc;
+    if (!h->hent.empty())
+        TQ_CUDA(cudaMemcpy(h->d_hent, h->hent.data(), h->hent.size() * sizeof(HEntry), cudaMemcpyHostToDevice));
+    h->hent_uploaded = true;
+    return TQ_OK;
+}
+
+// ---------------------------------------------------------------- plan compilation ---------------------------
+void fill_geometry(PassParams& pp, const Pass& p, int nbits) {
+    memset(&pp, 0, sizeof(pp));
+    pp.nbits = nbits;
+    pp.k = (int)p.local.size();
+    pp.lead = p.lead;
+    pp.n_nl = (int)p.nonlocal.size();
+    for (size_t i = 0; i < p.local.size(); ++i) pp.local[i] = (uint8_t)p.local[i];
+    for (size_t i = 0; i < p.nonlocal.size(); ++i) pp.nonlocal[i] = (uint8_t)p.nonlocal[i];
+}
+
+int threads_for(int k) {
+    int t = (1 << k) / 2;
+    t = std::max(32, std::min(kMaxThreads, t));
+    return (t + 31) / 32 * 32;
+}
+
+// which: 0 pure, 1 density matrix, 2 pure + trajectory noise
+int compile_plan(tq_handle h, int which) {
+    Plan& plan = which == 1 ? h->plan_dm : (which == 2 ? h->plan_traj : h->plan_sv);
+    if (plan.valid) return TQ_OK;
+    if (!h->have_circuit) return fail(h, TQ_ESTATE, "no circuit set (tq_set_circuit)");
+    const int n = h->n;
+    const int nbits = which == 1 ? 2 * n : n;
+    PlanOptions opt = h->opt;
+    opt.trajectory = (which == 2);
+    const bool single_tile = nbits <= opt.tile_bits;
+    std::string perr;
+
+    std::vector<uint64_t> cover;
+    if (which != 1 && !single_tile && h->have_pauli)
+        for (const HamGroup& g : h->groups)
+            if (g.x) cover.push_back(g.x);
+
+    std::vector<Pass> passes = which == 1 ? plan_density(n, h->gates, opt, &perr)
+                                          : plan_statevector(n, h->gates, opt, cover, &perr);
+    if (!perr.empty()) return fail(h, TQ_EINVAL, perr);
+    if (passes.empty()) {  // no gates: one pass that just stages the initial state
+        std::vector<int> dummy;
+        passes = plan_cover(nbits, {0ull}, opt, &dummy);
+    }
+    for (const Pass& p : passes)
+        if (p.ops.empty() && passes.size() > 1) return fail(h, TQ_EINVAL, "planner produced an empty pass");
+    const int n_gate_passes = (int)passes.size();
+
+    // expectation assignment (pure paths with more than one tile): group -> pass
+    std::vector<std::vector<int>> groups_of_pass(passes.size());
+    if (which != 1 && !single_tile && h->have_pauli) {
+        std::vector<uint64_t> todo;
+        std::vector<int> todo_group;
+        for (size_t g = 0; g < h->groups.size(); ++g) {
+            if (mask_is_local(passes.back(), h->groups[g].x)) groups_of_pass[n_gate_passes - 1].push_back((int)g);
+            else { todo.push_back(h->groups[g].x); todo_group.push_back((int)g); }
+        }
+        if (!todo.empty()) {
+            std::vector<int> assign;
+            std::vector<Pass> extra = plan_cover(n, todo, opt, &assign);
+            for (size_t i = 0; i < todo.size(); ++i) {
+                if (assign[i] < 0) return fail(h, TQ_EINVAL, "Hamiltonian term flips more qubits than a tile holds");
+            }
+            const size_t base = passes.size();
+            groups_of_pass.resize(base + extra.size());
+            for (size_t i = 0; i < todo.size(); ++i) groups_of_pass[base + assign[i]].push_back(todo_group[i]);
+            for (Pass& p : extra) passes.push_back(std::move(p));
+        }
+    }
+
+    // ---- serialise ops / groups / terms of every pass into one device blob ----
+    std::vector<unsigned char> blob;
+    auto append = [&](const void* data, size_t bytes) {
+        const size_t off = (blob.size() + 15) / 16 * 16;
+        blob.resize(off + bytes);
+        if (bytes) memcpy(blob.data() + off, data, bytes);
+        return off;
+    };
+    struct Offsets { size_t ops, groups, terms; int n_groups; };
+    std::vector<Offsets> offs(passes.size());
+    for (size_t i = 0; i < passes.size(); ++i) {
+        const Pass& p = passes[i];
+        offs[i].ops = append(p.ops.data(), p.ops.size() * sizeof(DevOp));
+        std::vector<ExpGroup> eg;
+        std::vector<ExpTerm> et;
+        for (int g : groups_of_pass[i]) {
+            ExpGroup x{};
+            x.xlocal = mask_to_local(p, h->groups[g].x);
+            x.term_begin = (int)et.size();
+            for (int t : h->groups[g].terms) {
+                ExpTerm term{};
+                term.zlocal = mask_to_local(p, h->pz[t]);
+                uint64_t lmask = 0;
+                for (int q : p.local) lmask |= 1ull << q;
+                term.zphys = h->pz[t] & ~lmask;
+                term.wre = h->pre[t];
+                term.wim = h->pim[t];
+                et.push_back(term);
+            }
+            x.term_end = (int)et.size();
+            eg.push_back(x);
+        }
+        offs[i].groups = append(eg.data(), eg.size() * sizeof(ExpGroup));
+        offs[i].terms = append(et.data(), et.size() * sizeof(ExpTerm));
+        offs[i].n_groups = (int)eg.size();
+    }
+    if (h->last_stream) TQ_CUDA(cudaStreamSynchronize(h->last_stream));
+    int rc = grow(h, &plan.arena, &plan.arena_cap, std::max<size_t>(blob.size(), 16));
+    if (rc) return rc;
+    if (!blob.empty()) TQ_CUDA(cudaMemcpy(plan.arena, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+
+    plan.passes.clear();
+    plan.nbits = nbits;
+    plan.n_gate_passes = n_gate_passes;
+    plan.slots = 0;
+    const unsigned char* base = (const unsigned char*)plan.arena;
+    for (size_t i = 0; i < passes.size(); ++i) {
+        DevPass dp;
+        fill_geometry(dp.proto, passes[i], nbits);
+        dp.threads = threads_for(dp.proto.k);
+        dp.n_tiles = 1 << dp.proto.n_nl;
+        dp.gate_pass = (int)i < n_gate_passes;
+        dp.proto.ops = (const DevOp*)(base + offs[i].ops);
+        dp.proto.n_ops = (int)passes[i].ops.size();
+        dp.n_groups = offs[i].n_groups;
+        if (which != 1) {
+            if (single_tile) {
+                dp.proto.exp_mode = 2;
+            } else if (dp.n_groups > 0) {
+                dp.proto.exp_mode = 1;
+                dp.proto.groups = (const ExpGroup*)(base + offs[i].groups);
+                dp.proto.n_groups = dp.n_groups;
+                dp.proto.terms = (const ExpTerm*)(base + offs[i].terms);
+            }
+            if (dp.proto.exp_mode) {
+                dp.proto.partial_off = plan.slots;
+                plan.slots += dp.n_tiles;
+            }
+        }
+        if (tile_pass_smem_bytes(dp.proto.k, dp.proto.lead) > 227 * 1024)
+            return fail(h, TQ_EINVAL, "tile does not fit shared memory (lower TQ_TILE_BITS)");
+        plan.passes.push_back(dp);
+    }
+    plan.n_unitary = plan.n_rot = 0;
+    for (const Gate& g : h->gates) {
+        if (g.kind <= TQ_Z) ++plan.n_unitary;
+        if (g.kind <= TQ_RZ) ++plan.n_rot;
+    }
+    plan.valid = true;
+    return TQ_OK;
+}
+
+int ensure_state(tq_handle h, size_t bytes) { return grow(h, (void**)&h->d_state, &h->state_cap, bytes); }
+
+int ensure_partial(tq_handle h, size_t doubles) {
+    size_t cap_bytes = h->partial_cap * sizeof(double);
+    int rc = grow(h, (void**)&h->d_partial, &cap_bytes, doubles * sizeof(double));
+    h->partial_cap = cap_bytes / sizeof(double);
+    return rc;
+}
+
+int check_launch(tq_handle h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, TQ_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return TQ_OK;
+}
+
+int ensure_init_rho(tq_handle h) {
+    if (!h->have_init || h->init_rho_valid) return TQ_OK;
+    const size_t dim = (size_t)1 << h->n;
+    std::vector<double> rho(2 * dim * dim);
+    const double* v = h->init_host.data();
+    for (size_t c = 0; c < dim; ++c)
+        for (size_t r = 0; r < dim; ++r) {  // rho[r][c] = v_r conj(v_c) at r + (c << n)
+            rho[2 * (r + (c << h->n))] = v[2 * r] * v[2 * c] + v[2 * r + 1] * v[2 * c + 1];
+            rho[2 * (r + (c << h->n)) + 1] = v[2 * r + 1] * v[2 * c] - v[2 * r] * v[2 * c + 1];
+        }
+    if (h->d_init_rho) TQ_CUDA(cudaFree(h->d_init_rho));
+    h->d_init_rho = nullptr;
+    TQ_CUDA(cudaMalloc((void**)&h->d_init_rho, rho.size() * sizeof(double)));
+    TQ_CUDA(cudaMemcpy(h->d_init_rho, rho.data(), rho.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->init_rho_valid = true;
+    return TQ_OK;
+}
+
+// Run the plan for `batch` elements.  mode: 0 energies, 1 final states into `states_out` (gate passes only).
+int run_plan(tq_handle h, int which, int batch, const double* params, int ld, const uint8_t* codes, int ldc,
+             double* out, double2* states_out, cudaStream_t stream) {
+    if (batch <= 0) return TQ_OK;
+    int rc = compile_plan(h, which);
+    if (rc) return rc;
+    Plan& plan = which == 1 ? h->plan_dm : (which == 2 ? h->plan_traj : h->plan_sv);
+    if (plan.n_rot > 0 && (!params || ld < h->n_params) && h->n_params > 0)
+        return fail(h, TQ_EINVAL, "params is NULL or ld_params < n_params");
+    if (which == 2 && h->n_slots > 0 && (!codes || ldc < h->n_slots))
+        return fail(h, TQ_EINVAL, "codes is NULL or ld_codes < number of noise slots");
+    const bool want_energy = states_out == nullptr;
+    const bool dm = which == 1;
+    const bool single_tile = plan.nbits <= h->opt.tile_bits;
+    if (want_energy) {
+        if (!h->have_pauli && !h->have_dense) return fail(h, TQ_ESTATE, "no Hamiltonian set");
+        if ((dm || single_tile)) {
+            if (h->n > kMaxTileBits) return fail(h, TQ_EINVAL, "density-matrix / dense path needs n_qubits <= 13");
+            rc = upload_entries(h);
+            if (rc) return rc;
+        } else if (!h->have_pauli)
+            return fail(h, TQ_ESTATE, "n_qubits exceeds one tile: set the Hamiltonian as a Pauli sum");
+    }
+    if (dm) { rc = ensure_init_rho(h); if (rc) return rc; }
+
+    const size_t elem_bytes = (size_t)16 << plan.nbits;
+    const int total_passes = want_energy ? (int)plan.passes.size() : plan.n_gate_passes;
+    const bool needs_buffer = states_out == nullptr && (total_passes > 1 || dm);
+    int chunk = batch;
+    if (needs_buffer) {
+        const size_t cap_elems = std::max<size_t>(1, h->max_scratch / elem_bytes);
+        chunk = (int)std::min<size_t>(batch, cap_elems);
+        const int forced = env_int("TQ_CHUNK_ELEMS", 0);
+        if (forced > 0) chunk = std::min(chunk, forced);
+        rc = ensure_state(h, (size_t)chunk * elem_bytes);
+        if (rc) return rc;
+    }
+    chunk = std::min(chunk, (int)(0x7fffffffu >> std::max(0, plan.nbits - h->opt.tile_bits)) / 2);  // grid.x limit
+    if (want_energy && !dm && plan.slots > 1) { rc = ensure_partial(h, (size_t)chunk * plan.slots); if (rc) return rc; }
+
+    h->last_stream = stream;
+    for (int b0 = 0; b0 < batch; b0 += chunk) {
+        const int bc = std::min(chunk, batch - b0);
+        double2* buf = states_out ? states_out + ((size_t)b0 << plan.nbits) : h->d_state;
+        for (int i = 0; i < total_passes; ++i) {
+            const DevPass& dp = plan.passes[i];
+            PassParams pp = dp.proto;
+            pp.params = params ? params + (size_t)b0 * ld : nullptr;
+            pp.ld_params = ld;
+            pp.codes = codes ? codes + (size_t)b0 * ldc : nullptr;
+            pp.ld_codes = ldc;
+            if (i == 0) {
+                if (h->have_init) { pp.src_mode = 1; pp.src = dm ? h->d_init_rho : h->d_init; }
+                else { pp.src_mode = 0; pp.src = nullptr; }
+            } else { pp.src_mode = 2; pp.src = buf; }
+            const bool is_last = (i == total_passes - 1);
+            pp.dst = (states_out || dm || !is_last) && dp.gate_pass ? buf : nullptr;
+            if (!want_energy || dm) pp.exp_mode = 0;
+            if (pp.exp_mode == 2) { pp.hent = h->d_hent; pp.n_hent = (int)h->hent.size(); }
+            if (pp.exp_mode) {
+                if (plan.slots == 1) { pp.partial = out + b0; pp.partial_ld = 1; pp.partial_off = 0; }
+                else { pp.partial = h->d_partial; pp.partial_ld = plan.slots; }
+            }
+            launch_tile_pass(pp, bc, dp.threads, stream);
+            ++h->launches;
+            rc = check_launch(h, "tile_pass_kernel");
+            if (rc) return rc;
+        }
+        if (want_energy) {
+            if (dm) {
+                launch_dm_expect(buf, h->n, h->d_hent, (int)h->hent.size(), out + b0, bc, stream);
+                ++h->launches;
+                rc = check_launch(h, "dm_expect_kernel");
+                if (rc) return rc;
+            } else if (plan.slots > 1) {
+                launch_reduce_partials(h->d_partial, plan.slots, plan.slots, out + b0, bc, stream);
+                ++h->launches;
+                rc = check_launch(h, "reduce_partials_kernel");
+                if (rc) return rc;
+            }
+        }
+    }
+    return TQ_OK;
+}
+
+int ensure_staging(tq_handle h, size_t bytes) {
+    if (bytes > h->h_pin_cap) {
+        if (h->h_pin) TQ_CUDA(cudaFreeHost(h->h_pin));
+        h->h_pin = nullptr;
+        h->h_pin_cap = 0;
+        TQ_CUDA(cudaMallocHost(&h->h_pin, bytes));
+        h->h_pin_cap = bytes;
+    }
+    return grow(h, &h->d_stage, &h->d_stage_cap, bytes);
+}
+
+// host-buffer front end shared by the *_host entry points
+int run_host(tq_handle h, int which, int batch, const double* params_host, int ld, const uint8_t* codes_host, int ldc,
+             double* out_host, double* states_host, size_t state_elems_per_batch) {
+    if (!h) return TQ_EINVAL;
+    if (batch <= 0) return TQ_OK;
+    TQ_CUDA(cudaSetDevice(h->device));
+    const size_t pbytes = params_host ? (size_t)batch * ld * sizeof(double) : 0;
+    const size_t cbytes = codes_host ? ((size_t)batch * ldc + 15) / 16 * 16 : 0;
+    const size_t obytes = (size_t)batch * sizeof(double);
+    const size_t sbytes = states_host ? (size_t)batch * state_elems_per_batch * 16 : 0;
+    const size_t p_off = 0, c_off = (pbytes + 15) / 16 * 16, o_off = c_off + cbytes;
+    const size_t s_off = (o_off + obytes + 15) / 16 * 16;
+    int rc = ensure_staging(h, s_off + sbytes + 16);
+    if (rc) return rc;
+    unsigned char* hp = (unsigned char*)h->h_pin;
+    unsigned char* dp = (unsigned char*)h->d_stage;
+    if (pbytes) {
+        memcpy(hp + p_off, params_host, pbytes);
+        TQ_CUDA(cudaMemcpyAsync(dp + p_off, hp + p_off, pbytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (cbytes) {
+        memcpy(hp + c_off, codes_host, (size_t)batch * ldc);
+        TQ_CUDA(cudaMemcpyAsync(dp + c_off, hp + c_off, cbytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = run_plan(h, which, batch, pbytes ? (const double*)(dp + p_off) : nullptr, ld,
+                  cbytes ? (const uint8_t*)(dp + c_off) : nullptr, ldc, (double*)(dp + o_off),
+                  states_host ? (double2*)(dp + s_off) : nullptr, h->stream);
+    if (rc) return rc;
+    if (states_host) {
+        TQ_CUDA(cudaMemcpyAsync(hp + s_off, dp + s_off, sbytes, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        TQ_CUDA(cudaMemcpyAsync(hp + o_off, dp + o_off, obytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    TQ_CUDA(cudaStreamSynchronize(h->stream));
+    if (states_host) memcpy(states_host, hp + s_off, sbytes);
+    else memcpy(out_host, hp + o_off, obytes);
+    return TQ_OK;
+}
+
+}  // namespace
+
+// =================================================================== C ABI ===================================
+extern "C" {
+
+int tq_version(void) { return TQ_VERSION; }
+
+int tq_create(int n_qubits, int device_id, tq_handle* out) {
+    if (!out) return TQ_EINVAL;
+    *out = nullptr;
+    if (n_qubits < 1 || n_qubits > 30) { g_create_error = "n_qubits must be in [1, 30]"; return TQ_EINVAL; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (libtqsim has no CPU fallback)";
+        return TQ_ENODEV;
+    }
+    if (device_id < 0 || device_id >= count) { g_create_error = "device_id out of range"; return TQ_EINVAL; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return TQ_ECUDA; }
+    if (prop.major != 10) {
+        g_create_error = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                         "; libtqsim is built for sm_100a (B200) only";
+        return TQ_ENODEV;
+    }
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return TQ_ECUDA; }
+    if ((e = tile_pass_configure()) != cudaSuccess) {
+        g_create_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+        return TQ_ECUDA;
+    }
+    tq_context* h = new tq_context();
+    h->n = n_qubits;
+    h->device = device_id;
+    h->opt.tile_bits = std::max(8, std::min(kMaxTileBits, env_int("TQ_TILE_BITS", 12)));
+    h->opt.low_bits = std::max(0, std::min(h->opt.tile_bits - 4, env_int("TQ_LOW_BITS", 4)));
+    h->max_scratch = (size_t)std::max(64, env_int("TQ_MAX_SCRATCH_MB", 16384)) << 20;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete h;
+        return TQ_ECUDA;
+    }
+    *out = h;
+    return TQ_OK;
+}
+
+int tq_destroy(tq_handle h) {
+    if (!h) return TQ_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (Plan* p : {&h->plan_sv, &h->plan_traj, &h->plan_dm})
+        if (p->arena) cudaFree(p->arena);
+    if (h->d_hent) cudaFree(h->d_hent);
+    if (h->d_init) cudaFree(h->d_init);
+    if (h->d_init_rho) cudaFree(h->d_init_rho);
+    if (h->d_state) cudaFree(h->d_state);
+    if (h->d_partial) cudaFree(h->d_partial);
+    if (h->d_stage) cudaFree(h->d_stage);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return TQ_OK;
+}
+
+const char* tq_last_error(tq_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int tq_set_pauli_hamiltonian(tq_handle h, int n_terms, const uint64_t* xmask, const uint64_t* zmask,
+                             const double* coeff_re, const double* coeff_im) {
+    if (!h) return TQ_EINVAL;
+    if (n_terms < 0 || (n_terms > 0 && (!xmask || !zmask || !coeff_re))) return fail(h, TQ_EINVAL, "bad Pauli term arrays");
+    const uint64_t valid = (h->n >= 64) ? ~0ull : ((1ull << h->n) - 1);
+    for (int t = 0; t < n_terms; ++t)
+        if ((xmask[t] | zmask[t]) & ~valid) return fail(h, TQ_EINVAL, "Pauli term " + std::to_string(t) + " touches a qubit >= n_qubits");
+    TQ_CUDA(cudaSetDevice(h->device));
+    h->px.assign(xmask, xmask + n_terms);
+    h->pz.assign(zmask, zmask + n_terms);
+    h->pre.resize(n_terms);
+    h->pim.resize(n_terms);
+    for (int t = 0; t < n_terms; ++t) {
+        const double re = coeff_re[t], im = coeff_im ? coeff_im[t] : 0.0;
+        switch (__builtin_popcountll(xmask[t] & zmask[t]) & 3) {  // times i^{#Y}
+        case 0: h->pre[t] = re; h->pim[t] = im; break;
+        case 1: h->pre[t] = -im; h->pim[t] = re; break;
+        case 2: h->pre[t] = -re; h->pim[t] = -im; break;
+        default: h->pre[t] = im; h->pim[t] = -re; break;
+        }
+    }
+    build_groups(h);
+    h->have_pauli = true;
+    h->have_dense = false;
+    h->hent.clear();
+    if (h->n <= kMaxTileBits) entries_from_pauli(h);
+    h->hent_uploaded = false;
+    invalidate_plans(h);
+    return TQ_OK;
+}
+
+int tq_set_dense_hamiltonian(tq_handle h, const double* h_matrix_host) {
+    if (!h) return TQ_EINVAL;
+    if (!h_matrix_host) return fail(h, TQ_EINVAL, "matrix is NULL");
+    if (h->n > kMaxTileBits) return fail(h, TQ_EINVAL, "dense Hamiltonian needs n_qubits <= 13");
+    entries_from_dense(h, h_matrix_host);
+    h->have_dense = true;
+    h->have_pauli = false;
+    h->groups.clear();
+    h->px.clear();
+    h->hent_uploaded = false;
+    invalidate_plans(h);
+    return TQ_OK;
+}
+
+int tq_set_init_state(tq_handle h, const double* psi) {
+    if (!h) return TQ_EINVAL;
+    TQ_CUDA(cudaSetDevice(h->device));
+    if (h->last_stream) TQ_CUDA(cudaStreamSynchronize(h->last_stream));
+    h->init_rho_valid = false;
+    if (!psi) { h->have_init = false; return TQ_OK; }
+    const size_t dim = (size_t)1 << h->n;
+    h->init_host.assign(psi, psi + 2 * dim);
+    if (!h->d_init) TQ_CUDA(cudaMalloc((void**)&h->d_init, dim * 16));
+    TQ_CUDA(cudaMemcpy(h->d_init, psi, dim * 16, cudaMemcpyHostToDevice));
+    h->have_init = true;
+    return TQ_OK;
+}
+
+int tq_set_circuit(tq_handle h, int n_gates, const int32_t* kind, const int32_t* q0, const int32_t* q1,
+                   const int32_t* param_idx, const double* fixed, int n_params) {
+    if (!h) return TQ_EINVAL;
+    if (n_gates < 0 || n_params < 0 || (n_gates > 0 && (!kind || !q0 || !q1 || !param_idx || !fixed)))
+        return fail(h, TQ_EINVAL, "bad circuit arrays");
+    std::vector<Gate> gates(n_gates);
+    int n_slots = 0;
+    for (int g = 0; g < n_gates; ++g) {
+        gates[g] = Gate{kind[g], q0[g], q1[g], param_idx[g], fixed[g]};
+        if (kind[g] <= TQ_RZ && kind[g] >= TQ_RX && param_idx[g] >= n_params)
+            return fail(h, TQ_EINVAL, "gate " + std::to_string(g) + ": param_idx >= n_params");
+        if (kind[g] == TQ_DEPOL1 || kind[g] == TQ_DEPOL2) {
+            n_slots = std::max(n_slots, param_idx[g] + 1);
+            if (!(fixed[g] >= 0.0 && fixed[g] <= 1.0)) return fail(h, TQ_EINVAL, "gate " + std::to_string(g) + ": probability outside [0, 1]");
+        }
+    }
+    std::string perr;
+    PlanOptions probe = h->opt;
+    (void)plan_statevector(h->n, gates, probe, {}, &perr);  // validates kinds / qubit ranges
+    if (!perr.empty()) return fail(h, TQ_EINVAL, perr);
+    h->gates.swap(gates);
+    h->n_params = n_params;
+    h->n_slots = n_slots;
+    h->have_circuit = true;
+    invalidate_plans(h);
+    return TQ_OK;
+}
+
+int tq_energy_batch(tq_handle h, int batch, const double* params_dev, int ld_params, double* out_dev, void* stream) {
+    if (!h || !out_dev) return TQ_EINVAL;
+    TQ_CUDA(cudaSetDevice(h->device));
+    return run_plan(h, 0, batch, params_dev, ld_params, nullptr, 0, out_dev, nullptr, (cudaStream_t)stream);
+}
+
+int tq_energy_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* out_host) {
+    if (!h || !out_host) return TQ_EINVAL;
+    return run_host(h, 0, batch, params_host, ld_params, nullptr, 0, out_host, nullptr, 0);
+}
+
+int tq_energy_traj_batch(tq_handle h, int batch, const double* params_dev, int ld_params, const uint8_t* codes_dev,
+                         int ld_codes, double* out_dev, void* stream) {
+    if (!h || !out_dev) return TQ_EINVAL;
+    TQ_CUDA(cudaSetDevice(h->device));
+    return run_plan(h, 2, batch, params_dev, ld_params, codes_dev, ld_codes, out_dev, nullptr, (cudaStream_t)stream);
+}
+
+int tq_energy_traj_batch_host(tq_handle h, int batch, const double* params_host, int ld_params,
+                              const uint8_t* codes_host, int ld_codes, double* out_host) {
+    if (!h || !out_host) return TQ_EINVAL;
+    return run_host(h, 2, batch, params_host, ld_params, codes_host, ld_codes, out_host, nullptr, 0);
+}
+
+int tq_energy_dm_batch(tq_handle h, int batch, const double* params_dev, int ld_params, double* out_dev, void* stream) {
+    if (!h || !out_dev) return TQ_EINVAL;
+    if (h->n > kMaxTileBits) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
+    TQ_CUDA(cudaSetDevice(h->device));
+    return run_plan(h, 1, batch, params_dev, ld_params, nullptr, 0, out_dev, nullptr, (cudaStream_t)stream);
+}
+
+int tq_energy_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* out_host) {
+    if (!h || !out_host) return TQ_EINVAL;
+    if (h->n > kMaxTileBits) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
+    return run_host(h, 1, batch, params_host, ld_params, nullptr, 0, out_host, nullptr, 0);
+}
+
+int tq_state_batch(tq_handle h, int batch, const double* params_dev, int ld_params, double* states_dev, void* stream) {
+    if (!h || !states_dev) return TQ_EINVAL;
+    TQ_CUDA(cudaSetDevice(h->device));
+    return run_plan(h, 0, batch, params_dev, ld_params, nullptr, 0, nullptr, (double2*)states_dev, (cudaStream_t)stream);
+}
+
+int tq_state_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* states_host) {
+    if (!h || !states_host) return TQ_EINVAL;
+    return run_host(h, 0, batch, params_host, ld_params, nullptr, 0, nullptr, states_host, (size_t)1 << h->n);
+}
+
+int tq_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* rho_host) {
+    if (!h || !rho_host) return TQ_EINVAL;
+    if (h->n > kMaxTileBits) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
+    return run_host(h, 1, batch, params_host, ld_params, nullptr, 0, nullptr, rho_host, (size_t)1 << (2 * h->n));
+}
+
+int tq_plan_info(tq_handle h, int which, int64_t* info8) {
+    if (!h || !info8 || which < 0 || which > 2) return TQ_EINVAL;
+    TQ_CUDA(cudaSetDevice(h->device));
+    int rc = compile_plan(h, which);
+    if (rc) return rc;
+    const Plan& plan = which == 1 ? h->plan_dm : (which == 2 ? h->plan_traj : h->plan_sv);
+    info8[0] = plan.n_gate_passes;
+    info8[1] = (int64_t)plan.passes.size() - plan.n_gate_passes;
+    info8[2] = plan.passes.empty() ? 0 : plan.passes[0].proto.k;
+    info8[3] = (int64_t)plan.passes.size() + ((which == 1) ? 1 : (plan.slots > 1 ? 1 : 0));
+    info8[4] = (int64_t)h->groups.size();
+    info8[5] = (int64_t)h->hent.size();
+    info8[6] = plan.n_unitary;
+    info8[7] = plan.n_rot;
+    return TQ_OK;
+}
+
+int64_t tq_launch_count(tq_handle h) { return h ? h->launches : 0; }
+
+// --------------------------------------------------------------------------------------------------------------
+// Planner dry run (no GPU needed): text dump of the passes for a gate list, used by the CPU test-suite to check
+// the compiler's invariants.  Caller frees the string with tq_free.
+//   which: 0 pure, 1 density matrix, 2 trajectory
+char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t* q0, const int32_t* q1,
+                   const int32_t* param_idx, const double* fixed, int which, int tile_bits, int low_bits,
+                   int n_cover, const uint64_t* cover_masks) {
+    std::vector<Gate> gates(n_gates);
+    for (int g = 0; g < n_gates; ++g) gates[g] = Gate{kind[g], q0[g], q1[g], param_idx[g], fixed[g]};
+    PlanOptions opt;
+    opt.tile_bits = tile_bits;
+    opt.low_bits = low_bits;
+    opt.trajectory = (which == 2);
+    std::vector<uint64_t> cover(cover_masks, cover_masks + n_cover);
+    std::string err;
+    std::vector<Pass> passes = which == 1 ? plan_density(n_qubits, gates, opt, &err)
+                                          : plan_statevector(n_qubits, gates, opt, cover, &err);
+    std::string out;
+    char line[256];
+    if (!err.empty()) out = "ERROR " + err + "\n";
+    for (const Pass& p : passes) {
+        out += "PASS lead=" + std::to_string(p.lead) + " local=";
+        for (size_t i = 0; i < p.local.size(); ++i) out += (i ? "," : "") + std::to_string(p.local[i]);
+        out += "\n";
+        for (const DevOp& d : p.ops) {
+            snprintf(line, sizeof line, "OP %d %d %d %d %d %.17g\n", d.op, d.a, d.b, d.t, d.flags, d.fixed);
+            out += line;
+        }
+    }
+    char* res = (char*)malloc(out.size() + 1);
+    memcpy(res, out.c_str(), out.size() + 1);
+    return res;
+}
+
+void tq_free(void* p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// tq_kernels.cuh -- sm_100a kernels of libtqsim (batched complex128 statevector / density-matrix passes).
+//
+// One kernel does the heavy lifting: tile_pass_kernel.  A CTA owns one tile (2^k amplitudes that differ only in
+// the pass's k local qubits) of one batch element: it stages the tile in shared memory with coalesced 16-byte
+// loads (runs of 2^lead consecutive amplitudes), applies the pass's whole gate list there, optionally evaluates
+// the Hamiltonian terms whose flip masks are local (one deterministic partial sum per tile), and writes the tile
+// back.  HBM traffic per pass is one read + one write of the state no matter how many gates the pass fused.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tq_plan.h"
+
+namespace tq {
+
+constexpr int kMaxTileBits = 13;
+constexpr int kOpsChunk = 128;   // ops staged in shared memory at a time (with their cos/sin)
+constexpr int kMaxThreads = 256;
+
+struct ExpGroup {   // one X/Y flip mask of the Hamiltonian, local to the pass
+    uint32_t xlocal;
+    int32_t term_begin, term_end;
+    int32_t pad;
+};
+struct ExpTerm {    // coefficient already multiplied by i^{#Y}
+    uint64_t zphys;   // Z/Y bits on physical (non-tile) positions -> sign from the tile's base index
+    uint32_t zlocal;  // Z/Y bits on tile positions
+    uint32_t pad;
+    double wre, wim;
+};
+struct HEntry {     // non-zero of the symmetrised Hamiltonian, upper triangle, off-diagonals pre-doubled
+    uint32_t r, c;
+    double re, im;
+};
+
+struct PassParams {
+    int nbits, k, lead, n_nl;
+    uint8_t local[16];
+    uint8_t nonlocal[32];
+    const double2* src;
+    int src_mode;  // 0: |0...0>, 1: one shared initial vector, 2: per-element state buffer
+    double2* dst;  // nullptr: tile is not written back
+    const DevOp* ops;
+    int n_ops;
+    const double* params;
+    int ld_params;
+    const uint8_t* codes;
+    int ld_codes;
+    int exp_mode;  // 0 none, 1 Pauli groups, 2 sparse entries (single-tile passes only)
+    const ExpGroup* groups;
+    int n_groups;
+    const ExpTerm* terms;
+    const HEntry* hent;
+    int n_hent;
+    double* partial;  // partial[b * partial_ld + partial_off + tile]
+    int partial_ld, partial_off;
+};
+
+size_t tile_pass_smem_bytes(int k, int lead);
+cudaError_t tile_pass_configure();  // opt in to > 48 KiB dynamic shared memory
+void launch_tile_pass(const PassParams& p, int batch, int threads, cudaStream_t stream);
+
+// out[b] = sum_{s < n} partial[b * ld + s], fixed order
+void launch_reduce_partials(const double* partial, int ld, int n, double* out, int batch, cudaStream_t stream);
+
+// out[b] = sum_e Re(h_e * rho_b[c_e + (r_e << n)])
+void launch_dm_expect(const double2* rho, int n, const HEntry* hent, int n_hent, double* out, int batch,
+                      cudaStream_t stream);
+
+}  // namespace tq

@@ -1,0 +1,199 @@
+"""`Simulator`: Python handle over the C ABI of libtqsim (include/tqsim.h).
+
+Host buffers are numpy arrays; device buffers are torch CUDA tensors (torch is the allocator / stream plumbing
+only -- all arithmetic happens in libtqsim's kernels).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .circuit import GateList
+
+
+class TqError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libtqsim error {code}: {message}")
+        self.code = code
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_lib.c_dbl_p)
+
+
+class Simulator:
+    """One handle per (n_qubits, device): tq_create / tq_destroy."""
+
+    def __init__(self, n_qubits, device=0):
+        self._L = _lib.lib()
+        self.n_qubits = int(n_qubits)
+        self.device = int(device)
+        self._h = ctypes.c_void_p()
+        rc = self._L.tq_create(self.n_qubits, self.device, ctypes.byref(self._h))
+        if rc != 0:
+            msg = self._L.tq_last_error(None).decode()
+            self._h = None
+            raise TqError(rc, msg)
+        self.n_params = 0
+        self.n_slots = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise TqError(rc, self._L.tq_last_error(self._h).decode())
+
+    # ------------------------------------------------------------------ problem definition
+    def set_pauli_hamiltonian(self, xmask, zmask, coeff):
+        x = np.ascontiguousarray(xmask, dtype=np.uint64)
+        z = np.ascontiguousarray(zmask, dtype=np.uint64)
+        c = np.asarray(coeff)
+        cre = np.ascontiguousarray(c.real, dtype=np.float64)
+        cim = np.ascontiguousarray(c.imag, dtype=np.float64) if np.iscomplexobj(c) else None
+        self._check(self._L.tq_set_pauli_hamiltonian(
+            self._h, len(x), x.ctypes.data_as(_lib.c_u64_p), z.ctypes.data_as(_lib.c_u64_p), _dptr(cre),
+            _dptr(cim) if cim is not None else None))
+
+    def set_dense_hamiltonian(self, H):
+        H = np.ascontiguousarray(H, dtype=np.complex128)
+        dim = 1 << self.n_qubits
+        if H.shape != (dim, dim):
+            raise ValueError(f"Hamiltonian must be {dim}x{dim}")
+        self._check(self._L.tq_set_dense_hamiltonian(self._h, H.ctypes.data_as(_lib.c_dbl_p)))
+
+    def set_init_state(self, psi=None):
+        if psi is None:
+            self._check(self._L.tq_set_init_state(self._h, None))
+            return
+        psi = np.ascontiguousarray(psi, dtype=np.complex128).reshape(-1)
+        if psi.shape[0] != 1 << self.n_qubits:
+            raise ValueError("initial state has the wrong dimension")
+        self._check(self._L.tq_set_init_state(self._h, psi.ctypes.data_as(_lib.c_dbl_p)))
+
+    def set_circuit(self, gl: GateList):
+        kind, q0, q1, pidx, fixed = gl.arrays()
+        ip = _lib.c_int_p
+        self._check(self._L.tq_set_circuit(self._h, len(gl), kind.ctypes.data_as(ip), q0.ctypes.data_as(ip),
+                                           q1.ctypes.data_as(ip), pidx.ctypes.data_as(ip), _dptr(fixed), gl.n_params))
+        self.n_params = gl.n_params
+        self.n_slots = gl.n_slots
+
+    # ------------------------------------------------------------------ host-buffer evaluation (copies inside)
+    def _params(self, params):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        if p.ndim == 1:
+            p = p.reshape(1, -1)
+        if p.shape[1] == 0:
+            p = np.zeros((p.shape[0], 1), dtype=np.float64)
+        return p
+
+    def energies(self, params):
+        """[B][P] host angles -> [B] energies (tq_energy_batch_host)."""
+        p = self._params(params)
+        out = np.empty(p.shape[0], dtype=np.float64)
+        self._check(self._L.tq_energy_batch_host(self._h, p.shape[0], _dptr(p), p.shape[1], _dptr(out)))
+        return out
+
+    def energies_traj(self, params, codes):
+        p = self._params(params)
+        c = np.ascontiguousarray(codes, dtype=np.uint8)
+        if c.ndim == 1:
+            c = c.reshape(1, -1)
+        if c.shape[1] == 0:
+            c = np.zeros((c.shape[0], 1), dtype=np.uint8)
+        if c.shape[0] != p.shape[0]:
+            raise ValueError("params and codes disagree on the batch size")
+        out = np.empty(p.shape[0], dtype=np.float64)
+        self._check(self._L.tq_energy_traj_batch_host(self._h, p.shape[0], _dptr(p), p.shape[1],
+                                                      c.ctypes.data_as(_lib.c_u8_p), c.shape[1], _dptr(out)))
+        return out
+
+    def energies_dm(self, params):
+        p = self._params(params)
+        out = np.empty(p.shape[0], dtype=np.float64)
+        self._check(self._L.tq_energy_dm_batch_host(self._h, p.shape[0], _dptr(p), p.shape[1], _dptr(out)))
+        return out
+
+    def states(self, params):
+        p = self._params(params)
+        out = np.empty((p.shape[0], 1 << self.n_qubits), dtype=np.complex128)
+        self._check(self._L.tq_state_batch_host(self._h, p.shape[0], _dptr(p), p.shape[1],
+                                                out.ctypes.data_as(_lib.c_dbl_p)))
+        return out
+
+    def density_matrices(self, params):
+        """[B][2^n (col)][2^n (row)] : entry rho[r][c] of element b is out[b, c, r]."""
+        p = self._params(params)
+        dim = 1 << self.n_qubits
+        out = np.empty((p.shape[0], dim, dim), dtype=np.complex128)
+        self._check(self._L.tq_dm_batch_host(self._h, p.shape[0], _dptr(p), p.shape[1],
+                                             out.ctypes.data_as(_lib.c_dbl_p)))
+        return out
+
+    # ------------------------------------------------------------------ device-buffer evaluation (async)
+    def energies_dev(self, params, out=None, stream=None, mode="pure", codes=None):
+        """params: torch float64 CUDA tensor [B][ld]; returns a torch float64 CUDA tensor [B] (no sync)."""
+        import torch
+        if not params.is_cuda or params.dtype != torch.float64 or not params.is_contiguous():
+            raise ValueError("params must be a contiguous float64 CUDA tensor")
+        batch, ld = params.shape
+        if out is None:
+            out = torch.empty(batch, dtype=torch.float64, device=params.device)
+        s = stream if stream is not None else torch.cuda.current_stream(params.device).cuda_stream
+        if mode == "pure":
+            rc = self._L.tq_energy_batch(self._h, batch, params.data_ptr(), ld, out.data_ptr(), s)
+        elif mode == "dm":
+            rc = self._L.tq_energy_dm_batch(self._h, batch, params.data_ptr(), ld, out.data_ptr(), s)
+        elif mode == "traj":
+            rc = self._L.tq_energy_traj_batch(self._h, batch, params.data_ptr(), ld, codes.data_ptr(),
+                                              codes.shape[1], out.data_ptr(), s)
+        else:
+            raise ValueError(mode)
+        self._check(rc)
+        return out
+
+    # ------------------------------------------------------------------ introspection
+    def plan_info(self, which=0):
+        info = (ctypes.c_int64 * 8)()
+        self._check(self._L.tq_plan_info(self._h, which, info))
+        keys = ("gate_passes", "expectation_passes", "tile_bits", "launches_per_call", "groups", "nnz", "unitary_gates",
+                "rotation_gates")
+        return dict(zip(keys, [int(v) for v in info]))
+
+    @property
+    def launch_count(self):
+        return int(self._L.tq_launch_count(self._h))
+
+
+def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=()):
+    """Planner dry run (no GPU): list of passes, each {'lead', 'local', 'ops': [(op, a, b, t, flags, fixed)]}."""
+    L = _lib.lib()
+    kind, q0, q1, pidx, fixed = gl.arrays()
+    cm = np.ascontiguousarray(cover_masks, dtype=np.uint64)
+    ip = _lib.c_int_p
+    ptr = L.tq_plan_dump(gl.n_qubits, len(gl), kind.ctypes.data_as(ip), q0.ctypes.data_as(ip), q1.ctypes.data_as(ip),
+                         pidx.ctypes.data_as(ip), fixed.ctypes.data_as(_lib.c_dbl_p), which, tile_bits, low_bits,
+                         len(cm), cm.ctypes.data_as(_lib.c_u64_p))
+    text = ctypes.string_at(ptr).decode()
+    L.tq_free(ptr)
+    passes = []
+    for line in text.splitlines():
+        tok = line.split()
+        if tok[0] == "ERROR":
+            raise ValueError(line[6:])
+        if tok[0] == "PASS":
+            lead = int(tok[1].split("=")[1])
+            local = [int(v) for v in tok[2].split("=")[1].split(",") if v != ""]
+            passes.append({"lead": lead, "local": local, "ops": []})
+        else:
+            passes[-1]["ops"].append((int(tok[1]), int(tok[2]), int(tok[3]), int(tok[4]), int(tok[5]), float(tok[6])))
+    return passes

@@ -1,0 +1,100 @@
+"""CPU tests of the circuit compiler (tq_plan.cpp) through the no-GPU tq_plan_dump entry point."""
+import numpy as np
+import pytest
+
+from tensorrl_qas_b200.circuit import GateList, brickwork_circuit, parameter_batch, synthetic_circuit
+from tensorrl_qas_b200.simulator import plan_dump
+
+from plan_emulator import check_invariants, run_plan
+
+
+def noisy_circuit(n, g, seed):
+    base = synthetic_circuit(n, g, seed)
+    gl = GateList(n)
+    for kind, q0, q1, pidx, fixed in base.tuples():
+        if kind == 3:
+            gl.add_cnot(q0, q1)
+            gl.add_depol2(q0, q1, 0.05)
+        else:
+            gl.add_rotation(kind, q0, fixed)
+            gl.add_depol1(q0, 0.01)
+    return gl
+
+
+@pytest.mark.parametrize("n,tile_bits,low_bits,seed", [(5, 12, 4, 0), (9, 8, 4, 1), (10, 8, 2, 2), (11, 8, 4, 3),
+                                                        (12, 9, 3, 4)])
+def test_pure_plan_equals_gate_list(built_lib, oracle, n, tile_bits, low_bits, seed):
+    gl = synthetic_circuit(n, 120, seed)
+    gl.add_pauli("X", 0)
+    gl.add_pauli("Y", n - 1)
+    gl.add_pauli("Z", n // 2)
+    params = parameter_batch(gl, 1)[0]
+    passes = plan_dump(gl, 0, tile_bits, low_bits)
+    check_invariants(passes, n, tile_bits, low_bits)
+    assert sum(len(p["ops"]) for p in passes) == len(gl)
+    got = run_plan(passes, n, params)
+    want = oracle.state(gl, params)
+    assert np.abs(got - want).max() < 1e-12
+    if n > tile_bits:
+        assert len(passes) > 1
+
+
+def test_brickwork_c5_plan_is_few_passes(built_lib):
+    gl = brickwork_circuit(20, 21, 41, 5)
+    assert len(gl) == 440
+    passes = plan_dump(gl, 0, 12, 4)
+    check_invariants(passes, 20, 12, 4)
+    assert sum(len(p["ops"]) for p in passes) == 440
+    assert len(passes) <= 6  # 440 gates fused into a handful of HBM passes
+
+
+def test_cover_masks_pulled_into_last_pass(built_lib):
+    gl = synthetic_circuit(14, 10, 7, qubits=(0, 1, 2))
+    mask = (1 << 12) | (1 << 13)
+    passes = plan_dump(gl, 0, 10, 4, cover_masks=[mask])
+    assert 12 in passes[-1]["local"] and 13 in passes[-1]["local"]
+
+
+@pytest.mark.parametrize("n,tile_bits,seed", [(3, 12, 0), (5, 8, 1), (6, 8, 2)])
+def test_density_plan_equals_oracle(built_lib, oracle, n, tile_bits, seed):
+    gl = noisy_circuit(n, 14, seed)
+    params = parameter_batch(gl, 1)[0]
+    passes = plan_dump(gl, 1, tile_bits, 4)
+    check_invariants(passes, 2 * n, tile_bits, 4)
+    got = run_plan(passes, 2 * n, params)
+    want = oracle.density_matrix(gl, params).reshape(-1)
+    assert np.abs(got - want).max() < 1e-12
+    rho = got.reshape(1 << n, 1 << n)
+    assert abs(np.trace(rho) - 1) < 1e-12 and np.abs(rho - rho.conj().T).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,tile_bits,seed", [(6, 12, 0), (10, 8, 1)])
+def test_trajectory_plan_equals_oracle(built_lib, oracle, n, tile_bits, seed):
+    gl = noisy_circuit(n, 40, seed)
+    params = parameter_batch(gl, 1)[0]
+    rng = np.random.default_rng(seed)
+    codes = np.zeros(gl.n_slots, dtype=np.uint8)
+    for g, (kind, *_r) in enumerate(gl.tuples()):
+        if kind == 7:
+            codes[gl.pidx[g]] = rng.integers(4)
+        elif kind == 8:
+            codes[gl.pidx[g]] = rng.integers(16)
+    passes = plan_dump(gl, 2, tile_bits, 4)
+    check_invariants(passes, n, tile_bits, 4)
+    got = run_plan(passes, n, params, codes=codes)
+    want = oracle.state(gl, params, codes=codes)
+    assert np.abs(got - want).max() < 1e-12
+    # the noise-free plan skips the noise gates
+    clean = run_plan(plan_dump(gl, 0, tile_bits, 4), n, params)
+    assert np.abs(clean - oracle.state(gl, params)).max() < 1e-12
+
+
+def test_bad_gate_is_reported(built_lib):
+    gl = GateList(4)
+    gl.add_cnot(1, 1)
+    with pytest.raises(ValueError):
+        plan_dump(gl, 0, 12, 4)
+    gl = GateList(4)
+    gl.add_rotation(0, 7, 0.1)
+    with pytest.raises(ValueError):
+        plan_dump(gl, 0, 12, 4)
