@@ -25,6 +25,7 @@ import types
 import numpy as np
 
 _rng = np.random.default_rng(0)
+noise_log = []  # Pauli code drawn by every probabilistic gate application, in order (0 = identity)
 
 
 def seed(s):
@@ -104,12 +105,15 @@ class _Gate:
         elif k == "DEPOL1":
             u = _rng.random()
             p = self.value
+            code = 0
             if u < p:
                 code = 1 + min(int(u / (p / 3.0)), 2)
                 state.vec = apply_1q(state.vec, n, self.q0, _mat("XYZ"[code - 1]))
+            noise_log.append(code)
         elif k == "DEPOL2":
             u = _rng.random()
             p = self.value
+            code = 0
             if u < p:
                 code = 1 + min(int(u / (p / 15.0)), 14)  # 1..15 = pa + 4 pb
                 pa, pb = code & 3, code >> 2
@@ -117,6 +121,7 @@ class _Gate:
                     state.vec = apply_1q(state.vec, n, self.q0, _mat("XYZ"[pa - 1]))
                 if pb:
                     state.vec = apply_1q(state.vec, n, self.q1, _mat("XYZ"[pb - 1]))
+            noise_log.append(code)
         else:
             state.vec = apply_1q(state.vec, n, self.q0, _mat(k, self.value))
 

@@ -1,0 +1,186 @@
+"""CPU suite: the oracle (C restatement + numpy restatement) against the committed golden vectors, analytic
+identities and itself.  No GPU."""
+import numpy as np
+import pytest
+
+from oracle import np_oracle
+from tensorrl_qas_b200 import loaders
+from tensorrl_qas_b200.circuit import GateList, parameter_batch, synthetic_circuit
+
+from golden_util import CASES, Case
+
+TOL = 1e-10  # BASELINE.json north_star: 1e-10 Ha absolute energy
+
+
+def test_single_gate_identities_qulacs_sign(oracle):
+    """RX(t)|0>: <Z> = cos t, <Y> = +sin t with R = exp(+i t/2 P)."""
+    t = 0.7321
+    gl = GateList(1)
+    gl.add_rotation(0, 0, t)
+    psi = oracle.state(gl, [t])
+    z = oracle.expect_pauli(psi, [0], [1], [1.0])
+    y = oracle.expect_pauli(psi, [1], [1], [1.0])
+    assert abs(z - np.cos(t)) < 1e-14 and abs(y - np.sin(t)) < 1e-14
+    gl = GateList(1)
+    gl.add_rotation(1, 0, t)
+    psi = oracle.state(gl, [t])  # RY = [[c, s], [-s, c]] -> <X> = -sin t
+    assert abs(oracle.expect_pauli(psi, [1], [0], [1.0]) + np.sin(t)) < 1e-14
+    gl = GateList(1)
+    gl.add_rotation(2, 0, t)
+    psi = oracle.state(gl, [t])
+    assert abs(psi[0] - np.exp(0.5j * t)) < 1e-15
+
+
+def test_cnot_truth_table_little_endian(oracle):
+    for c, t in ((0, 1), (1, 0), (2, 0)):
+        for basis in range(8):
+            init = np.zeros(8, dtype=np.complex128)
+            init[basis] = 1
+            gl = GateList(3)
+            gl.add_cnot(c, t)
+            out = oracle.state(gl, [0.0], init=init)
+            want = basis ^ (1 << t) if (basis >> c) & 1 else basis
+            assert out[want] == 1 and np.abs(out).sum() == 1
+
+
+@pytest.mark.parametrize("n", [2, 4, 6, 9])
+def test_heisenberg_analytic(oracle, n):
+    """E(|0..0>) = 2n - 1 ; Neel state (X on odd sites) E = -(n - 1) for even n."""
+    paulis, w = loaders.heisenberg_terms(n)
+    x, z = loaders.pauli_masks(paulis, n)
+    gl = GateList(n)
+    assert abs(oracle.energies(gl, [[0.0]], pauli=(x, z, w))[0] - (2 * n - 1)) < 1e-12
+    if n % 2 == 0:
+        for q in range(1, n, 2):
+            gl.add_pauli("X", q)
+        assert abs(oracle.energies(gl, [[0.0]], pauli=(x, z, w))[0] + (n - 1)) < 1e-12
+
+
+def test_heisenberg_terms_match_reference_file():
+    """Generator vs the shipped 5-qubit term list (dmrg-to-qc/mol_data/heisenberg_5q.npz via the golden file)."""
+    c = Case("heis_5q")
+    paulis, w = loaders.heisenberg_terms(5)
+    assert paulis == c.paulis and np.array_equal(w, c.weights)
+
+
+@pytest.mark.parametrize("key", CASES)
+def test_c_oracle_matches_reference_python_golden(oracle, key):
+    """Energies produced by the reference's VQE_qulacs*.py (run over np_oracle) reproduced by the C restatement
+    from the same float32 tensors: tensor decoding, gate order, parameter mapping, init-state load, dense form."""
+    c = Case(key)
+    g = c.g
+    # TN-in-agent
+    gl = c.gatelist("in")
+    assert gl.n_params == g["in_X"].shape[1]
+    H = c.dense(False)
+    assert abs(H[0, 0].real - c.h00) < 1e-12
+    e = oracle.energies(gl, g["in_X"], dense=H)
+    assert np.abs(e - g["in_E"]).max() < TOL
+    x, z = c.masks(False)
+    e = oracle.energies(gl, g["in_X"], pauli=(x, z, c.weights))
+    assert np.abs(e - g["in_E"]).max() < TOL
+    e0 = oracle.energies(gl, [gl.initial_angles], dense=H)[0]
+    assert abs(e0 - float(g["in_e_tensor"])) < TOL
+    # TN-not-in-agent
+    gl2 = c.gatelist("notin")
+    e = oracle.energies(gl2, g["notin_X"], dense=c.dense(True), init=g["notin_tn_state"])
+    assert np.abs(e - g["notin_E"]).max() < TOL
+    x, z = c.masks(True)
+    e = oracle.energies(gl2, g["notin_X"], pauli=(x, z, c.weights), init=g["notin_tn_state"])
+    assert np.abs(e - g["notin_E"]).max() < TOL
+    assert np.all(g["in_E"] > c.eig_min - 1e-9) and np.all(g["notin_E"] > c.eig_min - 1e-9)
+
+
+@pytest.mark.parametrize("key", CASES)
+def test_init_circuit_conventions(oracle, key):
+    """The MPS init circuit lands a few mHa above the shipped ground-state energy in BOTH environment conventions
+    (fixed: qiskit-order state + bit-reversed H; trainable: mirrored qubits, negated float32 angles, plain H)."""
+    c = Case(key)
+    circ = c.init_circuit()
+    assert circ.depth() == int(c.g["init_depth"]) == 27
+    tn = oracle.state(loaders.init_circuit_gatelist(circ), [0.0])
+    assert np.abs(tn - c.g["notin_tn_state"]).max() < 1e-13
+    x, z = c.masks(True)
+    e_fixed = oracle.expect_pauli(tn, x, z, c.weights)
+    assert abs(e_fixed - float(c.g["notin_e_first"])) < TOL
+    assert 0 < e_fixed - c.eig_min < 0.25
+    assert abs(float(c.g["in_e_first"]) - e_fixed) < 2e-8  # float32 angle rounding only
+    assert float(c.g["in_e_zero_param"]) > e_fixed
+
+
+@pytest.mark.parametrize("key", ["beh2_6q", "h2o_8q"])
+def test_noise_trajectories_match_reference_python_golden(oracle, key):
+    c = Case(key)
+    g = c.g
+    gl = c.gatelist("in", noise=(0.01, 0.05))
+    assert gl.n_slots == g["noise_codes"].shape[1]
+    X = np.stack([g["in_X"][r % 6] for r in range(len(g["noise_E"]))])
+    e = oracle.energies(gl, X, dense=c.dense(False), codes=g["noise_codes"])
+    assert np.abs(e - g["noise_E"]).max() < TOL
+
+
+@pytest.mark.parametrize("n,seed", [(3, 0), (5, 1), (7, 2)])
+def test_c_vs_numpy_restatement_and_pauli_vs_dense(oracle, n, seed):
+    gl = synthetic_circuit(n, 50, seed)
+    p = parameter_batch(gl, 2)
+    rng = np.random.default_rng(seed)
+    T = 12
+    x = rng.integers(0, 1 << n, size=T).astype(np.uint64)
+    z = rng.integers(0, 1 << n, size=T).astype(np.uint64)
+    w = rng.normal(size=T)
+    # make the sum Hermitian-real: w * P is Hermitian for any Pauli string P
+    H = sum(wi * np_oracle.pauli_matrix_le(n, int(xi), int(zi)) for xi, zi, wi in zip(x, z, w))
+    for b in range(2):
+        psi_c = oracle.state(gl, p[b])
+        psi_n = np_oracle.run_circuit(n, gl.tuples(), p[b])
+        assert np.abs(psi_c - psi_n).max() < 1e-13
+        e_dense = np_oracle.expect_dense(psi_n, H)
+        assert abs(oracle.expect_dense(psi_c, H) - e_dense) < 1e-12
+        assert abs(oracle.expect_pauli(psi_c, x, z, w) - e_dense) < 1e-12
+        assert abs(np_oracle.expect_pauli(psi_n, x, z, w) - e_dense) < 1e-12
+
+
+def test_density_matrix_oracle_properties(oracle):
+    n = 4
+    gl = synthetic_circuit(n, 30, 5)
+    p = parameter_batch(gl, 1)
+    paulis, w = loaders.heisenberg_terms(n)
+    x, z = loaders.pauli_masks(paulis, n)
+    # no noise: Tr(rho H) == <psi|H|psi>
+    e_sv = oracle.energies(gl, p, pauli=(x, z, w))
+    e_dm = oracle.dm_energies(gl, p, pauli=(x, z, w))
+    assert np.abs(e_sv - e_dm).max() < 1e-12
+    # with noise: trace 1, Hermitian, and equal to the mean over sampled trajectories (5 sigma)
+    noisy = GateList(n)
+    for kind, q0, q1, pidx, fixed in gl.tuples():
+        if kind == 3:
+            noisy.add_cnot(q0, q1)
+            noisy.add_depol2(q0, q1, 0.05)
+        else:
+            noisy.add_rotation(kind, q0, fixed)
+            noisy.add_depol1(q0, 0.01)
+    rho = oracle.density_matrix(noisy, p[0])
+    assert abs(np.trace(rho) - 1) < 1e-12 and np.abs(rho - rho.conj().T).max() < 1e-13
+    e_exact = oracle.dm_energies(noisy, p, pauli=(x, z, w))[0]
+    rng = np.random.default_rng(11)
+    S = 4000
+    codes = np.zeros((S, noisy.n_slots), dtype=np.uint8)
+    for g, kind in enumerate(noisy.kind):
+        if kind == 7:
+            u = rng.random(S)
+            codes[:, noisy.pidx[g]] = np.where(u < 0.01, 1 + np.minimum((u / (0.01 / 3)).astype(int), 2), 0)
+        elif kind == 8:
+            u = rng.random(S)
+            codes[:, noisy.pidx[g]] = np.where(u < 0.05, 1 + np.minimum((u / (0.05 / 15)).astype(int), 14), 0)
+    e_traj = oracle.energies(noisy, np.repeat(p, S, axis=0), pauli=(x, z, w), codes=codes)
+    assert abs(e_traj.mean() - e_exact) < 5 * e_traj.std() / np.sqrt(S)
+
+
+def test_dense_to_pauli_roundtrip():
+    c = Case("heis_5q")
+    H = c.dense(False)
+    x, z, coeff = loaders.dense_to_pauli(H)
+    assert len(x) == len(c.paulis)
+    H2 = sum(w * np_oracle.pauli_matrix_le(5, int(a), int(b)) for a, b, w in zip(x, z, coeff))
+    assert np.abs(H - H2).max() < 1e-13
+    assert np.abs(loaders.reverse_qargs(loaders.reverse_qargs(H)) - H).max() == 0
