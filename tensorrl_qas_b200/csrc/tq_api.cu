@@ -206,16 +206,15 @@ void fill_geometry(PassParams& pp, const Pass& p, int nbits) {
     memset(&pp, 0, sizeof(pp));
     pp.nbits = nbits;
     pp.k = (int)p.local.size();
+    pp.k_eff = std::max(pp.k, kMinTileBits);
     pp.lead = p.lead;
     pp.n_nl = (int)p.nonlocal.size();
     for (size_t i = 0; i < p.local.size(); ++i) pp.local[i] = (uint8_t)p.local[i];
     for (size_t i = 0; i < p.nonlocal.size(); ++i) pp.nonlocal[i] = (uint8_t)p.nonlocal[i];
 }
 
-int threads_for(int k) {
-    int t = (1 << k) / 2;
-    t = std::max(32, std::min(kMaxThreads, t));
-    return (t + 31) / 32 * 32;
+int threads_for(int k_eff) {  // one thread per 2^kRegBits amplitudes, at least a warp
+    return std::max(32, std::min(kMaxThreads, (1 << k_eff) >> kRegBits));
 }
 
 // which: 0 pure, 1 density matrix, 2 pure + trajectory noise
@@ -276,11 +275,12 @@ int compile_plan(tq_handle h, int which) {
         if (bytes) memcpy(blob.data() + off, data, bytes);
         return off;
     };
-    struct Offsets { size_t ops, groups, terms; int n_groups; };
+    struct Offsets { size_t windows, wops, groups, terms; int n_groups, n_terms; };
     std::vector<Offsets> offs(passes.size());
     for (size_t i = 0; i < passes.size(); ++i) {
         const Pass& p = passes[i];
-        offs[i].ops = append(p.ops.data(), p.ops.size() * sizeof(DevOp));
+        offs[i].windows = append(p.windows.data(), p.windows.size() * sizeof(Window));
+        offs[i].wops = append(p.wops.data(), p.wops.size() * sizeof(WinOp));
         std::vector<ExpGroup> eg;
         std::vector<ExpTerm> et;
         for (int g : groups_of_pass[i]) {
@@ -303,6 +303,7 @@ int compile_plan(tq_handle h, int which) {
         offs[i].groups = append(eg.data(), eg.size() * sizeof(ExpGroup));
         offs[i].terms = append(et.data(), et.size() * sizeof(ExpTerm));
         offs[i].n_groups = (int)eg.size();
+        offs[i].n_terms = (int)et.size();
     }
     if (h->last_stream) TQ_CUDA(cudaStreamSynchronize(h->last_stream));
     int rc = grow(h, &plan.arena, &plan.arena_cap, std::max<size_t>(blob.size(), 16));
@@ -317,11 +318,13 @@ int compile_plan(tq_handle h, int which) {
     for (size_t i = 0; i < passes.size(); ++i) {
         DevPass dp;
         fill_geometry(dp.proto, passes[i], nbits);
-        dp.threads = threads_for(dp.proto.k);
+        dp.threads = threads_for(dp.proto.k_eff);
         dp.n_tiles = 1 << dp.proto.n_nl;
         dp.gate_pass = (int)i < n_gate_passes;
-        dp.proto.ops = (const DevOp*)(base + offs[i].ops);
-        dp.proto.n_ops = (int)passes[i].ops.size();
+        dp.proto.windows = (const Window*)(base + offs[i].windows);
+        dp.proto.n_windows = (int)passes[i].windows.size();
+        dp.proto.wops = (const WinOp*)(base + offs[i].wops);
+        dp.proto.n_wops = (int)passes[i].wops.size();
         dp.n_groups = offs[i].n_groups;
         if (which != 1) {
             if (single_tile) {
@@ -331,13 +334,14 @@ int compile_plan(tq_handle h, int which) {
                 dp.proto.groups = (const ExpGroup*)(base + offs[i].groups);
                 dp.proto.n_groups = dp.n_groups;
                 dp.proto.terms = (const ExpTerm*)(base + offs[i].terms);
+                dp.proto.n_terms = offs[i].n_terms;
             }
             if (dp.proto.exp_mode) {
                 dp.proto.partial_off = plan.slots;
                 plan.slots += dp.n_tiles;
             }
         }
-        if (tile_pass_smem_bytes(dp.proto.k, dp.proto.lead) > 227 * 1024)
+        if (tile_pass_smem_bytes(dp.proto.k_eff, dp.proto.k, dp.proto.lead) > 100 * 1024)
             return fail(h, TQ_EINVAL, "tile does not fit shared memory (lower TQ_TILE_BITS)");
         plan.passes.push_back(dp);
     }
@@ -400,7 +404,7 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
     if (want_energy) {
         if (!h->have_pauli && !h->have_dense) return fail(h, TQ_ESTATE, "no Hamiltonian set");
         if ((dm || single_tile)) {
-            if (h->n > kMaxTileBits) return fail(h, TQ_EINVAL, "density-matrix / dense path needs n_qubits <= 13");
+            if (h->n > 13) return fail(h, TQ_EINVAL, "density-matrix / dense path needs n_qubits <= 13");
             rc = upload_entries(h);
             if (rc) return rc;
         } else if (!h->have_pauli)
@@ -552,7 +556,7 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     tq_context* h = new tq_context();
     h->n = n_qubits;
     h->device = device_id;
-    h->opt.tile_bits = std::max(8, std::min(kMaxTileBits, env_int("TQ_TILE_BITS", 12)));
+    h->opt.tile_bits = std::max(8, std::min(kMaxTileBits, env_int("TQ_TILE_BITS", 12)));  // kMaxTileBits = 12
     h->opt.low_bits = std::max(0, std::min(h->opt.tile_bits - 4, env_int("TQ_LOW_BITS", 4)));
     h->max_scratch = (size_t)std::max(64, env_int("TQ_MAX_SCRATCH_MB", 16384)) << 20;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -609,7 +613,7 @@ int tq_set_pauli_hamiltonian(tq_handle h, int n_terms, const uint64_t* xmask, co
     h->have_pauli = true;
     h->have_dense = false;
     h->hent.clear();
-    if (h->n <= kMaxTileBits) entries_from_pauli(h);
+    if (h->n <= 13) entries_from_pauli(h);
     h->hent_uploaded = false;
     invalidate_plans(h);
     return TQ_OK;
@@ -618,7 +622,7 @@ int tq_set_pauli_hamiltonian(tq_handle h, int n_terms, const uint64_t* xmask, co
 int tq_set_dense_hamiltonian(tq_handle h, const double* h_matrix_host) {
     if (!h) return TQ_EINVAL;
     if (!h_matrix_host) return fail(h, TQ_EINVAL, "matrix is NULL");
-    if (h->n > kMaxTileBits) return fail(h, TQ_EINVAL, "dense Hamiltonian needs n_qubits <= 13");
+    if (h->n > 13) return fail(h, TQ_EINVAL, "dense Hamiltonian needs n_qubits <= 13");
     entries_from_dense(h, h_matrix_host);
     h->have_dense = true;
     h->have_pauli = false;
@@ -697,14 +701,14 @@ int tq_energy_traj_batch_host(tq_handle h, int batch, const double* params_host,
 
 int tq_energy_dm_batch(tq_handle h, int batch, const double* params_dev, int ld_params, double* out_dev, void* stream) {
     if (!h || !out_dev) return TQ_EINVAL;
-    if (h->n > kMaxTileBits) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
+    if (h->n > 13) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
     TQ_CUDA(cudaSetDevice(h->device));
     return run_plan(h, 1, batch, params_dev, ld_params, nullptr, 0, out_dev, nullptr, (cudaStream_t)stream);
 }
 
 int tq_energy_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* out_host) {
     if (!h || !out_host) return TQ_EINVAL;
-    if (h->n > kMaxTileBits) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
+    if (h->n > 13) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
     return run_host(h, 1, batch, params_host, ld_params, nullptr, 0, out_host, nullptr, 0);
 }
 
@@ -721,7 +725,7 @@ int tq_state_batch_host(tq_handle h, int batch, const double* params_host, int l
 
 int tq_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* rho_host) {
     if (!h || !rho_host) return TQ_EINVAL;
-    if (h->n > kMaxTileBits) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
+    if (h->n > 13) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
     return run_host(h, 1, batch, params_host, ld_params, nullptr, 0, nullptr, rho_host, (size_t)1 << (2 * h->n));
 }
 
@@ -771,6 +775,20 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
         for (const DevOp& d : p.ops) {
             snprintf(line, sizeof line, "OP %d %d %d %d %d %.17g\n", d.op, d.a, d.b, d.t, d.flags, d.fixed);
             out += line;
+        }
+        const int k_eff = std::max<int>((int)p.local.size(), kMinTileBits);
+        for (const Window& w : p.windows) {
+            out += "WIN wpos=";
+            for (int i = 0; i < kRegBits; ++i) out += (i ? "," : "") + std::to_string(w.wpos[i]);
+            out += " tpos=";
+            for (int i = 0; i < k_eff - kRegBits; ++i) out += (i ? "," : "") + std::to_string(w.tpos[i]);
+            out += "\n";
+            for (int i = w.op_begin; i < w.op_end; ++i) {
+                const WinOp& o = p.wops[i];
+                snprintf(line, sizeof line, "WOP %u %u %u %u %u %d %.17g\n", o.w0 & 0xff, (o.w0 >> 8) & 0xf,
+                         (o.w0 >> 12) & 0xf, (o.w0 >> 16) & 0xff, (o.w0 >> 24) & 0xff, o.t, o.fixed);
+                out += line;
+            }
         }
     }
     char* res = (char*)malloc(out.size() + 1);

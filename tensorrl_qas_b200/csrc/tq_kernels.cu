@@ -4,166 +4,186 @@
 namespace tq {
 namespace {
 
-__device__ __forceinline__ uint32_t insert_zero(uint32_t m, int pos) {
-    return ((m >> pos) << (pos + 1)) | (m & ((1u << pos) - 1u));
+constexpr int NA = 1 << kRegBits;  // amplitudes per thread
+
+// ---- bank swizzle: slot(j) = j ^ fold(j >> 3); fold is GF(2)-linear, so slot(a ^ b) = slot(a) ^ slot(b) ----------
+constexpr uint32_t swz_mask(int out_bit) {
+    uint32_t m = 0;
+    for (int p = 3; p < 13; ++p)
+        if ((kSwizzleVec[p] >> out_bit) & 1) m |= 1u << (p - 3);
+    return m;
+}
+constexpr uint32_t kSwzM0 = swz_mask(0), kSwzM1 = swz_mask(1), kSwzM2 = swz_mask(2);
+
+__device__ __forceinline__ uint32_t swz(uint32_t j) {
+    const uint32_t h = j >> 3;
+    return j ^ ((__popc(h & kSwzM0) & 1u) | ((__popc(h & kSwzM1) & 1u) << 1) | ((__popc(h & kSwzM2) & 1u) << 2));
 }
 
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
+typedef double2 Amps[NA];
 
-struct TileCtx {
-    double2* amp;
-    int tile_amps;
-    int tid, nthreads;
-    uint64_t tile_base;  // physical index bits of the non-local qubits of this tile
-};
-
-// exp(+i theta/2 X) = [[c, i s], [i s, c]]
-__device__ __forceinline__ void op_rx(const TileCtx& t, int pos, double c, double s) {
-    const uint32_t bit = 1u << pos;
-    for (uint32_t m = t.tid; m < (uint32_t)(t.tile_amps >> 1); m += t.nthreads) {
-        const uint32_t i0 = insert_zero(m, pos), i1 = i0 | bit;
-        const double2 a0 = t.amp[i0], a1 = t.amp[i1];
-        t.amp[i0] = make_double2(c * a0.x - s * a1.y, c * a0.y + s * a1.x);
-        t.amp[i1] = make_double2(c * a1.x - s * a0.y, c * a1.y + s * a0.x);
+// ---- register-window gates.  RB = register bit of the target; all loops are fully unrolled (static indices) ------
+template <int RB>
+__device__ __forceinline__ void g_rx(Amps& a, double c, double s) {  // exp(+i t/2 X) = [[c, i s], [i s, c]]
+#pragma unroll
+    for (int m = 0; m < NA / 2; ++m) {
+        const int i0 = ((m >> RB) << (RB + 1)) | (m & ((1 << RB) - 1)), i1 = i0 | (1 << RB);
+        const double2 a0 = a[i0], a1 = a[i1];
+        a[i0] = make_double2(c * a0.x - s * a1.y, c * a0.y + s * a1.x);
+        a[i1] = make_double2(c * a1.x - s * a0.y, c * a1.y + s * a0.x);
     }
 }
-
-// exp(+i theta/2 Y) = [[c, s], [-s, c]]
-__device__ __forceinline__ void op_ry(const TileCtx& t, int pos, double c, double s) {
-    const uint32_t bit = 1u << pos;
-    for (uint32_t m = t.tid; m < (uint32_t)(t.tile_amps >> 1); m += t.nthreads) {
-        const uint32_t i0 = insert_zero(m, pos), i1 = i0 | bit;
-        const double2 a0 = t.amp[i0], a1 = t.amp[i1];
-        t.amp[i0] = make_double2(c * a0.x + s * a1.x, c * a0.y + s * a1.y);
-        t.amp[i1] = make_double2(c * a1.x - s * a0.x, c * a1.y - s * a0.y);
+template <int RB>
+__device__ __forceinline__ void g_ry(Amps& a, double c, double s) {  // exp(+i t/2 Y) = [[c, s], [-s, c]]
+#pragma unroll
+    for (int m = 0; m < NA / 2; ++m) {
+        const int i0 = ((m >> RB) << (RB + 1)) | (m & ((1 << RB) - 1)), i1 = i0 | (1 << RB);
+        const double2 a0 = a[i0], a1 = a[i1];
+        a[i0] = make_double2(c * a0.x + s * a1.x, c * a0.y + s * a1.y);
+        a[i1] = make_double2(c * a1.x - s * a0.x, c * a1.y - s * a0.y);
     }
 }
-
-// exp(+i theta/2 Z) = diag(c + i s, c - i s); `mask`/`value` select which amplitudes take the conjugate phase
-__device__ __forceinline__ void op_rz(const TileCtx& t, int pos, double c, double s) {
-    for (uint32_t j = t.tid; j < (uint32_t)t.tile_amps; j += t.nthreads) {
-        const double sj = ((j >> pos) & 1u) ? -s : s;
-        const double2 a = t.amp[j];
-        t.amp[j] = make_double2(c * a.x - sj * a.y, c * a.y + sj * a.x);
+template <int RB>
+__device__ __forceinline__ void g_rz(Amps& a, double c, double s) {  // diag(c + i s, c - i s)
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        const double sj = ((i >> RB) & 1) ? -s : s;
+        const double2 v = a[i];
+        a[i] = make_double2(c * v.x - sj * v.y, c * v.y + sj * v.x);
     }
 }
-
-__device__ __forceinline__ void op_phase_all(const TileCtx& t, double c, double s) {
-    for (uint32_t j = t.tid; j < (uint32_t)t.tile_amps; j += t.nthreads) {
-        const double2 a = t.amp[j];
-        t.amp[j] = make_double2(c * a.x - s * a.y, c * a.y + s * a.x);
+__device__ __forceinline__ void g_phase(Amps& a, double c, double s) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        const double2 v = a[i];
+        a[i] = make_double2(c * v.x - s * v.y, c * v.y + s * v.x);
     }
 }
-
-__device__ __forceinline__ void op_x(const TileCtx& t, int pos) {
-    const uint32_t bit = 1u << pos;
-    for (uint32_t m = t.tid; m < (uint32_t)(t.tile_amps >> 1); m += t.nthreads) {
-        const uint32_t i0 = insert_zero(m, pos), i1 = i0 | bit;
-        const double2 a0 = t.amp[i0];
-        t.amp[i0] = t.amp[i1];
-        t.amp[i1] = a0;
+template <int RB>
+__device__ __forceinline__ void g_x_if(Amps& a, bool pred) {  // X on RB where pred (per-thread control bit)
+#pragma unroll
+    for (int m = 0; m < NA / 2; ++m) {
+        const int i0 = ((m >> RB) << (RB + 1)) | (m & ((1 << RB) - 1)), i1 = i0 | (1 << RB);
+        const double2 a0 = a[i0], a1 = a[i1];
+        a[i0] = pred ? a1 : a0;
+        a[i1] = pred ? a0 : a1;
     }
 }
-
-// Y = [[0, -i], [i, 0]]; sign = -1 gives conj(Y) = -Y
-__device__ __forceinline__ void op_y(const TileCtx& t, int pos, double sign) {
-    const uint32_t bit = 1u << pos;
-    for (uint32_t m = t.tid; m < (uint32_t)(t.tile_amps >> 1); m += t.nthreads) {
-        const uint32_t i0 = insert_zero(m, pos), i1 = i0 | bit;
-        const double2 a0 = t.amp[i0], a1 = t.amp[i1];
-        t.amp[i0] = make_double2(sign * a1.y, -sign * a1.x);
-        t.amp[i1] = make_double2(-sign * a0.y, sign * a0.x);
-    }
-}
-
-__device__ __forceinline__ void op_z(const TileCtx& t, int pos) {
-    for (uint32_t j = t.tid; j < (uint32_t)t.tile_amps; j += t.nthreads) {
-        if ((j >> pos) & 1u) {
-            const double2 a = t.amp[j];
-            t.amp[j] = make_double2(-a.x, -a.y);
+template <int CB, int TB>
+__device__ __forceinline__ void g_cx(Amps& a) {  // both bits in the window: a register permutation
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        if (((i >> CB) & 1) && !((i >> TB) & 1)) {
+            const double2 t = a[i];
+            a[i] = a[i | (1 << TB)];
+            a[i | (1 << TB)] = t;
         }
     }
 }
-
-__device__ __forceinline__ void op_negate_all(const TileCtx& t) {
-    for (uint32_t j = t.tid; j < (uint32_t)t.tile_amps; j += t.nthreads) {
-        const double2 a = t.amp[j];
-        t.amp[j] = make_double2(-a.x, -a.y);
+template <int RB>
+__device__ __forceinline__ void g_y(Amps& a, double sign) {  // Y = [[0, -i], [i, 0]]; sign -1: conj(Y) = -Y
+#pragma unroll
+    for (int m = 0; m < NA / 2; ++m) {
+        const int i0 = ((m >> RB) << (RB + 1)) | (m & ((1 << RB) - 1)), i1 = i0 | (1 << RB);
+        const double2 a0 = a[i0], a1 = a[i1];
+        a[i0] = make_double2(sign * a1.y, -sign * a1.x);
+        a[i1] = make_double2(-sign * a0.y, sign * a0.x);
     }
 }
-
-__device__ __forceinline__ void op_cnot(const TileCtx& t, int cpos, int tpos) {
-    const uint32_t bit = 1u << tpos;
-    for (uint32_t m = t.tid; m < (uint32_t)(t.tile_amps >> 1); m += t.nthreads) {
-        const uint32_t i0 = insert_zero(m, tpos);
-        if ((i0 >> cpos) & 1u) {
-            const uint32_t i1 = i0 | bit;
-            const double2 a0 = t.amp[i0];
-            t.amp[i0] = t.amp[i1];
-            t.amp[i1] = a0;
-        }
-    }
+template <int RB>
+__device__ __forceinline__ void g_z(Amps& a) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+        if ((i >> RB) & 1) a[i] = make_double2(-a[i].x, -a[i].y);
 }
-
-__device__ __forceinline__ void op_pauli_code(const TileCtx& t, int pos, int code) {
-    if (code == 1) op_x(t, pos);
-    else if (code == 2) op_y(t, pos, 1.0);
-    else if (code == 3) op_z(t, pos);
+__device__ __forceinline__ void g_neg_if(Amps& a, bool pred) {
+    const double f = pred ? -1.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) a[i] = make_double2(f * a[i].x, f * a[i].y);
 }
-
-// exact 1-qubit depolarising channel on the (row bit, column bit) pair of a density matrix:
-// rho -> (1 - 4p/3) rho + (2p/3) Tr_q(rho) (x) I
-__device__ __forceinline__ void op_depol1_dm(const TileCtx& t, int pa, int pb, double p) {
-    const int lo = pa < pb ? pa : pb, hi = pa < pb ? pb : pa;
-    const uint32_t ba = 1u << pa, bb = 1u << pb;
+template <int RB>
+__device__ __forceinline__ void g_pauli(Amps& a, int code) {
+    if (code == 1) g_x_if<RB>(a, true);
+    else if (code == 2) g_y<RB>(a, 1.0);
+    else if (code == 3) g_z<RB>(a);
+}
+// exact 1-qubit depolarising channel on (row bit A, column bit B): rho -> (1-4p/3) rho + (2p/3) Tr_q(rho) (x) I
+template <int A, int B>
+__device__ __forceinline__ void g_depol1(Amps& a, double p) {
     const double keep = 1.0 - 2.0 * p / 3.0, mixw = 2.0 * p / 3.0, off = 1.0 - 4.0 * p / 3.0;
-    for (uint32_t m = t.tid; m < (uint32_t)(t.tile_amps >> 2); m += t.nthreads) {
-        const uint32_t i00 = insert_zero(insert_zero(m, lo), hi);
-        const double2 r00 = t.amp[i00], r11 = t.amp[i00 | ba | bb];
-        const double2 r10 = t.amp[i00 | ba], r01 = t.amp[i00 | bb];
-        t.amp[i00] = make_double2(keep * r00.x + mixw * r11.x, keep * r00.y + mixw * r11.y);
-        t.amp[i00 | ba | bb] = make_double2(keep * r11.x + mixw * r00.x, keep * r11.y + mixw * r00.y);
-        t.amp[i00 | ba] = make_double2(off * r10.x, off * r10.y);
-        t.amp[i00 | bb] = make_double2(off * r01.x, off * r01.y);
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        if (((i >> A) & 1) || ((i >> B) & 1)) continue;
+        const int i11 = i | (1 << A) | (1 << B), i10 = i | (1 << A), i01 = i | (1 << B);
+        const double2 r00 = a[i], r11 = a[i11];
+        a[i] = make_double2(keep * r00.x + mixw * r11.x, keep * r00.y + mixw * r11.y);
+        a[i11] = make_double2(keep * r11.x + mixw * r00.x, keep * r11.y + mixw * r00.y);
+        a[i10] = make_double2(off * a[i10].x, off * a[i10].y);
+        a[i01] = make_double2(off * a[i01].x, off * a[i01].y);
+    }
+}
+// exact 2-qubit depolarising channel; window = {P0, P1} (row/col of one qubit) + {P2, P3} (row/col of the other):
+// rho -> (1 - 16p/15) rho + (4p/15) Tr_ab(rho) (x) I_4
+template <int P0, int P1, int P2, int P3>
+__device__ __forceinline__ void g_depol2(Amps& a, double p) {
+    const double alpha = 1.0 - 16.0 * p / 15.0, beta = 4.0 * p / 15.0;
+    double2 tr = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+        if (((i >> P0) & 1) == ((i >> P1) & 1) && ((i >> P2) & 1) == ((i >> P3) & 1)) { tr.x += a[i].x; tr.y += a[i].y; }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        double2 v = make_double2(alpha * a[i].x, alpha * a[i].y);
+        if (((i >> P0) & 1) == ((i >> P1) & 1) && ((i >> P2) & 1) == ((i >> P3) & 1)) { v.x += beta * tr.x; v.y += beta * tr.y; }
+        a[i] = v;
     }
 }
 
-// exact 2-qubit depolarising channel: rho -> (1 - 16p/15) rho + (4p/15) Tr_ab(rho) (x) I_4
-__device__ __forceinline__ void op_depol2_dm(const TileCtx& t, int ra, int rb, int ca, int cb, double p) {
-    int s[4] = {ra, rb, ca, cb};
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3 - i; ++j)
-            if (s[j] > s[j + 1]) { const int tmp = s[j]; s[j] = s[j + 1]; s[j + 1] = tmp; }
-    const double alpha = 1.0 - 16.0 * p / 15.0, beta = 4.0 * p / 15.0;
-    for (uint32_t m = t.tid; m < (uint32_t)(t.tile_amps >> 4); m += t.nthreads) {
-        uint32_t base = m;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) base = insert_zero(base, s[i]);
-        double2 tr = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            const uint32_t idx = base | ((x & 1) ? (1u << ra) | (1u << ca) : 0u) | ((x & 2) ? (1u << rb) | (1u << cb) : 0u);
-            const double2 v = t.amp[idx];
-            tr.x += v.x;
-            tr.y += v.y;
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t idx = base | ((r & 1) ? (1u << ra) : 0u) | ((r & 2) ? (1u << rb) : 0u) |
-                                     ((c & 1) ? (1u << ca) : 0u) | ((c & 2) ? (1u << cb) : 0u);
-                double2 v = t.amp[idx];
-                v.x *= alpha;
-                v.y *= alpha;
-                if (r == c) { v.x += beta * tr.x; v.y += beta * tr.y; }
-                t.amp[idx] = v;
-            }
+#define TQ_RB4(FN, rb, ...)                                        \
+    switch (rb) {                                                  \
+    case 0: FN<0>(__VA_ARGS__); break;                             \
+    case 1: FN<1>(__VA_ARGS__); break;                             \
+    case 2: FN<2>(__VA_ARGS__); break;                             \
+    default: FN<3>(__VA_ARGS__); break;                            \
     }
+
+__device__ __forceinline__ void exec_cx_ww(Amps& a, int cb, int tb) {
+    switch (cb * 4 + tb) {
+    case 1: g_cx<0, 1>(a); break;
+    case 2: g_cx<0, 2>(a); break;
+    case 3: g_cx<0, 3>(a); break;
+    case 4: g_cx<1, 0>(a); break;
+    case 6: g_cx<1, 2>(a); break;
+    case 7: g_cx<1, 3>(a); break;
+    case 8: g_cx<2, 0>(a); break;
+    case 9: g_cx<2, 1>(a); break;
+    case 11: g_cx<2, 3>(a); break;
+    case 12: g_cx<3, 0>(a); break;
+    case 13: g_cx<3, 1>(a); break;
+    case 14: g_cx<3, 2>(a); break;
+    default: break;
+    }
+}
+
+__device__ __forceinline__ void exec_depol1(Amps& a, int ra, int rb, double p) {
+    const int lo = ra < rb ? ra : rb, hi = ra < rb ? rb : ra;
+    switch (lo * 4 + hi) {
+    case 1: g_depol1<0, 1>(a, p); break;
+    case 2: g_depol1<0, 2>(a, p); break;
+    case 3: g_depol1<0, 3>(a, p); break;
+    case 6: g_depol1<1, 2>(a, p); break;
+    case 7: g_depol1<1, 3>(a, p); break;
+    default: g_depol1<2, 3>(a, p); break;
+    }
+}
+
+__device__ __forceinline__ void exec_depol2(Amps& a, int rows, int cols, double p) {
+    // qubit a: row bit rows & 3, column bit cols & 3; the partner of register bit 0 decides the pairing
+    const int ra = rows & 3, ca = cols & 3, rb = (rows >> 2) & 3, cb = (cols >> 2) & 3;
+    const int partner0 = (ra == 0) ? ca : (ca == 0) ? ra : (rb == 0) ? cb : rb;
+    if (partner0 == 1) g_depol2<0, 1, 2, 3>(a, p);
+    else if (partner0 == 2) g_depol2<0, 2, 1, 3>(a, p);
+    else g_depol2<0, 3, 1, 2>(a, p);
 }
 
 // deterministic CTA-wide sum (fixed shuffle tree, then warps added in index order); result valid in thread 0
@@ -180,14 +200,17 @@ __device__ __forceinline__ double block_sum(double v, double* s_red, int tid, in
     return total;
 }
 
-__global__ void __launch_bounds__(kMaxThreads) tile_pass_kernel(const PassParams p) {
+#define TQ_SLOT(r) (slot_t ^ (((r) & 1) ? ws0 : 0u) ^ (((r) & 2) ? ws1 : 0u) ^ (((r) & 4) ? ws2 : 0u) ^ (((r) & 8) ? ws3 : 0u))
+
+__global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tile_amps = 1 << p.k;
+    const int tile_amps = 1 << p.k_eff;
+    const int valid_amps = 1 << p.k;
     double2* amp = reinterpret_cast<double2*>(smem_raw);
-    double2* s_trig = amp + tile_amps;
-    DevOp* s_ops = reinterpret_cast<DevOp*>(s_trig + kOpsChunk);
-    double* s_red = reinterpret_cast<double*>(s_ops + kOpsChunk);
-    uint32_t* hi_off = reinterpret_cast<uint32_t*>(s_red + 32);
+    double2* s_trig = amp + tile_amps;                                  // kOpsChunk entries
+    WinOp* s_wops = reinterpret_cast<WinOp*>(s_trig + kOpsChunk);       // kOpsChunk entries
+    double* s_red = reinterpret_cast<double*>(s_wops + kOpsChunk);      // 32 entries
+    uint32_t* hi_off = reinterpret_cast<uint32_t*>(s_red + 32);         // 2^(k - lead) entries
 
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const uint32_t ntiles = 1u << p.n_nl;
@@ -208,96 +231,147 @@ __global__ void __launch_bounds__(kMaxThreads) tile_pass_kernel(const PassParams
     const uint64_t elem_off = (uint64_t)b << p.nbits;
     const uint32_t lead_mask = (1u << p.lead) - 1u;
 
-    // ---- stage the tile ----
+    // ---- 1. stage the tile (coalesced global reads, swizzled shared-memory slots) ----
     if (p.src_mode == 0) {
         for (int j = tid; j < tile_amps; j += nthreads) amp[j] = make_double2(0.0, 0.0);
-        if (tile_base == 0 && tid == 0) amp[0] = make_double2(1.0, 0.0);
+        __syncthreads();
+        if (tile_base == 0 && tid == 0) amp[0] = make_double2(1.0, 0.0);  // swz(0) == 0
     } else {
         const double2* src = p.src + (p.src_mode == 2 ? elem_off : 0ull) + tile_base;
-        for (int j = tid; j < tile_amps; j += nthreads) amp[j] = src[hi_off[j >> p.lead] | (j & lead_mask)];
+        for (int j = tid; j < tile_amps; j += nthreads)
+            amp[swz(j)] = j < valid_amps ? src[hi_off[j >> p.lead] | (j & lead_mask)] : make_double2(0.0, 0.0);
     }
 
-    TileCtx t{amp, tile_amps, tid, nthreads, tile_base};
     const double* my_params = p.params ? p.params + (size_t)b * p.ld_params : nullptr;
     const uint8_t* my_codes = p.codes ? p.codes + (size_t)b * p.ld_codes : nullptr;
+    const bool active = tid < (tile_amps >> kRegBits);
+    const int n_tbits = p.k_eff - kRegBits;
 
-    // ---- gates, staged in chunks together with their cos/sin ----
-    for (int base = 0; base < p.n_ops; base += kOpsChunk) {
-        const int cnt = min(kOpsChunk, p.n_ops - base);
-        __syncthreads();
-        for (int i = tid; i < cnt; i += nthreads) {
-            const DevOp o = p.ops[base + i];
-            s_ops[i] = o;
-            if (o.op <= OP_RZ_NL) {
-                const double theta = o.t >= 0 ? my_params[o.t] : o.fixed;
-                double s, c;
-                sincos(0.5 * theta, &s, &c);
-                if ((o.flags & FLAG_CONJ) && o.op != OP_RY) s = -s;
-                s_trig[i] = make_double2(c, s);
+    // ---- 2. register windows ----
+    Amps a;
+    uint32_t slot_t = 0, ws0 = 0, ws1 = 0, ws2 = 0, ws3 = 0;
+    int staged_begin = 0, staged_end = 0;
+    for (int w = 0; w < p.n_windows; ++w) {
+        const Window* win = p.windows + w;
+        const int op_begin = win->op_begin, op_end = win->op_end;
+        if (w > 0) {
+            __syncthreads();  // every thread has finished the previous window (its loads and its staged ops)
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < NA; ++r) amp[TQ_SLOT(r)] = a[r];
+            }
+        }
+        // stage this window's ops with their cos/sin while no amplitudes are live in registers; the planner keeps
+        // a window's op range within kOpsChunk, so a staged chunk always covers whole windows (uniform branch)
+        if (op_end > staged_end) {
+            staged_begin = op_begin;
+            staged_end = min(op_begin + kOpsChunk, p.n_wops);
+            for (int i = tid; i < staged_end - staged_begin; i += nthreads) {
+                const WinOp wo = p.wops[staged_begin + i];
+                s_wops[i] = wo;
+                const int code = wo.w0 & 0xff;
+                if (code <= W_PHASE) {
+                    const double theta = wo.t >= 0 ? my_params[wo.t] : wo.fixed;
+                    double s, c;
+                    sincos(0.5 * theta, &s, &c);
+                    if (((wo.w0 >> 24) & FLAG_CONJ) && code != W_ROT_Y) s = -s;
+                    s_trig[i] = make_double2(c, s);
+                }
             }
         }
         __syncthreads();
-        for (int i = 0; i < cnt; ++i) {
-            const DevOp o = s_ops[i];
-            const double2 cs = s_trig[i];
-            switch (o.op) {
-            case OP_RX: op_rx(t, o.a, cs.x, cs.y); break;
-            case OP_RY: op_ry(t, o.a, cs.x, cs.y); break;
-            case OP_RZ: op_rz(t, o.a, cs.x, cs.y); break;
-            case OP_RZ_NL: op_phase_all(t, cs.x, ((tile_base >> o.a) & 1ull) ? -cs.y : cs.y); break;
-            case OP_CNOT: op_cnot(t, o.a, o.b); break;
-            case OP_CNOT_NL: if ((tile_base >> o.a) & 1ull) op_x(t, o.b); break;
-            case OP_X: op_x(t, o.a); break;
-            case OP_Y: op_y(t, o.a, (o.flags & FLAG_CONJ) ? -1.0 : 1.0); break;
-            case OP_Z: op_z(t, o.a); break;
-            case OP_Z_NL: if ((tile_base >> o.a) & 1ull) op_negate_all(t); break;
-            case OP_PAULI1: op_pauli_code(t, o.a, my_codes[o.t] & 3); break;
-            case OP_PAULI2: {
-                const int code = my_codes[o.t];
-                op_pauli_code(t, o.a, code & 3);
-                __syncthreads();
-                op_pauli_code(t, o.b, (code >> 2) & 3);
-                break;
+        uint32_t jt = 0;
+        uint64_t ctx = tile_base;  // physical index of this thread's amplitudes with the window bits cleared
+        for (int i = 0; i < n_tbits; ++i) {
+            if ((tid >> i) & 1) {
+                const int pos = win->tpos[i];
+                jt |= 1u << pos;
+                ctx |= 1ull << p.local[pos];
             }
-            case OP_DEPOL1_DM: op_depol1_dm(t, o.a, o.b, o.fixed); break;
-            case OP_DEPOL2_DM: op_depol2_dm(t, o.a & 0xff, (o.a >> 8) & 0xff, o.b & 0xff, (o.b >> 8) & 0xff, o.fixed); break;
-            default: break;
+        }
+        slot_t = swz(jt);
+        ws0 = swz(1u << win->wpos[0]);
+        ws1 = swz(1u << win->wpos[1]);
+        ws2 = swz(1u << win->wpos[2]);
+        ws3 = swz(1u << win->wpos[3]);
+        if (active) {
+#pragma unroll
+            for (int r = 0; r < NA; ++r) a[r] = amp[TQ_SLOT(r)];
+            for (int o = op_begin; o < op_end; ++o) {
+                const WinOp wo = s_wops[o - staged_begin];
+                const double2 cs = s_trig[o - staged_begin];
+                const int code = wo.w0 & 0xff, rb = (wo.w0 >> 8) & 0xf, rb2 = (wo.w0 >> 12) & 0xf;
+                const int qsel = (wo.w0 >> 16) & 0xff;
+                switch (code) {
+                case W_ROT_X: TQ_RB4(g_rx, rb, a, cs.x, cs.y); break;
+                case W_ROT_Y: TQ_RB4(g_ry, rb, a, cs.x, cs.y); break;
+                case W_ROT_Z: TQ_RB4(g_rz, rb, a, cs.x, cs.y); break;
+                case W_PHASE: g_phase(a, cs.x, ((ctx >> qsel) & 1ull) ? -cs.y : cs.y); break;
+                case W_CX_WW: exec_cx_ww(a, rb, rb2); break;
+                case W_CX_OW: TQ_RB4(g_x_if, rb, a, (bool)((ctx >> qsel) & 1ull)); break;
+                case W_X: TQ_RB4(g_x_if, rb, a, true); break;
+                case W_Y: TQ_RB4(g_y, rb, a, ((wo.w0 >> 24) & FLAG_CONJ) ? -1.0 : 1.0); break;
+                case W_Z: TQ_RB4(g_z, rb, a); break;
+                case W_Z_OUT: g_neg_if(a, (bool)((ctx >> qsel) & 1ull)); break;
+                case W_PAULI: { const int pc = (my_codes[wo.t] >> rb2) & 3; TQ_RB4(g_pauli, rb, a, pc); break; }
+                case W_DEPOL1: exec_depol1(a, rb, rb2, wo.fixed); break;
+                case W_DEPOL2: exec_depol2(a, rb, rb2, wo.fixed); break;
+                default: break;
+                }
             }
-            __syncthreads();
+        }
+    }
+    // registers -> shared memory (final layout of the pass)
+    if (p.n_windows > 0) {
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int r = 0; r < NA; ++r) amp[TQ_SLOT(r)] = a[r];
         }
     }
     __syncthreads();
 
-    // ---- write back ----
+    // ---- 4. write back ----
     if (p.dst) {
         double2* dst = p.dst + elem_off + tile_base;
-        for (int j = tid; j < tile_amps; j += nthreads) dst[hi_off[j >> p.lead] | (j & lead_mask)] = amp[j];
+        for (int j = tid; j < valid_amps; j += nthreads) dst[hi_off[j >> p.lead] | (j & lead_mask)] = amp[swz(j)];
     }
 
-    // ---- expectation of the Hamiltonian terms that are local to this pass ----
+    // ---- 3. expectation of the Hamiltonian terms that are local to this pass ----
     if (p.exp_mode != 0) {
         double acc = 0.0;
         if (p.exp_mode == 1) {
+            // terms staged in shared memory (re-using the op staging area: 8 KiB = 256 terms)
+            ExpTerm* s_terms = reinterpret_cast<ExpTerm*>(s_trig);
+            const int cap = (int)((kOpsChunk * (sizeof(double2) + sizeof(WinOp))) / sizeof(ExpTerm));
             for (int g = 0; g < p.n_groups; ++g) {
                 const ExpGroup grp = p.groups[g];
-                for (int j = tid; j < tile_amps; j += nthreads) {
-                    const double2 a = amp[j], bq = amp[j ^ grp.xlocal];
-                    const double px = bq.x * a.x + bq.y * a.y;  // conj(psi[j ^ x]) * psi[j]
-                    const double py = bq.x * a.y - bq.y * a.x;
-                    double fre = 0.0, fim = 0.0;
-                    for (int tt = grp.term_begin; tt < grp.term_end; ++tt) {
-                        const ExpTerm term = p.terms[tt];
-                        const int par = (__popc((uint32_t)j & term.zlocal) + __popcll(tile_base & term.zphys)) & 1;
-                        fre += par ? -term.wre : term.wre;
-                        fim += par ? -term.wim : term.wim;
+                const uint32_t xs = swz(grp.xlocal);
+                for (int t0 = grp.term_begin; t0 < grp.term_end; t0 += cap) {
+                    const int nt = min(cap, grp.term_end - t0);
+                    __syncthreads();
+                    for (int i = tid; i < nt; i += nthreads) s_terms[i] = p.terms[t0 + i];
+                    __syncthreads();
+                    for (int j = tid; j < valid_amps; j += nthreads) {
+                        const uint32_t sj = swz(j);
+                        const double2 v = amp[sj], bq = amp[sj ^ xs];
+                        const double px = bq.x * v.x + bq.y * v.y;  // conj(psi[j ^ x]) * psi[j]
+                        const double py = bq.x * v.y - bq.y * v.x;
+                        double fre = 0.0, fim = 0.0;
+                        for (int tt = 0; tt < nt; ++tt) {
+                            const ExpTerm term = s_terms[tt];
+                            const int par = (__popc((uint32_t)j & term.zlocal) + __popcll(tile_base & term.zphys)) & 1;
+                            fre += par ? -term.wre : term.wre;
+                            fim += par ? -term.wim : term.wim;
+                        }
+                        acc += fre * px - fim * py;
                     }
-                    acc += fre * px - fim * py;
                 }
             }
         } else {
             for (int e = tid; e < p.n_hent; e += nthreads) {
                 const HEntry h = p.hent[e];
-                const double2 ar = amp[h.r], ac = amp[h.c];
+                const double2 ar = amp[swz(h.r)], ac = amp[swz(h.c)];
                 const double px = ar.x * ac.x + ar.y * ac.y;  // conj(psi_r) * psi_c
                 const double py = ar.x * ac.y - ar.y * ac.x;
                 acc += h.re * px - h.im * py;
@@ -337,19 +411,19 @@ __global__ void __launch_bounds__(kMaxThreads) dm_expect_kernel(const double2* _
 
 }  // namespace
 
-size_t tile_pass_smem_bytes(int k, int lead) {
+size_t tile_pass_smem_bytes(int k_eff, int k, int lead) {
     const size_t n_hi = (size_t)1 << (k - lead);
-    return ((size_t)16 << k) + kOpsChunk * sizeof(double2) + kOpsChunk * sizeof(DevOp) + 32 * sizeof(double) +
+    return ((size_t)16 << k_eff) + kOpsChunk * (sizeof(double2) + sizeof(WinOp)) + 32 * sizeof(double) +
            n_hi * sizeof(uint32_t);
 }
 
 cudaError_t tile_pass_configure() {
-    return cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
 
 void launch_tile_pass(const PassParams& p, int batch, int threads, cudaStream_t stream) {
     const unsigned grid = (unsigned)batch << p.n_nl;
-    tile_pass_kernel<<<grid, threads, tile_pass_smem_bytes(p.k, p.lead), stream>>>(p);
+    tile_pass_kernel<<<grid, threads, tile_pass_smem_bytes(p.k_eff, p.k, p.lead), stream>>>(p);
 }
 
 void launch_reduce_partials(const double* partial, int ld, int n, double* out, int batch, cudaStream_t stream) {

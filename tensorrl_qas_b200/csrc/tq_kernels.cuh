@@ -1,10 +1,14 @@
 // tq_kernels.cuh -- sm_100a kernels of libtqsim (batched complex128 statevector / density-matrix passes).
 //
 // One kernel does the heavy lifting: tile_pass_kernel.  A CTA owns one tile (2^k amplitudes that differ only in
-// the pass's k local qubits) of one batch element: it stages the tile in shared memory with coalesced 16-byte
-// loads (runs of 2^lead consecutive amplitudes), applies the pass's whole gate list there, optionally evaluates
-// the Hamiltonian terms whose flip masks are local (one deterministic partial sum per tile), and writes the tile
-// back.  HBM traffic per pass is one read + one write of the state no matter how many gates the pass fused.
+// the pass's k local qubits) of one batch element:
+//   1. stage the tile in shared memory with coalesced 16-byte loads (runs of 2^lead consecutive amplitudes),
+//      bank-swizzled so that any later redistribution is conflict free;
+//   2. run the pass's register windows: every thread holds 16 amplitudes (4 window qubits) in registers and applies
+//      all gates of the window there; shared memory is touched only to switch windows;
+//   3. optionally evaluate the Hamiltonian terms whose flip masks are local (one deterministic partial per tile);
+//   4. write the tile back.
+// HBM traffic per pass is one read + one write of the state no matter how many gates the pass fused.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,9 +17,9 @@
 
 namespace tq {
 
-constexpr int kMaxTileBits = 13;
-constexpr int kOpsChunk = 128;   // ops staged in shared memory at a time (with their cos/sin)
-constexpr int kMaxThreads = 256;
+constexpr int kMaxTileBits = 12;
+constexpr int kOpsChunk = kMaxWindowOps;   // window ops staged in shared memory at a time (with their cos/sin)
+constexpr int kMaxThreads = 256; // 2^(kMaxTileBits - kRegBits)
 
 struct ExpGroup {   // one X/Y flip mask of the Hamiltonian, local to the pass
     uint32_t xlocal;
@@ -34,14 +38,16 @@ struct HEntry {     // non-zero of the symmetrised Hamiltonian, upper triangle, 
 };
 
 struct PassParams {
-    int nbits, k, lead, n_nl;
+    int nbits, k, k_eff, lead, n_nl;   // k = real tile bits, k_eff = max(k, kRegBits)
     uint8_t local[16];
     uint8_t nonlocal[32];
     const double2* src;
     int src_mode;  // 0: |0...0>, 1: one shared initial vector, 2: per-element state buffer
     double2* dst;  // nullptr: tile is not written back
-    const DevOp* ops;
-    int n_ops;
+    const Window* windows;
+    int n_windows;
+    const WinOp* wops;
+    int n_wops;
     const double* params;
     int ld_params;
     const uint8_t* codes;
@@ -50,13 +56,14 @@ struct PassParams {
     const ExpGroup* groups;
     int n_groups;
     const ExpTerm* terms;
+    int n_terms;
     const HEntry* hent;
     int n_hent;
     double* partial;  // partial[b * partial_ld + partial_off + tile]
     int partial_ld, partial_off;
 };
 
-size_t tile_pass_smem_bytes(int k, int lead);
+size_t tile_pass_smem_bytes(int k_eff, int k, int lead);
 cudaError_t tile_pass_configure();  // opt in to > 48 KiB dynamic shared memory
 void launch_tile_pass(const PassParams& p, int batch, int threads, cudaStream_t stream);
 

@@ -138,6 +138,7 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
         Pass p;
         finish_pass(p, nbits, L);
         for (int idx : mine) p.ops.push_back(emit(p, ops[idx]));
+        schedule_windows(p);
         passes.push_back(std::move(p));
         remaining.swap(deferred);
     }
@@ -161,6 +162,160 @@ bool validate(int n, const std::vector<Gate>& gates, std::string* err) {
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------- register windows ----
+namespace {
+
+struct TOp {          // tile-level op + the tile positions it mixes / only reads
+    DevOp d;
+    uint32_t mix = 0, diag = 0;
+};
+
+int popc32(uint32_t x) { return __builtin_popcount(x); }
+
+void tile_masks(TOp& t) {
+    const DevOp& d = t.d;
+    switch (d.op) {
+    case OP_RX: case OP_RY: case OP_X: case OP_Y: case OP_PAULI1: t.mix = 1u << d.a; break;
+    case OP_RZ: case OP_Z: t.diag = 1u << d.a; break;
+    case OP_CNOT: t.diag = 1u << d.a; t.mix = 1u << d.b; break;
+    case OP_CNOT_NL: t.mix = 1u << d.b; break;
+    case OP_DEPOL1_DM: t.mix = (1u << d.a) | (1u << d.b); break;
+    case OP_DEPOL2_DM:
+        t.mix = (1u << (d.a & 0xff)) | (1u << ((d.a >> 8) & 0xff)) | (1u << (d.b & 0xff)) | (1u << ((d.b >> 8) & 0xff));
+        break;
+    default: break;  // OP_RZ_NL / OP_Z_NL: diagonal on a bit outside the tile, commutes with everything here
+    }
+}
+
+bool independent3(int a, int b, int c) {
+    const int va = kSwizzleVec[a], vb = kSwizzleVec[b], vc = kSwizzleVec[c];
+    return va != vb && va != vc && vb != vc && (va ^ vb) != vc;
+}
+
+}  // namespace
+
+void schedule_windows(Pass& p) {
+    p.windows.clear();
+    p.wops.clear();
+    const int k_real = (int)p.local.size();
+    const int k = std::max(k_real, kMinTileBits);
+    std::vector<TOp> tops;
+    tops.reserve(p.ops.size() + 8);
+    for (const DevOp& d : p.ops) {
+        if (d.op == OP_PAULI2) {  // two independent one-qubit Paulis: codes in bits 0-1 and 2-3 of the slot byte
+            TOp t0, t1;
+            t0.d = d; t0.d.op = OP_PAULI1; t0.d.b = 0;
+            t1.d = d; t1.d.op = OP_PAULI1; t1.d.a = d.b; t1.d.b = 2;
+            tile_masks(t0);
+            tile_masks(t1);
+            tops.push_back(t0);
+            tops.push_back(t1);
+        } else {
+            TOp t;
+            t.d = d;
+            if (d.op == OP_PAULI1) t.d.b = 0;
+            tile_masks(t);
+            tops.push_back(t);
+        }
+    }
+    std::vector<int> remaining(tops.size());
+    for (size_t i = 0; i < tops.size(); ++i) remaining[i] = (int)i;
+
+    auto emit_window = [&](uint32_t W, const std::vector<int>& mine) {
+        for (int q = 0; q < k && popc32(W) < kRegBits; ++q) W |= 1u << q;  // fill with unused positions
+        Window w{};
+        int nb = 0;
+        int rb_of[32];
+        for (int q = 0; q < 32; ++q) rb_of[q] = -1;
+        for (int q = 0; q < k; ++q)
+            if ((W >> q) & 1) { w.wpos[nb] = (uint8_t)q; rb_of[q] = nb++; }
+        std::vector<int> rest;
+        for (int q = 0; q < k; ++q)
+            if (!((W >> q) & 1)) rest.push_back(q);
+        // lanes 0-7 of a quarter warp should hit eight different bank groups: lead with an independent triple
+        bool found = false;
+        for (size_t a = 0; a < rest.size() && !found; ++a)
+            for (size_t b = a + 1; b < rest.size() && !found; ++b)
+                for (size_t c = b + 1; c < rest.size() && !found; ++c)
+                    if (independent3(rest[a], rest[b], rest[c])) {
+                        std::vector<int> order = {rest[a], rest[b], rest[c]};
+                        for (size_t i = 0; i < rest.size(); ++i)
+                            if (i != a && i != b && i != c) order.push_back(rest[i]);
+                        rest.swap(order);
+                        found = true;
+                    }
+        for (size_t i = 0; i < rest.size() && i < sizeof(w.tpos); ++i) w.tpos[i] = (uint8_t)rest[i];
+        w.op_begin = (int32_t)p.wops.size();
+        auto phys = [&](int pos) { return pos < k_real ? p.local[pos] : 63; };
+        for (int idx : mine) {
+            const DevOp& d = tops[idx].d;
+            WinOp o{};
+            o.t = d.t;
+            o.fixed = d.fixed;
+            switch (d.op) {
+            case OP_RX: o.w0 = winop_pack(W_ROT_X, rb_of[d.a], 0, 0, d.flags); break;
+            case OP_RY: o.w0 = winop_pack(W_ROT_Y, rb_of[d.a], 0, 0, d.flags); break;
+            case OP_RZ:
+                if (rb_of[d.a] >= 0) o.w0 = winop_pack(W_ROT_Z, rb_of[d.a], 0, 0, d.flags);
+                else o.w0 = winop_pack(W_PHASE, 0, 0, phys(d.a), d.flags);
+                break;
+            case OP_RZ_NL: o.w0 = winop_pack(W_PHASE, 0, 0, d.a, d.flags); break;
+            case OP_CNOT:
+                if (rb_of[d.a] >= 0) o.w0 = winop_pack(W_CX_WW, rb_of[d.a], rb_of[d.b], 0, 0);
+                else o.w0 = winop_pack(W_CX_OW, rb_of[d.b], 0, phys(d.a), 0);
+                break;
+            case OP_CNOT_NL: o.w0 = winop_pack(W_CX_OW, rb_of[d.b], 0, d.a, 0); break;
+            case OP_X: o.w0 = winop_pack(W_X, rb_of[d.a], 0, 0, 0); break;
+            case OP_Y: o.w0 = winop_pack(W_Y, rb_of[d.a], 0, 0, d.flags); break;
+            case OP_Z:
+                if (rb_of[d.a] >= 0) o.w0 = winop_pack(W_Z, rb_of[d.a], 0, 0, 0);
+                else o.w0 = winop_pack(W_Z_OUT, 0, 0, phys(d.a), 0);
+                break;
+            case OP_Z_NL: o.w0 = winop_pack(W_Z_OUT, 0, 0, d.a, 0); break;
+            case OP_PAULI1: o.w0 = winop_pack(W_PAULI, rb_of[d.a], d.b, 0, 0); break;
+            case OP_DEPOL1_DM: o.w0 = winop_pack(W_DEPOL1, rb_of[d.a], rb_of[d.b], 0, 0); break;
+            case OP_DEPOL2_DM:
+                o.w0 = winop_pack(W_DEPOL2, rb_of[d.a & 0xff] | (rb_of[(d.a >> 8) & 0xff] << 2),
+                                  rb_of[d.b & 0xff] | (rb_of[(d.b >> 8) & 0xff] << 2), 0, 0);
+                break;
+            default: break;
+            }
+            p.wops.push_back(o);
+        }
+        w.op_end = (int32_t)p.wops.size();
+        // the kernel stages one window's ops at a time: split long windows (same layout, consecutive ranges)
+        for (int32_t lo = w.op_begin; lo < w.op_end || lo == w.op_begin; lo += kMaxWindowOps) {
+            Window part = w;
+            part.op_begin = lo;
+            part.op_end = std::min<int32_t>(w.op_end, lo + kMaxWindowOps);
+            p.windows.push_back(part);
+            if (w.op_end == w.op_begin) break;
+        }
+    };
+
+    while (!remaining.empty()) {
+        uint32_t W = 0, blocked_mix = 0, blocked_diag = 0;
+        std::vector<int> mine, deferred;
+        for (int idx : remaining) {
+            const TOp& t = tops[idx];
+            bool take = !((t.mix & (blocked_mix | blocked_diag)) || (t.diag & blocked_mix));
+            if (take) {
+                if (popc32(W | t.mix) <= kRegBits) W |= t.mix;
+                else take = false;
+            }
+            if (take) mine.push_back(idx);
+            else {
+                deferred.push_back(idx);
+                blocked_mix |= t.mix;
+                blocked_diag |= t.diag;
+            }
+        }
+        emit_window(W, mine);
+        remaining.swap(deferred);
+    }
+    if (p.windows.empty()) emit_window(0, {});  // no ops: one window that only carries the layout
+}
 
 bool mask_is_local(const Pass& p, uint64_t mask) {
     uint64_t l = 0;
@@ -274,6 +429,7 @@ std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const Pla
         for (int q = 0; q < n && __builtin_popcountll(L) < k; ++q) L |= bit(q);
         Pass p;
         finish_pass(p, n, L);
+        schedule_windows(p);
         passes.push_back(std::move(p));
         bool progressed = false;
         for (int a : *assignment) progressed |= (a == me);

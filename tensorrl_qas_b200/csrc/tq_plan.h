@@ -51,12 +51,62 @@ struct Gate {        // user-level gate (tq_set_circuit)
     double fixed;
 };
 
+// ---- second level: register windows inside a tile ---------------------------------------------------------------
+// Every thread of a CTA keeps 2^kRegBits amplitudes of the tile in registers: the ones that differ only in the
+// window's kRegBits tile positions.  Gates that mix only window positions run on registers without touching shared
+// memory; the tile is re-distributed through shared memory only when the window changes.
+constexpr int kRegBits = 4;
+constexpr int kMinTileBits = kRegBits;   // smaller states are padded with phantom positions
+constexpr int kMaxWindowOps = 256;       // ops per window (the kernel stages one window's ops at a time)
+
+// window-level opcodes (WinOp code); RB/CB/TB are register-bit indices inside the window
+enum : int32_t {
+    W_ROT_X = 0,    // rb
+    W_ROT_Y = 1,    // rb
+    W_ROT_Z = 2,    // rb
+    W_PHASE = 3,    // RZ on a bit outside the window: qsel = physical bit
+    W_CX_WW = 4,    // rb = control, rb2 = target
+    W_CX_OW = 5,    // qsel = physical control bit, rb = target
+    W_X = 6,        // rb
+    W_Y = 7,        // rb (flag conj: -Y)
+    W_Z = 8,        // rb
+    W_Z_OUT = 9,    // qsel = physical bit
+    W_PAULI = 10,   // rb, t = slot, rb2 = shift of the 2-bit code inside the slot byte (0 or 2)
+    W_DEPOL1 = 11,  // rb = row bit, rb2 = column bit, fixed = p
+    W_DEPOL2 = 12,  // the window is exactly {row a, row b, col a, col b}: rb = ra | rb << 2, rb2 = ca | cb << 2
+};
+
+struct WinOp {      // 16 bytes
+    uint32_t w0;    // code | rb << 8 | rb2 << 12 | qsel << 16 | flags << 24
+    int32_t t;      // rotations: parameter column or -1; W_PAULI: slot
+    double fixed;
+};
+inline uint32_t winop_pack(int code, int rb, int rb2, int qsel, int flags) {
+    return (uint32_t)code | ((uint32_t)rb << 8) | ((uint32_t)rb2 << 12) | ((uint32_t)qsel << 16) | ((uint32_t)flags << 24);
+}
+
+struct Window {     // 24 bytes, read by the kernel from global memory
+    uint8_t wpos[kRegBits];  // tile position of register bit r
+    uint8_t tpos[12];        // tile position of thread bit i (first k - kRegBits entries used); the first three
+                             // are chosen with independent bank-swizzle vectors (conflict-free exchanges)
+    int32_t op_begin, op_end;  // range in Pass::wops
+};
+
+// bank swizzle of the shared-memory tile: amplitude j lives in slot j ^ swizzle_fold(j >> 3), a GF(2)-linear map
+// that spreads any three independent tile positions over the eight 16-byte bank groups
+constexpr uint8_t kSwizzleVec[13] = {1, 2, 4, 3, 5, 6, 7, 1, 2, 4, 3, 5, 6};
+
 struct Pass {
     std::vector<int> local;     // physical bits of the tile, ascending; local[p] = physical bit of tile position p
     std::vector<int> nonlocal;  // remaining physical bits, ascending
-    std::vector<DevOp> ops;     // in execution order
+    std::vector<DevOp> ops;     // tile-level ops in a valid execution order (what the windows were scheduled from)
     int lead = 0;               // number of leading positions with local[p] == p (contiguous run in memory)
+    std::vector<Window> windows;  // register-window schedule of `ops`
+    std::vector<WinOp> wops;
 };
+
+// fills p.windows / p.wops from p.ops
+void schedule_windows(Pass& p);
 
 struct PlanOptions {
     int tile_bits = 12;   // k: tile = 2^k amplitudes (64 KiB of complex128)

@@ -175,7 +175,8 @@ class Simulator:
 
 
 def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=()):
-    """Planner dry run (no GPU): list of passes, each {'lead', 'local', 'ops': [(op, a, b, t, flags, fixed)]}."""
+    """Planner dry run (no GPU): list of passes, each {'lead', 'local', 'ops': [(op, a, b, t, flags, fixed)],
+    'windows': [{'wpos', 'tpos', 'ops': [(code, rb, rb2, qsel, flags, t, fixed)]}]}."""
     L = _lib.lib()
     kind, q0, q1, pidx, fixed = gl.arrays()
     cm = np.ascontiguousarray(cover_masks, dtype=np.uint64)
@@ -193,7 +194,13 @@ def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=()):
         if tok[0] == "PASS":
             lead = int(tok[1].split("=")[1])
             local = [int(v) for v in tok[2].split("=")[1].split(",") if v != ""]
-            passes.append({"lead": lead, "local": local, "ops": []})
-        else:
+            passes.append({"lead": lead, "local": local, "ops": [], "windows": []})
+        elif tok[0] == "OP":
             passes[-1]["ops"].append((int(tok[1]), int(tok[2]), int(tok[3]), int(tok[4]), int(tok[5]), float(tok[6])))
+        elif tok[0] == "WIN":
+            wpos = [int(v) for v in tok[1].split("=")[1].split(",") if v != ""]
+            tpos = [int(v) for v in tok[2].split("=")[1].split(",") if v != ""]
+            passes[-1]["windows"].append({"wpos": wpos, "tpos": tpos, "ops": []})
+        elif tok[0] == "WOP":  # (code, rb, rb2, qsel, flags, t, fixed)
+            passes[-1]["windows"][-1]["ops"].append(tuple(int(v) for v in tok[1:7]) + (float(tok[7]),))
     return passes

@@ -76,6 +76,57 @@ def run_plan(passes, nbits, params, init=None, codes=None):
     return vec
 
 
+(W_ROT_X, W_ROT_Y, W_ROT_Z, W_PHASE, W_CX_WW, W_CX_OW, W_X, W_Y, W_Z, W_Z_OUT, W_PAULI, W_DEPOL1, W_DEPOL2) = range(13)
+
+
+def run_plan_windows(passes, nbits, params, init=None, codes=None):
+    """Same as run_plan but from the register-window schedule (what the kernel executes): register bit r of a window
+    is tile position wpos[r], i.e. physical bit local[wpos[r]]; qsel is already a physical bit."""
+    vec = np.zeros(1 << nbits, dtype=np.complex128)
+    if init is None:
+        vec[0] = 1
+    else:
+        vec[:] = init
+    for p in passes:
+        loc = p["local"]
+        k_eff = max(len(loc), 4)
+        for w in p["windows"]:
+            assert len(w["wpos"]) == 4 and len(set(w["wpos"])) == 4
+            assert sorted(w["wpos"] + w["tpos"]) == list(range(k_eff))
+            assert len(w["ops"]) <= 256
+            phys = [loc[q] if q < len(loc) else None for q in w["wpos"]]
+            for code, rb, rb2, qsel, flags, t, fixed in w["ops"]:
+                conj = bool(flags & FLAG_CONJ)
+                if code in (W_ROT_X, W_ROT_Y, W_ROT_Z, W_PHASE):
+                    q = qsel if code == W_PHASE else phys[rb]
+                    theta = params[t] if t >= 0 else fixed
+                    m = _mat(("RX", "RY", "RZ", "RZ")[code], theta)
+                    vec = apply_1q(vec, nbits, q, np.conj(m) if conj else m)
+                elif code == W_CX_WW:
+                    vec = apply_cnot(vec, nbits, phys[rb], phys[rb2])
+                elif code == W_CX_OW:
+                    assert qsel not in [x for x in phys if x is not None]
+                    vec = apply_cnot(vec, nbits, qsel, phys[rb])
+                elif code in (W_X, W_Y, W_Z, W_Z_OUT):
+                    q = qsel if code == W_Z_OUT else phys[rb]
+                    m = _mat({W_X: "X", W_Y: "Y", W_Z: "Z", W_Z_OUT: "Z"}[code])
+                    vec = apply_1q(vec, nbits, q, np.conj(m) if conj else m)
+                elif code == W_PAULI:
+                    c = (codes[t] >> rb2) & 3
+                    if c:
+                        vec = apply_1q(vec, nbits, phys[rb], _mat("XYZ"[c - 1]))
+                elif code == W_DEPOL1:
+                    assert phys[rb2] == phys[rb] + nbits // 2
+                    vec = _depol_dm(vec, nbits, [phys[rb]], fixed)
+                elif code == W_DEPOL2:
+                    qa, qb = phys[rb & 3], phys[(rb >> 2) & 3]
+                    assert phys[rb2 & 3] == qa + nbits // 2 and phys[(rb2 >> 2) & 3] == qb + nbits // 2
+                    vec = _depol_dm(vec, nbits, [qa, qb], fixed)
+                else:
+                    raise ValueError(code)
+    return vec
+
+
 def check_invariants(passes, nbits, tile_bits, low_bits):
     """structural checks: tile size, forced low bits, every position operand is a valid tile position"""
     k = min(tile_bits, nbits)

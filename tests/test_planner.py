@@ -5,7 +5,7 @@ import pytest
 from tensorrl_qas_b200.circuit import GateList, brickwork_circuit, parameter_batch, synthetic_circuit
 from tensorrl_qas_b200.simulator import plan_dump
 
-from plan_emulator import check_invariants, run_plan
+from plan_emulator import check_invariants, run_plan, run_plan_windows
 
 
 def noisy_circuit(n, g, seed):
@@ -21,10 +21,11 @@ def noisy_circuit(n, g, seed):
     return gl
 
 
-@pytest.mark.parametrize("n,tile_bits,low_bits,seed", [(5, 12, 4, 0), (9, 8, 4, 1), (10, 8, 2, 2), (11, 8, 4, 3),
-                                                        (12, 9, 3, 4)])
+@pytest.mark.parametrize("n,tile_bits,low_bits,seed", [(1, 12, 4, 9), (2, 12, 4, 8), (3, 12, 4, 7), (5, 12, 4, 0),
+                                                        (9, 8, 4, 1), (10, 8, 2, 2), (11, 8, 4, 3), (12, 9, 3, 4),
+                                                        (12, 12, 4, 5)])
 def test_pure_plan_equals_gate_list(built_lib, oracle, n, tile_bits, low_bits, seed):
-    gl = synthetic_circuit(n, 120, seed)
+    gl = synthetic_circuit(n, 120 if n < 12 else 600, seed)
     gl.add_pauli("X", 0)
     gl.add_pauli("Y", n - 1)
     gl.add_pauli("Z", n // 2)
@@ -35,6 +36,7 @@ def test_pure_plan_equals_gate_list(built_lib, oracle, n, tile_bits, low_bits, s
     got = run_plan(passes, n, params)
     want = oracle.state(gl, params)
     assert np.abs(got - want).max() < 1e-12
+    assert np.abs(run_plan_windows(passes, n, params) - want).max() < 1e-12
     if n > tile_bits:
         assert len(passes) > 1
 
@@ -45,7 +47,10 @@ def test_brickwork_c5_plan_is_few_passes(built_lib):
     passes = plan_dump(gl, 0, 12, 4)
     check_invariants(passes, 20, 12, 4)
     assert sum(len(p["ops"]) for p in passes) == 440
+    assert sum(len(w["ops"]) for p in passes for w in p["windows"]) == 440
     assert len(passes) <= 6  # 440 gates fused into a handful of HBM passes
+    n_windows = sum(len(p["windows"]) for p in passes)
+    assert n_windows <= 60, n_windows  # ... and a few dozen shared-memory redistributions
 
 
 def test_cover_masks_pulled_into_last_pass(built_lib):
@@ -64,6 +69,7 @@ def test_density_plan_equals_oracle(built_lib, oracle, n, tile_bits, seed):
     got = run_plan(passes, 2 * n, params)
     want = oracle.density_matrix(gl, params).reshape(-1)
     assert np.abs(got - want).max() < 1e-12
+    assert np.abs(run_plan_windows(passes, 2 * n, params) - want).max() < 1e-12
     rho = got.reshape(1 << n, 1 << n)
     assert abs(np.trace(rho) - 1) < 1e-12 and np.abs(rho - rho.conj().T).max() < 1e-12
 
@@ -84,6 +90,7 @@ def test_trajectory_plan_equals_oracle(built_lib, oracle, n, tile_bits, seed):
     got = run_plan(passes, n, params, codes=codes)
     want = oracle.state(gl, params, codes=codes)
     assert np.abs(got - want).max() < 1e-12
+    assert np.abs(run_plan_windows(passes, n, params, codes=codes) - want).max() < 1e-12
     # the noise-free plan skips the noise gates
     clean = run_plan(plan_dump(gl, 0, tile_bits, 4), n, params)
     assert np.abs(clean - oracle.state(gl, params)).max() < 1e-12
