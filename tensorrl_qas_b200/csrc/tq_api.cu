@@ -39,8 +39,11 @@ struct Plan {
     int n_gate_passes = 0;
     int slots = 0;        // partial sums per element
     int n_unitary = 0, n_rot = 0;
-    void* arena = nullptr;  // device blob holding ops / groups / terms of all passes
+    void* arena = nullptr;  // device blob holding windows / ops / groups / terms of all passes + matrix programs
     size_t arena_cap = 0;
+    int n_mats = 0;
+    const MatDesc* d_descs = nullptr;
+    const MatGate* d_prog = nullptr;
 };
 
 }  // namespace
@@ -79,6 +82,8 @@ struct tq_context {
     size_t state_cap = 0;  // bytes
     double* d_partial = nullptr;
     size_t partial_cap = 0;  // doubles
+    double2* d_mats = nullptr;  // block matrices of the elements in flight
+    size_t mats_cap = 0;     // bytes
 
     // host-call staging
     cudaStream_t stream = nullptr;
@@ -234,9 +239,11 @@ int compile_plan(tq_handle h, int which) {
         for (const HamGroup& g : h->groups)
             if (g.x) cover.push_back(g.x);
 
-    std::vector<Pass> passes = which == 1 ? plan_density(n, h->gates, opt, &perr)
-                                          : plan_statevector(n, h->gates, opt, cover, &perr);
+    opt.fuse = env_int("TQ_FUSE", 1) != 0;
+    CompiledCircuit cc = which == 1 ? plan_density(n, h->gates, opt, &perr)
+                                    : plan_statevector(n, h->gates, opt, cover, &perr);
     if (!perr.empty()) return fail(h, TQ_EINVAL, perr);
+    std::vector<Pass>& passes = cc.passes;
     if (passes.empty()) {  // no gates: one pass that just stages the initial state
         std::vector<int> dummy;
         passes = plan_cover(nbits, {0ull}, opt, &dummy);
@@ -277,6 +284,8 @@ int compile_plan(tq_handle h, int which) {
     };
     struct Offsets { size_t windows, wops, groups, terms; int n_groups, n_terms; };
     std::vector<Offsets> offs(passes.size());
+    const size_t off_descs = append(cc.mats.data(), cc.mats.size() * sizeof(MatDesc));
+    const size_t off_prog = append(cc.prog.data(), cc.prog.size() * sizeof(MatGate));
     for (size_t i = 0; i < passes.size(); ++i) {
         const Pass& p = passes[i];
         offs[i].windows = append(p.windows.data(), p.windows.size() * sizeof(Window));
@@ -315,6 +324,9 @@ int compile_plan(tq_handle h, int which) {
     plan.n_gate_passes = n_gate_passes;
     plan.slots = 0;
     const unsigned char* base = (const unsigned char*)plan.arena;
+    plan.n_mats = (int)cc.mats.size();
+    plan.d_descs = (const MatDesc*)(base + off_descs);
+    plan.d_prog = (const MatGate*)(base + off_prog);
     for (size_t i = 0; i < passes.size(); ++i) {
         DevPass dp;
         fill_geometry(dp.proto, passes[i], nbits);
@@ -325,6 +337,7 @@ int compile_plan(tq_handle h, int which) {
         dp.proto.n_windows = (int)passes[i].windows.size();
         dp.proto.wops = (const WinOp*)(base + offs[i].wops);
         dp.proto.n_wops = (int)passes[i].wops.size();
+        dp.proto.n_mats = plan.n_mats;
         dp.n_groups = offs[i].n_groups;
         if (which != 1) {
             if (single_tile) {
@@ -426,18 +439,24 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
     }
     chunk = std::min(chunk, (int)(0x7fffffffu >> std::max(0, plan.nbits - h->opt.tile_bits)) / 2);  // grid.x limit
     if (want_energy && !dm && plan.slots > 1) { rc = ensure_partial(h, (size_t)chunk * plan.slots); if (rc) return rc; }
+    rc = grow(h, (void**)&h->d_mats, &h->mats_cap, std::max<size_t>(16, (size_t)chunk * plan.n_mats * kMatStride * 16));
+    if (rc) return rc;
 
     h->last_stream = stream;
     for (int b0 = 0; b0 < batch; b0 += chunk) {
         const int bc = std::min(chunk, batch - b0);
         double2* buf = states_out ? states_out + ((size_t)b0 << plan.nbits) : h->d_state;
+        if (plan.n_mats > 0) {
+            launch_prep_matrices(plan.d_descs, plan.d_prog, plan.n_mats, bc, params ? params + (size_t)b0 * ld : nullptr, ld,
+                                 codes ? codes + (size_t)b0 * ldc : nullptr, ldc, h->d_mats, stream);
+            ++h->launches;
+            rc = check_launch(h, "prep_matrices_kernel");
+            if (rc) return rc;
+        }
         for (int i = 0; i < total_passes; ++i) {
             const DevPass& dp = plan.passes[i];
             PassParams pp = dp.proto;
-            pp.params = params ? params + (size_t)b0 * ld : nullptr;
-            pp.ld_params = ld;
-            pp.codes = codes ? codes + (size_t)b0 * ldc : nullptr;
-            pp.ld_codes = ldc;
+            pp.mats = h->d_mats;
             if (i == 0) {
                 if (h->have_init) { pp.src_mode = 1; pp.src = dm ? h->d_init_rho : h->d_init; }
                 else { pp.src_mode = 0; pp.src = nullptr; }
@@ -579,6 +598,7 @@ int tq_destroy(tq_handle h) {
     if (h->d_init_rho) cudaFree(h->d_init_rho);
     if (h->d_state) cudaFree(h->d_state);
     if (h->d_partial) cudaFree(h->d_partial);
+    if (h->d_mats) cudaFree(h->d_mats);
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -738,7 +758,7 @@ int tq_plan_info(tq_handle h, int which, int64_t* info8) {
     info8[0] = plan.n_gate_passes;
     info8[1] = (int64_t)plan.passes.size() - plan.n_gate_passes;
     info8[2] = plan.passes.empty() ? 0 : plan.passes[0].proto.k;
-    info8[3] = (int64_t)plan.passes.size() + ((which == 1) ? 1 : (plan.slots > 1 ? 1 : 0));
+    info8[3] = (int64_t)plan.passes.size() + ((which == 1) ? 1 : (plan.slots > 1 ? 1 : 0)) + (plan.n_mats > 0 ? 1 : 0);
     info8[4] = (int64_t)h->groups.size();
     info8[5] = (int64_t)h->hent.size();
     info8[6] = plan.n_unitary;
@@ -763,12 +783,21 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
     opt.trajectory = (which == 2);
     std::vector<uint64_t> cover(cover_masks, cover_masks + n_cover);
     std::string err;
-    std::vector<Pass> passes = which == 1 ? plan_density(n_qubits, gates, opt, &err)
-                                          : plan_statevector(n_qubits, gates, opt, cover, &err);
+    opt.fuse = env_int("TQ_FUSE", 1) != 0;
+    CompiledCircuit cc = which == 1 ? plan_density(n_qubits, gates, opt, &err)
+                                    : plan_statevector(n_qubits, gates, opt, cover, &err);
     std::string out;
     char line[256];
     if (!err.empty()) out = "ERROR " + err + "\n";
-    for (const Pass& p : passes) {
+    for (const MatDesc& md : cc.mats) {
+        out += "MAT " + std::to_string(md.nq) + " " + std::to_string(md.diag) + "\n";
+        for (int g = md.begin; g < md.end; ++g) {
+            const MatGate& mg = cc.prog[g];
+            snprintf(line, sizeof line, "MG %d %d %d %.17g\n", mg.kind, mg.lq, mg.pidx, mg.fixed);
+            out += line;
+        }
+    }
+    for (const Pass& p : cc.passes) {
         out += "PASS lead=" + std::to_string(p.lead) + " local=";
         for (size_t i = 0; i < p.local.size(); ++i) out += (i ? "," : "") + std::to_string(p.local[i]);
         out += "\n";

@@ -22,48 +22,73 @@ __device__ __forceinline__ uint32_t swz(uint32_t j) {
 
 typedef double2 Amps[NA];
 
-// ---- register-window gates.  RB = register bit of the target; all loops are fully unrolled (static indices) ------
-template <int RB>
-__device__ __forceinline__ void g_rx(Amps& a, double c, double s) {  // exp(+i t/2 X) = [[c, i s], [i s, c]]
+// ---- register-window blocks.  RB.. = register bits; all loops are fully unrolled (static register indices) -------
+__device__ __forceinline__ double2 cmul(double2 m, double2 v) {
+    return make_double2(m.x * v.x - m.y * v.y, m.x * v.y + m.y * v.x);
+}
+__device__ __forceinline__ double2 cfma(double2 m, double2 v, double2 acc) {
+    return make_double2(fma(m.x, v.x, fma(-m.y, v.y, acc.x)), fma(m.x, v.y, fma(m.y, v.x, acc.y)));
+}
+
+// dense 4x4 block on register bits RA < RB (matrix index bit 0 = RA); m = 16 staged entries, row-major
+template <int RA, int RB>
+__device__ __forceinline__ void g_u2(Amps& a, const double2* __restrict__ m) {
+    constexpr int O0 = (RA != 0 && RB != 0) ? 0 : (RA != 1 && RB != 1) ? 1 : 2;
+    constexpr int O1 = (RA != 3 && RB != 3) ? 3 : (RA != 2 && RB != 2) ? 2 : 1;
 #pragma unroll
-    for (int m = 0; m < NA / 2; ++m) {
-        const int i0 = ((m >> RB) << (RB + 1)) | (m & ((1 << RB) - 1)), i1 = i0 | (1 << RB);
+    for (int gp = 0; gp < 2; ++gp) {  // two groups of four amplitudes per sweep over the matrix
+        const int base0 = (gp ? (1 << O1) : 0), base1 = base0 | (1 << O0);
+        double2 in0[4], in1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int off = ((k & 1) ? (1 << RA) : 0) | ((k & 2) ? (1 << RB) : 0);
+            in0[k] = a[base0 | off];
+            in1[k] = a[base1 | off];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int off = ((i & 1) ? (1 << RA) : 0) | ((i & 2) ? (1 << RB) : 0);
+            double2 mm = m[i * 4];
+            double2 o0 = cmul(mm, in0[0]), o1 = cmul(mm, in1[0]);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                mm = m[i * 4 + k];
+                o0 = cfma(mm, in0[k], o0);
+                o1 = cfma(mm, in1[k], o1);
+            }
+            a[base0 | off] = o0;
+            a[base1 | off] = o1;
+        }
+    }
+}
+// dense 2x2 block on register bit RB; m = {m00, m01, m10, m11}
+template <int RB>
+__device__ __forceinline__ void g_u1(Amps& a, const double2* __restrict__ m) {
+    const double2 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+#pragma unroll
+    for (int p = 0; p < NA / 2; ++p) {
+        const int i0 = ((p >> RB) << (RB + 1)) | (p & ((1 << RB) - 1)), i1 = i0 | (1 << RB);
         const double2 a0 = a[i0], a1 = a[i1];
-        a[i0] = make_double2(c * a0.x - s * a1.y, c * a0.y + s * a1.x);
-        a[i1] = make_double2(c * a1.x - s * a0.y, c * a1.y + s * a0.x);
+        a[i0] = cfma(m01, a1, cmul(m00, a0));
+        a[i1] = cfma(m11, a1, cmul(m10, a0));
     }
 }
+// diagonal block on register bit RB: m[0] on bit = 0, m[3] on bit = 1
 template <int RB>
-__device__ __forceinline__ void g_ry(Amps& a, double c, double s) {  // exp(+i t/2 Y) = [[c, s], [-s, c]]
+__device__ __forceinline__ void g_d1(Amps& a, const double2* __restrict__ m) {
+    const double2 d0 = m[0], d1 = m[3];
 #pragma unroll
-    for (int m = 0; m < NA / 2; ++m) {
-        const int i0 = ((m >> RB) << (RB + 1)) | (m & ((1 << RB) - 1)), i1 = i0 | (1 << RB);
-        const double2 a0 = a[i0], a1 = a[i1];
-        a[i0] = make_double2(c * a0.x + s * a1.x, c * a0.y + s * a1.y);
-        a[i1] = make_double2(c * a1.x - s * a0.x, c * a1.y - s * a0.y);
-    }
+    for (int i = 0; i < NA; ++i) a[i] = cmul(((i >> RB) & 1) ? d1 : d0, a[i]);
 }
-template <int RB>
-__device__ __forceinline__ void g_rz(Amps& a, double c, double s) {  // diag(c + i s, c - i s)
+__device__ __forceinline__ void g_scale(Amps& a, double2 d) {
 #pragma unroll
-    for (int i = 0; i < NA; ++i) {
-        const double sj = ((i >> RB) & 1) ? -s : s;
-        const double2 v = a[i];
-        a[i] = make_double2(c * v.x - sj * v.y, c * v.y + sj * v.x);
-    }
-}
-__device__ __forceinline__ void g_phase(Amps& a, double c, double s) {
-#pragma unroll
-    for (int i = 0; i < NA; ++i) {
-        const double2 v = a[i];
-        a[i] = make_double2(c * v.x - s * v.y, c * v.y + s * v.x);
-    }
+    for (int i = 0; i < NA; ++i) a[i] = cmul(d, a[i]);
 }
 template <int RB>
 __device__ __forceinline__ void g_x_if(Amps& a, bool pred) {  // X on RB where pred (per-thread control bit)
 #pragma unroll
-    for (int m = 0; m < NA / 2; ++m) {
-        const int i0 = ((m >> RB) << (RB + 1)) | (m & ((1 << RB) - 1)), i1 = i0 | (1 << RB);
+    for (int p = 0; p < NA / 2; ++p) {
+        const int i0 = ((p >> RB) << (RB + 1)) | (p & ((1 << RB) - 1)), i1 = i0 | (1 << RB);
         const double2 a0 = a[i0], a1 = a[i1];
         a[i0] = pred ? a1 : a0;
         a[i1] = pred ? a0 : a1;
@@ -79,33 +104,6 @@ __device__ __forceinline__ void g_cx(Amps& a) {  // both bits in the window: a r
             a[i | (1 << TB)] = t;
         }
     }
-}
-template <int RB>
-__device__ __forceinline__ void g_y(Amps& a, double sign) {  // Y = [[0, -i], [i, 0]]; sign -1: conj(Y) = -Y
-#pragma unroll
-    for (int m = 0; m < NA / 2; ++m) {
-        const int i0 = ((m >> RB) << (RB + 1)) | (m & ((1 << RB) - 1)), i1 = i0 | (1 << RB);
-        const double2 a0 = a[i0], a1 = a[i1];
-        a[i0] = make_double2(sign * a1.y, -sign * a1.x);
-        a[i1] = make_double2(-sign * a0.y, sign * a0.x);
-    }
-}
-template <int RB>
-__device__ __forceinline__ void g_z(Amps& a) {
-#pragma unroll
-    for (int i = 0; i < NA; ++i)
-        if ((i >> RB) & 1) a[i] = make_double2(-a[i].x, -a[i].y);
-}
-__device__ __forceinline__ void g_neg_if(Amps& a, bool pred) {
-    const double f = pred ? -1.0 : 1.0;
-#pragma unroll
-    for (int i = 0; i < NA; ++i) a[i] = make_double2(f * a[i].x, f * a[i].y);
-}
-template <int RB>
-__device__ __forceinline__ void g_pauli(Amps& a, int code) {
-    if (code == 1) g_x_if<RB>(a, true);
-    else if (code == 2) g_y<RB>(a, 1.0);
-    else if (code == 3) g_z<RB>(a);
 }
 // exact 1-qubit depolarising channel on (row bit A, column bit B): rho -> (1-4p/3) rho + (2p/3) Tr_q(rho) (x) I
 template <int A, int B>
@@ -165,6 +163,17 @@ __device__ __forceinline__ void exec_cx_ww(Amps& a, int cb, int tb) {
     }
 }
 
+__device__ __forceinline__ void exec_u2(Amps& a, int ra, int rb, const double2* m) {
+    switch (ra * 4 + rb) {
+    case 1: g_u2<0, 1>(a, m); break;
+    case 2: g_u2<0, 2>(a, m); break;
+    case 3: g_u2<0, 3>(a, m); break;
+    case 6: g_u2<1, 2>(a, m); break;
+    case 7: g_u2<1, 3>(a, m); break;
+    default: g_u2<2, 3>(a, m); break;
+    }
+}
+
 __device__ __forceinline__ void exec_depol1(Amps& a, int ra, int rb, double p) {
     const int lo = ra < rb ? ra : rb, hi = ra < rb ? rb : ra;
     switch (lo * 4 + hi) {
@@ -207,9 +216,9 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
     const int tile_amps = 1 << p.k_eff;
     const int valid_amps = 1 << p.k;
     double2* amp = reinterpret_cast<double2*>(smem_raw);
-    double2* s_trig = amp + tile_amps;                                  // kOpsChunk entries
-    WinOp* s_wops = reinterpret_cast<WinOp*>(s_trig + kOpsChunk);       // kOpsChunk entries
-    double* s_red = reinterpret_cast<double*>(s_wops + kOpsChunk);      // 32 entries
+    double2* s_mat = amp + tile_amps;                                          // kMaxWindowOps x 16 entries
+    WinOp* s_wops = reinterpret_cast<WinOp*>(s_mat + kMaxWindowOps * kMatStride);  // kMaxWindowOps entries
+    double* s_red = reinterpret_cast<double*>(s_wops + kMaxWindowOps);         // 32 entries
     uint32_t* hi_off = reinterpret_cast<uint32_t*>(s_red + 32);         // 2^(k - lead) entries
 
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -242,15 +251,13 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
             amp[swz(j)] = j < valid_amps ? src[hi_off[j >> p.lead] | (j & lead_mask)] : make_double2(0.0, 0.0);
     }
 
-    const double* my_params = p.params ? p.params + (size_t)b * p.ld_params : nullptr;
-    const uint8_t* my_codes = p.codes ? p.codes + (size_t)b * p.ld_codes : nullptr;
+    const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
     const bool active = tid < (tile_amps >> kRegBits);
     const int n_tbits = p.k_eff - kRegBits;
 
     // ---- 2. register windows ----
     Amps a;
     uint32_t slot_t = 0, ws0 = 0, ws1 = 0, ws2 = 0, ws3 = 0;
-    int staged_begin = 0, staged_end = 0;
     for (int w = 0; w < p.n_windows; ++w) {
         const Window* win = p.windows + w;
         const int op_begin = win->op_begin, op_end = win->op_end;
@@ -261,21 +268,24 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
                 for (int r = 0; r < NA; ++r) amp[TQ_SLOT(r)] = a[r];
             }
         }
-        // stage this window's ops with their cos/sin while no amplitudes are live in registers; the planner keeps
-        // a window's op range within kOpsChunk, so a staged chunk always covers whole windows (uniform branch)
-        if (op_end > staged_end) {
-            staged_begin = op_begin;
-            staged_end = min(op_begin + kOpsChunk, p.n_wops);
-            for (int i = tid; i < staged_end - staged_begin; i += nthreads) {
-                const WinOp wo = p.wops[staged_begin + i];
-                s_wops[i] = wo;
-                const int code = wo.w0 & 0xff;
-                if (code <= W_PHASE) {
-                    const double theta = wo.t >= 0 ? my_params[wo.t] : wo.fixed;
-                    double s, c;
-                    sincos(0.5 * theta, &s, &c);
-                    if (((wo.w0 >> 24) & FLAG_CONJ) && code != W_ROT_Y) s = -s;
-                    s_trig[i] = make_double2(c, s);
+        // stage this window's ops and their block matrices (this element's, from the prep kernel) while no
+        // amplitudes are live in registers; the planner keeps a window within kMaxWindowOps ops
+        {
+            const int n_ops_w = op_end - op_begin;
+            for (int i = tid; i < n_ops_w * kMatStride; i += nthreads) {
+                const int oi = i >> 4, e = i & 15;
+                const WinOp wo = p.wops[op_begin + oi];
+                if (e == 0) s_wops[oi] = wo;
+                const int code = wo.w0 & 0xff, flags = wo.w0 >> 24;
+                if (code <= W_D1_OUT && (code == W_U2 || e < 4)) {
+                    int src = e;
+                    if (code == W_U2 && (flags & FLAG_SWAP)) {  // matrix written for the other qubit order
+                        const int r = e >> 2, c = e & 3;
+                        src = ((((r & 1) << 1) | (r >> 1)) << 2) | ((c & 1) << 1) | (c >> 1);
+                    }
+                    double2 v = my_mats[(size_t)wo.t * kMatStride + src];
+                    if (flags & FLAG_CONJ) v.y = -v.y;
+                    s_mat[oi * kMatStride + e] = v;
                 }
             }
         }
@@ -297,23 +307,18 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
         if (active) {
 #pragma unroll
             for (int r = 0; r < NA; ++r) a[r] = amp[TQ_SLOT(r)];
-            for (int o = op_begin; o < op_end; ++o) {
-                const WinOp wo = s_wops[o - staged_begin];
-                const double2 cs = s_trig[o - staged_begin];
+            for (int o = 0; o < op_end - op_begin; ++o) {
+                const WinOp wo = s_wops[o];
+                const double2* m = s_mat + o * kMatStride;
                 const int code = wo.w0 & 0xff, rb = (wo.w0 >> 8) & 0xf, rb2 = (wo.w0 >> 12) & 0xf;
                 const int qsel = (wo.w0 >> 16) & 0xff;
                 switch (code) {
-                case W_ROT_X: TQ_RB4(g_rx, rb, a, cs.x, cs.y); break;
-                case W_ROT_Y: TQ_RB4(g_ry, rb, a, cs.x, cs.y); break;
-                case W_ROT_Z: TQ_RB4(g_rz, rb, a, cs.x, cs.y); break;
-                case W_PHASE: g_phase(a, cs.x, ((ctx >> qsel) & 1ull) ? -cs.y : cs.y); break;
+                case W_U2: exec_u2(a, rb, rb2, m); break;
+                case W_U1: TQ_RB4(g_u1, rb, a, m); break;
+                case W_D1: TQ_RB4(g_d1, rb, a, m); break;
+                case W_D1_OUT: g_scale(a, ((ctx >> qsel) & 1ull) ? m[3] : m[0]); break;
                 case W_CX_WW: exec_cx_ww(a, rb, rb2); break;
                 case W_CX_OW: TQ_RB4(g_x_if, rb, a, (bool)((ctx >> qsel) & 1ull)); break;
-                case W_X: TQ_RB4(g_x_if, rb, a, true); break;
-                case W_Y: TQ_RB4(g_y, rb, a, ((wo.w0 >> 24) & FLAG_CONJ) ? -1.0 : 1.0); break;
-                case W_Z: TQ_RB4(g_z, rb, a); break;
-                case W_Z_OUT: g_neg_if(a, (bool)((ctx >> qsel) & 1ull)); break;
-                case W_PAULI: { const int pc = (my_codes[wo.t] >> rb2) & 3; TQ_RB4(g_pauli, rb, a, pc); break; }
                 case W_DEPOL1: exec_depol1(a, rb, rb2, wo.fixed); break;
                 case W_DEPOL2: exec_depol2(a, rb, rb2, wo.fixed); break;
                 default: break;
@@ -342,8 +347,8 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
         double acc = 0.0;
         if (p.exp_mode == 1) {
             // terms staged in shared memory (re-using the op staging area: 8 KiB = 256 terms)
-            ExpTerm* s_terms = reinterpret_cast<ExpTerm*>(s_trig);
-            const int cap = (int)((kOpsChunk * (sizeof(double2) + sizeof(WinOp))) / sizeof(ExpTerm));
+            ExpTerm* s_terms = reinterpret_cast<ExpTerm*>(s_mat);
+            const int cap = (int)((kMaxWindowOps * kMatStride * sizeof(double2)) / sizeof(ExpTerm));
             for (int g = 0; g < p.n_groups; ++g) {
                 const ExpGroup grp = p.groups[g];
                 const uint32_t xs = swz(grp.xlocal);
@@ -382,6 +387,84 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
     }
 }
 
+// ---- block matrices: one thread per (batch element, fused block) evaluates the block's matrix program ---------
+__global__ void __launch_bounds__(128) prep_matrices_kernel(const MatDesc* __restrict__ descs, const MatGate* __restrict__ prog,
+                                                            int n_mats, int batch, const double* __restrict__ params,
+                                                            int ld_params, const uint8_t* __restrict__ codes,
+                                                            int ld_codes, double2* __restrict__ mats) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_mats * batch) return;
+    const int b = idx / n_mats, mi = idx - b * n_mats;
+    const MatDesc md = descs[mi];
+    double2 M[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) M[r][c] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+    for (int gi = md.begin; gi < md.end; ++gi) {
+        const MatGate g = prog[gi];
+        int kind = g.kind;
+        if (kind == MG_CX) {  // control = lq: swap the two rows with the control bit set
+            if (g.lq == 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { const double2 t = M[1][c]; M[1][c] = M[3][c]; M[3][c] = t; }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { const double2 t = M[2][c]; M[2][c] = M[3][c]; M[3][c] = t; }
+            }
+            continue;
+        }
+        if (kind == MG_PAULI_SLOT) {
+            const int code = (codes[(size_t)b * ld_codes + g.pidx] >> (int)g.fixed) & 3;
+            if (code == 0) continue;
+            kind = MG_X + code - 1;
+        }
+        double2 g00 = make_double2(0.0, 0.0), g01 = g00, g10 = g00, g11 = g00;
+        if (kind <= MG_RZ) {
+            const double theta = g.pidx >= 0 ? params[(size_t)b * ld_params + g.pidx] : g.fixed;
+            double s, c;
+            sincos(0.5 * theta, &s, &c);
+            if (kind == MG_RX) { g00.x = c; g01.y = s; g10.y = s; g11.x = c; }            // cos I + i sin X
+            else if (kind == MG_RY) { g00.x = c; g01.x = s; g10.x = -s; g11.x = c; }      // cos I + i sin Y
+            else { g00.x = c; g00.y = s; g11.x = c; g11.y = -s; }                         // diag(e^{+it/2}, e^{-it/2})
+        } else if (kind == MG_X) { g01.x = 1.0; g10.x = 1.0; }
+        else if (kind == MG_Y) { g01.y = -1.0; g10.y = 1.0; }
+        else { g00.x = 1.0; g11.x = -1.0; }
+        // M <- (G on block qubit lq) * M : mixes row pairs that differ in bit lq
+        if (g.lq == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; r += 2) {
+                    const double2 x0 = M[r][c], x1 = M[r + 1][c];
+                    M[r][c] = cfma(g01, x1, cmul(g00, x0));
+                    M[r + 1][c] = cfma(g11, x1, cmul(g10, x0));
+                }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const double2 x0 = M[r][c], x1 = M[r + 2][c];
+                    M[r][c] = cfma(g01, x1, cmul(g00, x0));
+                    M[r + 2][c] = cfma(g11, x1, cmul(g10, x0));
+                }
+        }
+    }
+    double2* out = mats + (size_t)idx * kMatStride;
+    if (md.nq == 2) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) out[r * 4 + c] = M[r][c];
+    } else {  // one-qubit block: the 2x2 matrix in entries 0..3
+        out[0] = M[0][0];
+        out[1] = M[0][1];
+        out[2] = M[1][0];
+        out[3] = M[1][1];
+    }
+}
+
 __global__ void reduce_partials_kernel(const double* __restrict__ partial, int ld, int n, double* __restrict__ out,
                                        int batch) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -413,8 +496,8 @@ __global__ void __launch_bounds__(kMaxThreads) dm_expect_kernel(const double2* _
 
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead) {
     const size_t n_hi = (size_t)1 << (k - lead);
-    return ((size_t)16 << k_eff) + kOpsChunk * (sizeof(double2) + sizeof(WinOp)) + 32 * sizeof(double) +
-           n_hi * sizeof(uint32_t);
+    return ((size_t)16 << k_eff) + kMaxWindowOps * (kMatStride * sizeof(double2) + sizeof(WinOp)) +
+           32 * sizeof(double) + n_hi * sizeof(uint32_t);
 }
 
 cudaError_t tile_pass_configure() {
@@ -424,6 +507,14 @@ cudaError_t tile_pass_configure() {
 void launch_tile_pass(const PassParams& p, int batch, int threads, cudaStream_t stream) {
     const unsigned grid = (unsigned)batch << p.n_nl;
     tile_pass_kernel<<<grid, threads, tile_pass_smem_bytes(p.k_eff, p.k, p.lead), stream>>>(p);
+}
+
+void launch_prep_matrices(const MatDesc* descs, const MatGate* prog, int n_mats, int batch, const double* params,
+                          int ld_params, const uint8_t* codes, int ld_codes, double2* mats, cudaStream_t stream) {
+    const int total = n_mats * batch;
+    if (total <= 0) return;
+    prep_matrices_kernel<<<(total + 127) / 128, 128, 0, stream>>>(descs, prog, n_mats, batch, params, ld_params, codes,
+                                                                   ld_codes, mats);
 }
 
 void launch_reduce_partials(const double* partial, int ld, int n, double* out, int batch, cudaStream_t stream) {

@@ -5,7 +5,8 @@
 //   1. stage the tile in shared memory with coalesced 16-byte loads (runs of 2^lead consecutive amplitudes),
 //      bank-swizzled so that any later redistribution is conflict free;
 //   2. run the pass's register windows: every thread holds 16 amplitudes (4 window qubits) in registers and applies
-//      all gates of the window there; shared memory is touched only to switch windows;
+//      all fused blocks of the window there (dense 4x4 / 2x2 / diagonal blocks whose per-element matrices come from
+//      prep_matrices_kernel, CNOTs, exact depolarising channels); shared memory is touched only to switch windows;
 //   3. optionally evaluate the Hamiltonian terms whose flip masks are local (one deterministic partial per tile);
 //   4. write the tile back.
 // HBM traffic per pass is one read + one write of the state no matter how many gates the pass fused.
@@ -18,7 +19,6 @@
 namespace tq {
 
 constexpr int kMaxTileBits = 12;
-constexpr int kOpsChunk = kMaxWindowOps;   // window ops staged in shared memory at a time (with their cos/sin)
 constexpr int kMaxThreads = 256; // 2^(kMaxTileBits - kRegBits)
 
 struct ExpGroup {   // one X/Y flip mask of the Hamiltonian, local to the pass
@@ -48,10 +48,8 @@ struct PassParams {
     int n_windows;
     const WinOp* wops;
     int n_wops;
-    const double* params;
-    int ld_params;
-    const uint8_t* codes;
-    int ld_codes;
+    const double2* mats;   // [batch][n_mats][kMatStride] block matrices of this call's elements (prep kernel output)
+    int n_mats;
     int exp_mode;  // 0 none, 1 Pauli groups, 2 sparse entries (single-tile passes only)
     const ExpGroup* groups;
     int n_groups;
@@ -66,6 +64,10 @@ struct PassParams {
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead);
 cudaError_t tile_pass_configure();  // opt in to > 48 KiB dynamic shared memory
 void launch_tile_pass(const PassParams& p, int batch, int threads, cudaStream_t stream);
+
+// block matrices of every (element, fused block): mats[(b * n_mats + m) * kMatStride ...]
+void launch_prep_matrices(const MatDesc* descs, const MatGate* prog, int n_mats, int batch, const double* params,
+                          int ld_params, const uint8_t* codes, int ld_codes, double2* mats, cudaStream_t stream);
 
 // out[b] = sum_{s < n} partial[b * ld + s], fixed order
 void launch_reduce_partials(const double* partial, int ld, int n, double* out, int batch, cudaStream_t stream);

@@ -1,4 +1,4 @@
-// tq_plan.cpp -- gate list -> tile passes (see tq_plan.h).  Pure host C++, no CUDA.
+// tq_plan.cpp -- gate list -> fused blocks -> tile passes -> register windows (see tq_plan.h).  Host C++ only.
 #include "tq_plan.h"
 
 #include <algorithm>
@@ -8,44 +8,154 @@
 namespace tq {
 namespace {
 
-// gate before tile positions are known: physical bits + how it acts on them
-struct AOp {
-    int32_t kind;          // TQ_* kind (rotations, CNOT, Paulis, DEPOL)
+inline uint64_t bit(int q) { return 1ull << q; }
+
+// ================================================================ 1. fusion =====================================
+enum { B_MAT = 0, B_CX = 1, B_DEPOL1 = 2, B_DEPOL2 = 3 };
+
+struct Blk {
+    int type = B_MAT;
+    int q0 = -1, q1 = -1;        // B_MAT: q0 < q1 physical (q1 = -1: one qubit); B_CX: q0 control, q1 target
+    std::vector<MatGate> prog;   // lq relative to (q0, q1)
+    bool diag = true;
+    double p = 0.0;
+    bool dead = false;
+};
+
+struct Fuser {
+    int n;
+    bool fuse;
+    std::vector<Blk> blks;
+    std::vector<int> open;  // open[q] = block that still accepts gates on q, or -1
+
+    Fuser(int n_, bool fuse_) : n(n_), fuse(fuse_), open(n_, -1) {}
+
+    void close_q(int q) {
+        const int b = open[q];
+        if (b < 0) return;
+        open[blks[b].q0] = -1;
+        if (blks[b].q1 >= 0) open[blks[b].q1] = -1;
+    }
+
+    void add_1q(int q, MatGate g, bool diagonal) {
+        int b = open[q];
+        if (b < 0) {
+            Blk nb;
+            nb.q0 = q;
+            blks.push_back(nb);
+            b = (int)blks.size() - 1;
+            if (fuse) open[q] = b;
+        }
+        g.lq = (blks[b].q1 >= 0 && q == blks[b].q1) ? 1 : 0;
+        blks[b].prog.push_back(g);
+        blks[b].diag = blks[b].diag && diagonal;
+    }
+
+    void add_cx(int c, int t) {
+        if (!fuse) {
+            Blk nb;
+            nb.type = B_CX;
+            nb.q0 = c;
+            nb.q1 = t;
+            blks.push_back(nb);
+            return;
+        }
+        MatGate g{MG_CX, 0, -1, 0, 0.0};
+        const int bc = open[c], bt = open[t];
+        if (bc >= 0 && bc == bt) {  // both already in the same open two-qubit block
+            g.lq = (c == blks[bc].q0) ? 0 : 1;
+            blks[bc].prog.push_back(g);
+            blks[bc].diag = false;
+            return;
+        }
+        Blk nb;
+        nb.q0 = std::min(c, t);
+        nb.q1 = std::max(c, t);
+        nb.diag = false;
+        for (int q : {nb.q0, nb.q1}) {
+            const int b = open[q];
+            if (b < 0) continue;
+            if (blks[b].q1 < 0) {  // open one-qubit block: its gates move into the new block
+                for (MatGate m : blks[b].prog) {
+                    m.lq = (q == nb.q0) ? 0 : 1;
+                    nb.prog.push_back(m);
+                }
+                blks[b].dead = true;
+                open[q] = -1;
+            } else {
+                close_q(q);
+            }
+        }
+        g.lq = (c == nb.q0) ? 0 : 1;
+        nb.prog.push_back(g);
+        blks.push_back(nb);
+        open[c] = open[t] = (int)blks.size() - 1;
+    }
+
+    void add_channel(int type, int qa, int qb, double p) {
+        close_q(qa);
+        if (qb >= 0) close_q(qb);
+        Blk nb;
+        nb.type = type;
+        nb.q0 = qa;
+        nb.q1 = qb;
+        nb.p = p;
+        blks.push_back(nb);
+    }
+};
+
+// mode: 0 pure (noise gates skipped), 1 density matrix (noise gates = exact channels), 2 trajectory (sampled Paulis)
+std::vector<Blk> fuse_gates(int n, const std::vector<Gate>& gates, int mode, bool fuse) {
+    Fuser f(n, fuse);
+    for (const Gate& g : gates) {
+        switch (g.kind) {
+        case TQ_RX: f.add_1q(g.q0, MatGate{MG_RX, 0, g.pidx, 0, g.fixed}, false); break;
+        case TQ_RY: f.add_1q(g.q0, MatGate{MG_RY, 0, g.pidx, 0, g.fixed}, false); break;
+        case TQ_RZ: f.add_1q(g.q0, MatGate{MG_RZ, 0, g.pidx, 0, g.fixed}, true); break;
+        case TQ_X: f.add_1q(g.q0, MatGate{MG_X, 0, -1, 0, 0.0}, false); break;
+        case TQ_Y: f.add_1q(g.q0, MatGate{MG_Y, 0, -1, 0, 0.0}, false); break;
+        case TQ_Z: f.add_1q(g.q0, MatGate{MG_Z, 0, -1, 0, 0.0}, true); break;
+        case TQ_CNOT: f.add_cx(g.q0, g.q1); break;
+        case TQ_DEPOL1:
+            if (mode == 1) f.add_channel(B_DEPOL1, g.q0, -1, g.fixed);
+            else if (mode == 2 && g.pidx >= 0) f.add_1q(g.q0, MatGate{MG_PAULI_SLOT, 0, g.pidx, 0, 0.0}, false);
+            break;
+        case TQ_DEPOL2:
+            if (mode == 1) f.add_channel(B_DEPOL2, g.q0, g.q1, g.fixed);
+            else if (mode == 2 && g.pidx >= 0) {
+                f.add_1q(g.q0, MatGate{MG_PAULI_SLOT, 0, g.pidx, 0, 0.0}, false);
+                f.add_1q(g.q1, MatGate{MG_PAULI_SLOT, 0, g.pidx, 0, 2.0}, false);
+            }
+            break;
+        default: break;
+        }
+    }
+    std::vector<Blk> out;
+    for (Blk& b : f.blks) {
+        if (b.dead) continue;
+        if (b.type == B_MAT && b.q1 >= 0 && b.prog.size() == 1 && b.prog[0].kind == MG_CX) {  // a lone CNOT
+            Blk cx;
+            cx.type = B_CX;
+            cx.q0 = b.prog[0].lq == 0 ? b.q0 : b.q1;
+            cx.q1 = b.prog[0].lq == 0 ? b.q1 : b.q0;
+            out.push_back(cx);
+        } else {
+            out.push_back(std::move(b));
+        }
+    }
+    return out;
+}
+
+// ================================================================ 2. passes =====================================
+struct AOp {               // block before tile positions are known: physical bits + how it acts on them
+    int32_t op = 0;        // OP_U2 / OP_U1 / OP_D1 / OP_CNOT / OP_DEPOL1_DM / OP_DEPOL2_DM
     int q[4] = {0, 0, 0, 0};
-    int nq = 0;
     int32_t t = -1;
     int32_t flags = 0;
     double fixed = 0.0;
-    uint64_t mix = 0;      // bits the gate mixes amplitudes across -> must be local
-    uint64_t diag = 0;     // bits the gate only reads (control / diagonal phase) -> may be non-local
-    bool trajectory = false;
+    uint64_t mix = 0;      // bits the block mixes amplitudes across -> must be local (and in the window)
+    uint64_t diag = 0;     // bits the block only reads (control / diagonal phase) -> may be anywhere
 };
-
-inline uint64_t bit(int q) { return 1ull << q; }
-
-AOp make_1q(int32_t kind, int q, int32_t t, double fixed, int32_t flags) {
-    AOp a;
-    a.kind = kind;
-    a.q[0] = q;
-    a.nq = 1;
-    a.t = t;
-    a.fixed = fixed;
-    a.flags = flags;
-    if (kind == TQ_RZ || kind == TQ_Z) a.diag = bit(q);
-    else a.mix = bit(q);
-    return a;
-}
-
-AOp make_cnot(int c, int tg) {
-    AOp a;
-    a.kind = TQ_CNOT;
-    a.q[0] = c;
-    a.q[1] = tg;
-    a.nq = 2;
-    a.diag = bit(c);
-    a.mix = bit(tg);
-    return a;
-}
 
 int pos_of(const Pass& p, int phys) {
     auto it = std::lower_bound(p.local.begin(), p.local.end(), phys);
@@ -59,34 +169,22 @@ DevOp emit(const Pass& p, const AOp& a) {
     d.flags = a.flags;
     d.fixed = a.fixed;
     const int p0 = pos_of(p, a.q[0]);
-    switch (a.kind) {
-    case TQ_RX: d.op = OP_RX; d.a = p0; break;
-    case TQ_RY: d.op = OP_RY; d.a = p0; break;
-    case TQ_RZ:
-        if (p0 >= 0) { d.op = OP_RZ; d.a = p0; } else { d.op = OP_RZ_NL; d.a = a.q[0]; }
+    switch (a.op) {
+    case OP_U2: d.op = OP_U2; d.a = p0; d.b = pos_of(p, a.q[1]); break;
+    case OP_U1: d.op = OP_U1; d.a = p0; break;
+    case OP_D1:
+        if (p0 >= 0) { d.op = OP_D1; d.a = p0; } else { d.op = OP_D1_NL; d.a = a.q[0]; }
         break;
-    case TQ_CNOT:
+    case OP_CNOT:
         d.b = pos_of(p, a.q[1]);
         if (p0 >= 0) { d.op = OP_CNOT; d.a = p0; } else { d.op = OP_CNOT_NL; d.a = a.q[0]; }
         break;
-    case TQ_X: d.op = OP_X; d.a = p0; break;
-    case TQ_Y: d.op = OP_Y; d.a = p0; break;
-    case TQ_Z:
-        if (p0 >= 0) { d.op = OP_Z; d.a = p0; } else { d.op = OP_Z_NL; d.a = a.q[0]; }
+    case OP_DEPOL1_DM: d.op = OP_DEPOL1_DM; d.a = p0; d.b = pos_of(p, a.q[1]); break;
+    default:
+        d.op = OP_DEPOL2_DM;
+        d.a = p0 | (pos_of(p, a.q[1]) << 8);
+        d.b = pos_of(p, a.q[2]) | (pos_of(p, a.q[3]) << 8);
         break;
-    case TQ_DEPOL1:
-        if (a.trajectory) { d.op = OP_PAULI1; d.a = p0; }
-        else { d.op = OP_DEPOL1_DM; d.a = p0; d.b = pos_of(p, a.q[1]); }
-        break;
-    case TQ_DEPOL2:
-        if (a.trajectory) { d.op = OP_PAULI2; d.a = p0; d.b = pos_of(p, a.q[1]); }
-        else {
-            d.op = OP_DEPOL2_DM;
-            d.a = p0 | (pos_of(p, a.q[1]) << 8);
-            d.b = pos_of(p, a.q[2]) | (pos_of(p, a.q[3]) << 8);
-        }
-        break;
-    default: d.op = OP_Z_NL; d.a = 63; break;  // unreachable (validated by the caller)
     }
     return d;
 }
@@ -99,7 +197,7 @@ void finish_pass(Pass& p, int nbits, uint64_t lmask) {
     while (p.lead < (int)p.local.size() && p.local[p.lead] == p.lead) ++p.lead;
 }
 
-// greedy packing of abstract ops into passes
+// greedy packing of blocks into passes
 std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions& opt,
                        const std::vector<uint64_t>& cover_masks) {
     std::vector<Pass> passes;
@@ -114,7 +212,7 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
         std::vector<int> mine, deferred;
         for (int idx : remaining) {
             const AOp& a = ops[idx];
-            // commutes with every deferred gate iff on each shared bit both act diagonally
+            // commutes with every deferred block iff on each shared bit both act diagonally
             const bool clash = (a.mix & (blocked_mix | blocked_diag)) || (a.diag & blocked_mix);
             bool take = !clash;
             if (take) {
@@ -129,8 +227,7 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
                 blocked_diag |= a.diag;
             }
         }
-        const bool last = deferred.empty();
-        if (last) {
+        if (deferred.empty()) {
             for (uint64_t m : cover_masks)
                 if (__builtin_popcountll(L | m) <= k) L |= m;
         }
@@ -161,11 +258,68 @@ bool validate(int n, const std::vector<Gate>& gates, std::string* err) {
     return true;
 }
 
-}  // namespace
+// blocks -> matrix table + abstract ops.  shift > 0 adds the conjugated column-side copy (density matrix).
+void lower(const std::vector<Blk>& blks, int n, bool density, CompiledCircuit& cc, std::vector<AOp>& ops) {
+    for (const Blk& b : blks) {
+        if (b.type == B_MAT) {
+            MatDesc md{(int32_t)cc.prog.size(), 0, b.q1 >= 0 ? 2 : 1, b.diag ? 1 : 0};
+            for (const MatGate& g : b.prog) cc.prog.push_back(g);
+            md.end = (int32_t)cc.prog.size();
+            const int32_t mat = (int32_t)cc.mats.size();
+            cc.mats.push_back(md);
+            for (int side = 0; side < (density ? 2 : 1); ++side) {
+                const int sh = side ? n : 0;
+                AOp a;
+                a.t = mat;
+                a.flags = side ? FLAG_CONJ : 0;
+                a.q[0] = b.q0 + sh;
+                if (b.q1 >= 0) {
+                    a.op = OP_U2;
+                    a.q[1] = b.q1 + sh;
+                    a.mix = bit(a.q[0]) | bit(a.q[1]);
+                } else if (b.diag) {
+                    a.op = OP_D1;
+                    a.diag = bit(a.q[0]);
+                } else {
+                    a.op = OP_U1;
+                    a.mix = bit(a.q[0]);
+                }
+                ops.push_back(a);
+            }
+        } else if (b.type == B_CX) {
+            for (int side = 0; side < (density ? 2 : 1); ++side) {
+                const int sh = side ? n : 0;
+                AOp a;
+                a.op = OP_CNOT;
+                a.q[0] = b.q0 + sh;
+                a.q[1] = b.q1 + sh;
+                a.diag = bit(a.q[0]);
+                a.mix = bit(a.q[1]);
+                ops.push_back(a);
+            }
+        } else if (b.type == B_DEPOL1) {
+            AOp a;
+            a.op = OP_DEPOL1_DM;
+            a.q[0] = b.q0;
+            a.q[1] = b.q0 + n;
+            a.fixed = b.p;
+            a.mix = bit(a.q[0]) | bit(a.q[1]);
+            ops.push_back(a);
+        } else {
+            AOp a;
+            a.op = OP_DEPOL2_DM;
+            a.q[0] = b.q0;
+            a.q[1] = b.q1;
+            a.q[2] = b.q0 + n;
+            a.q[3] = b.q1 + n;
+            a.fixed = b.p;
+            a.mix = bit(a.q[0]) | bit(a.q[1]) | bit(a.q[2]) | bit(a.q[3]);
+            ops.push_back(a);
+        }
+    }
+}
 
-// ---------------------------------------------------------------------------------------- register windows ----
-namespace {
-
+// ================================================================ 3. register windows ===========================
 struct TOp {          // tile-level op + the tile positions it mixes / only reads
     DevOp d;
     uint32_t mix = 0, diag = 0;
@@ -176,15 +330,16 @@ int popc32(uint32_t x) { return __builtin_popcount(x); }
 void tile_masks(TOp& t) {
     const DevOp& d = t.d;
     switch (d.op) {
-    case OP_RX: case OP_RY: case OP_X: case OP_Y: case OP_PAULI1: t.mix = 1u << d.a; break;
-    case OP_RZ: case OP_Z: t.diag = 1u << d.a; break;
+    case OP_U2: t.mix = (1u << d.a) | (1u << d.b); break;
+    case OP_U1: t.mix = 1u << d.a; break;
+    case OP_D1: t.diag = 1u << d.a; break;
     case OP_CNOT: t.diag = 1u << d.a; t.mix = 1u << d.b; break;
     case OP_CNOT_NL: t.mix = 1u << d.b; break;
     case OP_DEPOL1_DM: t.mix = (1u << d.a) | (1u << d.b); break;
     case OP_DEPOL2_DM:
         t.mix = (1u << (d.a & 0xff)) | (1u << ((d.a >> 8) & 0xff)) | (1u << (d.b & 0xff)) | (1u << ((d.b >> 8) & 0xff));
         break;
-    default: break;  // OP_RZ_NL / OP_Z_NL: diagonal on a bit outside the tile, commutes with everything here
+    default: break;  // OP_D1_NL: diagonal on a bit outside the tile, commutes with everything here
     }
 }
 
@@ -200,24 +355,10 @@ void schedule_windows(Pass& p) {
     p.wops.clear();
     const int k_real = (int)p.local.size();
     const int k = std::max(k_real, kMinTileBits);
-    std::vector<TOp> tops;
-    tops.reserve(p.ops.size() + 8);
-    for (const DevOp& d : p.ops) {
-        if (d.op == OP_PAULI2) {  // two independent one-qubit Paulis: codes in bits 0-1 and 2-3 of the slot byte
-            TOp t0, t1;
-            t0.d = d; t0.d.op = OP_PAULI1; t0.d.b = 0;
-            t1.d = d; t1.d.op = OP_PAULI1; t1.d.a = d.b; t1.d.b = 2;
-            tile_masks(t0);
-            tile_masks(t1);
-            tops.push_back(t0);
-            tops.push_back(t1);
-        } else {
-            TOp t;
-            t.d = d;
-            if (d.op == OP_PAULI1) t.d.b = 0;
-            tile_masks(t);
-            tops.push_back(t);
-        }
+    std::vector<TOp> tops(p.ops.size());
+    for (size_t i = 0; i < p.ops.size(); ++i) {
+        tops[i].d = p.ops[i];
+        tile_masks(tops[i]);
     }
     std::vector<int> remaining(tops.size());
     for (size_t i = 0; i < tops.size(); ++i) remaining[i] = (int)i;
@@ -254,43 +395,39 @@ void schedule_windows(Pass& p) {
             o.t = d.t;
             o.fixed = d.fixed;
             switch (d.op) {
-            case OP_RX: o.w0 = winop_pack(W_ROT_X, rb_of[d.a], 0, 0, d.flags); break;
-            case OP_RY: o.w0 = winop_pack(W_ROT_Y, rb_of[d.a], 0, 0, d.flags); break;
-            case OP_RZ:
-                if (rb_of[d.a] >= 0) o.w0 = winop_pack(W_ROT_Z, rb_of[d.a], 0, 0, d.flags);
-                else o.w0 = winop_pack(W_PHASE, 0, 0, phys(d.a), d.flags);
+            case OP_U2: {
+                const int ra = rb_of[d.a], rb = rb_of[d.b];
+                if (ra < rb) o.w0 = winop_pack(W_U2, ra, rb, 0, d.flags);
+                else o.w0 = winop_pack(W_U2, rb, ra, 0, d.flags | FLAG_SWAP);
                 break;
-            case OP_RZ_NL: o.w0 = winop_pack(W_PHASE, 0, 0, d.a, d.flags); break;
+            }
+            case OP_U1: o.w0 = winop_pack(W_U1, rb_of[d.a], 0, 0, d.flags); break;
+            case OP_D1:
+                if (rb_of[d.a] >= 0) o.w0 = winop_pack(W_D1, rb_of[d.a], 0, 0, d.flags);
+                else o.w0 = winop_pack(W_D1_OUT, 0, 0, phys(d.a), d.flags);
+                break;
+            case OP_D1_NL: o.w0 = winop_pack(W_D1_OUT, 0, 0, d.a, d.flags); break;
             case OP_CNOT:
                 if (rb_of[d.a] >= 0) o.w0 = winop_pack(W_CX_WW, rb_of[d.a], rb_of[d.b], 0, 0);
                 else o.w0 = winop_pack(W_CX_OW, rb_of[d.b], 0, phys(d.a), 0);
                 break;
             case OP_CNOT_NL: o.w0 = winop_pack(W_CX_OW, rb_of[d.b], 0, d.a, 0); break;
-            case OP_X: o.w0 = winop_pack(W_X, rb_of[d.a], 0, 0, 0); break;
-            case OP_Y: o.w0 = winop_pack(W_Y, rb_of[d.a], 0, 0, d.flags); break;
-            case OP_Z:
-                if (rb_of[d.a] >= 0) o.w0 = winop_pack(W_Z, rb_of[d.a], 0, 0, 0);
-                else o.w0 = winop_pack(W_Z_OUT, 0, 0, phys(d.a), 0);
-                break;
-            case OP_Z_NL: o.w0 = winop_pack(W_Z_OUT, 0, 0, d.a, 0); break;
-            case OP_PAULI1: o.w0 = winop_pack(W_PAULI, rb_of[d.a], d.b, 0, 0); break;
             case OP_DEPOL1_DM: o.w0 = winop_pack(W_DEPOL1, rb_of[d.a], rb_of[d.b], 0, 0); break;
-            case OP_DEPOL2_DM:
+            default:
                 o.w0 = winop_pack(W_DEPOL2, rb_of[d.a & 0xff] | (rb_of[(d.a >> 8) & 0xff] << 2),
                                   rb_of[d.b & 0xff] | (rb_of[(d.b >> 8) & 0xff] << 2), 0, 0);
                 break;
-            default: break;
             }
             p.wops.push_back(o);
         }
         w.op_end = (int32_t)p.wops.size();
         // the kernel stages one window's ops at a time: split long windows (same layout, consecutive ranges)
-        for (int32_t lo = w.op_begin; lo < w.op_end || lo == w.op_begin; lo += kMaxWindowOps) {
+        for (int32_t lo = w.op_begin;; lo += kMaxWindowOps) {
             Window part = w;
             part.op_begin = lo;
             part.op_end = std::min<int32_t>(w.op_end, lo + kMaxWindowOps);
             p.windows.push_back(part);
-            if (w.op_end == w.op_begin) break;
+            if (part.op_end >= w.op_end) break;
         }
     };
 
@@ -330,82 +467,23 @@ uint32_t mask_to_local(const Pass& p, uint64_t mask) {
     return out;
 }
 
-std::vector<Pass> plan_statevector(int n, const std::vector<Gate>& gates, const PlanOptions& opt,
-                                   const std::vector<uint64_t>& cover_masks, std::string* err) {
-    if (!validate(n, gates, err)) return {};
+CompiledCircuit plan_statevector(int n, const std::vector<Gate>& gates, const PlanOptions& opt,
+                                 const std::vector<uint64_t>& cover_masks, std::string* err) {
+    CompiledCircuit cc;
+    if (!validate(n, gates, err)) return cc;
     std::vector<AOp> ops;
-    ops.reserve(gates.size());
-    for (const Gate& g : gates) {
-        switch (g.kind) {
-        case TQ_CNOT: ops.push_back(make_cnot(g.q0, g.q1)); break;
-        case TQ_DEPOL1:
-            if (opt.trajectory && g.pidx >= 0) {
-                AOp a = make_1q(TQ_DEPOL1, g.q0, g.pidx, g.fixed, 0);
-                a.trajectory = true;
-                ops.push_back(a);
-            }
-            break;
-        case TQ_DEPOL2:
-            if (opt.trajectory && g.pidx >= 0) {
-                AOp a;
-                a.kind = TQ_DEPOL2;
-                a.q[0] = g.q0;
-                a.q[1] = g.q1;
-                a.nq = 2;
-                a.t = g.pidx;
-                a.fixed = g.fixed;
-                a.mix = bit(g.q0) | bit(g.q1);
-                a.trajectory = true;
-                ops.push_back(a);
-            }
-            break;
-        default: ops.push_back(make_1q(g.kind, g.q0, g.pidx, g.fixed, 0)); break;
-        }
-    }
-    return pack(n, ops, opt, cover_masks);
+    lower(fuse_gates(n, gates, opt.trajectory ? 2 : 0, opt.fuse), n, false, cc, ops);
+    cc.passes = pack(n, ops, opt, cover_masks);
+    return cc;
 }
 
-std::vector<Pass> plan_density(int n, const std::vector<Gate>& gates, const PlanOptions& opt, std::string* err) {
-    if (!validate(n, gates, err)) return {};
+CompiledCircuit plan_density(int n, const std::vector<Gate>& gates, const PlanOptions& opt, std::string* err) {
+    CompiledCircuit cc;
+    if (!validate(n, gates, err)) return cc;
     std::vector<AOp> ops;
-    ops.reserve(2 * gates.size());
-    for (const Gate& g : gates) {
-        switch (g.kind) {
-        case TQ_CNOT:
-            ops.push_back(make_cnot(g.q0, g.q1));
-            ops.push_back(make_cnot(g.q0 + n, g.q1 + n));
-            break;
-        case TQ_DEPOL1: {
-            AOp a;
-            a.kind = TQ_DEPOL1;
-            a.q[0] = g.q0;
-            a.q[1] = g.q0 + n;
-            a.nq = 2;
-            a.fixed = g.fixed;
-            a.mix = bit(g.q0) | bit(g.q0 + n);
-            ops.push_back(a);
-            break;
-        }
-        case TQ_DEPOL2: {
-            AOp a;
-            a.kind = TQ_DEPOL2;
-            a.q[0] = g.q0;
-            a.q[1] = g.q1;
-            a.q[2] = g.q0 + n;
-            a.q[3] = g.q1 + n;
-            a.nq = 4;
-            a.fixed = g.fixed;
-            a.mix = bit(g.q0) | bit(g.q1) | bit(g.q0 + n) | bit(g.q1 + n);
-            ops.push_back(a);
-            break;
-        }
-        default:
-            ops.push_back(make_1q(g.kind, g.q0, g.pidx, g.fixed, 0));
-            ops.push_back(make_1q(g.kind, g.q0 + n, g.pidx, g.fixed, FLAG_CONJ));
-            break;
-        }
-    }
-    return pack(2 * n, ops, opt, {});
+    lower(fuse_gates(n, gates, 1, opt.fuse), n, true, cc, ops);
+    cc.passes = pack(2 * n, ops, opt, {});
+    return cc;
 }
 
 std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const PlanOptions& opt,
@@ -418,12 +496,14 @@ std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const Pla
     while (left > 0) {
         uint64_t L = (n <= k) ? all : (bit(std::min(opt.low_bits, k)) - 1);
         const int me = int(passes.size());
+        bool progressed = false;
         for (size_t i = 0; i < todo.size(); ++i) {
             if ((*assignment)[i] >= 0) continue;
             if (__builtin_popcountll(L | todo[i]) <= k) {
                 L |= todo[i];
                 (*assignment)[i] = me;
                 --left;
+                progressed = true;
             }
         }
         for (int q = 0; q < n && __builtin_popcountll(L) < k; ++q) L |= bit(q);
@@ -431,8 +511,6 @@ std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const Pla
         finish_pass(p, n, L);
         schedule_windows(p);
         passes.push_back(std::move(p));
-        bool progressed = false;
-        for (int a : *assignment) progressed |= (a == me);
         if (!progressed) break;  // a mask wider than the tile: caller reports the error
     }
     return passes;

@@ -1,14 +1,20 @@
-// tq_plan.h -- host-side circuit compiler of libtqsim: turns a gate list into tile passes.
-//
-// A "pass" streams the batch of state vectors through shared memory once: every CTA loads one tile of 2^k
-// amplitudes (the amplitudes that differ only in the pass's k "local" qubits), applies the pass's gates to the
-// tile and writes it back.  Gates whose mixing qubits are all local can run in the pass; diagonal action on a
-// non-local qubit (RZ, Z, the control of a CNOT) only needs the tile's fixed bit and is allowed too.
-// The planner packs as many gates as possible into each pass (gates that act on disjoint qubits commute, so
-// a gate that does not fit is deferred together with everything that later touches its qubits).
+// tq_plan.h -- host-side circuit compiler of libtqsim: gate list -> fused blocks -> tile passes -> register windows.
 //
 // Reference behaviour being replaced: qulacs applies one gate per full-state pass
-// (circuit.update_quantum_state, environments/VQAs/VQE_qulacs.py:83); see DESIGN.md section 3.
+// (circuit.update_quantum_state, environments/VQAs/VQE_qulacs.py:83).  Here:
+//
+//  1. FUSION.  Runs of gates that act on the same one or two qubits are merged into one dense 2x2 / 4x4 block
+//     (the transpiled SU(4) bricks of the MPS init circuit collapse to one block each).  A block's matrix depends
+//     on the batch element's angles (and, for trajectory noise, on its sampled Pauli codes), so it is described
+//     by a small "matrix program" that a prep kernel evaluates per (element, block).  RZ/Z-only runs stay
+//     diagonal; a lone CNOT stays a CNOT (its control only needs to be read, not mixed).
+//  2. PASSES.  A pass streams the batch of state vectors through shared memory once: every CTA loads one tile of
+//     2^k amplitudes (those that differ only in the pass's k "local" qubits), applies the pass's blocks and
+//     writes the tile back.  Blocks whose mixing qubits are all local can run in the pass; diagonal action on a
+//     non-local qubit (a diagonal block, the control of a CNOT) only needs the tile's fixed bit.  Blocks that act
+//     on disjoint qubits commute, so a block that does not fit is deferred with everything that later touches it.
+//  3. WINDOWS.  Inside a tile every thread keeps 2^kRegBits amplitudes in registers (the window's qubits); blocks
+//     on window qubits run on registers, shared memory is touched only to switch windows.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -16,34 +22,38 @@
 
 namespace tq {
 
-// device-side opcodes (DevOp.op); positions are tile-local bit positions unless noted
-enum : int32_t {
-    OP_RX = 0,        // a = pos, t = angle source (see DevOp)
-    OP_RY = 1,
-    OP_RZ = 2,
-    OP_RZ_NL = 3,     // a = physical bit (non-local): whole tile times e^{+-i theta/2}
-    OP_CNOT = 4,      // a = control pos, b = target pos
-    OP_CNOT_NL = 5,   // a = physical control bit (non-local), b = target pos: X on target if the tile's bit is set
-    OP_X = 6,         // a = pos
-    OP_Y = 7,         // a = pos;  flag conj: -Y (column side of a density matrix)
-    OP_Z = 8,         // a = pos
-    OP_Z_NL = 9,      // a = physical bit
-    OP_PAULI1 = 10,   // trajectory noise slot: a = pos, t = slot (code column)
-    OP_PAULI2 = 11,   // a = pos(q0), b = pos(q1), t = slot
-    OP_DEPOL1_DM = 12, // a = pos(q), b = pos(q + n), fixed = p
-    OP_DEPOL2_DM = 13, // a = pos(qa) | pos(qb) << 8, b = pos(qa + n) | pos(qb + n) << 8, fixed = p
+// ---- matrix programs (evaluated per batch element by prep_matrices_kernel) -------------------------------------
+enum : int32_t {  // MatGate.kind
+    MG_RX = 0, MG_RY = 1, MG_RZ = 2,   // on block qubit lq; angle = params[pidx] or fixed
+    MG_CX = 3,                         // control = block qubit lq, target = the other one
+    MG_X = 4, MG_Y = 5, MG_Z = 6,      // fixed Paulis on lq
+    MG_PAULI_SLOT = 7,                 // Pauli (codes[pidx] >> shift) & 3 on lq (trajectory noise); shift in `fixed`
 };
+struct MatGate {   // 24 bytes
+    int32_t kind, lq, pidx, pad;
+    double fixed;
+};
+struct MatDesc {   // one fused block: gates [begin, end) of the program, 1 or 2 qubits
+    int32_t begin, end, nq, diag;   // diag: all gates diagonal -> only entries (0,0), (1,1) are used
+};
+constexpr int kMatStride = 16;      // complex entries per block matrix in device memory (4x4, row-major)
 
-enum : int32_t { FLAG_CONJ = 1 };  // rotation / Y acts as its complex conjugate (density-matrix column side)
+// ---- tile-level ops (positions are tile-local bit positions unless noted) --------------------------------------
+enum : int32_t {
+    OP_U2 = 0,        // a = pos(q0), b = pos(q1) (q0 < q1 physical; matrix index bit 0 = q0), t = matrix
+    OP_U1 = 1,        // a = pos, t = matrix
+    OP_D1 = 2,        // diagonal 1-qubit block: a = pos, t = matrix
+    OP_D1_NL = 3,     // a = physical bit (non-local): whole tile times d0 or d1
+    OP_CNOT = 4,      // a = control pos, b = target pos
+    OP_CNOT_NL = 5,   // a = physical control bit (non-local), b = target pos
+    OP_DEPOL1_DM = 6, // a = pos(q), b = pos(q + n), fixed = p
+    OP_DEPOL2_DM = 7, // a = pos(qa) | pos(qb) << 8, b = pos(qa + n) | pos(qb + n) << 8, fixed = p
+};
+enum : int32_t { FLAG_CONJ = 1, FLAG_SWAP = 2 };  // conj: column side of a density matrix; swap: matrix qubit order
 
-struct DevOp {       // 32 bytes, read by the kernels straight from global memory
-    int32_t op;
-    int32_t a;
-    int32_t b;
-    int32_t t;       // rotations: parameter column, or -1 -> use `fixed`; PAULI*: slot
-    int32_t flags;
-    int32_t pad;
-    double fixed;    // rotations with t == -1: theta; DEPOL*: probability
+struct DevOp {
+    int32_t op, a, b, t, flags, pad;
+    double fixed;
 };
 
 struct Gate {        // user-level gate (tq_set_circuit)
@@ -51,40 +61,29 @@ struct Gate {        // user-level gate (tq_set_circuit)
     double fixed;
 };
 
-// ---- second level: register windows inside a tile ---------------------------------------------------------------
-// Every thread of a CTA keeps 2^kRegBits amplitudes of the tile in registers: the ones that differ only in the
-// window's kRegBits tile positions.  Gates that mix only window positions run on registers without touching shared
-// memory; the tile is re-distributed through shared memory only when the window changes.
+// ---- register windows -------------------------------------------------------------------------------------------
 constexpr int kRegBits = 4;
 constexpr int kMinTileBits = kRegBits;   // smaller states are padded with phantom positions
-constexpr int kMaxWindowOps = 256;       // ops per window (the kernel stages one window's ops at a time)
+constexpr int kMaxWindowOps = 32;        // ops per window (the kernel stages one window's ops + matrices at a time)
 
-// window-level opcodes (WinOp code); RB/CB/TB are register-bit indices inside the window
-enum : int32_t {
-    W_ROT_X = 0,    // rb
-    W_ROT_Y = 1,    // rb
-    W_ROT_Z = 2,    // rb
-    W_PHASE = 3,    // RZ on a bit outside the window: qsel = physical bit
+enum : int32_t {    // WinOp code; rb / rb2 are register-bit indices inside the window
+    W_U2 = 0,       // rb < rb2: register bits of matrix index bits 0 / 1 (FLAG_SWAP if the block's q0 sits on rb2)
+    W_U1 = 1,       // rb
+    W_D1 = 2,       // rb
+    W_D1_OUT = 3,   // diagonal block on a bit outside the window: qsel = physical bit
     W_CX_WW = 4,    // rb = control, rb2 = target
     W_CX_OW = 5,    // qsel = physical control bit, rb = target
-    W_X = 6,        // rb
-    W_Y = 7,        // rb (flag conj: -Y)
-    W_Z = 8,        // rb
-    W_Z_OUT = 9,    // qsel = physical bit
-    W_PAULI = 10,   // rb, t = slot, rb2 = shift of the 2-bit code inside the slot byte (0 or 2)
-    W_DEPOL1 = 11,  // rb = row bit, rb2 = column bit, fixed = p
-    W_DEPOL2 = 12,  // the window is exactly {row a, row b, col a, col b}: rb = ra | rb << 2, rb2 = ca | cb << 2
+    W_DEPOL1 = 6,   // rb = row bit, rb2 = column bit, fixed = p
+    W_DEPOL2 = 7,   // window = {row a, row b, col a, col b}: rb = ra | rb << 2, rb2 = ca | cb << 2
 };
-
 struct WinOp {      // 16 bytes
     uint32_t w0;    // code | rb << 8 | rb2 << 12 | qsel << 16 | flags << 24
-    int32_t t;      // rotations: parameter column or -1; W_PAULI: slot
+    int32_t t;      // matrix index (W_U2 / W_U1 / W_D1 / W_D1_OUT)
     double fixed;
 };
 inline uint32_t winop_pack(int code, int rb, int rb2, int qsel, int flags) {
     return (uint32_t)code | ((uint32_t)rb << 8) | ((uint32_t)rb2 << 12) | ((uint32_t)qsel << 16) | ((uint32_t)flags << 24);
 }
-
 struct Window {     // 24 bytes, read by the kernel from global memory
     uint8_t wpos[kRegBits];  // tile position of register bit r
     uint8_t tpos[12];        // tile position of thread bit i (first k - kRegBits entries used); the first three
@@ -92,8 +91,8 @@ struct Window {     // 24 bytes, read by the kernel from global memory
     int32_t op_begin, op_end;  // range in Pass::wops
 };
 
-// bank swizzle of the shared-memory tile: amplitude j lives in slot j ^ swizzle_fold(j >> 3), a GF(2)-linear map
-// that spreads any three independent tile positions over the eight 16-byte bank groups
+// bank swizzle of the shared-memory tile: amplitude j lives in slot j ^ fold(j >> 3), a GF(2)-linear map that
+// spreads any three independent tile positions over the eight 16-byte bank groups
 constexpr uint8_t kSwizzleVec[13] = {1, 2, 4, 3, 5, 6, 7, 1, 2, 4, 3, 5, 6};
 
 struct Pass {
@@ -105,32 +104,34 @@ struct Pass {
     std::vector<WinOp> wops;
 };
 
-// fills p.windows / p.wops from p.ops
-void schedule_windows(Pass& p);
-
 struct PlanOptions {
     int tile_bits = 12;   // k: tile = 2^k amplitudes (64 KiB of complex128)
     int low_bits = 4;     // c: physical bits 0..c-1 are local in every pass (2^c * 16 B contiguous runs)
-    bool trajectory = false;  // TQ_DEPOL* become per-element sampled Pauli slots (else skipped on the pure path)
+    bool trajectory = false;  // TQ_DEPOL* become per-element sampled Pauli gates (else skipped on the pure path)
+    bool fuse = true;     // false: every gate is its own block (debugging / A-B comparisons)
 };
 
-// Pure-state plan over nbits = n qubits.
-// cover_masks: flip masks (physical bits) of the Hamiltonian groups the LAST pass should try to keep local.
-std::vector<Pass> plan_statevector(int n, const std::vector<Gate>& gates, const PlanOptions& opt,
-                                   const std::vector<uint64_t>& cover_masks, std::string* err);
+struct CompiledCircuit {
+    std::vector<Pass> passes;
+    std::vector<MatDesc> mats;
+    std::vector<MatGate> prog;
+};
 
-// Density-matrix plan over nbits = 2n: each unitary is applied to bit q and, conjugated, to bit q + n;
-// TQ_DEPOL* become the exact channels.
-std::vector<Pass> plan_density(int n, const std::vector<Gate>& gates, const PlanOptions& opt, std::string* err);
+// Pure-state plan over n qubits.  cover_masks: flip masks (physical bits) of the Hamiltonian groups the LAST pass
+// should try to keep local.
+CompiledCircuit plan_statevector(int n, const std::vector<Gate>& gates, const PlanOptions& opt,
+                                 const std::vector<uint64_t>& cover_masks, std::string* err);
+
+// Density-matrix plan over 2n bits: each block acts on bit q and, conjugated, on bit q + n; TQ_DEPOL* are the
+// exact channels.
+CompiledCircuit plan_density(int n, const std::vector<Gate>& gates, const PlanOptions& opt, std::string* err);
 
 // Expectation-only passes that cover the flip masks `todo` (those not local in the last gate pass).
-// Returns one Pass (no ops) per tile shape; `assignment[i]` = index of the pass that evaluates todo[i].
 std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const PlanOptions& opt,
                              std::vector<int>* assignment);
 
-// true if every bit of mask is local in the pass
+void schedule_windows(Pass& p);
 bool mask_is_local(const Pass& p, uint64_t mask);
-// tile-local image of a physical mask (bits that are not local are dropped)
 uint32_t mask_to_local(const Pass& p, uint64_t mask);
 
 }  // namespace tq

@@ -174,9 +174,10 @@ class Simulator:
         return int(self._L.tq_launch_count(self._h))
 
 
-def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=()):
+def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=(), with_mats=False):
     """Planner dry run (no GPU): list of passes, each {'lead', 'local', 'ops': [(op, a, b, t, flags, fixed)],
-    'windows': [{'wpos', 'tpos', 'ops': [(code, rb, rb2, qsel, flags, t, fixed)]}]}."""
+    'windows': [{'wpos', 'tpos', 'ops': [(code, rb, rb2, qsel, flags, t, fixed)]}]}.  with_mats=True also returns the
+    fused blocks' matrix programs: {'passes': [...], 'mats': [{'nq', 'diag', 'gates': [(kind, lq, pidx, fixed)]}]}."""
     L = _lib.lib()
     kind, q0, q1, pidx, fixed = gl.arrays()
     cm = np.ascontiguousarray(cover_masks, dtype=np.uint64)
@@ -187,11 +188,16 @@ def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=()):
     text = ctypes.string_at(ptr).decode()
     L.tq_free(ptr)
     passes = []
+    mats = []
     for line in text.splitlines():
         tok = line.split()
         if tok[0] == "ERROR":
             raise ValueError(line[6:])
-        if tok[0] == "PASS":
+        if tok[0] == "MAT":
+            mats.append({"nq": int(tok[1]), "diag": int(tok[2]), "gates": []})
+        elif tok[0] == "MG":  # (kind, lq, pidx, fixed)
+            mats[-1]["gates"].append((int(tok[1]), int(tok[2]), int(tok[3]), float(tok[4])))
+        elif tok[0] == "PASS":
             lead = int(tok[1].split("=")[1])
             local = [int(v) for v in tok[2].split("=")[1].split(",") if v != ""]
             passes.append({"lead": lead, "local": local, "ops": [], "windows": []})
@@ -203,4 +209,4 @@ def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=()):
             passes[-1]["windows"].append({"wpos": wpos, "tpos": tpos, "ops": []})
         elif tok[0] == "WOP":  # (code, rb, rb2, qsel, flags, t, fixed)
             passes[-1]["windows"][-1]["ops"].append(tuple(int(v) for v in tok[1:7]) + (float(tok[7]),))
-    return passes
+    return {"passes": passes, "mats": mats} if with_mats else passes

@@ -1,13 +1,58 @@
-"""numpy execution of the tile passes the circuit compiler emits (tq_plan_dump), used on CPU to check that a plan
-is equivalent to the gate list it was compiled from.  Test-only: mirrors the DevOp semantics documented in
-tensorrl_qas_b200/csrc/tq_plan.h on the full vector (tile position p of a pass = physical bit local[p])."""
+"""numpy execution of what the circuit compiler emits (tq_plan_dump): fused-block matrix programs, tile passes and
+register-window schedules.  Used on CPU to check that a compiled plan is equivalent to the gate list it came from.
+Test-only: mirrors the op semantics documented in tensorrl_qas_b200/csrc/tq_plan.h on the full vector (tile
+position p of a pass = physical bit local[p]; register bit r of a window = tile position wpos[r])."""
 import numpy as np
 
 from oracle.np_oracle import _mat, apply_1q, apply_cnot
 
-(OP_RX, OP_RY, OP_RZ, OP_RZ_NL, OP_CNOT, OP_CNOT_NL, OP_X, OP_Y, OP_Z, OP_Z_NL, OP_PAULI1, OP_PAULI2, OP_DEPOL1_DM,
- OP_DEPOL2_DM) = range(14)
-FLAG_CONJ = 1
+OP_U2, OP_U1, OP_D1, OP_D1_NL, OP_CNOT, OP_CNOT_NL, OP_DEPOL1_DM, OP_DEPOL2_DM = range(8)
+W_U2, W_U1, W_D1, W_D1_OUT, W_CX_WW, W_CX_OW, W_DEPOL1, W_DEPOL2 = range(8)
+MG_RX, MG_RY, MG_RZ, MG_CX, MG_X, MG_Y, MG_Z, MG_PAULI_SLOT = range(8)
+FLAG_CONJ, FLAG_SWAP = 1, 2
+
+
+def block_matrix(mat, params, codes):
+    """Matrix of a fused block (index bit 0 = block qubit 0), by running its program on the identity."""
+    nq = mat["nq"]
+    dim = 1 << nq
+    M = np.eye(dim, dtype=np.complex128)
+    for kind, lq, pidx, fixed in mat["gates"]:
+        if kind == MG_CX:
+            G = np.zeros((4, 4), dtype=np.complex128)
+            for i in range(4):
+                G[i ^ ((2 >> lq) if (i >> lq) & 1 else 0), i] = 1  # control bit lq set -> flip the other bit
+            M = G @ M
+            continue
+        if kind == MG_PAULI_SLOT:
+            code = (codes[pidx] >> int(fixed)) & 3
+            if code == 0:
+                continue
+            g = _mat("XYZ"[code - 1])
+        elif kind <= MG_RZ:
+            g = _mat(("RX", "RY", "RZ")[kind], params[pidx] if pidx >= 0 else fixed)
+        else:
+            g = _mat({MG_X: "X", MG_Y: "Y", MG_Z: "Z"}[kind])
+        if nq == 1:
+            M = g @ M
+        else:
+            G = np.kron(g, np.eye(2)) if lq == 1 else np.kron(np.eye(2), g)  # kron's first factor = high bit
+            M = G @ M
+    if mat["diag"]:
+        assert np.abs(M - np.diag(np.diag(M))).max() == 0
+    return M
+
+
+def apply_2q(vec, nbits, q0, q1, M):
+    """M's index bit 0 = q0, bit 1 = q1."""
+    idx = np.arange(1 << nbits)
+    base = idx[((idx >> q0) & 1 == 0) & ((idx >> q1) & 1 == 0)]
+    sub = np.stack([vec[base | (((k & 1) << q0) | ((k >> 1) << q1))] for k in range(4)])
+    out = M @ sub
+    res = vec.copy()
+    for k in range(4):
+        res[base | (((k & 1) << q0) | ((k >> 1) << q1))] = out[k]
+    return res
 
 
 def _pauli_both(vec, nbits, n, q, code):
@@ -31,39 +76,34 @@ def _depol_dm(vec, nbits, qubits, p):
     return (1 - p) * vec + (p / (15.0 if two else 3.0)) * acc
 
 
-def run_plan(passes, nbits, params, init=None, codes=None):
+def _init(nbits, init):
     vec = np.zeros(1 << nbits, dtype=np.complex128)
     if init is None:
         vec[0] = 1
     else:
         vec[:] = init
-    for p in passes:
+    return vec
+
+
+def run_plan(plan, nbits, params, init=None, codes=None):
+    """Execute the tile-level ops of every pass."""
+    vec = _init(nbits, init)
+    mats = [block_matrix(m, params, codes) for m in plan["mats"]]
+    for p in plan["passes"]:
         loc = p["local"]
         for op, a, b, t, flags, fixed in p["ops"]:
-            conj = bool(flags & FLAG_CONJ)
-            if op in (OP_RX, OP_RY, OP_RZ, OP_RZ_NL):
-                q = a if op == OP_RZ_NL else loc[a]
-                theta = params[t] if t >= 0 else fixed
-                m = _mat(("RX", "RY", "RZ", "RZ")[op], theta)
-                vec = apply_1q(vec, nbits, q, np.conj(m) if conj else m)
+            M = None if t < 0 or op >= OP_CNOT else (np.conj(mats[t]) if flags & FLAG_CONJ else mats[t])
+            if op == OP_U2:
+                assert loc[a] < loc[b]
+                vec = apply_2q(vec, nbits, loc[a], loc[b], M)
+            elif op == OP_U1:
+                vec = apply_1q(vec, nbits, loc[a], M)
+            elif op in (OP_D1, OP_D1_NL):
+                vec = apply_1q(vec, nbits, a if op == OP_D1_NL else loc[a], M)
             elif op == OP_CNOT:
                 vec = apply_cnot(vec, nbits, loc[a], loc[b])
             elif op == OP_CNOT_NL:
                 vec = apply_cnot(vec, nbits, a, loc[b])
-            elif op in (OP_X, OP_Y, OP_Z, OP_Z_NL):
-                q = a if op == OP_Z_NL else loc[a]
-                m = _mat({OP_X: "X", OP_Y: "Y", OP_Z: "Z", OP_Z_NL: "Z"}[op])
-                vec = apply_1q(vec, nbits, q, np.conj(m) if conj else m)
-            elif op == OP_PAULI1:
-                c = codes[t] & 3
-                if c:
-                    vec = apply_1q(vec, nbits, loc[a], _mat("XYZ"[c - 1]))
-            elif op == OP_PAULI2:
-                ca, cb = codes[t] & 3, (codes[t] >> 2) & 3
-                if ca:
-                    vec = apply_1q(vec, nbits, loc[a], _mat("XYZ"[ca - 1]))
-                if cb:
-                    vec = apply_1q(vec, nbits, loc[b], _mat("XYZ"[cb - 1]))
             elif op == OP_DEPOL1_DM:
                 assert loc[b] == loc[a] + nbits // 2
                 vec = _depol_dm(vec, nbits, [loc[a]], fixed)
@@ -76,45 +116,38 @@ def run_plan(passes, nbits, params, init=None, codes=None):
     return vec
 
 
-(W_ROT_X, W_ROT_Y, W_ROT_Z, W_PHASE, W_CX_WW, W_CX_OW, W_X, W_Y, W_Z, W_Z_OUT, W_PAULI, W_DEPOL1, W_DEPOL2) = range(13)
-
-
-def run_plan_windows(passes, nbits, params, init=None, codes=None):
-    """Same as run_plan but from the register-window schedule (what the kernel executes): register bit r of a window
-    is tile position wpos[r], i.e. physical bit local[wpos[r]]; qsel is already a physical bit."""
-    vec = np.zeros(1 << nbits, dtype=np.complex128)
-    if init is None:
-        vec[0] = 1
-    else:
-        vec[:] = init
-    for p in passes:
+def run_plan_windows(plan, nbits, params, init=None, codes=None):
+    """Execute the register-window schedule (what the kernel runs); qsel is already a physical bit."""
+    vec = _init(nbits, init)
+    mats = [block_matrix(m, params, codes) for m in plan["mats"]]
+    for p in plan["passes"]:
         loc = p["local"]
         k_eff = max(len(loc), 4)
         for w in p["windows"]:
             assert len(w["wpos"]) == 4 and len(set(w["wpos"])) == 4
             assert sorted(w["wpos"] + w["tpos"]) == list(range(k_eff))
-            assert len(w["ops"]) <= 256
+            assert len(w["ops"]) <= 32
             phys = [loc[q] if q < len(loc) else None for q in w["wpos"]]
             for code, rb, rb2, qsel, flags, t, fixed in w["ops"]:
-                conj = bool(flags & FLAG_CONJ)
-                if code in (W_ROT_X, W_ROT_Y, W_ROT_Z, W_PHASE):
-                    q = qsel if code == W_PHASE else phys[rb]
-                    theta = params[t] if t >= 0 else fixed
-                    m = _mat(("RX", "RY", "RZ", "RZ")[code], theta)
-                    vec = apply_1q(vec, nbits, q, np.conj(m) if conj else m)
+                M = None
+                if code <= W_D1_OUT:
+                    M = np.conj(mats[t]) if flags & FLAG_CONJ else mats[t]
+                if code == W_U2:
+                    assert rb < rb2
+                    if flags & FLAG_SWAP:  # the block's qubit 0 sits on rb2
+                        vec = apply_2q(vec, nbits, phys[rb2], phys[rb], M)
+                    else:
+                        vec = apply_2q(vec, nbits, phys[rb], phys[rb2], M)
+                elif code in (W_U1, W_D1):
+                    vec = apply_1q(vec, nbits, phys[rb], M)
+                elif code == W_D1_OUT:
+                    assert qsel not in [x for x in phys if x is not None]
+                    vec = apply_1q(vec, nbits, qsel, M)
                 elif code == W_CX_WW:
                     vec = apply_cnot(vec, nbits, phys[rb], phys[rb2])
                 elif code == W_CX_OW:
                     assert qsel not in [x for x in phys if x is not None]
                     vec = apply_cnot(vec, nbits, qsel, phys[rb])
-                elif code in (W_X, W_Y, W_Z, W_Z_OUT):
-                    q = qsel if code == W_Z_OUT else phys[rb]
-                    m = _mat({W_X: "X", W_Y: "Y", W_Z: "Z", W_Z_OUT: "Z"}[code])
-                    vec = apply_1q(vec, nbits, q, np.conj(m) if conj else m)
-                elif code == W_PAULI:
-                    c = (codes[t] >> rb2) & 3
-                    if c:
-                        vec = apply_1q(vec, nbits, phys[rb], _mat("XYZ"[c - 1]))
                 elif code == W_DEPOL1:
                     assert phys[rb2] == phys[rb] + nbits // 2
                     vec = _depol_dm(vec, nbits, [phys[rb]], fixed)
@@ -127,10 +160,10 @@ def run_plan_windows(passes, nbits, params, init=None, codes=None):
     return vec
 
 
-def check_invariants(passes, nbits, tile_bits, low_bits):
+def check_invariants(plan, nbits, tile_bits, low_bits):
     """structural checks: tile size, forced low bits, every position operand is a valid tile position"""
     k = min(tile_bits, nbits)
-    for p in passes:
+    for p in plan["passes"]:
         loc = p["local"]
         assert len(loc) == k and loc == sorted(loc) and len(set(loc)) == k
         if nbits > k:
@@ -139,12 +172,15 @@ def check_invariants(passes, nbits, tile_bits, low_bits):
         while lead < k and loc[lead] == lead:
             lead += 1
         assert p["lead"] == lead
+        assert sum(len(w["ops"]) for w in p["windows"]) == len(p["ops"])
         for op, a, b, t, flags, fixed in p["ops"]:
-            if op in (OP_RX, OP_RY, OP_RZ, OP_X, OP_Y, OP_Z, OP_PAULI1):
+            if op in (OP_U1, OP_D1):
                 assert 0 <= a < k
-            if op in (OP_CNOT, OP_PAULI2, OP_DEPOL1_DM):
+            if op in (OP_U2, OP_CNOT, OP_DEPOL1_DM):
                 assert 0 <= a < k and 0 <= b < k and a != b
             if op == OP_CNOT_NL:
                 assert 0 <= b < k and a not in loc
-            if op in (OP_RZ_NL, OP_Z_NL):
+            if op == OP_D1_NL:
                 assert a not in loc and 0 <= a < nbits
+            if op <= OP_D1_NL:
+                assert 0 <= t < len(plan["mats"])

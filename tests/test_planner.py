@@ -1,4 +1,7 @@
-"""CPU tests of the circuit compiler (tq_plan.cpp) through the no-GPU tq_plan_dump entry point."""
+"""CPU tests of the circuit compiler (tq_plan.cpp: fusion, pass packing, register windows) through the no-GPU
+tq_plan_dump entry point."""
+import os
+
 import numpy as np
 import pytest
 
@@ -21,6 +24,10 @@ def noisy_circuit(n, g, seed):
     return gl
 
 
+def n_blocks(plan):
+    return sum(len(p["ops"]) for p in plan["passes"])
+
+
 @pytest.mark.parametrize("n,tile_bits,low_bits,seed", [(1, 12, 4, 9), (2, 12, 4, 8), (3, 12, 4, 7), (5, 12, 4, 0),
                                                         (9, 8, 4, 1), (10, 8, 2, 2), (11, 8, 4, 3), (12, 9, 3, 4),
                                                         (12, 12, 4, 5)])
@@ -30,27 +37,42 @@ def test_pure_plan_equals_gate_list(built_lib, oracle, n, tile_bits, low_bits, s
     gl.add_pauli("Y", n - 1)
     gl.add_pauli("Z", n // 2)
     params = parameter_batch(gl, 1)[0]
-    passes = plan_dump(gl, 0, tile_bits, low_bits)
-    check_invariants(passes, n, tile_bits, low_bits)
-    assert sum(len(p["ops"]) for p in passes) == len(gl)
-    got = run_plan(passes, n, params)
+    plan = plan_dump(gl, 0, tile_bits, low_bits, with_mats=True)
+    check_invariants(plan, n, tile_bits, low_bits)
+    assert sum(len(m["gates"]) for m in plan["mats"]) + sum(
+        1 for p in plan["passes"] for o in p["ops"] if o[0] in (4, 5)) == len(gl)  # every gate lands exactly once
     want = oracle.state(gl, params)
-    assert np.abs(got - want).max() < 1e-12
-    assert np.abs(run_plan_windows(passes, n, params) - want).max() < 1e-12
+    assert np.abs(run_plan(plan, n, params) - want).max() < 1e-12
+    assert np.abs(run_plan_windows(plan, n, params) - want).max() < 1e-12
     if n > tile_bits:
-        assert len(passes) > 1
+        assert len(plan["passes"]) > 1
+    if n >= 2:
+        assert n_blocks(plan) < len(gl)  # fusion merged something
 
 
-def test_brickwork_c5_plan_is_few_passes(built_lib):
+def test_unfused_plan_matches_too(built_lib, oracle, monkeypatch):
+    monkeypatch.setenv("TQ_FUSE", "0")
+    gl = synthetic_circuit(9, 80, 3)
+    params = parameter_batch(gl, 1)[0]
+    plan = plan_dump(gl, 0, 8, 4, with_mats=True)
+    assert n_blocks(plan) == len(gl)
+    assert np.abs(run_plan_windows(plan, 9, params) - oracle.state(gl, params)).max() < 1e-12
+
+
+def test_brickwork_c5_plan_is_few_passes(built_lib, oracle):
     gl = brickwork_circuit(20, 21, 41, 5)
     assert len(gl) == 440
-    passes = plan_dump(gl, 0, 12, 4)
-    check_invariants(passes, 20, 12, 4)
-    assert sum(len(p["ops"]) for p in passes) == 440
-    assert sum(len(w["ops"]) for p in passes for w in p["windows"]) == 440
-    assert len(passes) <= 6  # 440 gates fused into a handful of HBM passes
-    n_windows = sum(len(p["windows"]) for p in passes)
-    assert n_windows <= 60, n_windows  # ... and a few dozen shared-memory redistributions
+    plan = plan_dump(gl, 0, 12, 4, with_mats=True)
+    check_invariants(plan, 20, 12, 4)
+    assert len(plan["passes"]) <= 6  # 440 gates fused into a handful of HBM passes
+    n_windows = sum(len(p["windows"]) for p in plan["passes"])
+    assert n_windows <= 40, n_windows  # ... a few dozen shared-memory redistributions
+    assert n_blocks(plan) <= 80, n_blocks(plan)  # ... and a few dozen dense blocks (19 bricks + agent gates)
+    # a 12-qubit circuit of the same shape is cheap enough to emulate end to end
+    g12 = brickwork_circuit(12, 21, 30, 6)
+    params = parameter_batch(g12, 1)[0]
+    p12 = plan_dump(g12, 0, 8, 4, with_mats=True)
+    assert np.abs(run_plan_windows(p12, 12, params) - oracle.state(g12, params)).max() < 1e-12
 
 
 def test_cover_masks_pulled_into_last_pass(built_lib):
@@ -64,14 +86,23 @@ def test_cover_masks_pulled_into_last_pass(built_lib):
 def test_density_plan_equals_oracle(built_lib, oracle, n, tile_bits, seed):
     gl = noisy_circuit(n, 14, seed)
     params = parameter_batch(gl, 1)[0]
-    passes = plan_dump(gl, 1, tile_bits, 4)
-    check_invariants(passes, 2 * n, tile_bits, 4)
-    got = run_plan(passes, 2 * n, params)
+    plan = plan_dump(gl, 1, tile_bits, 4, with_mats=True)
+    check_invariants(plan, 2 * n, tile_bits, 4)
     want = oracle.density_matrix(gl, params).reshape(-1)
+    got = run_plan(plan, 2 * n, params)
     assert np.abs(got - want).max() < 1e-12
-    assert np.abs(run_plan_windows(passes, 2 * n, params) - want).max() < 1e-12
+    assert np.abs(run_plan_windows(plan, 2 * n, params) - want).max() < 1e-12
     rho = got.reshape(1 << n, 1 << n)
     assert abs(np.trace(rho) - 1) < 1e-12 and np.abs(rho - rho.conj().T).max() < 1e-12
+
+
+def test_density_plan_without_noise_fuses(built_lib, oracle):
+    n = 5
+    gl = synthetic_circuit(n, 40, 11)
+    params = parameter_batch(gl, 1)[0]
+    plan = plan_dump(gl, 1, 8, 4, with_mats=True)
+    want = oracle.density_matrix(gl, params).reshape(-1)
+    assert np.abs(run_plan_windows(plan, 2 * n, params) - want).max() < 1e-12
 
 
 @pytest.mark.parametrize("n,tile_bits,seed", [(6, 12, 0), (10, 8, 1)])
@@ -85,14 +116,13 @@ def test_trajectory_plan_equals_oracle(built_lib, oracle, n, tile_bits, seed):
             codes[gl.pidx[g]] = rng.integers(4)
         elif kind == 8:
             codes[gl.pidx[g]] = rng.integers(16)
-    passes = plan_dump(gl, 2, tile_bits, 4)
-    check_invariants(passes, n, tile_bits, 4)
-    got = run_plan(passes, n, params, codes=codes)
+    plan = plan_dump(gl, 2, tile_bits, 4, with_mats=True)
+    check_invariants(plan, n, tile_bits, 4)
     want = oracle.state(gl, params, codes=codes)
-    assert np.abs(got - want).max() < 1e-12
-    assert np.abs(run_plan_windows(passes, n, params, codes=codes) - want).max() < 1e-12
+    assert np.abs(run_plan(plan, n, params, codes=codes) - want).max() < 1e-12
+    assert np.abs(run_plan_windows(plan, n, params, codes=codes) - want).max() < 1e-12
     # the noise-free plan skips the noise gates
-    clean = run_plan(plan_dump(gl, 0, tile_bits, 4), n, params)
+    clean = run_plan_windows(plan_dump(gl, 0, tile_bits, 4, with_mats=True), n, params)
     assert np.abs(clean - oracle.state(gl, params)).max() < 1e-12
 
 
