@@ -282,17 +282,30 @@ int compile_plan(tq_handle h, int which) {
         if (bytes) memcpy(blob.data() + off, data, bytes);
         return off;
     };
-    struct Offsets { size_t windows, wops, groups, terms; int n_groups, n_terms; };
+    struct Offsets { size_t windows, wops, groups, terms, eterms; int n_groups, n_terms; };
     std::vector<Offsets> offs(passes.size());
     const size_t off_descs = append(cc.mats.data(), cc.mats.size() * sizeof(MatDesc));
     const size_t off_prog = append(cc.prog.data(), cc.prog.size() * sizeof(MatGate));
     for (size_t i = 0; i < passes.size(); ++i) {
-        const Pass& p = passes[i];
+        Pass& p = passes[i];
+        // groups whose flips fit a register window are evaluated there; wider ones through shared memory
+        std::vector<ExpGroupIn> gin;
+        for (int g : groups_of_pass[i]) {
+            ExpGroupIn x;
+            x.x = h->groups[g].x;
+            for (int t : h->groups[g].terms) x.terms.push_back(ExpTermIn{h->pz[t], h->pre[t], h->pim[t]});
+            gin.push_back(std::move(x));
+        }
+        std::vector<int> wide;
+        if (!gin.empty()) append_expectation_windows(p, gin, &wide);
+        std::vector<int> wide_groups;
+        for (int wi : wide) wide_groups.push_back(groups_of_pass[i][wi]);
         offs[i].windows = append(p.windows.data(), p.windows.size() * sizeof(Window));
         offs[i].wops = append(p.wops.data(), p.wops.size() * sizeof(WinOp));
+        offs[i].eterms = append(p.eterms.data(), p.eterms.size() * sizeof(ExpTermW));
         std::vector<ExpGroup> eg;
         std::vector<ExpTerm> et;
-        for (int g : groups_of_pass[i]) {
+        for (int g : wide_groups) {
             ExpGroup x{};
             x.xlocal = mask_to_local(p, h->groups[g].x);
             x.term_begin = (int)et.size();
@@ -338,11 +351,13 @@ int compile_plan(tq_handle h, int which) {
         dp.proto.wops = (const WinOp*)(base + offs[i].wops);
         dp.proto.n_wops = (int)passes[i].wops.size();
         dp.proto.n_mats = plan.n_mats;
+        dp.proto.n_gate_windows = passes[i].n_gate_windows;
+        dp.proto.eterms = (const ExpTermW*)(base + offs[i].eterms);
         dp.n_groups = offs[i].n_groups;
         if (which != 1) {
             if (single_tile) {
                 dp.proto.exp_mode = 2;
-            } else if (dp.n_groups > 0) {
+            } else if (!groups_of_pass[i].empty()) {
                 dp.proto.exp_mode = 1;
                 dp.proto.groups = (const ExpGroup*)(base + offs[i].groups);
                 dp.proto.n_groups = dp.n_groups;

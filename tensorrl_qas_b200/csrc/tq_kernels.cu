@@ -195,6 +195,83 @@ __device__ __forceinline__ void exec_depol2(Amps& a, int rows, int cols, double 
     else g_depol2<0, 3, 1, 2>(a, p);
 }
 
+// ---- expectation of one flip-mask group on registers: XR = flip mask over the register bits -----------------------
+// sum over this thread's 16 amplitudes of Re( f(j) conj(psi[j ^ x]) psi[j] ),  f(j) = sum_t w_t (-1)^{parity(j & z_t)}
+template <int XR>
+__device__ __forceinline__ double g_exp(const Amps& a, uint64_t ctx, const ExpTermW* __restrict__ terms, int nt) {
+    double total = 0.0;
+    if (XR == 0) {
+        double nrm[NA];
+#pragma unroll
+        for (int r = 0; r < NA; ++r) nrm[r] = a[r].x * a[r].x + a[r].y * a[r].y;
+        for (int t = 0; t < nt; ++t) {
+            const ExpTermW term = terms[t];
+            const uint32_t m = term.sgnmask;
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < NA; ++r) s += ((m >> r) & 1u) ? -nrm[r] : nrm[r];
+            const double w = (__popcll(ctx & term.zphys) & 1) ? -term.wre : term.wre;
+            total = fma(w, s, total);
+        }
+    } else {
+        constexpr int NP = NA / 2;
+        double px[NP], py[NP];  // conj(psi[r ^ x]) * psi[r] for the pairs r < r ^ x, times two
+        {
+            int q = 0;
+#pragma unroll
+            for (int r = 0; r < NA; ++r) {
+                if ((r ^ XR) > r) {
+                    const double2 v = a[r], w = a[r ^ XR];
+                    px[q] = 2.0 * (w.x * v.x + w.y * v.y);
+                    py[q] = 2.0 * (w.x * v.y - w.y * v.x);
+                    ++q;
+                }
+            }
+        }
+        for (int t = 0; t < nt; ++t) {
+            const ExpTermW term = terms[t];
+            const uint32_t m = term.sgnmask;
+            double sa = 0.0, sb = 0.0;
+            int q = 0;
+#pragma unroll
+            for (int r = 0; r < NA; ++r) {
+                if ((r ^ XR) > r) {
+                    const bool sr = (m >> r) & 1u, sx = (m >> (r ^ XR)) & 1u;
+                    sa += (sr == sx) ? (sr ? -px[q] : px[q]) : 0.0;   // (sigma(r) + sigma(r^x)) Re p
+                    sb += (sr != sx) ? (sr ? -py[q] : py[q]) : 0.0;   // (sigma(r) - sigma(r^x)) Im p
+                    ++q;
+                }
+            }
+            const bool neg = __popcll(ctx & term.zphys) & 1;
+            const double wre = neg ? -term.wre : term.wre, wim = neg ? -term.wim : term.wim;
+            // Re(f(r) p) + Re(f(r^x) conj(p)) = wre * px * (s_r + s_x) - wim * py * (s_r - s_x), s = +-1
+            total += wre * sa - wim * sb;
+        }
+    }
+    return total;
+}
+
+__device__ __forceinline__ double exec_exp(const Amps& a, uint64_t ctx, int xr, const ExpTermW* terms, int nt) {
+    switch (xr) {
+    case 0: return g_exp<0>(a, ctx, terms, nt);
+    case 1: return g_exp<1>(a, ctx, terms, nt);
+    case 2: return g_exp<2>(a, ctx, terms, nt);
+    case 3: return g_exp<3>(a, ctx, terms, nt);
+    case 4: return g_exp<4>(a, ctx, terms, nt);
+    case 5: return g_exp<5>(a, ctx, terms, nt);
+    case 6: return g_exp<6>(a, ctx, terms, nt);
+    case 7: return g_exp<7>(a, ctx, terms, nt);
+    case 8: return g_exp<8>(a, ctx, terms, nt);
+    case 9: return g_exp<9>(a, ctx, terms, nt);
+    case 10: return g_exp<10>(a, ctx, terms, nt);
+    case 11: return g_exp<11>(a, ctx, terms, nt);
+    case 12: return g_exp<12>(a, ctx, terms, nt);
+    case 13: return g_exp<13>(a, ctx, terms, nt);
+    case 14: return g_exp<14>(a, ctx, terms, nt);
+    default: return g_exp<15>(a, ctx, terms, nt);
+    }
+}
+
 // deterministic CTA-wide sum (fixed shuffle tree, then warps added in index order); result valid in thread 0
 __device__ __forceinline__ double block_sum(double v, double* s_red, int tid, int nthreads) {
 #pragma unroll
@@ -258,16 +335,20 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
     // ---- 2. register windows ----
     Amps a;
     uint32_t slot_t = 0, ws0 = 0, ws1 = 0, ws2 = 0, ws3 = 0;
-    for (int w = 0; w < p.n_windows; ++w) {
+    double acc = 0.0;            // this thread's share of the energy (expectation windows)
+    bool regs_dirty = false;     // registers hold amplitudes that shared memory does not have yet
+    const int n_run = p.exp_mode == 1 ? p.n_windows : p.n_gate_windows;
+    for (int w = 0; w < n_run; ++w) {
         const Window* win = p.windows + w;
         const int op_begin = win->op_begin, op_end = win->op_end;
         if (w > 0) {
             __syncthreads();  // every thread has finished the previous window (its loads and its staged ops)
-            if (active) {
+            if (regs_dirty && active) {
 #pragma unroll
                 for (int r = 0; r < NA; ++r) amp[TQ_SLOT(r)] = a[r];
             }
         }
+        regs_dirty = !(win->tpos[11] & kWinFlagReadOnly);
         // stage this window's ops and their block matrices (this element's, from the prep kernel) while no
         // amplitudes are live in registers; the planner keeps a window within kMaxWindowOps ops
         {
@@ -277,7 +358,10 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
                 const WinOp wo = p.wops[op_begin + oi];
                 if (e == 0) s_wops[oi] = wo;
                 const int code = wo.w0 & 0xff, flags = wo.w0 >> 24;
-                if (code <= W_D1_OUT && (code == W_U2 || e < 4)) {
+                if (code == W_EXP) {  // the op's terms (32 bytes each) ride in its matrix slot
+                    if (e < 2 * (int)((wo.w0 >> 16) & 0xff))
+                        s_mat[oi * kMatStride + e] = reinterpret_cast<const double2*>(p.eterms)[(size_t)wo.t * 2 + e];
+                } else if (code <= W_D1_OUT && (code == W_U2 || e < 4)) {
                     int src = e;
                     if (code == W_U2 && (flags & FLAG_SWAP)) {  // matrix written for the other qubit order
                         const int r = e >> 2, c = e & 3;
@@ -321,13 +405,14 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
                 case W_CX_OW: TQ_RB4(g_x_if, rb, a, (bool)((ctx >> qsel) & 1ull)); break;
                 case W_DEPOL1: exec_depol1(a, rb, rb2, wo.fixed); break;
                 case W_DEPOL2: exec_depol2(a, rb, rb2, wo.fixed); break;
+                case W_EXP: acc += exec_exp(a, ctx, rb, reinterpret_cast<const ExpTermW*>(m), qsel); break;
                 default: break;
                 }
             }
         }
     }
     // registers -> shared memory (final layout of the pass)
-    if (p.n_windows > 0) {
+    if (regs_dirty) {
         __syncthreads();
         if (active) {
 #pragma unroll
@@ -344,8 +429,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
 
     // ---- 3. expectation of the Hamiltonian terms that are local to this pass ----
     if (p.exp_mode != 0) {
-        double acc = 0.0;
-        if (p.exp_mode == 1) {
+        if (p.exp_mode == 1) {  // groups that flip more than kRegBits qubits: partner amplitudes via shared memory
             // terms staged in shared memory (re-using the op staging area: 8 KiB = 256 terms)
             ExpTerm* s_terms = reinterpret_cast<ExpTerm*>(s_mat);
             const int cap = (int)((kMaxWindowOps * kMatStride * sizeof(double2)) / sizeof(ExpTerm));

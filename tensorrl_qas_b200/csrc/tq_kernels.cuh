@@ -45,12 +45,13 @@ struct PassParams {
     int src_mode;  // 0: |0...0>, 1: one shared initial vector, 2: per-element state buffer
     double2* dst;  // nullptr: tile is not written back
     const Window* windows;
-    int n_windows;
+    int n_windows, n_gate_windows;   // expectation windows follow the gate windows
+    const ExpTermW* eterms;
     const WinOp* wops;
     int n_wops;
     const double2* mats;   // [batch][n_mats][kMatStride] block matrices of this call's elements (prep kernel output)
     int n_mats;
-    int exp_mode;  // 0 none, 1 Pauli groups, 2 sparse entries (single-tile passes only)
+    int exp_mode;  // 0 none, 1 Pauli sum (expectation windows + shared-memory groups), 2 sparse entries (single tile)
     const ExpGroup* groups;
     int n_groups;
     const ExpTerm* terms;

@@ -452,6 +452,89 @@ void schedule_windows(Pass& p) {
         remaining.swap(deferred);
     }
     if (p.windows.empty()) emit_window(0, {});  // no ops: one window that only carries the layout
+    p.n_gate_windows = (int)p.windows.size();
+}
+
+void append_expectation_windows(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover) {
+    const int k_real = (int)p.local.size();
+    const int k = std::max(k_real, kMinTileBits);
+    std::vector<uint32_t> xl(groups.size());
+    std::vector<char> done(groups.size(), 0);
+    size_t left = 0;
+    for (size_t g = 0; g < groups.size(); ++g) {
+        xl[g] = mask_to_local(p, groups[g].x);
+        if (popc32(xl[g]) > kRegBits) { leftover->push_back((int)g); done[g] = 1; }
+        else ++left;
+    }
+    while (left > 0) {
+        uint32_t W = 0;
+        std::vector<int> mine;
+        for (size_t g = 0; g < groups.size(); ++g) {
+            if (done[g]) continue;
+            if (popc32(W | xl[g]) <= kRegBits) { W |= xl[g]; mine.push_back((int)g); done[g] = 1; --left; }
+        }
+        for (int q = 0; q < k && popc32(W) < kRegBits; ++q) W |= 1u << q;
+        Window w{};
+        int nb = 0;
+        int rb_of[32];
+        for (int q = 0; q < 32; ++q) rb_of[q] = -1;
+        for (int q = 0; q < k; ++q)
+            if ((W >> q) & 1) { w.wpos[nb] = (uint8_t)q; rb_of[q] = nb++; }
+        std::vector<int> rest;
+        for (int q = 0; q < k; ++q)
+            if (!((W >> q) & 1)) rest.push_back(q);
+        bool found = false;
+        for (size_t a = 0; a < rest.size() && !found; ++a)
+            for (size_t b = a + 1; b < rest.size() && !found; ++b)
+                for (size_t c = b + 1; c < rest.size() && !found; ++c)
+                    if (independent3(rest[a], rest[b], rest[c])) {
+                        std::vector<int> order = {rest[a], rest[b], rest[c]};
+                        for (size_t i = 0; i < rest.size(); ++i)
+                            if (i != a && i != b && i != c) order.push_back(rest[i]);
+                        rest.swap(order);
+                        found = true;
+                    }
+        for (size_t i = 0; i < rest.size() && i < 11; ++i) w.tpos[i] = (uint8_t)rest[i];
+        w.tpos[11] = kWinFlagReadOnly;
+        uint64_t wphys = 0;  // physical bits of the window
+        for (int r = 0; r < kRegBits; ++r)
+            if (w.wpos[r] < k_real) wphys |= bit(p.local[w.wpos[r]]);
+        std::vector<WinOp> ops;
+        for (int g : mine) {
+            uint32_t xr = 0;
+            for (int r = 0; r < kRegBits; ++r)
+                if ((xl[g] >> w.wpos[r]) & 1) xr |= 1u << r;
+            const auto& terms = groups[g].terms;
+            for (size_t t0 = 0; t0 < terms.size(); t0 += kExpChunk) {
+                const int nt = (int)std::min<size_t>(kExpChunk, terms.size() - t0);
+                WinOp o{};
+                o.w0 = winop_pack(W_EXP, (int)xr, 0, nt, 0);
+                o.t = (int32_t)p.eterms.size();
+                for (int i = 0; i < nt; ++i) {
+                    const ExpTermIn& in = terms[t0 + i];
+                    ExpTermW e{};
+                    e.zphys = in.z & ~wphys;
+                    uint32_t zr = 0;
+                    for (int r = 0; r < kRegBits; ++r)
+                        if (w.wpos[r] < k_real && ((in.z >> p.local[w.wpos[r]]) & 1)) zr |= 1u << r;
+                    for (uint32_t r = 0; r < (1u << kRegBits); ++r)
+                        if (__builtin_parity(r & zr)) e.sgnmask |= 1u << r;
+                    e.wre = in.wre;
+                    e.wim = in.wim;
+                    p.eterms.push_back(e);
+                }
+                ops.push_back(o);
+            }
+        }
+        for (size_t lo = 0; lo < ops.size() || lo == 0; lo += kMaxWindowOps) {
+            Window part = w;
+            part.op_begin = (int32_t)p.wops.size();
+            for (size_t i = lo; i < std::min(ops.size(), lo + kMaxWindowOps); ++i) p.wops.push_back(ops[i]);
+            part.op_end = (int32_t)p.wops.size();
+            p.windows.push_back(part);
+            if (lo + kMaxWindowOps >= ops.size()) break;
+        }
+    }
 }
 
 bool mask_is_local(const Pass& p, uint64_t mask) {

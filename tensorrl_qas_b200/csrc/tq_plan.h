@@ -75,7 +75,20 @@ enum : int32_t {    // WinOp code; rb / rb2 are register-bit indices inside the 
     W_CX_OW = 5,    // qsel = physical control bit, rb = target
     W_DEPOL1 = 6,   // rb = row bit, rb2 = column bit, fixed = p
     W_DEPOL2 = 7,   // window = {row a, row b, col a, col b}: rb = ra | rb << 2, rb2 = ca | cb << 2
+    W_EXP = 8,      // expectation of (a chunk of) one flip-mask group whose flips are window bits: rb = flip mask
+                    // over the register bits, qsel = number of terms (<= kExpChunk), t = first term (Pass::eterms)
 };
+constexpr int kExpChunk = 8;   // terms per W_EXP op (they are staged in the op's 256-byte matrix slot)
+constexpr int kWinFlagReadOnly = 1;  // Window::tpos[11]: the window does not change the amplitudes
+
+struct ExpTermW {   // 32 bytes: one Pauli term as seen from an expectation window
+    uint64_t zphys;     // Z/Y bits, physical; the thread's context index has the window bits cleared
+    uint32_t sgnmask;   // bit r = parity(register index r & Z/Y bits inside the window)
+    uint32_t pad;
+    double wre, wim;    // coefficient times i^{#Y}
+};
+struct ExpTermIn { uint64_t z; double wre, wim; };
+struct ExpGroupIn { uint64_t x; std::vector<ExpTermIn> terms; };
 struct WinOp {      // 16 bytes
     uint32_t w0;    // code | rb << 8 | rb2 << 12 | qsel << 16 | flags << 24
     int32_t t;      // matrix index (W_U2 / W_U1 / W_D1 / W_D1_OUT)
@@ -100,8 +113,10 @@ struct Pass {
     std::vector<int> nonlocal;  // remaining physical bits, ascending
     std::vector<DevOp> ops;     // tile-level ops in a valid execution order (what the windows were scheduled from)
     int lead = 0;               // number of leading positions with local[p] == p (contiguous run in memory)
-    std::vector<Window> windows;  // register-window schedule of `ops`
+    std::vector<Window> windows;  // register-window schedule of `ops` (+ expectation windows after them)
     std::vector<WinOp> wops;
+    int n_gate_windows = 0;       // windows [0, n_gate_windows) change the state, the rest only read it
+    std::vector<ExpTermW> eterms; // terms of the expectation windows
 };
 
 struct PlanOptions {
@@ -131,6 +146,9 @@ std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const Pla
                              std::vector<int>* assignment);
 
 void schedule_windows(Pass& p);
+// Appends read-only windows that evaluate the given Hamiltonian groups (flip masks must be local to the pass) on
+// registers; groups that flip more than kRegBits qubits are returned in `leftover` (shared-memory fallback).
+void append_expectation_windows(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover);
 bool mask_is_local(const Pass& p, uint64_t mask);
 uint32_t mask_to_local(const Pass& p, uint64_t mask);
 
