@@ -323,9 +323,19 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
         __syncthreads();
         if (tile_base == 0 && tid == 0) amp[0] = make_double2(1.0, 0.0);  // swz(0) == 0
     } else {
+        // all of a thread's loads are issued before the first one is consumed (NA independent 16-byte loads in flight)
         const double2* src = p.src + (p.src_mode == 2 ? elem_off : 0ull) + tile_base;
-        for (int j = tid; j < tile_amps; j += nthreads)
-            amp[swz(j)] = j < valid_amps ? src[hi_off[j >> p.lead] | (j & lead_mask)] : make_double2(0.0, 0.0);
+        double2 v[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int j = tid + i * nthreads;
+            v[i] = j < valid_amps ? __ldcs(src + (hi_off[j >> p.lead] | (j & lead_mask))) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int j = tid + i * nthreads;
+            if (j < tile_amps) amp[swz(j)] = v[i];
+        }
     }
 
     const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
@@ -424,7 +434,11 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
     // ---- 4. write back ----
     if (p.dst) {
         double2* dst = p.dst + elem_off + tile_base;
-        for (int j = tid; j < valid_amps; j += nthreads) dst[hi_off[j >> p.lead] | (j & lead_mask)] = amp[swz(j)];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int j = tid + i * nthreads;
+            if (j < valid_amps) dst[hi_off[j >> p.lead] | (j & lead_mask)] = amp[swz(j)];
+        }
     }
 
     // ---- 3. expectation of the Hamiltonian terms that are local to this pass ----
