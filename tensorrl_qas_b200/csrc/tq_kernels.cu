@@ -5,6 +5,9 @@ namespace tq {
 namespace {
 
 constexpr int NA = 1 << kRegBits;  // amplitudes per thread
+constexpr int kOpSlots = 48;       // ops (+ their 256-byte matrix / term slots) resident in shared memory
+constexpr int kWinSlots = 32;      // window headers resident in shared memory
+static_assert(kOpSlots >= kMaxWindowOps, "a window's ops must fit the staged range");
 
 // ---- bank swizzle: slot(j) = j ^ fold(j >> 3); fold is GF(2)-linear, so slot(a ^ b) = slot(a) ^ slot(b) ----------
 constexpr uint32_t swz_mask(int out_bit) {
@@ -30,34 +33,35 @@ __device__ __forceinline__ double2 cfma(double2 m, double2 v, double2 acc) {
     return make_double2(fma(m.x, v.x, fma(-m.y, v.y, acc.x)), fma(m.x, v.y, fma(m.y, v.x, acc.y)));
 }
 
-// dense 4x4 block on register bits RA < RB (matrix index bit 0 = RA); m = 16 staged entries, row-major
+// dense 4x4 block on register bits RA < RB (matrix index bit 0 = RA); m = 16 staged entries, row-major.
+// Two groups of four amplitudes per sweep over the matrix: inputs are read in place, the eight outputs are
+// collected in temporaries and written back at the end of the sweep.
 template <int RA, int RB>
 __device__ __forceinline__ void g_u2(Amps& a, const double2* __restrict__ m) {
     constexpr int O0 = (RA != 0 && RB != 0) ? 0 : (RA != 1 && RB != 1) ? 1 : 2;
     constexpr int O1 = (RA != 3 && RB != 3) ? 3 : (RA != 2 && RB != 2) ? 2 : 1;
 #pragma unroll
-    for (int gp = 0; gp < 2; ++gp) {  // two groups of four amplitudes per sweep over the matrix
+    for (int gp = 0; gp < 2; ++gp) {
         const int base0 = (gp ? (1 << O1) : 0), base1 = base0 | (1 << O0);
-        double2 in0[4], in1[4];
+        double2 o0[4], o1[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int off = ((k & 1) ? (1 << RA) : 0) | ((k & 2) ? (1 << RB) : 0);
-            in0[k] = a[base0 | off];
-            in1[k] = a[base1 | off];
+        for (int i = 0; i < 4; ++i) {
+            double2 mm = m[i * 4];
+            o0[i] = cmul(mm, a[base0]);
+            o1[i] = cmul(mm, a[base1]);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                const int off = ((k & 1) ? (1 << RA) : 0) | ((k & 2) ? (1 << RB) : 0);
+                mm = m[i * 4 + k];
+                o0[i] = cfma(mm, a[base0 | off], o0[i]);
+                o1[i] = cfma(mm, a[base1 | off], o1[i]);
+            }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int off = ((i & 1) ? (1 << RA) : 0) | ((i & 2) ? (1 << RB) : 0);
-            double2 mm = m[i * 4];
-            double2 o0 = cmul(mm, in0[0]), o1 = cmul(mm, in1[0]);
-#pragma unroll
-            for (int k = 1; k < 4; ++k) {
-                mm = m[i * 4 + k];
-                o0 = cfma(mm, in0[k], o0);
-                o1 = cfma(mm, in1[k], o1);
-            }
-            a[base0 | off] = o0;
-            a[base1 | off] = o1;
+            a[base0 | off] = o0[i];
+            a[base1 | off] = o1[i];
         }
     }
 }
@@ -286,17 +290,39 @@ __device__ __forceinline__ double block_sum(double v, double* s_red, int tid, in
     return total;
 }
 
-#define TQ_SLOT(r) (slot_t ^ (((r) & 1) ? ws0 : 0u) ^ (((r) & 2) ? ws1 : 0u) ^ (((r) & 4) ? ws2 : 0u) ^ (((r) & 8) ? ws3 : 0u))
+#define TQ_SEL4(i, v0, v1, v2, v3, OP) ((((i) & 1) ? (v0) : 0u) OP (((i) & 2) ? (v1) : 0u) OP (((i) & 4) ? (v2) : 0u) OP (((i) & 8) ? (v3) : 0u))
+#define TQ_SLOT(r) (slot_t ^ TQ_SEL4(r, ws0, ws1, ws2, ws3, ^))
+#define TQ_IO_SLOT(i) (io_slot ^ TQ_SEL4(i, iw0, iw1, iw2, iw3, ^))
+#define TQ_IO_GOFF(i) (io_goff | TQ_SEL4(i, ig0, ig1, ig2, ig3, |))
+
+// flat dispatch ids (computed while staging a window's ops; the planner's WinOp codes stay symbolic)
+enum : int { F_U2 = 0, F_U1 = 6, F_D1 = 10, F_D1_OUT = 14, F_CX_WW = 15, F_CX_OW = 31, F_DEPOL1 = 35, F_DEPOL2 = 36, F_EXP = 37 };
+
+__device__ __forceinline__ int flat_code(uint32_t w0) {
+    const int code = w0 & 0xff, rb = (w0 >> 8) & 0xf, rb2 = (w0 >> 12) & 0xf;
+    switch (code) {
+    case W_U2: return F_U2 + (rb == 0 ? rb2 - 1 : rb == 1 ? rb2 + 1 : 5);  // (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+    case W_U1: return F_U1 + rb;
+    case W_D1: return F_D1 + rb;
+    case W_D1_OUT: return F_D1_OUT;
+    case W_CX_WW: return F_CX_WW + rb * 4 + rb2;
+    case W_CX_OW: return F_CX_OW + rb;
+    case W_DEPOL1: return F_DEPOL1;
+    case W_DEPOL2: return F_DEPOL2;
+    default: return F_EXP;
+    }
+}
 
 __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tile_amps = 1 << p.k_eff;
     const int valid_amps = 1 << p.k;
     double2* amp = reinterpret_cast<double2*>(smem_raw);
-    double2* s_mat = amp + tile_amps;                                          // kMaxWindowOps x 16 entries
-    WinOp* s_wops = reinterpret_cast<WinOp*>(s_mat + kMaxWindowOps * kMatStride);  // kMaxWindowOps entries
-    double* s_red = reinterpret_cast<double*>(s_wops + kMaxWindowOps);         // 32 entries
-    uint32_t* hi_off = reinterpret_cast<uint32_t*>(s_red + 32);         // 2^(k - lead) entries
+    double2* s_mat = amp + tile_amps;                                          // kOpSlots x 16 entries
+    WinOp* s_wops = reinterpret_cast<WinOp*>(s_mat + kOpSlots * kMatStride);   // kOpSlots entries
+    double* s_red = reinterpret_cast<double*>(s_wops + kOpSlots);              // 32 entries
+    uint2* s_win = reinterpret_cast<uint2*>(s_red + 32);                       // kWinSlots x 3 (24-byte headers)
+    uint32_t* hi_off = reinterpret_cast<uint32_t*>(s_win + 3 * kWinSlots);     // 2^(k - lead) entries
 
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const uint32_t ntiles = 1u << p.n_nl;
@@ -306,6 +332,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
     uint64_t tile_base = 0;
     for (int i = 0; i < p.n_nl; ++i) tile_base |= (uint64_t)((tile >> i) & 1u) << p.nonlocal[i];
 
+    // hi_off[h]: physical offset of the tile positions above the contiguous lead run
     const int n_hi = 1 << (p.k - p.lead);
     for (int h = tid; h < n_hi; h += nthreads) {
         uint32_t off = 0;
@@ -313,44 +340,96 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
         hi_off[h] = off;
     }
     __syncthreads();
+    const uint32_t lead_mask = (1u << p.lead) - 1u;
+    // physical offset of tile index j (j < 2^k)
+#define TQ_PHYS(j) ((uint32_t)(((j) & lead_mask) | hi_off[(j) >> p.lead]))
+
+    // I/O layout: amplitude i of thread t is tile index t + i * nthreads; both the swizzled slot and the physical
+    // offset are bitwise-linear in the index, so they split into a per-thread part and four per-bit constants
+    const uint32_t io_slot = swz(tid);
+    const uint32_t iw0 = swz(nthreads), iw1 = swz(nthreads << 1), iw2 = swz(nthreads << 2), iw3 = swz(nthreads << 3);
+    const uint32_t io_goff = tid < valid_amps ? TQ_PHYS(tid) : 0u;
+    const uint32_t ig0 = nthreads < valid_amps ? TQ_PHYS(nthreads) : 0u;
+    const uint32_t ig1 = (nthreads << 1) < valid_amps ? TQ_PHYS(nthreads << 1) : 0u;
+    const uint32_t ig2 = (nthreads << 2) < valid_amps ? TQ_PHYS(nthreads << 2) : 0u;
+    const uint32_t ig3 = (nthreads << 3) < valid_amps ? TQ_PHYS(nthreads << 3) : 0u;
 
     const uint64_t elem_off = (uint64_t)b << p.nbits;
-    const uint32_t lead_mask = (1u << p.lead) - 1u;
-
-    // ---- 1. stage the tile (coalesced global reads, swizzled shared-memory slots) ----
-    if (p.src_mode == 0) {
-        for (int j = tid; j < tile_amps; j += nthreads) amp[j] = make_double2(0.0, 0.0);
-        __syncthreads();
-        if (tile_base == 0 && tid == 0) amp[0] = make_double2(1.0, 0.0);  // swz(0) == 0
-    } else {
-        // all of a thread's loads are issued before the first one is consumed (NA independent 16-byte loads in flight)
-        const double2* src = p.src + (p.src_mode == 2 ? elem_off : 0ull) + tile_base;
-        double2 v[NA];
-#pragma unroll
-        for (int i = 0; i < NA; ++i) {
-            const int j = tid + i * nthreads;
-            v[i] = j < valid_amps ? __ldcs(src + (hi_off[j >> p.lead] | (j & lead_mask))) : make_double2(0.0, 0.0);
-        }
-#pragma unroll
-        for (int i = 0; i < NA; ++i) {
-            const int j = tid + i * nthreads;
-            if (j < tile_amps) amp[swz(j)] = v[i];
-        }
-    }
 
     const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
     const bool active = tid < (tile_amps >> kRegBits);
     const int n_tbits = p.k_eff - kRegBits;
+    const int n_run = p.exp_mode == 1 ? p.n_windows : p.n_gate_windows;
+
+    // ops [staged_begin, staged_end) of the pass live in shared memory with their block matrices / term lists
+    int staged_begin = 0, staged_end = 0;
+    auto stage_ops = [&](int first) {
+        staged_begin = first;
+        staged_end = min(first + kOpSlots, p.n_wops);
+        for (int i = tid; i < (staged_end - staged_begin) * kMatStride; i += nthreads) {
+            const int oi = i >> 4, e = i & 15;
+            WinOp wo = p.wops[staged_begin + oi];
+            const int code = wo.w0 & 0xff, flags = wo.w0 >> 24;
+            if (e == 0) {
+                wo.w0 = (wo.w0 & ~0xffu) | (uint32_t)flat_code(wo.w0);
+                s_wops[oi] = wo;
+            }
+            if (code == W_EXP) {  // the op's terms (32 bytes each) ride in its matrix slot
+                if (e < 2 * (int)((wo.w0 >> 16) & 0xff))
+                    s_mat[oi * kMatStride + e] = reinterpret_cast<const double2*>(p.eterms)[(size_t)wo.t * 2 + e];
+            } else if (code <= W_D1_OUT && (code == W_U2 || e < 4)) {
+                int src = e;
+                if (code == W_U2 && (flags & FLAG_SWAP)) {  // matrix written for the other qubit order
+                    const int r = e >> 2, c = e & 3;
+                    src = ((((r & 1) << 1) | (r >> 1)) << 2) | ((c & 1) << 1) | (c >> 1);
+                }
+                double2 v = my_mats[(size_t)wo.t * kMatStride + src];
+                if (flags & FLAG_CONJ) v.y = -v.y;
+                s_mat[oi * kMatStride + e] = v;
+            }
+        }
+    };
+
+    // ---- 1. stage the tile (coalesced global reads, swizzled shared-memory slots), the window headers and the
+    //         first kOpSlots ops of the pass; all global loads are in flight together ----
+    {
+        double2 v[NA];
+        if (p.src_mode != 0) {
+            const double2* src = p.src + (p.src_mode == 2 ? elem_off : 0ull) + tile_base;
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+                v[i] = (tid + i * nthreads < valid_amps) ? __ldcs(src + TQ_IO_GOFF(i)) : make_double2(0.0, 0.0);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NA; ++i) v[i] = make_double2((tile_base == 0 && tid == 0 && i == 0) ? 1.0 : 0.0, 0.0);
+        }
+        for (int i = tid; i < 3 * min(n_run, kWinSlots); i += nthreads)
+            s_win[i] = __ldg(reinterpret_cast<const uint2*>(p.windows) + i);
+        stage_ops(0);
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+            if (tid + i * nthreads < tile_amps) amp[TQ_IO_SLOT(i)] = v[i];
+    }
 
     // ---- 2. register windows ----
     Amps a;
     uint32_t slot_t = 0, ws0 = 0, ws1 = 0, ws2 = 0, ws3 = 0;
     double acc = 0.0;            // this thread's share of the energy (expectation windows)
     bool regs_dirty = false;     // registers hold amplitudes that shared memory does not have yet
-    const int n_run = p.exp_mode == 1 ? p.n_windows : p.n_gate_windows;
     for (int w = 0; w < n_run; ++w) {
-        const Window* win = p.windows + w;
-        const int op_begin = win->op_begin, op_end = win->op_end;
+        // window header: 24 bytes = wpos[4] | tpos[12] | op_begin | op_end
+        uint2 h0, h1, h2;
+        if (w < kWinSlots) {
+            if (w == 0) __syncthreads();  // headers (and the tile) staged above
+            h0 = s_win[3 * w]; h1 = s_win[3 * w + 1]; h2 = s_win[3 * w + 2];
+        } else {
+            const uint2* wraw = reinterpret_cast<const uint2*>(p.windows + w);
+            h0 = __ldg(wraw); h1 = __ldg(wraw + 1); h2 = __ldg(wraw + 2);
+        }
+        const uint32_t wpos4 = h0.x;
+        const uint64_t tpos8 = (uint64_t)h0.y | ((uint64_t)h1.x << 32);  // thread bits 0..7
+        const bool read_only = (h1.y >> 24) & kWinFlagReadOnly;          // tpos[11]
+        const int op_begin = (int)h2.x, op_end = (int)h2.y;
         if (w > 0) {
             __syncthreads();  // every thread has finished the previous window (its loads and its staged ops)
             if (regs_dirty && active) {
@@ -358,64 +437,68 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
                 for (int r = 0; r < NA; ++r) amp[TQ_SLOT(r)] = a[r];
             }
         }
-        regs_dirty = !(win->tpos[11] & kWinFlagReadOnly);
-        // stage this window's ops and their block matrices (this element's, from the prep kernel) while no
-        // amplitudes are live in registers; the planner keeps a window within kMaxWindowOps ops
-        {
-            const int n_ops_w = op_end - op_begin;
-            for (int i = tid; i < n_ops_w * kMatStride; i += nthreads) {
-                const int oi = i >> 4, e = i & 15;
-                const WinOp wo = p.wops[op_begin + oi];
-                if (e == 0) s_wops[oi] = wo;
-                const int code = wo.w0 & 0xff, flags = wo.w0 >> 24;
-                if (code == W_EXP) {  // the op's terms (32 bytes each) ride in its matrix slot
-                    if (e < 2 * (int)((wo.w0 >> 16) & 0xff))
-                        s_mat[oi * kMatStride + e] = reinterpret_cast<const double2*>(p.eterms)[(size_t)wo.t * 2 + e];
-                } else if (code <= W_D1_OUT && (code == W_U2 || e < 4)) {
-                    int src = e;
-                    if (code == W_U2 && (flags & FLAG_SWAP)) {  // matrix written for the other qubit order
-                        const int r = e >> 2, c = e & 3;
-                        src = ((((r & 1) << 1) | (r >> 1)) << 2) | ((c & 1) << 1) | (c >> 1);
-                    }
-                    double2 v = my_mats[(size_t)wo.t * kMatStride + src];
-                    if (flags & FLAG_CONJ) v.y = -v.y;
-                    s_mat[oi * kMatStride + e] = v;
-                }
-            }
+        regs_dirty = !read_only;
+        // ops beyond the staged range (long passes only): restage from this window on; no amplitudes are live in
+        // registers here and every thread is past the previous window's ops (uniform branch)
+        if (op_end > staged_end) {
+            if (w == 0) __syncthreads();
+            stage_ops(op_begin);
         }
         __syncthreads();
+        // this thread's tile index with the window bits cleared, and the matching physical index
         uint32_t jt = 0;
-        uint64_t ctx = tile_base;  // physical index of this thread's amplitudes with the window bits cleared
-        for (int i = 0; i < n_tbits; ++i) {
-            if ((tid >> i) & 1) {
-                const int pos = win->tpos[i];
-                jt |= 1u << pos;
-                ctx |= 1ull << p.local[pos];
-            }
-        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < n_tbits && ((tid >> i) & 1)) jt |= 1u << ((uint32_t)(tpos8 >> (8 * i)) & 0xffu);
+        const uint64_t ctx = tile_base | (jt < (uint32_t)valid_amps ? TQ_PHYS(jt) : 0u);
         slot_t = swz(jt);
-        ws0 = swz(1u << win->wpos[0]);
-        ws1 = swz(1u << win->wpos[1]);
-        ws2 = swz(1u << win->wpos[2]);
-        ws3 = swz(1u << win->wpos[3]);
+        ws0 = swz(1u << (wpos4 & 0xffu));
+        ws1 = swz(1u << ((wpos4 >> 8) & 0xffu));
+        ws2 = swz(1u << ((wpos4 >> 16) & 0xffu));
+        ws3 = swz(1u << (wpos4 >> 24));
         if (active) {
 #pragma unroll
             for (int r = 0; r < NA; ++r) a[r] = amp[TQ_SLOT(r)];
-            for (int o = 0; o < op_end - op_begin; ++o) {
+            for (int o = op_begin - staged_begin; o < op_end - staged_begin; ++o) {
                 const WinOp wo = s_wops[o];
                 const double2* m = s_mat + o * kMatStride;
-                const int code = wo.w0 & 0xff, rb = (wo.w0 >> 8) & 0xf, rb2 = (wo.w0 >> 12) & 0xf;
+                const int fc = wo.w0 & 0xff, rb = (wo.w0 >> 8) & 0xf, rb2 = (wo.w0 >> 12) & 0xf;
                 const int qsel = (wo.w0 >> 16) & 0xff;
-                switch (code) {
-                case W_U2: exec_u2(a, rb, rb2, m); break;
-                case W_U1: TQ_RB4(g_u1, rb, a, m); break;
-                case W_D1: TQ_RB4(g_d1, rb, a, m); break;
-                case W_D1_OUT: g_scale(a, ((ctx >> qsel) & 1ull) ? m[3] : m[0]); break;
-                case W_CX_WW: exec_cx_ww(a, rb, rb2); break;
-                case W_CX_OW: TQ_RB4(g_x_if, rb, a, (bool)((ctx >> qsel) & 1ull)); break;
-                case W_DEPOL1: exec_depol1(a, rb, rb2, wo.fixed); break;
-                case W_DEPOL2: exec_depol2(a, rb, rb2, wo.fixed); break;
-                case W_EXP: acc += exec_exp(a, ctx, rb, reinterpret_cast<const ExpTermW*>(m), qsel); break;
+                switch (fc) {
+                case F_U2 + 0: g_u2<0, 1>(a, m); break;
+                case F_U2 + 1: g_u2<0, 2>(a, m); break;
+                case F_U2 + 2: g_u2<0, 3>(a, m); break;
+                case F_U2 + 3: g_u2<1, 2>(a, m); break;
+                case F_U2 + 4: g_u2<1, 3>(a, m); break;
+                case F_U2 + 5: g_u2<2, 3>(a, m); break;
+                case F_U1 + 0: g_u1<0>(a, m); break;
+                case F_U1 + 1: g_u1<1>(a, m); break;
+                case F_U1 + 2: g_u1<2>(a, m); break;
+                case F_U1 + 3: g_u1<3>(a, m); break;
+                case F_D1 + 0: g_d1<0>(a, m); break;
+                case F_D1 + 1: g_d1<1>(a, m); break;
+                case F_D1 + 2: g_d1<2>(a, m); break;
+                case F_D1 + 3: g_d1<3>(a, m); break;
+                case F_D1_OUT: g_scale(a, ((ctx >> qsel) & 1ull) ? m[3] : m[0]); break;
+                case F_CX_WW + 1: g_cx<0, 1>(a); break;
+                case F_CX_WW + 2: g_cx<0, 2>(a); break;
+                case F_CX_WW + 3: g_cx<0, 3>(a); break;
+                case F_CX_WW + 4: g_cx<1, 0>(a); break;
+                case F_CX_WW + 6: g_cx<1, 2>(a); break;
+                case F_CX_WW + 7: g_cx<1, 3>(a); break;
+                case F_CX_WW + 8: g_cx<2, 0>(a); break;
+                case F_CX_WW + 9: g_cx<2, 1>(a); break;
+                case F_CX_WW + 11: g_cx<2, 3>(a); break;
+                case F_CX_WW + 12: g_cx<3, 0>(a); break;
+                case F_CX_WW + 13: g_cx<3, 1>(a); break;
+                case F_CX_WW + 14: g_cx<3, 2>(a); break;
+                case F_CX_OW + 0: g_x_if<0>(a, (bool)((ctx >> qsel) & 1ull)); break;
+                case F_CX_OW + 1: g_x_if<1>(a, (bool)((ctx >> qsel) & 1ull)); break;
+                case F_CX_OW + 2: g_x_if<2>(a, (bool)((ctx >> qsel) & 1ull)); break;
+                case F_CX_OW + 3: g_x_if<3>(a, (bool)((ctx >> qsel) & 1ull)); break;
+                case F_DEPOL1: exec_depol1(a, rb, rb2, wo.fixed); break;
+                case F_DEPOL2: exec_depol2(a, rb, rb2, wo.fixed); break;
+                case F_EXP: acc += exec_exp(a, ctx, rb, reinterpret_cast<const ExpTermW*>(m), qsel); break;
                 default: break;
                 }
             }
@@ -435,10 +518,8 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
     if (p.dst) {
         double2* dst = p.dst + elem_off + tile_base;
 #pragma unroll
-        for (int i = 0; i < NA; ++i) {
-            const int j = tid + i * nthreads;
-            if (j < valid_amps) dst[hi_off[j >> p.lead] | (j & lead_mask)] = amp[swz(j)];
-        }
+        for (int i = 0; i < NA; ++i)
+            if (tid + i * nthreads < valid_amps) dst[TQ_IO_GOFF(i)] = amp[TQ_IO_SLOT(i)];
     }
 
     // ---- 3. expectation of the Hamiltonian terms that are local to this pass ----
@@ -446,7 +527,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassPar
         if (p.exp_mode == 1) {  // groups that flip more than kRegBits qubits: partner amplitudes via shared memory
             // terms staged in shared memory (re-using the op staging area: 8 KiB = 256 terms)
             ExpTerm* s_terms = reinterpret_cast<ExpTerm*>(s_mat);
-            const int cap = (int)((kMaxWindowOps * kMatStride * sizeof(double2)) / sizeof(ExpTerm));
+            const int cap = (int)((kOpSlots * kMatStride * sizeof(double2)) / sizeof(ExpTerm));
             for (int g = 0; g < p.n_groups; ++g) {
                 const ExpGroup grp = p.groups[g];
                 const uint32_t xs = swz(grp.xlocal);
@@ -594,8 +675,8 @@ __global__ void __launch_bounds__(kMaxThreads) dm_expect_kernel(const double2* _
 
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead) {
     const size_t n_hi = (size_t)1 << (k - lead);
-    return ((size_t)16 << k_eff) + kMaxWindowOps * (kMatStride * sizeof(double2) + sizeof(WinOp)) +
-           32 * sizeof(double) + n_hi * sizeof(uint32_t);
+    return ((size_t)16 << k_eff) + kOpSlots * (kMatStride * sizeof(double2) + sizeof(WinOp)) + 32 * sizeof(double) +
+           3 * kWinSlots * sizeof(uint2) + n_hi * sizeof(uint32_t);
 }
 
 cudaError_t tile_pass_configure() {
