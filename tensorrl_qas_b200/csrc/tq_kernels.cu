@@ -4,6 +4,9 @@
 namespace tq {
 namespace {
 
+#ifndef TQ_MIN_BLOCKS
+#define TQ_MIN_BLOCKS 2
+#endif
 constexpr int NA = 1 << kRegBits;  // amplitudes per thread
 constexpr int kOpSlots = 48;       // ops (+ their 256-byte matrix / term slots) resident in shared memory
 constexpr int kWinSlots = 32;      // window headers resident in shared memory
@@ -34,8 +37,9 @@ __device__ __forceinline__ double2 cfma(double2 m, double2 v, double2 acc) {
 }
 
 // dense 4x4 block on register bits RA < RB (matrix index bit 0 = RA); m = 16 staged entries, row-major.
-// Two groups of four amplitudes per sweep over the matrix: inputs are read in place, the eight outputs are
-// collected in temporaries and written back at the end of the sweep.
+// Two groups of four amplitudes per sweep over the matrix, column by column: each column's four entries update all
+// eight outputs, i.e. sixteen independent FMA chains in flight; inputs are read in place, outputs collected in
+// temporaries and written back at the end of the sweep.
 template <int RA, int RB>
 __device__ __forceinline__ void g_u2(Amps& a, const double2* __restrict__ m) {
     constexpr int O0 = (RA != 0 && RB != 0) ? 0 : (RA != 1 && RB != 1) ? 1 : 2;
@@ -45,16 +49,25 @@ __device__ __forceinline__ void g_u2(Amps& a, const double2* __restrict__ m) {
         const int base0 = (gp ? (1 << O1) : 0), base1 = base0 | (1 << O0);
         double2 o0[4], o1[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            double2 mm = m[i * 4];
-            o0[i] = cmul(mm, a[base0]);
-            o1[i] = cmul(mm, a[base1]);
+        for (int k = 0; k < 4; ++k) {
+            const int off = ((k & 1) ? (1 << RA) : 0) | ((k & 2) ? (1 << RB) : 0);
+            const double2 x0 = a[base0 | off], x1 = a[base1 | off];
 #pragma unroll
-            for (int k = 1; k < 4; ++k) {
-                const int off = ((k & 1) ? (1 << RA) : 0) | ((k & 2) ? (1 << RB) : 0);
-                mm = m[i * 4 + k];
-                o0[i] = cfma(mm, a[base0 | off], o0[i]);
-                o1[i] = cfma(mm, a[base1 | off], o1[i]);
+            for (int i = 0; i < 4; ++i) {
+                const double2 mm = m[i * 4 + k];
+                if (k == 0) {
+                    o0[i] = make_double2(mm.x * x0.x, mm.x * x0.y);
+                    o1[i] = make_double2(mm.x * x1.x, mm.x * x1.y);
+                } else {
+                    o0[i].x = fma(mm.x, x0.x, o0[i].x);
+                    o0[i].y = fma(mm.x, x0.y, o0[i].y);
+                    o1[i].x = fma(mm.x, x1.x, o1[i].x);
+                    o1[i].y = fma(mm.x, x1.y, o1[i].y);
+                }
+                o0[i].x = fma(-mm.y, x0.y, o0[i].x);
+                o0[i].y = fma(mm.y, x0.x, o0[i].y);
+                o1[i].x = fma(-mm.y, x1.y, o1[i].x);
+                o1[i].y = fma(mm.y, x1.x, o1[i].y);
             }
         }
 #pragma unroll
@@ -313,7 +326,7 @@ __device__ __forceinline__ int flat_code(uint32_t w0) {
     }
 }
 
-__global__ void __launch_bounds__(kMaxThreads, 2) tile_pass_kernel(const PassParams p) {
+__global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(const PassParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tile_amps = 1 << p.k_eff;
     const int valid_amps = 1 << p.k;
