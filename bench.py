@@ -187,14 +187,14 @@ def main():
     sim.set_circuit(gl)
     info = sim.plan_info(0)
 
+    from tensorrl_qas_b200.sharding import gather_energies
     p_dev = torch.from_numpy(params).to(dev)
     out = torch.empty(B, dtype=torch.float64, device=dev)
-    gathered = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
 
     def step():
         sim.energies_dev(p_dev, out=out)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+        if world > 1:  # the path's only collective: every rank receives all B * world energies
+            gather_energies(out, B * world)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -262,14 +262,16 @@ def main():
     passes_rw = info["gate_passes"]
     passes_ro = info["expectation_passes"]
     moved = state_bytes * (2 * passes_rw - 1 + passes_ro)  # first pass does not read, last gate pass writes iff followed
-    traffic = None
+    traffic = None  # ncu dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step (B = 64)
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+        tj = json.load(open(tpath))
+        if tj.get("batch") == B:
+            traffic = tj.get("dram_bytes_per_step")
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-        "peak_source": peak_src, "kernel": "tile_pass_kernel",
-        "algorithmic_bytes_per_eval": bytes_eval,
+        "peak_source": peak_src, "kernel": "tile_pass_kernel (5 launches per step, 99.5 % of the step; per-step totals)",
+        "algorithmic_bytes_per_eval": bytes_eval, "algorithmic_bytes_per_step": bytes_eval * B,
         "note": "algorithmic bytes = qulacs' unfused model 16*2^n*(2G+M); the fused passes move far fewer real bytes, "
                 "so frac > 1 is expected -- see hbm_actual",
         "hbm_actual": {"bytes_per_eval_model": moved, "gbs_model": moved * per_gpu_evals_s / 1e9,

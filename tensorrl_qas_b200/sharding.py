@@ -1,0 +1,56 @@
+"""Batch sharding of independent energy evaluations over the GPUs of one box.
+
+Units of work (one parameter set -> one float64) are independent, so the only collective on the path is the
+all-gather of the per-rank energies.  One process per GPU; `torch.distributed` is plumbing (NCCL on GPUs, gloo in the
+CPU tests).  The reference itself is single-process (no distributed code at all)."""
+import numpy as np
+
+
+def shard_bounds(batch, rank, world):
+    """Contiguous slice [lo, hi) of a global batch owned by `rank`; sizes differ by at most one."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank / world size")
+    base, extra = divmod(int(batch), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_energies(local, batch, group=None):
+    """All-gather the ranks' energy slices (torch tensor, CPU for gloo / CUDA for NCCL) into the global [batch] vector.
+    Ragged shards are padded to the largest shard for the collective and trimmed afterwards."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    width = max(shard_bounds(batch, r, world)[1] - shard_bounds(batch, r, world)[0] for r in range(world))
+    lo, hi = shard_bounds(batch, rank, world)
+    if local.numel() != hi - lo:
+        raise ValueError(f"rank {rank} holds {local.numel()} energies, expected {hi - lo}")
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[:hi - lo] = local
+    out = torch.empty(world * width, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    parts = []
+    for r in range(world):
+        a, b = shard_bounds(batch, r, world)
+        parts.append(out[r * width:r * width + (b - a)])
+    return torch.cat(parts)
+
+
+def sharded_energies(evaluate, params, group=None):
+    """Evaluate a global [B][P] parameter matrix: every rank runs `evaluate` (-> numpy [b]) on its slice of the rows and
+    all ranks receive the full [B] vector.  `evaluate` is e.g. `Simulator.energies`."""
+    import torch
+    import torch.distributed as dist
+    params = np.asarray(params, dtype=np.float64)
+    batch = params.shape[0]
+    if not (dist.is_available() and dist.is_initialized()):
+        return np.asarray(evaluate(params))
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(batch, rank, world)
+    local = np.asarray(evaluate(params[lo:hi]), dtype=np.float64) if hi > lo else np.zeros(0)
+    t = torch.from_numpy(local.copy())
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    return gather_energies(t, batch, group).cpu().numpy()
