@@ -302,7 +302,7 @@ int compile_plan(tq_handle h, int which) {
         for (int wi : wide) wide_groups.push_back(groups_of_pass[i][wi]);
         offs[i].windows = append(p.windows.data(), p.windows.size() * sizeof(Window));
         offs[i].wops = append(p.wops.data(), p.wops.size() * sizeof(WinOp));
-        offs[i].eterms = append(p.eterms.data(), p.eterms.size() * sizeof(ExpTermW));
+        offs[i].eterms = append(p.eterms.data(), p.eterms.size() * sizeof(EUnit));
         std::vector<ExpGroup> eg;
         std::vector<ExpTerm> et;
         for (int g : wide_groups) {
@@ -352,7 +352,7 @@ int compile_plan(tq_handle h, int which) {
         dp.proto.n_wops = (int)passes[i].wops.size();
         dp.proto.n_mats = plan.n_mats;
         dp.proto.n_gate_windows = passes[i].n_gate_windows;
-        dp.proto.eterms = (const ExpTermW*)(base + offs[i].eterms);
+        dp.proto.eterms = (const EUnit*)(base + offs[i].eterms);
         dp.n_groups = offs[i].n_groups;
         if (which != 1) {
             if (single_tile) {

@@ -212,80 +212,76 @@ __device__ __forceinline__ void exec_depol2(Amps& a, int rows, int cols, double 
     else g_depol2<0, 3, 1, 2>(a, p);
 }
 
-// ---- expectation of one flip-mask group on registers: XR = flip mask over the register bits -----------------------
-// sum over this thread's 16 amplitudes of Re( f(j) conj(psi[j ^ x]) psi[j] ),  f(j) = sum_t w_t (-1)^{parity(j & z_t)}
-template <int XR>
-__device__ __forceinline__ double g_exp(const Amps& a, uint64_t ctx, const ExpTermW* __restrict__ terms, int nt) {
+// ---- expectation on registers (see W_EXPC / W_EXPD in tq_plan.h) ------------------------------------------------
+// one class of an off-diagonal group: XR = flip mask over the register bits; d[0] = Z/Y mask outside the window,
+// d[1..8] = (cA, cB) per register pair
+template <int XR, bool IMAG>
+__device__ __forceinline__ double g_expc(const Amps& a, uint64_t ctx, const double2* __restrict__ d) {
+    double sum = 0.0;
+    int q = 0;
+#pragma unroll
+    for (int r = 0; r < NA; ++r) {
+        if ((r ^ XR) > r) {
+            const double2 v = a[r], w = a[r ^ XR], c = d[1 + q];
+            sum = fma(c.x, w.x * v.x + w.y * v.y, sum);                 // cA * Re(conj(psi[r^x]) psi[r])
+            if (IMAG) sum = fma(-c.y, w.x * v.y - w.y * v.x, sum);      // -cB * Im(...)
+            ++q;
+        }
+    }
+    const uint64_t zphys = (uint64_t)__double_as_longlong(d[0].x);
+    return (__popcll(ctx & zphys) & 1) ? -sum : sum;
+}
+
+// all diagonal terms: Walsh-Hadamard transform of the 16 probabilities, then one signed weight sum per class
+__device__ __forceinline__ double g_expd(const Amps& a, uint64_t ctx, const double2* __restrict__ head,
+                                         const double2* __restrict__ terms) {
+    double n[NA];
+#pragma unroll
+    for (int r = 0; r < NA; ++r) n[r] = a[r].x * a[r].x + a[r].y * a[r].y;
+#pragma unroll
+    for (int bitp = 0; bitp < kRegBits; ++bitp)
+#pragma unroll
+        for (int r = 0; r < NA; ++r)
+            if (!((r >> bitp) & 1)) {
+                const double x = n[r], y = n[r | (1 << bitp)];
+                n[r] = x + y;
+                n[r | (1 << bitp)] = x - y;
+            }
+    const unsigned short* cnt = reinterpret_cast<const unsigned short*>(head);
     double total = 0.0;
-    if (XR == 0) {
-        double nrm[NA];
+    int idx = 0;
 #pragma unroll
-        for (int r = 0; r < NA; ++r) nrm[r] = a[r].x * a[r].x + a[r].y * a[r].y;
-        for (int t = 0; t < nt; ++t) {
-            const ExpTermW term = terms[t];
-            const uint32_t m = term.sgnmask;
-            double s = 0.0;
-#pragma unroll
-            for (int r = 0; r < NA; ++r) s += ((m >> r) & 1u) ? -nrm[r] : nrm[r];
-            const double w = (__popcll(ctx & term.zphys) & 1) ? -term.wre : term.wre;
-            total = fma(w, s, total);
+    for (int zr = 0; zr < NA; ++zr) {
+        const int c = cnt[zr];
+        double s = 0.0;
+        for (int i = 0; i < c; ++i) {
+            const double2 t = __ldg(terms + idx + i);
+            s += (__popcll(ctx & (uint64_t)__double_as_longlong(t.x)) & 1) ? -t.y : t.y;
         }
-    } else {
-        constexpr int NP = NA / 2;
-        double px[NP], py[NP];  // conj(psi[r ^ x]) * psi[r] for the pairs r < r ^ x, times two
-        {
-            int q = 0;
-#pragma unroll
-            for (int r = 0; r < NA; ++r) {
-                if ((r ^ XR) > r) {
-                    const double2 v = a[r], w = a[r ^ XR];
-                    px[q] = 2.0 * (w.x * v.x + w.y * v.y);
-                    py[q] = 2.0 * (w.x * v.y - w.y * v.x);
-                    ++q;
-                }
-            }
-        }
-        for (int t = 0; t < nt; ++t) {
-            const ExpTermW term = terms[t];
-            const uint32_t m = term.sgnmask;
-            double sa = 0.0, sb = 0.0;
-            int q = 0;
-#pragma unroll
-            for (int r = 0; r < NA; ++r) {
-                if ((r ^ XR) > r) {
-                    const bool sr = (m >> r) & 1u, sx = (m >> (r ^ XR)) & 1u;
-                    sa += (sr == sx) ? (sr ? -px[q] : px[q]) : 0.0;   // (sigma(r) + sigma(r^x)) Re p
-                    sb += (sr != sx) ? (sr ? -py[q] : py[q]) : 0.0;   // (sigma(r) - sigma(r^x)) Im p
-                    ++q;
-                }
-            }
-            const bool neg = __popcll(ctx & term.zphys) & 1;
-            const double wre = neg ? -term.wre : term.wre, wim = neg ? -term.wim : term.wim;
-            // Re(f(r) p) + Re(f(r^x) conj(p)) = wre * px * (s_r + s_x) - wim * py * (s_r - s_x), s = +-1
-            total += wre * sa - wim * sb;
-        }
+        idx += c;
+        total = fma(s, n[zr], total);
     }
     return total;
 }
 
-__device__ __forceinline__ double exec_exp(const Amps& a, uint64_t ctx, int xr, const ExpTermW* terms, int nt) {
+template <bool IMAG>
+__device__ __forceinline__ double exec_expc(const Amps& a, uint64_t ctx, int xr, const double2* d) {
     switch (xr) {
-    case 0: return g_exp<0>(a, ctx, terms, nt);
-    case 1: return g_exp<1>(a, ctx, terms, nt);
-    case 2: return g_exp<2>(a, ctx, terms, nt);
-    case 3: return g_exp<3>(a, ctx, terms, nt);
-    case 4: return g_exp<4>(a, ctx, terms, nt);
-    case 5: return g_exp<5>(a, ctx, terms, nt);
-    case 6: return g_exp<6>(a, ctx, terms, nt);
-    case 7: return g_exp<7>(a, ctx, terms, nt);
-    case 8: return g_exp<8>(a, ctx, terms, nt);
-    case 9: return g_exp<9>(a, ctx, terms, nt);
-    case 10: return g_exp<10>(a, ctx, terms, nt);
-    case 11: return g_exp<11>(a, ctx, terms, nt);
-    case 12: return g_exp<12>(a, ctx, terms, nt);
-    case 13: return g_exp<13>(a, ctx, terms, nt);
-    case 14: return g_exp<14>(a, ctx, terms, nt);
-    default: return g_exp<15>(a, ctx, terms, nt);
+    case 1: return g_expc<1, IMAG>(a, ctx, d);
+    case 2: return g_expc<2, IMAG>(a, ctx, d);
+    case 3: return g_expc<3, IMAG>(a, ctx, d);
+    case 4: return g_expc<4, IMAG>(a, ctx, d);
+    case 5: return g_expc<5, IMAG>(a, ctx, d);
+    case 6: return g_expc<6, IMAG>(a, ctx, d);
+    case 7: return g_expc<7, IMAG>(a, ctx, d);
+    case 8: return g_expc<8, IMAG>(a, ctx, d);
+    case 9: return g_expc<9, IMAG>(a, ctx, d);
+    case 10: return g_expc<10, IMAG>(a, ctx, d);
+    case 11: return g_expc<11, IMAG>(a, ctx, d);
+    case 12: return g_expc<12, IMAG>(a, ctx, d);
+    case 13: return g_expc<13, IMAG>(a, ctx, d);
+    case 14: return g_expc<14, IMAG>(a, ctx, d);
+    default: return g_expc<15, IMAG>(a, ctx, d);
     }
 }
 
@@ -309,7 +305,7 @@ __device__ __forceinline__ double block_sum(double v, double* s_red, int tid, in
 #define TQ_IO_GOFF(i) (io_goff | TQ_SEL4(i, ig0, ig1, ig2, ig3, |))
 
 // flat dispatch ids (computed while staging a window's ops; the planner's WinOp codes stay symbolic)
-enum : int { F_U2 = 0, F_U1 = 6, F_D1 = 10, F_D1_OUT = 14, F_CX_WW = 15, F_CX_OW = 31, F_DEPOL1 = 35, F_DEPOL2 = 36, F_EXP = 37 };
+enum : int { F_U2 = 0, F_U1 = 6, F_D1 = 10, F_D1_OUT = 14, F_CX_WW = 15, F_CX_OW = 31, F_DEPOL1 = 35, F_DEPOL2 = 36, F_EXPC = 37, F_EXPC_IMAG = 38, F_EXPD = 39 };
 
 __device__ __forceinline__ int flat_code(uint32_t w0) {
     const int code = w0 & 0xff, rb = (w0 >> 8) & 0xf, rb2 = (w0 >> 12) & 0xf;
@@ -322,7 +318,8 @@ __device__ __forceinline__ int flat_code(uint32_t w0) {
     case W_CX_OW: return F_CX_OW + rb;
     case W_DEPOL1: return F_DEPOL1;
     case W_DEPOL2: return F_DEPOL2;
-    default: return F_EXP;
+    case W_EXPC: return (rb2 & 1) ? F_EXPC_IMAG : F_EXPC;
+    default: return F_EXPD;
     }
 }
 
@@ -387,9 +384,9 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
                 wo.w0 = (wo.w0 & ~0xffu) | (uint32_t)flat_code(wo.w0);
                 s_wops[oi] = wo;
             }
-            if (code == W_EXP) {  // the op's terms (32 bytes each) ride in its matrix slot
-                if (e < 2 * (int)((wo.w0 >> 16) & 0xff))
-                    s_mat[oi * kMatStride + e] = reinterpret_cast<const double2*>(p.eterms)[(size_t)wo.t * 2 + e];
+            if (code >= W_EXPC) {  // expectation data (qsel 16-byte units) rides in the op's matrix slot
+                if (e < (int)((wo.w0 >> 16) & 0xff))
+                    s_mat[oi * kMatStride + e] = reinterpret_cast<const double2*>(p.eterms)[(size_t)wo.t + e];
             } else if (code <= W_D1_OUT && (code == W_U2 || e < 4)) {
                 int src = e;
                 if (code == W_U2 && (flags & FLAG_SWAP)) {  // matrix written for the other qubit order
@@ -511,7 +508,9 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
                 case F_CX_OW + 3: g_x_if<3>(a, (bool)((ctx >> qsel) & 1ull)); break;
                 case F_DEPOL1: exec_depol1(a, rb, rb2, wo.fixed); break;
                 case F_DEPOL2: exec_depol2(a, rb, rb2, wo.fixed); break;
-                case F_EXP: acc += exec_exp(a, ctx, rb, reinterpret_cast<const ExpTermW*>(m), qsel); break;
+                case F_EXPC: acc += exec_expc<false>(a, ctx, rb, m); break;
+                case F_EXPC_IMAG: acc += exec_expc<true>(a, ctx, rb, m); break;
+                case F_EXPD: acc += g_expd(a, ctx, m, reinterpret_cast<const double2*>(p.eterms) + wo.t + 2); break;
                 default: break;
                 }
             }

@@ -46,7 +46,7 @@ struct PassParams {
     double2* dst;  // nullptr: tile is not written back
     const Window* windows;
     int n_windows, n_gate_windows;   // expectation windows follow the gate windows
-    const ExpTermW* eterms;
+    const EUnit* eterms;
     const WinOp* wops;
     int n_wops;
     const double2* mats;   // [batch][n_mats][kMatStride] block matrices of this call's elements (prep kernel output)

@@ -2,6 +2,7 @@
 #include "tq_plan.h"
 
 #include <algorithm>
+#include <cstring>
 
 #include "../../include/tqsim.h"
 
@@ -500,29 +501,71 @@ void append_expectation_windows(Pass& p, const std::vector<ExpGroupIn>& groups, 
         for (int r = 0; r < kRegBits; ++r)
             if (w.wpos[r] < k_real) wphys |= bit(p.local[w.wpos[r]]);
         std::vector<WinOp> ops;
+        auto unit_dd = [](double a, double b) { EUnit u; memcpy(&u.w[0], &a, 8); memcpy(&u.w[1], &b, 8); return u; };
+        auto zr_of = [&](uint64_t z) {
+            uint32_t zr = 0;
+            for (int r = 0; r < kRegBits; ++r)
+                if (w.wpos[r] < k_real && ((z >> p.local[w.wpos[r]]) & 1)) zr |= 1u << r;
+            return zr;
+        };
         for (int g : mine) {
             uint32_t xr = 0;
             for (int r = 0; r < kRegBits; ++r)
                 if ((xl[g] >> w.wpos[r]) & 1) xr |= 1u << r;
             const auto& terms = groups[g].terms;
-            for (size_t t0 = 0; t0 < terms.size(); t0 += kExpChunk) {
-                const int nt = (int)std::min<size_t>(kExpChunk, terms.size() - t0);
+            if (xr == 0) {  // diagonal terms: one op, terms sorted by their Z bits inside the window
+                std::vector<std::vector<const ExpTermIn*>> cls(1u << kRegBits);
+                for (const ExpTermIn& in : terms) cls[zr_of(in.z)].push_back(&in);
                 WinOp o{};
-                o.w0 = winop_pack(W_EXP, (int)xr, 0, nt, 0);
+                o.w0 = winop_pack(W_EXPD, 0, 0, 2, 0);
                 o.t = (int32_t)p.eterms.size();
-                for (int i = 0; i < nt; ++i) {
-                    const ExpTermIn& in = terms[t0 + i];
-                    ExpTermW e{};
-                    e.zphys = in.z & ~wphys;
-                    uint32_t zr = 0;
-                    for (int r = 0; r < kRegBits; ++r)
-                        if (w.wpos[r] < k_real && ((in.z >> p.local[w.wpos[r]]) & 1)) zr |= 1u << r;
-                    for (uint32_t r = 0; r < (1u << kRegBits); ++r)
-                        if (__builtin_parity(r & zr)) e.sgnmask |= 1u << r;
-                    e.wre = in.wre;
-                    e.wim = in.wim;
-                    p.eterms.push_back(e);
+                EUnit cnt[2] = {};
+                for (uint32_t zr = 0; zr < (1u << kRegBits); ++zr) {
+                    const uint64_t c = std::min<size_t>(cls[zr].size(), 0xffff);
+                    cnt[zr / 8].w[(zr % 8) / 4] |= c << (16 * (zr % 4));
                 }
+                p.eterms.push_back(cnt[0]);
+                p.eterms.push_back(cnt[1]);
+                for (uint32_t zr = 0; zr < (1u << kRegBits); ++zr)
+                    for (size_t i = 0; i < std::min<size_t>(cls[zr].size(), 0xffff); ++i) {
+                        EUnit u;
+                        u.w[0] = cls[zr][i]->z & ~wphys;
+                        memcpy(&u.w[1], &cls[zr][i]->wre, 8);  // Re(w |psi|^2): only the real part contributes
+                        p.eterms.push_back(u);
+                    }
+                ops.push_back(o);
+                continue;
+            }
+            // off-diagonal group: classes = distinct Z/Y masks outside the window
+            std::vector<uint64_t> keys;
+            for (const ExpTermIn& in : terms) {
+                const uint64_t key = in.z & ~wphys;
+                if (std::find(keys.begin(), keys.end(), key) == keys.end()) keys.push_back(key);
+            }
+            for (uint64_t key : keys) {
+                double fre[1 << kRegBits] = {}, fim[1 << kRegBits] = {};
+                for (const ExpTermIn& in : terms) {
+                    if ((in.z & ~wphys) != key) continue;
+                    const uint32_t zr = zr_of(in.z);
+                    for (uint32_t r = 0; r < (1u << kRegBits); ++r) {
+                        const double sg = __builtin_parity(r & zr) ? -1.0 : 1.0;
+                        fre[r] += sg * in.wre;
+                        fim[r] += sg * in.wim;
+                    }
+                }
+                WinOp o{};
+                o.t = (int32_t)p.eterms.size();
+                EUnit head{};
+                head.w[0] = key;
+                p.eterms.push_back(head);
+                bool imag = false;
+                for (uint32_t r = 0; r < (1u << kRegBits); ++r) {
+                    if ((r ^ xr) < r) continue;
+                    const double ca = fre[r] + fre[r ^ xr], cb = fim[r] - fim[r ^ xr];
+                    imag = imag || cb != 0.0;
+                    p.eterms.push_back(unit_dd(ca, cb));
+                }
+                o.w0 = winop_pack(W_EXPC, (int)xr, imag ? 1 : 0, 9, 0);
                 ops.push_back(o);
             }
         }

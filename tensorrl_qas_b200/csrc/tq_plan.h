@@ -75,18 +75,18 @@ enum : int32_t {    // WinOp code; rb / rb2 are register-bit indices inside the 
     W_CX_OW = 5,    // qsel = physical control bit, rb = target
     W_DEPOL1 = 6,   // rb = row bit, rb2 = column bit, fixed = p
     W_DEPOL2 = 7,   // window = {row a, row b, col a, col b}: rb = ra | rb << 2, rb2 = ca | cb << 2
-    W_EXP = 8,      // expectation of (a chunk of) one flip-mask group whose flips are window bits: rb = flip mask
-                    // over the register bits, qsel = number of terms (<= kExpChunk), t = first term (Pass::eterms)
+    W_EXPC = 8,     // expectation, flip mask rb != 0 over the register bits: the terms of the group that share the same
+                    // Z/Y bits outside the window ("class").  Data (9 units at Pass::eterms[t]): unit 0 = those outside
+                    // bits (physical mask), units 1..8 = (cA[q], cB[q]) for the 8 register pairs r < r ^ rb:
+                    //   E += sign(ctx) * sum_q (cA[q] Re p_q - cB[q] Im p_q),  p_q = conj(psi[r ^ rb]) psi[r];
+                    // rb2 bit 0: some cB != 0
+    W_EXPD = 9,     // expectation of all diagonal terms (flip mask 0): units 0..1 at eterms[t] = 16 uint16 counts of the
+                    // terms per class zr (= Z bits inside the window), then one unit (outside Z mask, weight) per term,
+                    // sorted by class:  E += sum_zr WHT(|psi|^2)[zr] * sum_{t in zr} w_t sign_t(ctx)
 };
-constexpr int kExpChunk = 8;   // terms per W_EXP op (they are staged in the op's 256-byte matrix slot)
 constexpr int kWinFlagReadOnly = 1;  // Window::tpos[11]: the window does not change the amplitudes
 
-struct ExpTermW {   // 32 bytes: one Pauli term as seen from an expectation window
-    uint64_t zphys;     // Z/Y bits, physical; the thread's context index has the window bits cleared
-    uint32_t sgnmask;   // bit r = parity(register index r & Z/Y bits inside the window)
-    uint32_t pad;
-    double wre, wim;    // coefficient times i^{#Y}
-};
+struct EUnit { uint64_t w[2]; };   // 16 bytes of expectation data (bit patterns of masks / doubles)
 struct ExpTermIn { uint64_t z; double wre, wim; };
 struct ExpGroupIn { uint64_t x; std::vector<ExpTermIn> terms; };
 struct WinOp {      // 16 bytes
@@ -116,7 +116,7 @@ struct Pass {
     std::vector<Window> windows;  // register-window schedule of `ops` (+ expectation windows after them)
     std::vector<WinOp> wops;
     int n_gate_windows = 0;       // windows [0, n_gate_windows) change the state, the rest only read it
-    std::vector<ExpTermW> eterms; // terms of the expectation windows
+    std::vector<EUnit> eterms;    // data of the expectation-window ops (see W_EXPC / W_EXPD)
 };
 
 struct PlanOptions {
