@@ -484,7 +484,7 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 if (plan.slots == 1) { pp.partial = out + b0; pp.partial_ld = 1; pp.partial_off = 0; }
                 else { pp.partial = h->d_partial; pp.partial_ld = plan.slots; }
             }
-            launch_tile_pass(pp, bc, dp.threads, stream);
+            launch_tile_pass(pp, bc, dp.threads, dm, stream);
             ++h->launches;
             rc = check_launch(h, "tile_pass_kernel");
             if (rc) return rc;

@@ -314,7 +314,6 @@ __device__ __forceinline__ int flat_code(uint32_t w0) {
     case W_U1: return F_U1 + rb;
     case W_D1: return F_D1 + rb;
     case W_D1_OUT: return F_D1_OUT;
-    case W_CX_WW: return F_CX_WW + rb * 4 + rb2;
     case W_CX_OW: return F_CX_OW + rb;
     case W_DEPOL1: return F_DEPOL1;
     case W_DEPOL2: return F_DEPOL2;
@@ -323,6 +322,7 @@ __device__ __forceinline__ int flat_code(uint32_t w0) {
     }
 }
 
+template <bool DM>
 __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(const PassParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tile_amps = 1 << p.k_eff;
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
     const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
     const bool active = tid < (tile_amps >> kRegBits);
     const int n_tbits = p.k_eff - kRegBits;
-    const int n_run = p.exp_mode == 1 ? p.n_windows : p.n_gate_windows;
+    const int n_run = (!DM && p.exp_mode == 1) ? p.n_windows : p.n_gate_windows;
 
     // ops [staged_begin, staged_end) of the pass live in shared memory with their block matrices / term lists
     int staged_begin = 0, staged_end = 0;
@@ -426,53 +426,55 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
     uint32_t slot_t = 0, ws0 = 0, ws1 = 0, ws2 = 0, ws3 = 0;
     double acc = 0.0;            // this thread's share of the energy (expectation windows)
     bool regs_dirty = false;     // registers hold amplitudes that shared memory does not have yet
-    for (int w = 0; w < n_run; ++w) {
-        // window header: 24 bytes = wpos[4] | tpos[12] | op_begin | op_end
-        uint2 h0, h1, h2;
-        if (w < kWinSlots) {
-            if (w == 0) __syncthreads();  // headers (and the tile) staged above
-            h0 = s_win[3 * w]; h1 = s_win[3 * w + 1]; h2 = s_win[3 * w + 2];
-        } else {
-            const uint2* wraw = reinterpret_cast<const uint2*>(p.windows + w);
-            h0 = __ldg(wraw); h1 = __ldg(wraw + 1); h2 = __ldg(wraw + 2);
-        }
-        const uint32_t wpos4 = h0.x;
-        const uint64_t tpos8 = (uint64_t)h0.y | ((uint64_t)h1.x << 32);  // thread bits 0..7
-        const bool read_only = (h1.y >> 24) & kWinFlagReadOnly;          // tpos[11]
-        const int op_begin = (int)h2.x, op_end = (int)h2.y;
-        if (w > 0) {
-            __syncthreads();  // every thread has finished the previous window (its loads and its staged ops)
-            if (regs_dirty && active) {
-#pragma unroll
-                for (int r = 0; r < NA; ++r) amp[TQ_SLOT(r)] = a[r];
-            }
-        }
-        regs_dirty = !read_only;
-        // ops beyond the staged range (long passes only): restage from this window on; no amplitudes are live in
-        // registers here and every thread is past the previous window's ops (uniform branch)
-        if (op_end > staged_end) {
-            if (w == 0) __syncthreads();
-            stage_ops(op_begin);
-        }
-        __syncthreads();
-        // this thread's tile index with the window bits cleared, and the matching physical index
-        uint32_t jt = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (i < n_tbits && ((tid >> i) & 1)) jt |= 1u << ((uint32_t)(tpos8 >> (8 * i)) & 0xffu);
-        const uint64_t ctx = tile_base | (jt < (uint32_t)valid_amps ? TQ_PHYS(jt) : 0u);
-        slot_t = swz(jt);
-        ws0 = swz(1u << (wpos4 & 0xffu));
-        ws1 = swz(1u << ((wpos4 >> 8) & 0xffu));
-        ws2 = swz(1u << ((wpos4 >> 16) & 0xffu));
-        ws3 = swz(1u << (wpos4 >> 24));
+    // entering window w: flush the previous window's registers if they changed, (re)stage ops if needed, compute this
+    // thread's layout (slot_t, ws*, ctx) and load its 16 amplitudes.  Defines op_begin / op_end / ctx in scope.
+#define TQ_ENTER_WINDOW(w)                                                                                         \
+    uint2 h0, h1, h2;                                                                                              \
+    if ((w) < kWinSlots) {                                                                                         \
+        if ((w) == 0) __syncthreads(); /* headers (and the tile) staged above */                                   \
+        h0 = s_win[3 * (w)]; h1 = s_win[3 * (w) + 1]; h2 = s_win[3 * (w) + 2];                                     \
+    } else {                                                                                                       \
+        const uint2* wraw = reinterpret_cast<const uint2*>(p.windows + (w));                                       \
+        h0 = __ldg(wraw); h1 = __ldg(wraw + 1); h2 = __ldg(wraw + 2);                                              \
+    }                                                                                                              \
+    const uint32_t wpos4 = h0.x;                                                                                   \
+    const uint64_t tpos8 = (uint64_t)h0.y | ((uint64_t)h1.x << 32); /* thread bits 0..7 */                         \
+    const bool read_only = (h1.y >> 24) & kWinFlagReadOnly;        /* tpos[11] */                                  \
+    const int op_begin = (int)h2.x, op_end = (int)h2.y;                                                            \
+    if ((w) > 0) {                                                                                                 \
+        __syncthreads(); /* every thread has finished the previous window (its loads and its staged ops) */        \
+        if (regs_dirty && active) {                                                                                \
+            _Pragma("unroll") for (int r = 0; r < NA; ++r) amp[TQ_SLOT(r)] = a[r];                                 \
+        }                                                                                                          \
+    }                                                                                                              \
+    regs_dirty = !read_only;                                                                                       \
+    /* ops beyond the staged range (long passes only): restage from this window on (uniform branch) */             \
+    if (op_end > staged_end) {                                                                                     \
+        if ((w) == 0) __syncthreads();                                                                             \
+        stage_ops(op_begin);                                                                                       \
+    }                                                                                                              \
+    __syncthreads();                                                                                               \
+    uint32_t jt = 0;                                                                                               \
+    _Pragma("unroll") for (int i = 0; i < 8; ++i)                                                                  \
+        if (i < n_tbits && ((tid >> i) & 1)) jt |= 1u << ((uint32_t)(tpos8 >> (8 * i)) & 0xffu);                   \
+    const uint64_t ctx = tile_base | (jt < (uint32_t)valid_amps ? TQ_PHYS(jt) : 0u);                               \
+    slot_t = swz(jt);                                                                                              \
+    ws0 = swz(1u << (wpos4 & 0xffu));                                                                              \
+    ws1 = swz(1u << ((wpos4 >> 8) & 0xffu));                                                                       \
+    ws2 = swz(1u << ((wpos4 >> 16) & 0xffu));                                                                      \
+    ws3 = swz(1u << (wpos4 >> 24));                                                                                \
+    if (active) {                                                                                                  \
+        _Pragma("unroll") for (int r = 0; r < NA; ++r) a[r] = amp[TQ_SLOT(r)];                                     \
+    }
+
+    // ---- 2a. gate windows ----
+    for (int w = 0; w < p.n_gate_windows; ++w) {
+        TQ_ENTER_WINDOW(w)
         if (active) {
-#pragma unroll
-            for (int r = 0; r < NA; ++r) a[r] = amp[TQ_SLOT(r)];
             for (int o = op_begin - staged_begin; o < op_end - staged_begin; ++o) {
                 const WinOp wo = s_wops[o];
                 const double2* m = s_mat + o * kMatStride;
-                const int fc = wo.w0 & 0xff, rb = (wo.w0 >> 8) & 0xf, rb2 = (wo.w0 >> 12) & 0xf;
+                const int fc = wo.w0 & 0xff;
                 const int qsel = (wo.w0 >> 16) & 0xff;
                 switch (fc) {
                 case F_U2 + 0: g_u2<0, 1>(a, m); break;
@@ -490,28 +492,33 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
                 case F_D1 + 2: g_d1<2>(a, m); break;
                 case F_D1 + 3: g_d1<3>(a, m); break;
                 case F_D1_OUT: g_scale(a, ((ctx >> qsel) & 1ull) ? m[3] : m[0]); break;
-                case F_CX_WW + 1: g_cx<0, 1>(a); break;
-                case F_CX_WW + 2: g_cx<0, 2>(a); break;
-                case F_CX_WW + 3: g_cx<0, 3>(a); break;
-                case F_CX_WW + 4: g_cx<1, 0>(a); break;
-                case F_CX_WW + 6: g_cx<1, 2>(a); break;
-                case F_CX_WW + 7: g_cx<1, 3>(a); break;
-                case F_CX_WW + 8: g_cx<2, 0>(a); break;
-                case F_CX_WW + 9: g_cx<2, 1>(a); break;
-                case F_CX_WW + 11: g_cx<2, 3>(a); break;
-                case F_CX_WW + 12: g_cx<3, 0>(a); break;
-                case F_CX_WW + 13: g_cx<3, 1>(a); break;
-                case F_CX_WW + 14: g_cx<3, 2>(a); break;
                 case F_CX_OW + 0: g_x_if<0>(a, (bool)((ctx >> qsel) & 1ull)); break;
                 case F_CX_OW + 1: g_x_if<1>(a, (bool)((ctx >> qsel) & 1ull)); break;
                 case F_CX_OW + 2: g_x_if<2>(a, (bool)((ctx >> qsel) & 1ull)); break;
                 case F_CX_OW + 3: g_x_if<3>(a, (bool)((ctx >> qsel) & 1ull)); break;
-                case F_DEPOL1: exec_depol1(a, rb, rb2, wo.fixed); break;
-                case F_DEPOL2: exec_depol2(a, rb, rb2, wo.fixed); break;
-                case F_EXPC: acc += exec_expc<false>(a, ctx, rb, m); break;
-                case F_EXPC_IMAG: acc += exec_expc<true>(a, ctx, rb, m); break;
-                case F_EXPD: acc += g_expd(a, ctx, m, reinterpret_cast<const double2*>(p.eterms) + wo.t + 2); break;
-                default: break;
+                default:
+                    if (DM) {
+                        const int rb = (wo.w0 >> 8) & 0xf, rb2 = (wo.w0 >> 12) & 0xf;
+                        if (fc == F_DEPOL1) exec_depol1(a, rb, rb2, wo.fixed);
+                        else if (fc == F_DEPOL2) exec_depol2(a, rb, rb2, wo.fixed);
+                    }
+                    break;
+                }
+            }
+        }
+    }
+    // ---- 2b. expectation windows (read-only) ----
+    if (!DM && p.exp_mode == 1) {
+        for (int w = p.n_gate_windows; w < p.n_windows; ++w) {
+            TQ_ENTER_WINDOW(w)
+            if (active) {
+                for (int o = op_begin - staged_begin; o < op_end - staged_begin; ++o) {
+                    const WinOp wo = s_wops[o];
+                    const double2* m = s_mat + o * kMatStride;
+                    const int fc = wo.w0 & 0xff, rb = (wo.w0 >> 8) & 0xf;
+                    if (fc == F_EXPC) acc += exec_expc<false>(a, ctx, rb, m);
+                    else if (fc == F_EXPC_IMAG) acc += exec_expc<true>(a, ctx, rb, m);
+                    else acc += g_expd(a, ctx, m, reinterpret_cast<const double2*>(p.eterms) + wo.t + 2);
                 }
             }
         }
@@ -692,12 +699,16 @@ size_t tile_pass_smem_bytes(int k_eff, int k, int lead) {
 }
 
 cudaError_t tile_pass_configure() {
-    return cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tile_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tile_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
 
-void launch_tile_pass(const PassParams& p, int batch, int threads, cudaStream_t stream) {
+void launch_tile_pass(const PassParams& p, int batch, int threads, bool density, cudaStream_t stream) {
     const unsigned grid = (unsigned)batch << p.n_nl;
-    tile_pass_kernel<<<grid, threads, tile_pass_smem_bytes(p.k_eff, p.k, p.lead), stream>>>(p);
+    const size_t smem = tile_pass_smem_bytes(p.k_eff, p.k, p.lead);
+    if (density) tile_pass_kernel<true><<<grid, threads, smem, stream>>>(p);
+    else tile_pass_kernel<false><<<grid, threads, smem, stream>>>(p);
 }
 
 void launch_prep_matrices(const MatDesc* descs, const MatGate* prog, int n_mats, int batch, const double* params,

@@ -64,7 +64,7 @@ struct PassParams {
 
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead);
 cudaError_t tile_pass_configure();  // opt in to > 48 KiB dynamic shared memory
-void launch_tile_pass(const PassParams& p, int batch, int threads, cudaStream_t stream);
+void launch_tile_pass(const PassParams& p, int batch, int threads, bool density, cudaStream_t stream);
 
 // block matrices of every (element, fused block): mats[(b * n_mats + m) * kMatStride ...]
 void launch_prep_matrices(const MatDesc* descs, const MatGate* prog, int n_mats, int batch, const double* params,

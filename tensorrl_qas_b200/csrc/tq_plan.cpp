@@ -288,9 +288,17 @@ void lower(const std::vector<Blk>& blks, int n, bool density, CompiledCircuit& c
                 ops.push_back(a);
             }
         } else if (b.type == B_CX) {
+            // a lone CNOT also gets a (constant) 4x4 matrix: when its control ends up inside the register window it
+            // runs as a dense block, otherwise as a predicated swap that only reads the control bit
+            MatDesc md{(int32_t)cc.prog.size(), 0, 2, 0};
+            cc.prog.push_back(MatGate{MG_CX, b.q0 < b.q1 ? 0 : 1, -1, 0, 0.0});
+            md.end = (int32_t)cc.prog.size();
+            const int32_t mat = (int32_t)cc.mats.size();
+            cc.mats.push_back(md);
             for (int side = 0; side < (density ? 2 : 1); ++side) {
                 const int sh = side ? n : 0;
                 AOp a;
+                a.t = mat;
                 a.op = OP_CNOT;
                 a.q[0] = b.q0 + sh;
                 a.q[1] = b.q1 + sh;
@@ -409,8 +417,12 @@ void schedule_windows(Pass& p) {
                 break;
             case OP_D1_NL: o.w0 = winop_pack(W_D1_OUT, 0, 0, d.a, d.flags); break;
             case OP_CNOT:
-                if (rb_of[d.a] >= 0) o.w0 = winop_pack(W_CX_WW, rb_of[d.a], rb_of[d.b], 0, 0);
-                else o.w0 = winop_pack(W_CX_OW, rb_of[d.b], 0, phys(d.a), 0);
+                if (rb_of[d.a] >= 0) {  // control in the window: dense block with the CNOT's matrix (index bit 0 =
+                                        // the physically lower qubit, i.e. the lower tile position)
+                    const int r0 = rb_of[std::min(d.a, d.b)], r1 = rb_of[std::max(d.a, d.b)];
+                    if (r0 < r1) o.w0 = winop_pack(W_U2, r0, r1, 0, 0);
+                    else o.w0 = winop_pack(W_U2, r1, r0, 0, FLAG_SWAP);
+                } else o.w0 = winop_pack(W_CX_OW, rb_of[d.b], 0, phys(d.a), 0);
                 break;
             case OP_CNOT_NL: o.w0 = winop_pack(W_CX_OW, rb_of[d.b], 0, d.a, 0); break;
             case OP_DEPOL1_DM: o.w0 = winop_pack(W_DEPOL1, rb_of[d.a], rb_of[d.b], 0, 0); break;

@@ -134,6 +134,8 @@ def run_plan_windows(plan, nbits, params, init=None, codes=None):
                     M = np.conj(mats[t]) if flags & FLAG_CONJ else mats[t]
                 if code == W_U2:
                     assert rb < rb2
+                    if M.shape != (4, 4):
+                        raise AssertionError("W_U2 needs a two-qubit matrix")
                     if flags & FLAG_SWAP:  # the block's qubit 0 sits on rb2
                         vec = apply_2q(vec, nbits, phys[rb2], phys[rb], M)
                     else:
