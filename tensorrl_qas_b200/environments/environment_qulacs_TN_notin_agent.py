@@ -1,0 +1,15 @@
+"""Drop-in for the reference's environments/environment_qulacs_TN_notin_agent.py -- noiseless, MPS state loaded before the agent's gates ("fixed" drivers).
+Same module name, class name and public surface; the logic lives in `_core.CircuitEnvBase`."""
+from ..VQAs import VQE_qulacs_TN_notin_RL as vc
+from ._core import CircuitEnvBase
+
+
+class CircuitEnv(CircuitEnvBase):
+    vc = vc
+    tn_in_agent = False
+    shot_args = False
+    restricted = False
+
+
+if __name__ == "__main__":
+    pass

@@ -1,0 +1,176 @@
+"""CircuitEnv drop-ins (tensorrl_qas_b200/environments) replayed against episodes of the reference's own CircuitEnv
+classes (tests/golden/env_golden.npz, made by tests/golden/make_env_golden.py).
+
+  * not gpu: the environments' host logic -- tensor encoding of the MPS circuit, gate placement, the one-step
+    optimisation lag, float32 write-backs, reward / termination / curriculum, the stateful illegal-action mask, the
+    COBYLA call -- with the energy supplied by the oracle-backed stand-in of the VQA shim: everything must be
+    IDENTICAL to the reference run (same scipy build, same arithmetic), bit for bit.
+  * gpu: the same replay through the real shims (libtqsim); identical actions, masks, done flags, gate placement
+    and nfev, energies within 1e-10 Ha (BASELINE.json north_star tolerance).
+"""
+import importlib
+import json
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import env_fixture as fx
+
+ENERGY_TOL = 1e-10   # Ha, BASELINE.json north_star
+
+VARIANT = {   # episode key -> (module, tn_state_arg, gate noise, shot args, shot noise)
+    "fixed_h2o8": ("environment_qulacs_TN_notin_agent", True, False, False, False),
+    "fixed_beh2": ("environment_qulacs_TN_notin_agent", True, False, False, False),
+    "fixed_heis5": ("environment_qulacs_TN_notin_agent", True, False, False, False),
+    "trainable_beh2": ("environment_qulacs", False, False, False, False),
+    "structure_heis5": ("environment_qulacs", False, False, False, False),
+    "trainable_h2o8_angles": ("environment_qulacs", False, False, False, False),
+    "noise_trainable_h2o8": ("environment_qulacs_noise", False, True, True, False),
+    "noise_fixed_h2o8": ("environment_qulacs_TN_notin_agent_noise", True, True, True, False),
+    "restricted_h2o8": ("environment_qulacs_TN_notin_agent_noise_restricted", True, False, True, True),
+}
+SEED = {"fixed_h2o8": 11, "fixed_beh2": 12, "fixed_heis5": 13, "trainable_beh2": 14, "structure_heis5": 15,
+        "trainable_h2o8_angles": 16, "noise_trainable_h2o8": 17, "noise_fixed_h2o8": 18, "restricted_h2o8": 19}
+
+
+def _action_table(module_name, n):
+    from tensorrl_qas_b200.environments.utils import utils, utils_topology_restrict as utr
+    if module_name.endswith("restricted"):
+        return utr.dictionary_of_actions_hexagon_connectivity(n)   # the agent's dictionary (agents/DeepQ_restricted.py:47)
+    return utils.dictionary_of_actions(n)
+
+
+def _make_env(key, tmp_path, monkeypatch, backend):
+    ep = fx.Episode(key)
+    module_name, tn_arg, noise, shot_args, shot_noise = VARIANT[key]
+    fx.materialize(str(tmp_path), ep)
+    monkeypatch.setenv("TQ_DATA_ROOT", str(tmp_path))
+    mod = importlib.import_module(f"tensorrl_qas_b200.environments.{module_name}")
+    seed = SEED[key]
+    if backend == "oracle":
+        vc = fx.oracle_vc(tn_arg, noise, shot_args, shot_noise)
+        monkeypatch.setattr(mod.CircuitEnv, "vc", vc)
+        monkeypatch.setattr(mod.CircuitEnv, "_simulate_init_circuit",
+                            lambda self: fx.oracle_statevector(self.tenor_circ))
+    else:
+        vc = mod.CircuitEnv.vc
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if hasattr(vc, "seed"):
+        vc.seed(seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = mod.CircuitEnv(ep.conf, device=torch.device("cpu"))
+    return ep, env, _action_table(module_name, env.num_qubits)
+
+
+def _replay(ep, env, table, exact):
+    d = ep.d
+    assert env.action_size == int(d["action_size"]) and env.state_size == int(d["state_size"])
+    assert env.num_layers_termination == int(d["num_layers_termination"])
+    obs = env.reset()
+    assert obs.dtype == torch.float32 and obs.shape[0] == int(d["obs_len"])
+    assert np.array_equal(obs.numpy(), d["obs0"])
+    if exact:
+        assert float(env.prev_energy) == float(d["first_energy"])
+    else:
+        assert abs(float(env.prev_energy) - float(d["first_energy"])) < ENERGY_TOL
+    worst = 0.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")   # COBYLA's "MAXFUN raised to num_vars + 2" notice on the shortened cfgs
+        for i in range(ep.n_steps):
+            ill = env.illegal_action_new()
+            assert [int(a) for a in ill] == ep.illegal(i), f"step {i}: illegal-action mask"
+            a = int(d["action"][i])
+            obs, reward, done = env.step(list(table[a]))
+            assert isinstance(done, int) and done == int(d["done"][i]), f"step {i}: done"
+            assert reward.dtype == torch.float32 and reward.ndim == 0
+            assert type(env.error) is float
+            # gate placement: the one-hot part of the tensor never depends on arithmetic
+            n = env.num_qubits
+            assert np.array_equal(env.state.numpy()[:, :n + 3], d["state"][i][:, :n + 3]), f"step {i}: gate placement"
+            assert int(env.nfev) == int(d["nfev"][i]), f"step {i}: nfev {env.nfev} vs {int(d['nfev'][i])}"
+            if exact:
+                assert float(env.energy) == float(d["energy"][i]), f"step {i}: energy"
+                assert float(reward) == float(np.float32(d["reward"][i]))
+                assert np.array_equal(env.state.numpy(), d["state"][i])
+                assert np.array_equal(np.asarray(env.opt_ang_save, dtype=np.float64).reshape(-1), ep.opt_ang(i))
+                assert float(obs.double().sum()) == float(d["obs_sum"][i])
+                assert float(env.done_threshold) == float(d["done_threshold"][i])
+            else:
+                err = abs(float(env.energy) - float(d["energy"][i]))
+                worst = max(worst, err)
+                assert err < ENERGY_TOL, f"step {i}: |dE| = {err:.3e}"
+                assert abs(float(reward) - float(d["reward"][i])) < 1e-5
+                assert np.abs(env.state.numpy() - d["state"][i]).max() < 1e-5
+            if done:
+                break
+    return worst
+
+
+@pytest.mark.parametrize("key", list(VARIANT))
+def test_env_replay_host_logic_exact(key, tmp_path, monkeypatch):
+    ep, env, table = _make_env(key, tmp_path, monkeypatch, "oracle")
+    _replay(ep, env, table, exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", list(VARIANT))
+def test_env_replay_gpu(key, tmp_path, monkeypatch):
+    from tensorrl_qas_b200.VQAs import _backend
+    _backend.reset_backends()
+    ep, env, table = _make_env(key, tmp_path, monkeypatch, "gpu")
+    if "tn_state" in ep.d:
+        assert np.abs(np.asarray(env.TN_state) - ep.d["tn_state"]).max() < 1e-12
+    worst = _replay(ep, env, table, exact=False)
+    print(f"{key}: max |dE| vs reference episode = {worst:.2e}")
+    _backend.reset_backends()
+
+
+def test_get_config_schema(tmp_path):
+    """INI -> typed dict rules of environments/utils/utils.py:6-36 on a cfg with the shipped schema."""
+    from tensorrl_qas_b200.environments.utils.utils import get_config
+    (tmp_path / "exp").mkdir()
+    (tmp_path / "exp" / "x.cfg").write_text(
+        "[general]\nepisodes = 10000\n[env]\nnum_qubits = 8\nTN_init = 1\naccept_err = 1.6e-3\nthresholds = [1.6e-3]\n"
+        "switch_episodes = [100000]\nnoise_values = 0\nfn_type = incremental_with_fixed_ends\n"
+        "[problem]\nham_type = H2O\ngeometry = H -0.021 -0.002 0.000; O 0.835 0.452 0.000\nmapping = jordan_wigner\n"
+        "[agent]\nlearning_rate = 0.0003\nneurons = [1000,1000]\ndropout = 0.\nangles = 0\n"
+        "[non_local_opt]\na = 0.\nalpha = 0.\nglobal_iters = 1000\nmethod = scipy_each_step\noptim_alg = COBYLA\n")
+    c = get_config("exp/", "x.cfg", path=str(tmp_path))
+    assert "DEFAULT" not in c and set(c) == {"general", "env", "problem", "agent", "non_local_opt"}
+    assert c["general"]["episodes"] == 10000                      # json list key holding a scalar
+    assert c["env"]["tn_init"] == 1 and "TN_init" not in c["env"]  # keys are lower-cased
+    assert c["env"]["accept_err"] == 1.6e-3 and c["env"]["thresholds"] == [1.6e-3]
+    assert c["agent"]["learning_rate"] == 0.0003 and c["agent"]["dropout"] == 0.0 and c["agent"]["neurons"] == [1000, 1000]
+    assert c["non_local_opt"]["a"] == "0." and c["non_local_opt"]["alpha"] == 0.0   # 'a' is not a float key: stays a string
+    assert c["problem"]["geometry"].startswith("H -0.021")
+
+
+def test_action_dictionaries():
+    from tensorrl_qas_b200.environments.utils import utils, utils_topology_restrict as utr
+    for n in (4, 6, 8):
+        d, r = utils.dictionary_of_actions(n), utils.dict_of_actions_revert_q(n)
+        assert len(d) == len(r) == n * (n + 2)
+        assert d[0] == [0, 1, n, 0] and d[n * (n - 1)] == [n, 0, 0, 1] and d[len(d) - 1] == [n, 0, n - 1, 3]
+        assert r[0] == [n - 1, n - 1, n, 0] and r[len(r) - 1] == [n, 0, 0, 3]
+        assert sorted(map(tuple, d.values())) == sorted(map(tuple, r.values()))
+    # hexagon dictionaries keep CNOTs only, keys count down
+    assert len(utr.dictionary_of_actions_hexagon_connectivity(6)) == 5
+    assert len(utr.dictionary_of_actions_hexagon_connectivity(8)) == 14
+    assert len(utr.dictionary_of_actions_hexagon_connectivity_reverted(8)) == 7
+    assert len(utr.dictionary_of_actions_hexagon_connectivity(10)) == 9
+    f = utr.dictionary_of_actions_hexagon_connectivity(6)
+    assert f[4] == [0, 1, 6, 0] and all(a[2] == 6 for a in f.values())
+
+
+def test_install_alias():
+    import sys
+    import tensorrl_qas_b200.environments as envs
+    envs.install("environments_b200_alias")
+    from environments_b200_alias.environment_qulacs_TN_notin_agent import CircuitEnv  # noqa: F401
+    from environments_b200_alias.utils.utils import get_config  # noqa: F401
+    from environments_b200_alias.VQAs import VQE_qulacs  # noqa: F401
+    assert sys.modules["environments_b200_alias.VQAs.VQE_qulacs"] is sys.modules["tensorrl_qas_b200.VQAs.VQE_qulacs"]
