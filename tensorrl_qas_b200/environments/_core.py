@@ -57,6 +57,7 @@ class CircuitEnvBase:
     # ------------------------------------------------------------------------------------------ construction ----
     def __init__(self, conf, device):
         env, problem = conf["env"], conf["problem"]
+        self.device = device
         n = self.num_qubits = env["num_qubits"]
         self.num_layers = env["num_layers"]
         self.random_halt = int(env["rand_halt"])
@@ -114,7 +115,6 @@ class CircuitEnvBase:
         self.curriculum_dict = {
             self.ham_type: curricula.__dict__[env["curriculum_type"]](env, target_energy=min_eig)}
 
-        self.device = device
         self.done_threshold = env["accept_err"]
         stdout.flush()
         self.state_size = self.num_layers * n * (n + 3 + 3)
