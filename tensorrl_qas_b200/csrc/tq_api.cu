@@ -240,6 +240,7 @@ int compile_plan(tq_handle h, int which) {
             if (g.x) cover.push_back(g.x);
 
     opt.fuse = env_int("TQ_FUSE", 1) != 0;
+    opt.mma = env_int("TQ_MMA", 1) != 0;
     CompiledCircuit cc = which == 1 ? plan_density(n, h->gates, opt, &perr)
                                     : plan_statevector(n, h->gates, opt, cover, &perr);
     if (!perr.empty()) return fail(h, TQ_EINVAL, perr);
@@ -297,10 +298,14 @@ int compile_plan(tq_handle h, int which) {
             gin.push_back(std::move(x));
         }
         std::vector<int> wide;
-        if (!gin.empty()) append_expectation_windows(p, gin, &wide);
+        if (!gin.empty()) {
+            if (p.mma) append_expectation_windows_mma(p, gin, &wide);
+            else append_expectation_windows(p, gin, &wide);
+        }
         std::vector<int> wide_groups;
         for (int wi : wide) wide_groups.push_back(groups_of_pass[i][wi]);
-        offs[i].windows = append(p.windows.data(), p.windows.size() * sizeof(Window));
+        offs[i].windows = p.mma ? append(p.mwindows.data(), p.mwindows.size() * sizeof(MmaWindow))
+                                : append(p.windows.data(), p.windows.size() * sizeof(Window));
         offs[i].wops = append(p.wops.data(), p.wops.size() * sizeof(WinOp));
         offs[i].eterms = append(p.eterms.data(), p.eterms.size() * sizeof(EUnit));
         std::vector<ExpGroup> eg;
@@ -346,8 +351,13 @@ int compile_plan(tq_handle h, int which) {
         dp.threads = threads_for(dp.proto.k_eff);
         dp.n_tiles = 1 << dp.proto.n_nl;
         dp.gate_pass = (int)i < n_gate_passes;
-        dp.proto.windows = (const Window*)(base + offs[i].windows);
-        dp.proto.n_windows = (int)passes[i].windows.size();
+        if (passes[i].mma) {
+            dp.proto.mwindows = (const MmaWindow*)(base + offs[i].windows);
+            dp.proto.n_windows = (int)passes[i].mwindows.size();
+        } else {
+            dp.proto.windows = (const Window*)(base + offs[i].windows);
+            dp.proto.n_windows = (int)passes[i].windows.size();
+        }
         dp.proto.wops = (const WinOp*)(base + offs[i].wops);
         dp.proto.n_wops = (int)passes[i].wops.size();
         dp.proto.n_mats = plan.n_mats;
@@ -799,6 +809,7 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
     std::vector<uint64_t> cover(cover_masks, cover_masks + n_cover);
     std::string err;
     opt.fuse = env_int("TQ_FUSE", 1) != 0;
+    opt.mma = env_int("TQ_MMA", 1) != 0;
     CompiledCircuit cc = which == 1 ? plan_density(n_qubits, gates, opt, &err)
                                     : plan_statevector(n_qubits, gates, opt, cover, &err);
     std::string out;
@@ -821,6 +832,22 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
             out += line;
         }
         const int k_eff = std::max<int>((int)p.local.size(), kMinTileBits);
+        for (const MmaWindow& w : p.mwindows) {
+            auto list = [&](const uint8_t* v, int cnt) {
+                std::string t;
+                for (int i = 0; i < cnt; ++i) t += (i ? "," : "") + std::to_string(v[i]);
+                return t;
+            };
+            out += "MWIN r=" + list(w.rpos, kMmaRegBits) + " ql=" + std::to_string(w.qlpos) + " g=" + list(w.gpos, 3) +
+                   " w=" + list(w.wpos, std::max(0, (int)p.local.size() - 9)) + " rout=" + list(w.rpos_out, kMmaRegBits) +
+                   " qlout=" + std::to_string(w.qlpos_out) + " flags=" + std::to_string(w.flags) + "\n";
+            for (int i = w.op_begin; i < w.op_end; ++i) {
+                const WinOp& o = p.wops[i];
+                snprintf(line, sizeof line, "WOP %u %u %u %u %u %d %.17g\n", o.w0 & 0xff, (o.w0 >> 8) & 0xf,
+                         (o.w0 >> 12) & 0xf, (o.w0 >> 16) & 0xff, (o.w0 >> 24) & 0xff, o.t, o.fixed);
+                out += line;
+            }
+        }
         for (const Window& w : p.windows) {
             out += "WIN wpos=";
             for (int i = 0; i < kRegBits; ++i) out += (i ? "," : "") + std::to_string(w.wpos[i]);

@@ -585,6 +585,417 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
     }
 }
 
+// =================================================================================================================
+// Tensor-core pass kernel (pure states, tiles of >= 2^9 amplitudes): the windows of tq_plan.h "DMMA windows".
+// A thread holds NR = 32 doubles: component c = lane & 1 (real / imaginary part) of the 32 amplitudes that differ in
+// the window's register qubits; lane bit 1 = QL, lane bits 2..4 and the warp index = untouched tile positions.
+// =================================================================================================================
+constexpr int NR = 1 << kMmaRegBits;
+typedef double Regs[NR];
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b, double c0, double c1) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+        : "=d"(d0), "=d"(d1)
+        : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
+// 4x4 complex block on (QL, RX) as an 8x8 real product: for every pair of registers (RX = 0, RX = 1) two chained
+// DMMAs; A = the registers themselves (row = lane group, k = (QL, re/im) of the lane), B = (b0, b1) from the block's
+// matrix, D = the new pair.
+template <int X>
+__device__ __forceinline__ void m_u2(Regs& a, double b0, double b1) {
+#pragma unroll
+    for (int p = 0; p < NR / 2; ++p) {
+        const int r0 = ((p >> X) << (X + 1)) | (p & ((1 << X) - 1)), r1 = r0 | (1 << X);
+        double d0, d1;
+        dmma884(d0, d1, a[r0], b0, 0.0, 0.0);
+        dmma884(d0, d1, a[r1], b1, d0, d1);
+        a[r0] = d0;
+        a[r1] = d1;
+    }
+}
+// QL <-> RX: the registers with RX != (lane's QL bit) cross to lane ^ 2
+template <int X>
+__device__ __forceinline__ void m_swapql(Regs& a, bool l1) {
+#pragma unroll
+    for (int p = 0; p < NR / 2; ++p) {
+        const int r0 = ((p >> X) << (X + 1)) | (p & ((1 << X) - 1)), r1 = r0 | (1 << X);
+        const double send = l1 ? a[r0] : a[r1];
+        const double recv = __shfl_xor_sync(kFull, send, 2);
+        if (l1) a[r0] = recv;
+        else a[r1] = recv;
+    }
+}
+template <int X>
+__device__ __forceinline__ void m_cx_out(Regs& a, bool pred) {
+#pragma unroll
+    for (int p = 0; p < NR / 2; ++p) {
+        const int r0 = ((p >> X) << (X + 1)) | (p & ((1 << X) - 1)), r1 = r0 | (1 << X);
+        const double a0 = a[r0], a1 = a[r1];
+        a[r0] = pred ? a1 : a0;
+        a[r1] = pred ? a0 : a1;
+    }
+}
+template <int CB, int TB>
+__device__ __forceinline__ void m_cx_rr(Regs& a) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        if (((i >> CB) & 1) && !((i >> TB) & 1)) {
+            const double t = a[i];
+            a[i] = a[i | (1 << TB)];
+            a[i | (1 << TB)] = t;
+        }
+    }
+}
+__device__ __forceinline__ void exec_m_cx_rr(Regs& a, int cb, int tb) {
+#define TQ_RR(C, T) case C * 5 + T: m_cx_rr<C, T>(a); break;
+    switch (cb * 5 + tb) {
+        TQ_RR(0, 1) TQ_RR(0, 2) TQ_RR(0, 3) TQ_RR(0, 4) TQ_RR(1, 0) TQ_RR(1, 2) TQ_RR(1, 3) TQ_RR(1, 4)
+        TQ_RR(2, 0) TQ_RR(2, 1) TQ_RR(2, 3) TQ_RR(2, 4) TQ_RR(3, 0) TQ_RR(3, 1) TQ_RR(3, 2) TQ_RR(3, 4)
+        TQ_RR(4, 0) TQ_RR(4, 1) TQ_RR(4, 2) TQ_RR(4, 3)
+    default: break;
+    }
+#undef TQ_RR
+}
+
+// expectation class on registers: every lane contributes the products of ITS component; the two lanes of a pair are
+// summed by the CTA-wide reduction.  Im(conj(w) v) needs the other component of v: one shuffle per register pair.
+template <int XR>
+__device__ __forceinline__ double m_expc(const Regs& a, const double* __restrict__ cA, const double* __restrict__ cB,
+                                         bool im_lane) {
+    double sum = 0.0;
+    int q = 0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        if ((r ^ XR) > r) {
+            const double v = a[r], w = a[r ^ XR];
+            sum = fma(cA[q], w * v, sum);
+            if (cB) {  // CTA-uniform
+                const double vp = __shfl_xor_sync(kFull, v, 1);
+                const double im = im_lane ? -(w * vp) : w * vp;   // w.x v.y  |  -w.y v.x
+                sum = fma(-__ldg(cB + q), im, sum);
+            }
+            ++q;
+        }
+    }
+    return sum;
+}
+__device__ __forceinline__ double exec_m_expc(const Regs& a, int xr, const double* cA, const double* cB, bool im_lane) {
+#define TQ_XC(V) case V: return m_expc<V>(a, cA, cB, im_lane);
+    switch (xr) {
+        TQ_XC(1) TQ_XC(2) TQ_XC(3) TQ_XC(4) TQ_XC(5) TQ_XC(6) TQ_XC(7) TQ_XC(8) TQ_XC(9) TQ_XC(10) TQ_XC(11)
+        TQ_XC(12) TQ_XC(13) TQ_XC(14) TQ_XC(15) TQ_XC(16) TQ_XC(17) TQ_XC(18) TQ_XC(19) TQ_XC(20) TQ_XC(21)
+        TQ_XC(22) TQ_XC(23) TQ_XC(24) TQ_XC(25) TQ_XC(26) TQ_XC(27) TQ_XC(28) TQ_XC(29) TQ_XC(30)
+    default: return m_expc<31>(a, cA, cB, im_lane);
+    }
+#undef TQ_XC
+}
+// diagonal terms over register bits 0..3 of one half (register bit 4 fixed): WHT of 16 squared components, then one
+// signed weight sum per class
+template <int HALF>
+__device__ __forceinline__ double m_expd_half(const Regs& a, uint64_t ctx, const double2* __restrict__ head,
+                                              const double2* __restrict__ terms) {
+    double n[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) n[r] = a[HALF * 16 + r] * a[HALF * 16 + r];
+#pragma unroll
+    for (int bitp = 0; bitp < 4; ++bitp)
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if (!((r >> bitp) & 1)) {
+                const double x = n[r], y = n[r | (1 << bitp)];
+                n[r] = x + y;
+                n[r | (1 << bitp)] = x - y;
+            }
+    const unsigned short* cnt = reinterpret_cast<const unsigned short*>(head);
+    double total = 0.0;
+    int idx = 0;
+#pragma unroll
+    for (int zr = 0; zr < 16; ++zr) {
+        const int c = cnt[zr];
+        double s = 0.0;
+        for (int i = 0; i < c; ++i) {
+            const double2 t = __ldg(terms + idx + i);
+            s += (__popcll(ctx & (uint64_t)__double_as_longlong(t.x)) & 1) ? -t.y : t.y;
+        }
+        idx += c;
+        total = fma(s, n[zr], total);
+    }
+    return total;
+}
+
+enum : int { FM_U2 = 0, FM_SCAL = 5, FM_SWAP = 6, FM_CXO = 11, FM_CXRR = 16, FM_EXPC = 17, FM_EXPD = 18 };
+
+__device__ __forceinline__ int flat_code_mma(uint32_t w0) {
+    const int code = w0 & 0xff, rb = (w0 >> 8) & 0xf, rb2 = (w0 >> 12) & 0xf;
+    switch (code) {
+    case M_U2: return rb2 == 4 ? FM_SCAL : FM_U2 + rb;
+    case M_SWAPQL: return FM_SWAP + rb;
+    case M_CX_OUT: return FM_CXO + rb;
+    case M_CX_RR: return FM_CXRR;
+    case M_EXPC: return FM_EXPC;
+    default: return FM_EXPD;
+    }
+}
+
+#define TQ_SEL5(i, v0, v1, v2, v3, v4) ((((i) & 1) ? (v0) : 0u) ^ (((i) & 2) ? (v1) : 0u) ^ (((i) & 4) ? (v2) : 0u) ^ (((i) & 8) ? (v3) : 0u) ^ (((i) & 16) ? (v4) : 0u))
+
+__global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kernel(const PassParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tile_amps = 1 << p.k;   // k >= 9: k_eff == k, every thread of every warp is active
+    double2* amp = reinterpret_cast<double2*>(smem_raw);
+    double* ampd = reinterpret_cast<double*>(smem_raw);
+    double2* s_mat = amp + tile_amps;
+    WinOp* s_wops = reinterpret_cast<WinOp*>(s_mat + kOpSlots * kMatStride);
+    double* s_red = reinterpret_cast<double*>(s_wops + kOpSlots);
+    MmaWindow* s_win = reinterpret_cast<MmaWindow*>(s_red + 32);                 // kWinSlots headers
+    uint32_t* hi_off = reinterpret_cast<uint32_t*>(s_win + kWinSlots);
+
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int comp = lane & 1;
+    const bool l1 = (lane >> 1) & 1;
+    const uint32_t ntiles = 1u << p.n_nl;
+    const uint32_t tile = blockIdx.x & (ntiles - 1u);
+    const uint32_t b = blockIdx.x >> p.n_nl;
+
+    uint64_t tile_base = 0;
+    for (int i = 0; i < p.n_nl; ++i) tile_base |= (uint64_t)((tile >> i) & 1u) << p.nonlocal[i];
+
+    const int n_hi = 1 << (p.k - p.lead);
+    for (int h = tid; h < n_hi; h += nthreads) {
+        uint32_t off = 0;
+        for (int i = p.lead; i < p.k; ++i) off |= ((uint32_t)(h >> (i - p.lead)) & 1u) << p.local[i];
+        hi_off[h] = off;
+    }
+    __syncthreads();
+    const uint32_t lead_mask = (1u << p.lead) - 1u;
+
+    // I/O layout as in tile_pass_kernel: amplitude i of thread t is tile index t + i * nthreads (16 per thread)
+    const uint32_t io_slot = swz(tid);
+    const uint32_t iw0 = swz(nthreads), iw1 = swz(nthreads << 1), iw2 = swz(nthreads << 2), iw3 = swz(nthreads << 3);
+    const uint32_t io_goff = TQ_PHYS(tid);
+    const uint32_t ig0 = TQ_PHYS(nthreads), ig1 = TQ_PHYS(nthreads << 1), ig2 = TQ_PHYS(nthreads << 2),
+                   ig3 = TQ_PHYS(nthreads << 3);
+    const uint64_t elem_off = (uint64_t)b << p.nbits;
+    const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
+    const int n_run = (p.exp_mode == 1) ? p.n_windows : p.n_gate_windows;
+
+    // B-fragment coordinates of this lane: B[k = lane & 3][n = lane >> 2]; n = (QL', c', RX'), k = (QL, c)
+    const int g = lane >> 2;
+    const int brow = (g >> 2) | ((g & 1) << 1);            // staged matrix row: index bit 0 = QL, bit 1 = RX
+    const int bcol = (lane >> 1) & 1;                      // column for RX = 0; RX = 1 adds 2
+    const bool bsame = ((g >> 1) & 1) == comp;             // output and input component agree -> real part
+    const bool bco = (g >> 1) & 1;                         // output component (sign of the imaginary part)
+
+    int staged_begin = 0, staged_end = 0;
+    auto stage_ops = [&](int first) {
+        staged_begin = first;
+        staged_end = min(first + kOpSlots, p.n_wops);
+        for (int i = tid; i < (staged_end - staged_begin) * kMatStride; i += nthreads) {
+            const int oi = i >> 4, e = i & 15;
+            WinOp wo = p.wops[staged_begin + oi];
+            const int code = wo.w0 & 0xff, mode = (wo.w0 >> 12) & 0xf;
+            if (e == 0) {
+                wo.w0 = (wo.w0 & ~0xffu) | (uint32_t)flat_code_mma(wo.w0);
+                s_wops[oi] = wo;
+            }
+            if (code >= M_EXPC) {
+                if (e < (code == M_EXPC ? 9 : 2))   // class header + cA[16] | the 16 class counts
+                    s_mat[oi * kMatStride + e] = reinterpret_cast<const double2*>(p.eterms)[(size_t)wo.t + e];
+            } else if (code == M_U2) {
+                // expand to a 4x4 with index bit 0 = QL, bit 1 = RX
+                const double2* M = my_mats + (size_t)wo.t * kMatStride;
+                const int r = e >> 2, c = e & 3;
+                double2 v = make_double2(0.0, 0.0);
+                if (mode == 0) v = M[e];
+                else if (mode == 1) v = M[((((r & 1) << 1) | (r >> 1)) << 2) | ((c & 1) << 1) | (c >> 1)];
+                else if (mode == 2) { if ((r & 1) == (c & 1)) v = M[(r >> 1) * 2 + (c >> 1)]; }
+                else if (mode == 3) { if ((r >> 1) == (c >> 1)) v = M[(r & 1) * 2 + (c & 1)]; }
+                else { if (e == 0 || e == 3) v = M[e]; }
+                s_mat[oi * kMatStride + e] = v;
+            }
+        }
+    };
+
+    // ---- 1. stage the tile, the window headers and the first ops ----
+    {
+        double2 v[16];
+        if (p.src_mode != 0) {
+            const double2* src = p.src + (p.src_mode == 2 ? elem_off : 0ull) + tile_base;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __ldcs(src + TQ_IO_GOFF(i));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = make_double2((tile_base == 0 && tid == 0 && i == 0) ? 1.0 : 0.0, 0.0);
+        }
+        for (int i = tid; i < 2 * min(n_run, kWinSlots); i += nthreads)
+            reinterpret_cast<uint4*>(s_win)[i] = __ldg(reinterpret_cast<const uint4*>(p.mwindows) + i);
+        stage_ops(0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) amp[TQ_IO_SLOT(i)] = v[i];
+    }
+    __syncthreads();
+
+    // ---- 2. windows ----
+    Regs a;
+    double acc = 0.0;
+    bool wrote_back = false;
+    auto write_back = [&]() {   // shared memory holds the final tile
+        if (p.dst && !wrote_back) {
+            double2* dst = p.dst + elem_off + tile_base;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[TQ_IO_GOFF(i)] = amp[TQ_IO_SLOT(i)];
+        }
+        wrote_back = true;
+    };
+    for (int w = 0; w < n_run; ++w) {
+        if (w == p.n_gate_windows) write_back();
+        MmaWindow hdr;
+        if (w < kWinSlots) hdr = s_win[w];
+        else {
+            const uint4* raw = reinterpret_cast<const uint4*>(p.mwindows + w);
+            reinterpret_cast<uint4*>(&hdr)[0] = __ldg(raw);
+            reinterpret_cast<uint4*>(&hdr)[1] = __ldg(raw + 1);
+        }
+        const bool read_only = hdr.flags & kWinFlagReadOnly;
+        const int op_begin = hdr.op_begin, op_end = hdr.op_end;
+        if (op_end > staged_end) {   // CTA-uniform: restage from this window on
+            __syncthreads();
+            stage_ops(op_begin);
+            __syncthreads();
+        }
+        // this thread's part of the tile index: lane bits 1..4 and the warp bits
+        uint32_t jrest = ((uint32_t)((lane >> 2) & 1) << hdr.gpos[0]) | ((uint32_t)((lane >> 3) & 1) << hdr.gpos[1]) |
+                         ((uint32_t)((lane >> 4) & 1) << hdr.gpos[2]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (i < p.k - 9) jrest |= (uint32_t)((warp >> i) & 1) << hdr.wpos[i];
+        // physical index bits of everything this thread does not hold in registers (QL as it sits on entry: gate
+        // windows never read QL through ctx, expectation windows never move it)
+        const uint64_t ctx = tile_base | TQ_PHYS(jrest | ((uint32_t)l1 << hdr.qlpos));
+        {
+            const uint32_t slot_t = swz(jrest | ((uint32_t)l1 << hdr.qlpos));
+            const uint32_t r0 = swz(1u << hdr.rpos[0]), r1 = swz(1u << hdr.rpos[1]), r2 = swz(1u << hdr.rpos[2]),
+                           r3 = swz(1u << hdr.rpos[3]), r4 = swz(1u << hdr.rpos[4]);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) a[r] = ampd[2 * (slot_t ^ TQ_SEL5(r, r0, r1, r2, r3, r4)) + comp];
+        }
+        if (!read_only) __syncthreads();   // everyone holds its entry data: the tile may be overwritten from here on
+
+        for (int o = op_begin - staged_begin; o < op_end - staged_begin; ++o) {
+            const WinOp wo = s_wops[o];
+            const double2* m = s_mat + o * kMatStride;
+            const int fc = wo.w0 & 0xff;
+            const int qsel = (wo.w0 >> 16) & 0xff;
+            if (fc <= FM_SCAL) {
+                double2 u0, u1;
+                if (fc == FM_SCAL) {
+                    const double2 d = ((ctx >> qsel) & 1ull) ? m[3] : m[0];
+                    const double2 z = make_double2(0.0, 0.0);
+                    u0 = (brow == bcol) ? d : z;
+                    u1 = (brow == (bcol | 2)) ? d : z;
+                } else {
+                    u0 = m[brow * 4 + bcol];
+                    u1 = m[brow * 4 + bcol + 2];
+                }
+                const double b0 = bsame ? u0.x : (bco ? u0.y : -u0.y);
+                const double b1 = bsame ? u1.x : (bco ? u1.y : -u1.y);
+                switch (fc) {
+                case FM_U2 + 1: m_u2<1>(a, b0, b1); break;
+                case FM_U2 + 2: m_u2<2>(a, b0, b1); break;
+                case FM_U2 + 3: m_u2<3>(a, b0, b1); break;
+                case FM_U2 + 4: m_u2<4>(a, b0, b1); break;
+                default: m_u2<0>(a, b0, b1); break;   // FM_U2 + 0 and FM_SCAL
+                }
+            } else {
+                switch (fc) {
+                case FM_SWAP + 0: m_swapql<0>(a, l1); break;
+                case FM_SWAP + 1: m_swapql<1>(a, l1); break;
+                case FM_SWAP + 2: m_swapql<2>(a, l1); break;
+                case FM_SWAP + 3: m_swapql<3>(a, l1); break;
+                case FM_SWAP + 4: m_swapql<4>(a, l1); break;
+                case FM_CXO + 0: m_cx_out<0>(a, (bool)((ctx >> qsel) & 1ull)); break;
+                case FM_CXO + 1: m_cx_out<1>(a, (bool)((ctx >> qsel) & 1ull)); break;
+                case FM_CXO + 2: m_cx_out<2>(a, (bool)((ctx >> qsel) & 1ull)); break;
+                case FM_CXO + 3: m_cx_out<3>(a, (bool)((ctx >> qsel) & 1ull)); break;
+                case FM_CXO + 4: m_cx_out<4>(a, (bool)((ctx >> qsel) & 1ull)); break;
+                case FM_CXRR: exec_m_cx_rr(a, (wo.w0 >> 8) & 0xf, (wo.w0 >> 12) & 0xf); break;
+                case FM_EXPC: {
+                    const double* cA = reinterpret_cast<const double*>(m + 1);
+                    const double* cB = ((wo.w0 >> 12) & 1)
+                                           ? reinterpret_cast<const double*>(reinterpret_cast<const double2*>(p.eterms) + wo.t + 9)
+                                           : nullptr;
+                    const double sum = exec_m_expc(a, (int)(wo.w0 >> 24), cA, cB, comp != 0);
+                    const uint64_t zphys = (uint64_t)__double_as_longlong(m[0].x);
+                    acc += (__popcll(ctx & zphys) & 1) ? -sum : sum;
+                    break;
+                }
+                default: {  // FM_EXPD: register bit 4 is treated as a bit outside the window (physical bit qsel)
+                    const double2* terms = reinterpret_cast<const double2*>(p.eterms) + wo.t + 2;
+                    acc += m_expd_half<0>(a, ctx, m, terms);
+                    acc += m_expd_half<1>(a, ctx | (1ull << qsel), m, terms);
+                    break;
+                }
+                }
+            }
+        }
+        if (!read_only) {
+            const uint32_t slot_t = swz(jrest | ((uint32_t)l1 << hdr.qlpos_out));
+            const uint32_t r0 = swz(1u << hdr.rpos_out[0]), r1 = swz(1u << hdr.rpos_out[1]),
+                           r2 = swz(1u << hdr.rpos_out[2]), r3 = swz(1u << hdr.rpos_out[3]),
+                           r4 = swz(1u << hdr.rpos_out[4]);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) ampd[2 * (slot_t ^ TQ_SEL5(r, r0, r1, r2, r3, r4)) + comp] = a[r];
+            __syncthreads();   // the tile is complete in shared memory again
+        }
+    }
+    write_back();
+
+    // ---- 3. Hamiltonian terms evaluated from shared memory (flip masks wider than a window / sparse entries) ----
+    if (p.exp_mode != 0) {
+        if (p.exp_mode == 1) {
+            ExpTerm* s_terms = reinterpret_cast<ExpTerm*>(s_mat);
+            const int cap = (int)((kOpSlots * kMatStride * sizeof(double2)) / sizeof(ExpTerm));
+            for (int gi = 0; gi < p.n_groups; ++gi) {
+                const ExpGroup grp = p.groups[gi];
+                const uint32_t xs = swz(grp.xlocal);
+                for (int t0 = grp.term_begin; t0 < grp.term_end; t0 += cap) {
+                    const int nt = min(cap, grp.term_end - t0);
+                    __syncthreads();
+                    for (int i = tid; i < nt; i += nthreads) s_terms[i] = p.terms[t0 + i];
+                    __syncthreads();
+                    for (int j = tid; j < tile_amps; j += nthreads) {
+                        const uint32_t sj = swz(j);
+                        const double2 v = amp[sj], bq = amp[sj ^ xs];
+                        const double px = bq.x * v.x + bq.y * v.y;
+                        const double py = bq.x * v.y - bq.y * v.x;
+                        double fre = 0.0, fim = 0.0;
+                        for (int tt = 0; tt < nt; ++tt) {
+                            const ExpTerm term = s_terms[tt];
+                            const int par = (__popc((uint32_t)j & term.zlocal) + __popcll(tile_base & term.zphys)) & 1;
+                            fre += par ? -term.wre : term.wre;
+                            fim += par ? -term.wim : term.wim;
+                        }
+                        acc += fre * px - fim * py;
+                    }
+                }
+            }
+        } else {
+            for (int e = tid; e < p.n_hent; e += nthreads) {
+                const HEntry h = p.hent[e];
+                const double2 ar = amp[swz(h.r)], ac = amp[swz(h.c)];
+                const double px = ar.x * ac.x + ar.y * ac.y;
+                const double py = ar.x * ac.y - ar.y * ac.x;
+                acc += h.re * px - h.im * py;
+            }
+        }
+        const double total = block_sum(acc, s_red, tid, nthreads);
+        if (tid == 0) p.partial[(size_t)b * p.partial_ld + p.partial_off + tile] = total;
+    }
+}
+
 // ---- block matrices: one thread per (batch element, fused block) evaluates the block's matrix program ---------
 __global__ void __launch_bounds__(128) prep_matrices_kernel(const MatDesc* __restrict__ descs, const MatGate* __restrict__ prog,
                                                             int n_mats, int batch, const double* __restrict__ params,
@@ -695,19 +1106,22 @@ __global__ void __launch_bounds__(kMaxThreads) dm_expect_kernel(const double2* _
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead) {
     const size_t n_hi = (size_t)1 << (k - lead);
     return ((size_t)16 << k_eff) + kOpSlots * (kMatStride * sizeof(double2) + sizeof(WinOp)) + 32 * sizeof(double) +
-           3 * kWinSlots * sizeof(uint2) + n_hi * sizeof(uint32_t);
+           kWinSlots * sizeof(MmaWindow) + n_hi * sizeof(uint32_t);   // MmaWindow (32 B) >= Window (24 B)
 }
 
 cudaError_t tile_pass_configure() {
     cudaError_t e = cudaFuncSetAttribute(tile_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tile_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    e = cudaFuncSetAttribute(tile_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tile_pass_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
 
 void launch_tile_pass(const PassParams& p, int batch, int threads, bool density, cudaStream_t stream) {
     const unsigned grid = (unsigned)batch << p.n_nl;
     const size_t smem = tile_pass_smem_bytes(p.k_eff, p.k, p.lead);
-    if (density) tile_pass_kernel<true><<<grid, threads, smem, stream>>>(p);
+    if (p.mwindows) tile_pass_mma_kernel<<<grid, threads, smem, stream>>>(p);
+    else if (density) tile_pass_kernel<true><<<grid, threads, smem, stream>>>(p);
     else tile_pass_kernel<false><<<grid, threads, smem, stream>>>(p);
 }
 

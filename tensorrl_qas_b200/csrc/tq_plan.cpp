@@ -200,7 +200,7 @@ void finish_pass(Pass& p, int nbits, uint64_t lmask) {
 
 // greedy packing of blocks into passes
 std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions& opt,
-                       const std::vector<uint64_t>& cover_masks) {
+                       const std::vector<uint64_t>& cover_masks, bool mma) {
     std::vector<Pass> passes;
     const int k = std::min(opt.tile_bits, nbits);
     const uint64_t all = nbits >= 64 ? ~0ull : (bit(nbits) - 1);
@@ -236,7 +236,8 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
         Pass p;
         finish_pass(p, nbits, L);
         for (int idx : mine) p.ops.push_back(emit(p, ops[idx]));
-        schedule_windows(p);
+        if (mma && (int)p.local.size() >= kMmaMinTileBits) schedule_windows_mma(p);
+        else schedule_windows(p);
         passes.push_back(std::move(p));
         remaining.swap(deferred);
     }
@@ -468,6 +469,338 @@ void schedule_windows(Pass& p) {
     p.n_gate_windows = (int)p.windows.size();
 }
 
+// ================================================================ 3b. DMMA windows ==============================
+namespace {
+
+// tile positions outside the window -> three lane-group positions (independent bank-swizzle vectors when possible,
+// so the sixteen amplitudes a warp touches per shared-memory access spread over all bank groups) + warp positions
+void split_rest(const std::vector<int>& rest_in, uint8_t gpos[3], uint8_t wpos[3]) {
+    std::vector<int> rest = rest_in;
+    bool found = false;
+    for (size_t a = 0; a < rest.size() && !found; ++a)
+        for (size_t b = a + 1; b < rest.size() && !found; ++b)
+            for (size_t c = b + 1; c < rest.size() && !found; ++c)
+                if (independent3(rest[a], rest[b], rest[c])) {
+                    std::vector<int> order = {rest[a], rest[b], rest[c]};
+                    for (size_t i = 0; i < rest.size(); ++i)
+                        if (i != a && i != b && i != c) order.push_back(rest[i]);
+                    rest.swap(order);
+                    found = true;
+                }
+    for (int i = 0; i < 3; ++i) gpos[i] = (uint8_t)rest[i];
+    for (int i = 0; i < 3; ++i) wpos[i] = (uint8_t)(3 + i < (int)rest.size() ? rest[3 + i] : 0);
+}
+
+}  // namespace
+
+void schedule_windows_mma(Pass& p) {
+    p.mma = true;
+    p.mwindows.clear();
+    p.windows.clear();
+    p.wops.clear();
+    const int k = (int)p.local.size();
+    std::vector<TOp> tops(p.ops.size());
+    for (size_t i = 0; i < p.ops.size(); ++i) {
+        tops[i].d = p.ops[i];
+        tile_masks(tops[i]);
+    }
+    auto phys = [&](int pos) { return p.local[pos]; };
+
+    auto emit_window = [&](uint32_t W, const std::vector<int>& mine) {
+        for (int q = 0; q < k && popc32(W) < kMmaWinBits; ++q) W |= 1u << q;
+        std::vector<int> act, rest;
+        for (int q = 0; q < k; ++q) (((W >> q) & 1) ? act : rest).push_back(q);
+
+        // dependencies inside the window (same rule as between passes: two ops commute unless one mixes a position the
+        // other touches)
+        const int m = (int)mine.size();
+        std::vector<std::vector<int>> deps(m);
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < j; ++i) {
+                const TOp &a = tops[mine[i]], &b = tops[mine[j]];
+                if ((a.mix & (b.mix | b.diag)) || (a.diag & b.mix)) deps[j].push_back(i);
+            }
+        std::vector<char> done(m, 0);
+        auto uses_left = [&](int pos) {
+            int c = 0;
+            for (int j = 0; j < m; ++j)
+                if (!done[j] && tops[mine[j]].d.op == OP_U2 && ((tops[mine[j]].mix >> pos) & 1)) ++c;
+            return c;
+        };
+        // does op j run as is with QL on position ql (-1: not chosen yet)?
+        auto fits = [&](int j, int ql) {
+            const DevOp& d = tops[mine[j]].d;
+            if (d.op == OP_U2) return ql == d.a || ql == d.b;
+            if ((d.op == OP_CNOT && !((W >> d.a) & 1)) || d.op == OP_CNOT_NL) return ql != d.b;
+            return true;
+        };
+
+        int ql = -1;
+        int rp[kMmaRegBits];
+        struct Emit { WinOp o; };
+        std::vector<WinOp> out;
+        MmaWindow w{};
+        bool have_layout = false;
+        auto fix_layout = [&](int ql0) {   // entry layout: QL = ql0, register bits = the other window positions
+            ql = ql0;
+            int nb = 0;
+            for (int q : act)
+                if (q != ql0) rp[nb++] = q;
+            for (int r = 0; r < kMmaRegBits; ++r) w.rpos[r] = (uint8_t)rp[r];
+            w.qlpos = (uint8_t)ql0;
+            have_layout = true;
+        };
+        auto rb_of = [&](int pos) {
+            for (int r = 0; r < kMmaRegBits; ++r)
+                if (rp[r] == pos) return r;
+            return -1;
+        };
+        auto swap_ql = [&](int pos) {
+            const int x = rb_of(pos);
+            out.push_back(WinOp{winop_pack(M_SWAPQL, x, 0, 0, 0), -1, 0.0});
+            rp[x] = ql;
+            ql = pos;
+        };
+        auto better_ql = [&](int a, int b) { return uses_left(a) >= uses_left(b) ? a : b; };
+
+        for (int step = 0; step < m; ++step) {
+            std::vector<int> ready;
+            for (int j = 0; j < m; ++j) {
+                if (done[j]) continue;
+                bool ok = true;
+                for (int i : deps[j]) ok = ok && done[i];
+                if (ok) ready.push_back(j);
+            }
+            int pick = -1;
+            if (have_layout)
+                for (int j : ready)
+                    if (fits(j, ql)) { pick = j; break; }
+            if (pick < 0) {
+                // prefer a dense block: it decides where QL should sit
+                for (int j : ready)
+                    if (tops[mine[j]].d.op == OP_U2) { pick = j; break; }
+                if (pick < 0) pick = ready.front();
+                const DevOp& d = tops[mine[pick]].d;
+                int want;
+                if (d.op == OP_U2) {
+                    done[pick] = 1;  // count the uses AFTER this block
+                    want = better_ql(d.a, d.b);
+                    done[pick] = 0;
+                } else {  // CNOT controlled from outside the window whose target sits on QL: move QL elsewhere
+                    want = -1;
+                    for (int q : act)
+                        if (q != d.b && (want < 0 || uses_left(q) > uses_left(want))) want = q;
+                }
+                if (!have_layout) fix_layout(want);
+                else swap_ql(want);
+            }
+            const DevOp& d = tops[mine[pick]].d;
+            WinOp o{};
+            o.t = d.t;
+            o.fixed = d.fixed;
+            switch (d.op) {
+            case OP_U2: {  // matrix index bit 0 = position d.a (physically lower qubit)
+                const int other = (ql == d.a) ? d.b : d.a;
+                o.w0 = winop_pack(M_U2, rb_of(other), ql == d.a ? 0 : 1, 0, 0);
+                break;
+            }
+            case OP_U1:
+            case OP_D1:
+                if (d.op == OP_D1 && !((W >> d.a) & 1)) o.w0 = winop_pack(M_U2, 0, 4, phys(d.a), 0);
+                else if (d.a == ql) o.w0 = winop_pack(M_U2, 0, 3, 0, 0);
+                else o.w0 = winop_pack(M_U2, rb_of(d.a), 2, 0, 0);
+                break;
+            case OP_D1_NL: o.w0 = winop_pack(M_U2, 0, 4, d.a, 0); break;
+            case OP_CNOT:
+                if (!((W >> d.a) & 1)) o.w0 = winop_pack(M_CX_OUT, rb_of(d.b), 0, phys(d.a), 0);
+                else if (ql == d.a || ql == d.b) {
+                    // the CNOT's constant matrix has index bit 0 = the physically lower qubit = the lower position
+                    const int lo = std::min(d.a, d.b), other = (ql == d.a) ? d.b : d.a;
+                    o.w0 = winop_pack(M_U2, rb_of(other), ql == lo ? 0 : 1, 0, 0);
+                } else o.w0 = winop_pack(M_CX_RR, rb_of(d.a), rb_of(d.b), 0, 0);
+                break;
+            case OP_CNOT_NL: o.w0 = winop_pack(M_CX_OUT, rb_of(d.b), 0, d.a, 0); break;
+            default: break;  // density-matrix ops never reach a DMMA pass
+            }
+            out.push_back(o);
+            done[pick] = 1;
+        }
+        if (!have_layout) fix_layout(act[0]);
+        split_rest(rest, w.gpos, w.wpos);
+        if (out.empty()) w.flags = kWinFlagReadOnly;   // layout-only window (expectation-only passes)
+
+        // emit, splitting at kMaxWindowOps (a continuation window re-enters with the layout the previous part left)
+        MmaWindow cur = w;
+        int cql = w.qlpos;
+        int crp[kMmaRegBits];
+        for (int r = 0; r < kMmaRegBits; ++r) crp[r] = w.rpos[r];
+        size_t lo = 0;
+        do {
+            const size_t hi = std::min(out.size(), lo + (size_t)kMaxWindowOps);
+            for (int r = 0; r < kMmaRegBits; ++r) cur.rpos[r] = (uint8_t)crp[r];
+            cur.qlpos = (uint8_t)cql;
+            cur.op_begin = (int32_t)p.wops.size();
+            for (size_t i = lo; i < hi; ++i) {
+                p.wops.push_back(out[i]);
+                if ((out[i].w0 & 0xff) == M_SWAPQL) std::swap(cql, crp[(out[i].w0 >> 8) & 0xf]);
+            }
+            cur.op_end = (int32_t)p.wops.size();
+            for (int r = 0; r < kMmaRegBits; ++r) cur.rpos_out[r] = (uint8_t)crp[r];
+            cur.qlpos_out = (uint8_t)cql;
+            p.mwindows.push_back(cur);
+            lo = hi;
+        } while (lo < out.size());
+    };
+
+    std::vector<int> remaining(tops.size());
+    for (size_t i = 0; i < tops.size(); ++i) remaining[i] = (int)i;
+    while (!remaining.empty()) {
+        uint32_t W = 0, blocked_mix = 0, blocked_diag = 0;
+        std::vector<int> mine, deferred;
+        for (int idx : remaining) {
+            const TOp& t = tops[idx];
+            bool take = !((t.mix & (blocked_mix | blocked_diag)) || (t.diag & blocked_mix));
+            // a CNOT whose control is inside the window must have it among the window's positions: count it
+            const uint32_t need = t.mix;
+            if (take) {
+                if (popc32(W | need) <= kMmaWinBits) W |= need;
+                else take = false;
+            }
+            if (take) mine.push_back(idx);
+            else {
+                deferred.push_back(idx);
+                blocked_mix |= t.mix;
+                blocked_diag |= t.diag;
+            }
+        }
+        emit_window(W, mine);
+        remaining.swap(deferred);
+    }
+    if (p.mwindows.empty()) emit_window(0, {});
+    p.n_gate_windows = (int)p.mwindows.size();
+}
+
+void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover) {
+    const int k = (int)p.local.size();
+    constexpr int NR = 1 << kMmaRegBits;
+    std::vector<uint32_t> xl(groups.size());
+    std::vector<char> done(groups.size(), 0);
+    size_t left = 0;
+    for (size_t g = 0; g < groups.size(); ++g) {
+        xl[g] = mask_to_local(p, groups[g].x);
+        if (popc32(xl[g]) > kMmaRegBits) { leftover->push_back((int)g); done[g] = 1; }
+        else ++left;
+    }
+    while (left > 0) {
+        uint32_t W = 0;
+        std::vector<int> mine;
+        for (size_t g = 0; g < groups.size(); ++g) {
+            if (done[g]) continue;
+            if (popc32(W | xl[g]) <= kMmaRegBits) { W |= xl[g]; mine.push_back((int)g); done[g] = 1; --left; }
+        }
+        for (int q = 0; q < k && popc32(W) < kMmaRegBits; ++q) W |= 1u << q;
+        MmaWindow w{};
+        std::vector<int> rest;
+        int nb = 0;
+        for (int q = 0; q < k; ++q) {
+            if ((W >> q) & 1) w.rpos[nb++] = (uint8_t)q;
+            else rest.push_back(q);
+        }
+        w.qlpos = (uint8_t)rest.back();   // any position outside the flip masks
+        rest.pop_back();
+        split_rest(rest, w.gpos, w.wpos);
+        for (int r = 0; r < kMmaRegBits; ++r) w.rpos_out[r] = w.rpos[r];
+        w.qlpos_out = w.qlpos;
+        w.flags = kWinFlagReadOnly;
+        uint64_t wphys = 0;
+        for (int r = 0; r < kMmaRegBits; ++r) wphys |= bit(p.local[w.rpos[r]]);
+        auto zr_of = [&](uint64_t z) {
+            uint32_t zr = 0;
+            for (int r = 0; r < kMmaRegBits; ++r)
+                if ((z >> p.local[w.rpos[r]]) & 1) zr |= 1u << r;
+            return zr;
+        };
+        std::vector<WinOp> ops;
+        for (int g : mine) {
+            uint32_t xr = 0;
+            for (int r = 0; r < kMmaRegBits; ++r)
+                if ((xl[g] >> w.rpos[r]) & 1) xr |= 1u << r;
+            const auto& terms = groups[g].terms;
+            if (xr == 0) {
+                // diagonal terms: classes over register bits 0..3 only; register bit 4 counts as an outside bit (the
+                // kernel evaluates the two halves separately to stay within its register budget)
+                const int r4phys = p.local[w.rpos[4]];
+                const uint64_t wphys4 = wphys & ~bit(r4phys);
+                std::vector<std::vector<const ExpTermIn*>> cls(16);
+                for (const ExpTermIn& in : terms) cls[zr_of(in.z) & 15].push_back(&in);
+                WinOp o{};
+                o.w0 = winop_pack(M_EXPD, 0, 0, r4phys, 0);
+                o.t = (int32_t)p.eterms.size();
+                EUnit cnt[2] = {};
+                for (uint32_t zr = 0; zr < 16; ++zr) {
+                    const uint64_t c = std::min<size_t>(cls[zr].size(), 0xffff);
+                    cnt[zr / 8].w[(zr % 8) / 4] |= c << (16 * (zr % 4));
+                }
+                p.eterms.push_back(cnt[0]);
+                p.eterms.push_back(cnt[1]);
+                for (uint32_t zr = 0; zr < 16; ++zr)
+                    for (size_t i = 0; i < std::min<size_t>(cls[zr].size(), 0xffff); ++i) {
+                        EUnit u;
+                        u.w[0] = cls[zr][i]->z & ~wphys4;
+                        memcpy(&u.w[1], &cls[zr][i]->wre, 8);
+                        p.eterms.push_back(u);
+                    }
+                ops.push_back(o);
+                continue;
+            }
+            std::vector<uint64_t> keys;
+            for (const ExpTermIn& in : terms) {
+                const uint64_t key = in.z & ~wphys;
+                if (std::find(keys.begin(), keys.end(), key) == keys.end()) keys.push_back(key);
+            }
+            for (uint64_t key : keys) {
+                double fre[NR] = {}, fim[NR] = {};
+                for (const ExpTermIn& in : terms) {
+                    if ((in.z & ~wphys) != key) continue;
+                    const uint32_t zr = zr_of(in.z);
+                    for (uint32_t r = 0; r < (uint32_t)NR; ++r) {
+                        const double sg = __builtin_parity(r & zr) ? -1.0 : 1.0;
+                        fre[r] += sg * in.wre;
+                        fim[r] += sg * in.wim;
+                    }
+                }
+                double ca[NR / 2], cb[NR / 2];
+                bool imag = false;
+                int q = 0;
+                for (uint32_t r = 0; r < (uint32_t)NR; ++r) {
+                    if ((r ^ xr) < r) continue;
+                    ca[q] = fre[r] + fre[r ^ xr];
+                    cb[q] = fim[r] - fim[r ^ xr];
+                    imag = imag || cb[q] != 0.0;
+                    ++q;
+                }
+                WinOp o{};
+                o.t = (int32_t)p.eterms.size();
+                EUnit head{};
+                head.w[0] = key;
+                p.eterms.push_back(head);
+                for (int i = 0; i < NR / 2; i += 2) { EUnit u; memcpy(&u.w[0], &ca[i], 8); memcpy(&u.w[1], &ca[i + 1], 8); p.eterms.push_back(u); }
+                for (int i = 0; i < NR / 2; i += 2) { EUnit u; memcpy(&u.w[0], &cb[i], 8); memcpy(&u.w[1], &cb[i + 1], 8); p.eterms.push_back(u); }
+                o.w0 = winop_pack(M_EXPC, 0, imag ? 1 : 0, 9, (int)xr);
+                ops.push_back(o);
+            }
+        }
+        for (size_t lo = 0; lo < ops.size() || lo == 0; lo += kMaxWindowOps) {
+            MmaWindow part = w;
+            part.op_begin = (int32_t)p.wops.size();
+            for (size_t i = lo; i < std::min(ops.size(), lo + kMaxWindowOps); ++i) p.wops.push_back(ops[i]);
+            part.op_end = (int32_t)p.wops.size();
+            p.mwindows.push_back(part);
+            if (lo + kMaxWindowOps >= ops.size()) break;
+        }
+    }
+}
+
 void append_expectation_windows(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover) {
     const int k_real = (int)p.local.size();
     const int k = std::max(k_real, kMinTileBits);
@@ -611,7 +944,7 @@ CompiledCircuit plan_statevector(int n, const std::vector<Gate>& gates, const Pl
     if (!validate(n, gates, err)) return cc;
     std::vector<AOp> ops;
     lower(fuse_gates(n, gates, opt.trajectory ? 2 : 0, opt.fuse), n, false, cc, ops);
-    cc.passes = pack(n, ops, opt, cover_masks);
+    cc.passes = pack(n, ops, opt, cover_masks, opt.mma);
     return cc;
 }
 
@@ -620,7 +953,7 @@ CompiledCircuit plan_density(int n, const std::vector<Gate>& gates, const PlanOp
     if (!validate(n, gates, err)) return cc;
     std::vector<AOp> ops;
     lower(fuse_gates(n, gates, 1, opt.fuse), n, true, cc, ops);
-    cc.passes = pack(2 * n, ops, opt, {});
+    cc.passes = pack(2 * n, ops, opt, {}, false);
     return cc;
 }
 
@@ -647,7 +980,8 @@ std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const Pla
         for (int q = 0; q < n && __builtin_popcountll(L) < k; ++q) L |= bit(q);
         Pass p;
         finish_pass(p, n, L);
-        schedule_windows(p);
+        if (opt.mma && (int)p.local.size() >= kMmaMinTileBits) schedule_windows_mma(p);
+        else schedule_windows(p);
         passes.push_back(std::move(p));
         if (!progressed) break;  // a mask wider than the tile: caller reports the error
     }

@@ -108,7 +108,48 @@ struct Window {     // 24 bytes, read by the kernel from global memory
 // spreads any three independent tile positions over the eight 16-byte bank groups
 constexpr uint8_t kSwizzleVec[13] = {1, 2, 4, 3, 5, 6, 7, 1, 2, 4, 3, 5, 6};
 
+// ---- tensor-core (DMMA) windows -----------------------------------------------------------------------------------
+// Pure-state passes with tiles of >= 2^9 amplitudes run their blocks on the FP64 tensor cores (mma.sync m8n8k4.f64).
+// A warp owns 2^9 amplitudes; a thread holds 32 doubles: ONE component (lane bit 0: real / imaginary part) of the 32
+// amplitudes that differ in the window's five "register qubits" R0..R4.  Lane bit 1 is one more window qubit, "QL";
+// lane bits 2..4 and the warp index are six tile positions the window does not act on.  A 4x4 complex block on
+// (QL, Rx) is the 8x8 real matrix product  D[group][out] = sum_k A[group][k] B[k][out]  over k = (Rx, QL, re/im): the
+// A fragments are the thread's own registers with Rx = 0 / 1 (two chained DMMAs), the D fragment lands in the same
+// two registers, and B is two doubles per thread taken from the block's matrix -- no data movement at all.  Any of
+// the five register qubits can pair with QL; a block on two register qubits first exchanges one of them with QL
+// (M_SWAPQL: half of the registers cross to lane ^ 2 by shuffle).
+constexpr int kMmaRegBits = 5;
+constexpr int kMmaWinBits = kMmaRegBits + 1;   // qubits a window can act on
+constexpr int kMmaMinTileBits = 9;             // one warp
+enum : int32_t {    // WinOp codes of DMMA windows; rb / rb2 are 4-bit fields, qsel and flags 8-bit fields
+    M_U2 = 16,      // dense block: rb = x (register bit paired with QL), rb2 = mode:
+                    //   0: 4x4, matrix index bit 0 = QL, bit 1 = Rx     1: 4x4, index bit 0 = Rx, bit 1 = QL
+                    //   2: 2x2 on Rx (identity on QL)                   3: 2x2 on QL (identity on Rx)
+                    //   4: scalar m[0] / m[3] selected by physical bit qsel (diagonal block outside the window)
+    M_SWAPQL = 17,  // rb = x: exchange the roles of QL and Rx
+    M_CX_OUT = 18,  // rb = target register bit, qsel = physical control bit (outside the window)
+    M_CX_RR = 19,   // rb = control register bit, rb2 = target register bit
+    M_EXPC = 20,    // expectation class: flags = flip mask over the register bits (!= 0), rb2 bit 0 = has imaginary
+                    // coefficients.  Data at eterms[t]: unit 0 = Z/Y mask outside the window; units 1..8 = cA[16]
+                    // (one per register pair r < r ^ flip); units 9..16 = cB[16]
+    M_EXPD = 21,    // all diagonal terms: units 0..3 at eterms[t] = 32 uint16 class counts, then one unit per term
+};
+struct MmaWindow {  // 32 bytes
+    uint8_t rpos[kMmaRegBits];      // tile position of register bit r when the window is entered
+    uint8_t qlpos;                  // tile position of lane bit 1 (QL) on entry
+    uint8_t gpos[3];                // tile positions of lane bits 2, 3, 4
+    uint8_t wpos[3];                // tile positions of the warp-index bits (first k - 9 used)
+    uint8_t rpos_out[kMmaRegBits];  // the same after the window's M_SWAPQL ops (layout written back)
+    uint8_t qlpos_out;
+    uint8_t flags;                  // kWinFlagReadOnly
+    uint8_t pad[5];
+    int32_t op_begin, op_end;
+};
+static_assert(sizeof(MmaWindow) == 32, "MmaWindow layout");
+
 struct Pass {
+    bool mma = false;           // windows are MmaWindow (tensor-core kernel) instead of Window
+    std::vector<MmaWindow> mwindows;
     std::vector<int> local;     // physical bits of the tile, ascending; local[p] = physical bit of tile position p
     std::vector<int> nonlocal;  // remaining physical bits, ascending
     std::vector<DevOp> ops;     // tile-level ops in a valid execution order (what the windows were scheduled from)
@@ -124,6 +165,7 @@ struct PlanOptions {
     int low_bits = 4;     // c: physical bits 0..c-1 are local in every pass (2^c * 16 B contiguous runs)
     bool trajectory = false;  // TQ_DEPOL* become per-element sampled Pauli gates (else skipped on the pure path)
     bool fuse = true;     // false: every gate is its own block (debugging / A-B comparisons)
+    bool mma = true;      // pure-state passes with >= 2^9-amplitude tiles use DMMA windows
 };
 
 struct CompiledCircuit {
@@ -146,6 +188,8 @@ std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const Pla
                              std::vector<int>* assignment);
 
 void schedule_windows(Pass& p);
+void schedule_windows_mma(Pass& p);   // needs >= kMmaMinTileBits local qubits, no density-matrix ops
+void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover);
 // Appends read-only windows that evaluate the given Hamiltonian groups (flip masks must be local to the pass) on
 // registers; groups that flip more than kRegBits qubits are returned in `leftover` (shared-memory fallback).
 void append_expectation_windows(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover);

@@ -207,6 +207,12 @@ def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=(), w
             wpos = [int(v) for v in tok[1].split("=")[1].split(",") if v != ""]
             tpos = [int(v) for v in tok[2].split("=")[1].split(",") if v != ""]
             passes[-1]["windows"].append({"wpos": wpos, "tpos": tpos, "ops": []})
+        elif tok[0] == "MWIN":  # tensor-core window: r, ql, g, w (entry layout), rout, qlout (exit layout), flags
+            kv = dict(t.split("=") for t in tok[1:])
+            ints = lambda v: [int(x) for x in v.split(",") if x != ""]  # noqa: E731
+            passes[-1]["windows"].append({"mma": True, "r": ints(kv["r"]), "ql": int(kv["ql"]), "g": ints(kv["g"]),
+                                          "w": ints(kv["w"]), "rout": ints(kv["rout"]), "qlout": int(kv["qlout"]),
+                                          "flags": int(kv["flags"]), "ops": []})
         elif tok[0] == "WOP":  # (code, rb, rb2, qsel, flags, t, fixed)
             passes[-1]["windows"][-1]["ops"].append(tuple(int(v) for v in tok[1:7]) + (float(tok[7]),))
     return {"passes": passes, "mats": mats} if with_mats else passes

@@ -10,6 +10,7 @@ OP_U2, OP_U1, OP_D1, OP_D1_NL, OP_CNOT, OP_CNOT_NL, OP_DEPOL1_DM, OP_DEPOL2_DM =
 W_U2, W_U1, W_D1, W_D1_OUT, W_CX_WW, W_CX_OW, W_DEPOL1, W_DEPOL2 = range(8)
 MG_RX, MG_RY, MG_RZ, MG_CX, MG_X, MG_Y, MG_Z, MG_PAULI_SLOT = range(8)
 FLAG_CONJ, FLAG_SWAP = 1, 2
+M_U2, M_SWAPQL, M_CX_OUT, M_CX_RR, M_EXPC, M_EXPD = range(16, 22)
 
 
 def block_matrix(mat, params, codes):
@@ -124,6 +125,9 @@ def run_plan_windows(plan, nbits, params, init=None, codes=None):
         loc = p["local"]
         k_eff = max(len(loc), 4)
         for w in p["windows"]:
+            if w.get("mma"):
+                vec = _run_mma_window(vec, nbits, loc, w, mats)
+                continue
             assert len(w["wpos"]) == 4 and len(set(w["wpos"])) == 4
             assert sorted(w["wpos"] + w["tpos"]) == list(range(k_eff))
             assert len(w["ops"]) <= 32
@@ -162,6 +166,51 @@ def run_plan_windows(plan, nbits, params, init=None, codes=None):
     return vec
 
 
+def _run_mma_window(vec, nbits, loc, w, mats):
+    """Tensor-core window (tq_plan.h "DMMA windows"): ops act on (QL, register bit) pairs; M_SWAPQL only relabels."""
+    k = len(loc)
+    assert k >= 9 and len(w["r"]) == 5 and len(w["g"]) == 3 and len(w["w"]) == k - 9
+    assert sorted(w["r"] + [w["ql"]] + w["g"] + w["w"]) == list(range(k)), "entry layout is not a permutation"
+    assert len(w["ops"]) <= 32
+    r, ql = list(w["r"]), w["ql"]
+    fixed_pos = set(w["g"] + w["w"])
+    for code, rb, rb2, qsel, flags, t, fixed in w["ops"]:
+        inside = [loc[q] for q in r] + [loc[ql]]
+        if code == M_U2:
+            M = mats[t]
+            pq, px = loc[ql], loc[r[rb]]
+            if rb2 == 0:      # 4x4, index bit 0 = QL
+                assert M.shape == (4, 4)
+                vec = apply_2q(vec, nbits, pq, px, M)
+            elif rb2 == 1:    # 4x4, index bit 0 = RX
+                assert M.shape == (4, 4)
+                vec = apply_2q(vec, nbits, px, pq, M)
+            elif rb2 == 2:
+                assert M.shape == (2, 2)
+                vec = apply_1q(vec, nbits, px, M)
+            elif rb2 == 3:
+                assert M.shape == (2, 2)
+                vec = apply_1q(vec, nbits, pq, M)
+            else:             # diagonal block on a bit outside the window
+                assert rb2 == 4 and M.shape == (2, 2) and M[0, 1] == 0 and M[1, 0] == 0 and qsel not in inside
+                vec = apply_1q(vec, nbits, qsel, M)
+        elif code == M_SWAPQL:
+            r[rb], ql = ql, r[rb]
+        elif code == M_CX_OUT:
+            assert qsel not in inside
+            vec = apply_cnot(vec, nbits, qsel, loc[r[rb]])
+        elif code == M_CX_RR:
+            assert rb != rb2
+            vec = apply_cnot(vec, nbits, loc[r[rb]], loc[r[rb2]])
+        else:
+            raise ValueError(code)
+    assert r == w["rout"] and ql == w["qlout"], "exit layout does not match the swaps"
+    assert not (set(r) | {ql}) & fixed_pos
+    if not w["ops"]:
+        assert w["flags"] & 1, "layout-only windows are read-only"
+    return vec
+
+
 def check_invariants(plan, nbits, tile_bits, low_bits):
     """structural checks: tile size, forced low bits, every position operand is a valid tile position"""
     k = min(tile_bits, nbits)
@@ -174,7 +223,8 @@ def check_invariants(plan, nbits, tile_bits, low_bits):
         while lead < k and loc[lead] == lead:
             lead += 1
         assert p["lead"] == lead
-        assert sum(len(w["ops"]) for w in p["windows"]) == len(p["ops"])
+        n_real = sum(1 for w in p["windows"] for o in w["ops"] if o[0] != M_SWAPQL)
+        assert n_real == len(p["ops"])
         for op, a, b, t, flags, fixed in p["ops"]:
             if op in (OP_U1, OP_D1):
                 assert 0 <= a < k

@@ -50,6 +50,32 @@ def test_pure_plan_equals_gate_list(built_lib, oracle, n, tile_bits, low_bits, s
         assert n_blocks(plan) < len(gl)  # fusion merged something
 
 
+@pytest.mark.parametrize("n,tile_bits,low_bits,seed,gates", [(9, 12, 4, 21, 200), (10, 9, 3, 22, 300), (13, 10, 3, 23, 400),
+                                                              (14, 12, 3, 24, 500), (13, 11, 2, 25, 900)])
+def test_tensor_core_windows_equal_gate_list(built_lib, oracle, n, tile_bits, low_bits, seed, gates):
+    """Tiles of >= 2^9 amplitudes are scheduled as DMMA windows (QL + five register qubits, M_SWAPQL relabelling)."""
+    gl = synthetic_circuit(n, gates, seed)
+    gl.add_pauli("Z", 0)
+    params = parameter_batch(gl, 1)[0]
+    plan = plan_dump(gl, 0, tile_bits, low_bits, with_mats=True)
+    check_invariants(plan, n, tile_bits, low_bits)
+    wins = [w for p in plan["passes"] for w in p["windows"]]
+    assert wins and all(w.get("mma") for w in wins)
+    codes = {o[0] for w in wins for o in w["ops"]}
+    assert 16 in codes  # dense blocks on the tensor cores
+    assert np.abs(run_plan_windows(plan, n, params) - oracle.state(gl, params)).max() < 1e-12
+
+
+def test_register_windows_still_available(built_lib, oracle, monkeypatch):
+    """TQ_MMA=0 keeps the FP64-pipe register-window schedule for large tiles too (A/B comparisons)."""
+    monkeypatch.setenv("TQ_MMA", "0")
+    gl = synthetic_circuit(12, 300, 31)
+    params = parameter_batch(gl, 1)[0]
+    plan = plan_dump(gl, 0, 12, 4, with_mats=True)
+    assert not any(w.get("mma") for p in plan["passes"] for w in p["windows"])
+    assert np.abs(run_plan_windows(plan, 12, params) - oracle.state(gl, params)).max() < 1e-12
+
+
 def test_unfused_plan_matches_too(built_lib, oracle, monkeypatch):
     monkeypatch.setenv("TQ_FUSE", "0")
     gl = synthetic_circuit(9, 80, 3)
