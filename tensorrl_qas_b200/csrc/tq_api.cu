@@ -304,8 +304,13 @@ int compile_plan(tq_handle h, int which) {
         }
         std::vector<int> wide_groups;
         for (int wi : wide) wide_groups.push_back(groups_of_pass[i][wi]);
-        offs[i].windows = p.mma ? append(p.mwindows.data(), p.mwindows.size() * sizeof(MmaWindow))
-                                : append(p.windows.data(), p.windows.size() * sizeof(Window));
+        if (p.mma) {
+            std::vector<MmaWindowDev> dev;
+            for (const MmaWindow& w : p.mwindows) dev.push_back(resolve_window(w, p));
+            offs[i].windows = append(dev.data(), dev.size() * sizeof(MmaWindowDev));
+        } else {
+            offs[i].windows = append(p.windows.data(), p.windows.size() * sizeof(Window));
+        }
         offs[i].wops = append(p.wops.data(), p.wops.size() * sizeof(WinOp));
         offs[i].eterms = append(p.eterms.data(), p.eterms.size() * sizeof(EUnit));
         std::vector<ExpGroup> eg;
@@ -352,7 +357,7 @@ int compile_plan(tq_handle h, int which) {
         dp.n_tiles = 1 << dp.proto.n_nl;
         dp.gate_pass = (int)i < n_gate_passes;
         if (passes[i].mma) {
-            dp.proto.mwindows = (const MmaWindow*)(base + offs[i].windows);
+            dp.proto.mwindows = (const MmaWindowDev*)(base + offs[i].windows);
             dp.proto.n_windows = (int)passes[i].mwindows.size();
         } else {
             dp.proto.windows = (const Window*)(base + offs[i].windows);

@@ -595,24 +595,39 @@ typedef double Regs[NR];
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b, double c0, double c1) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
         : "=d"(d0), "=d"(d1)
         : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
 
-// 4x4 complex block on (QL, RX) as an 8x8 real product: for every pair of registers (RX = 0, RX = 1) two chained
-// DMMAs; A = the registers themselves (row = lane group, k = (QL, re/im) of the lane), B = (b0, b1) from the block's
-// matrix, D = the new pair.
+// 4x4 complex block on (QL, RX) as an 8x8 real product: per register pair (RX = 0, RX = 1) two chained DMMAs;
+// A = the registers themselves (row = lane group, k = (QL, re/im) of the lane), B = (b0, b1) from the block's matrix,
+// D = the new pair, which the instruction delivers in two ADJACENT registers.  With RX on register bit 0 that is the
+// pair itself.  With RX on bit X != 0 the four registers of (bit X, bit 0) are processed together and written back
+// with the two bits' roles exchanged -- still in place, no register moves; the planner tracks the relabelling.
 template <int X>
 __device__ __forceinline__ void m_u2(Regs& a, double b0, double b1) {
+    if (X == 0) {
 #pragma unroll
-    for (int p = 0; p < NR / 2; ++p) {
-        const int r0 = ((p >> X) << (X + 1)) | (p & ((1 << X) - 1)), r1 = r0 | (1 << X);
-        double d0, d1;
-        dmma884(d0, d1, a[r0], b0, 0.0, 0.0);
-        dmma884(d0, d1, a[r1], b1, d0, d1);
-        a[r0] = d0;
-        a[r1] = d1;
+        for (int p = 0; p < NR; p += 4) {   // two independent chains in flight
+            double t0, t1, u0, u1;
+            dmma884(t0, t1, a[p], b0, 0.0, 0.0);
+            dmma884(u0, u1, a[p + 2], b0, 0.0, 0.0);
+            dmma884(a[p], a[p + 1], a[p + 1], b1, t0, t1);
+            dmma884(a[p + 2], a[p + 3], a[p + 3], b1, u0, u1);
+        }
+    } else {
+#pragma unroll
+        for (int o = 0; o < NR / 4; ++o) {
+            // o enumerates the register bits other than 0 and X
+            const int lo = o & ((1 << (X - 1)) - 1), hi = o >> (X - 1);
+            const int p00 = (hi << (X + 1)) | (lo << 1), p01 = p00 | 1, p10 = p00 | (1 << X), p11 = p10 | 1;
+            double t0, t1, u0, u1;
+            dmma884(t0, t1, a[p00], b0, 0.0, 0.0);   // bit-0 qubit = 0: inputs RX = 0 / 1 are p00 / p10
+            dmma884(u0, u1, a[p01], b0, 0.0, 0.0);   // bit-0 qubit = 1: inputs p01 / p11
+            dmma884(a[p00], a[p01], a[p10], b1, t0, t1);   // -> (bit X = 0; bit 0 = RX')
+            dmma884(a[p10], a[p11], a[p11], b1, u0, u1);   // -> (bit X = 1; bit 0 = RX')
+        }
     }
 }
 // QL <-> RX: the registers with RX != (lane's QL bit) cross to lane ^ 2
@@ -637,28 +652,6 @@ __device__ __forceinline__ void m_cx_out(Regs& a, bool pred) {
         a[r1] = pred ? a0 : a1;
     }
 }
-template <int CB, int TB>
-__device__ __forceinline__ void m_cx_rr(Regs& a) {
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-        if (((i >> CB) & 1) && !((i >> TB) & 1)) {
-            const double t = a[i];
-            a[i] = a[i | (1 << TB)];
-            a[i | (1 << TB)] = t;
-        }
-    }
-}
-__device__ __forceinline__ void exec_m_cx_rr(Regs& a, int cb, int tb) {
-#define TQ_RR(C, T) case C * 5 + T: m_cx_rr<C, T>(a); break;
-    switch (cb * 5 + tb) {
-        TQ_RR(0, 1) TQ_RR(0, 2) TQ_RR(0, 3) TQ_RR(0, 4) TQ_RR(1, 0) TQ_RR(1, 2) TQ_RR(1, 3) TQ_RR(1, 4)
-        TQ_RR(2, 0) TQ_RR(2, 1) TQ_RR(2, 3) TQ_RR(2, 4) TQ_RR(3, 0) TQ_RR(3, 1) TQ_RR(3, 2) TQ_RR(3, 4)
-        TQ_RR(4, 0) TQ_RR(4, 1) TQ_RR(4, 2) TQ_RR(4, 3)
-    default: break;
-    }
-#undef TQ_RR
-}
-
 // expectation class on registers: every lane contributes the products of ITS component; the two lanes of a pair are
 // summed by the CTA-wide reduction.  Im(conj(w) v) needs the other component of v: one shuffle per register pair.
 template <int XR>
@@ -725,7 +718,7 @@ __device__ __forceinline__ double m_expd_half(const Regs& a, uint64_t ctx, const
     return total;
 }
 
-enum : int { FM_U2 = 0, FM_SCAL = 5, FM_SWAP = 6, FM_CXO = 11, FM_CXRR = 16, FM_EXPC = 17, FM_EXPD = 18 };
+enum : int { FM_U2 = 0, FM_SCAL = 5, FM_SWAP = 6, FM_CXO = 11, FM_EXPC = 17, FM_EXPD = 18 };
 
 __device__ __forceinline__ int flat_code_mma(uint32_t w0) {
     const int code = w0 & 0xff, rb = (w0 >> 8) & 0xf, rb2 = (w0 >> 12) & 0xf;
@@ -733,7 +726,6 @@ __device__ __forceinline__ int flat_code_mma(uint32_t w0) {
     case M_U2: return rb2 == 4 ? FM_SCAL : FM_U2 + rb;
     case M_SWAPQL: return FM_SWAP + rb;
     case M_CX_OUT: return FM_CXO + rb;
-    case M_CX_RR: return FM_CXRR;
     case M_EXPC: return FM_EXPC;
     default: return FM_EXPD;
     }
@@ -749,7 +741,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     double2* s_mat = amp + tile_amps;
     WinOp* s_wops = reinterpret_cast<WinOp*>(s_mat + kOpSlots * kMatStride);
     double* s_red = reinterpret_cast<double*>(s_wops + kOpSlots);
-    MmaWindow* s_win = reinterpret_cast<MmaWindow*>(s_red + 32);                 // kWinSlots headers
+    MmaWindowDev* s_win = reinterpret_cast<MmaWindowDev*>(s_red + 32);           // kWinSlots headers
     uint32_t* hi_off = reinterpret_cast<uint32_t*>(s_win + kWinSlots);
 
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -787,7 +779,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     const int brow = (g >> 2) | ((g & 1) << 1);            // staged matrix row: index bit 0 = QL, bit 1 = RX
     const int bcol = (lane >> 1) & 1;                      // column for RX = 0; RX = 1 adds 2
     const bool bsame = ((g >> 1) & 1) == comp;             // output and input component agree -> real part
-    const bool bco = (g >> 1) & 1;                         // output component (sign of the imaginary part)
+    const long long bneg = ((g >> 1) & 1) ? 0ll : (long long)(1ull << 63);   // output = real part: -Im
 
     int staged_begin = 0, staged_end = 0;
     auto stage_ops = [&](int first) {
@@ -830,7 +822,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = make_double2((tile_base == 0 && tid == 0 && i == 0) ? 1.0 : 0.0, 0.0);
         }
-        for (int i = tid; i < 2 * min(n_run, kWinSlots); i += nthreads)
+        for (int i = tid; i < 4 * min(n_run, kWinSlots); i += nthreads)
             reinterpret_cast<uint4*>(s_win)[i] = __ldg(reinterpret_cast<const uint4*>(p.mwindows) + i);
         stage_ops(0);
 #pragma unroll
@@ -841,54 +833,53 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     // ---- 2. windows ----
     Regs a;
     double acc = 0.0;
-    bool wrote_back = false;
-    auto write_back = [&]() {   // shared memory holds the final tile
-        if (p.dst && !wrote_back) {
-            double2* dst = p.dst + elem_off + tile_base;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) dst[TQ_IO_GOFF(i)] = amp[TQ_IO_SLOT(i)];
-        }
-        wrote_back = true;
-    };
-    for (int w = 0; w < n_run; ++w) {
-        if (w == p.n_gate_windows) write_back();
-        MmaWindow hdr;
-        if (w < kWinSlots) hdr = s_win[w];
-        else {
-            const uint4* raw = reinterpret_cast<const uint4*>(p.mwindows + w);
-            reinterpret_cast<uint4*>(&hdr)[0] = __ldg(raw);
-            reinterpret_cast<uint4*>(&hdr)[1] = __ldg(raw + 1);
-        }
-        const bool read_only = hdr.flags & kWinFlagReadOnly;
-        const int op_begin = hdr.op_begin, op_end = hdr.op_end;
-        if (op_end > staged_end) {   // CTA-uniform: restage from this window on
+    uint32_t slot_rest = 0;
+    uint64_t ctx = 0;
+    // entering window w: (re)stage ops if needed, compute this thread's layout and load its 32 doubles
+    auto enter = [&](int w) -> const MmaWindowDev* {
+        const MmaWindowDev* hdr = (w < kWinSlots) ? s_win + w : nullptr;
+        if (!hdr) {   // very long passes: header from global memory into slot 0 (windows run in order)
             __syncthreads();
-            stage_ops(op_begin);
+            if (tid < 4) reinterpret_cast<uint4*>(s_win)[tid] = __ldg(reinterpret_cast<const uint4*>(p.mwindows + w) + tid);
+            __syncthreads();
+            hdr = s_win;
+        }
+        if (hdr->op_end > staged_end) {   // CTA-uniform: restage from this window on
+            __syncthreads();
+            stage_ops(hdr->op_begin);
             __syncthreads();
         }
-        // this thread's part of the tile index: lane bits 1..4 and the warp bits
-        uint32_t jrest = ((uint32_t)((lane >> 2) & 1) << hdr.gpos[0]) | ((uint32_t)((lane >> 3) & 1) << hdr.gpos[1]) |
-                         ((uint32_t)((lane >> 4) & 1) << hdr.gpos[2]);
+        // this thread's part of the tile index (lane bits 1..4 and the warp bits): shared-memory slot and physical
+        // index bits.  ctx holds QL as it sits on entry: gate windows never read QL through ctx, expectation windows
+        // never move it.
+        slot_rest = (((lane >> 2) & 1) ? hdr->gslot[0] : 0u) ^ (((lane >> 3) & 1) ? hdr->gslot[1] : 0u) ^
+                    (((lane >> 4) & 1) ? hdr->gslot[2] : 0u);
+        ctx = tile_base | ((uint64_t)((lane >> 2) & 1) << hdr->gphys[0]) | ((uint64_t)((lane >> 3) & 1) << hdr->gphys[1]) |
+              ((uint64_t)((lane >> 4) & 1) << hdr->gphys[2]) | ((uint64_t)l1 << hdr->qlphys);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
-            if (i < p.k - 9) jrest |= (uint32_t)((warp >> i) & 1) << hdr.wpos[i];
-        // physical index bits of everything this thread does not hold in registers (QL as it sits on entry: gate
-        // windows never read QL through ctx, expectation windows never move it)
-        const uint64_t ctx = tile_base | TQ_PHYS(jrest | ((uint32_t)l1 << hdr.qlpos));
-        {
-            const uint32_t slot_t = swz(jrest | ((uint32_t)l1 << hdr.qlpos));
-            const uint32_t r0 = swz(1u << hdr.rpos[0]), r1 = swz(1u << hdr.rpos[1]), r2 = swz(1u << hdr.rpos[2]),
-                           r3 = swz(1u << hdr.rpos[3]), r4 = swz(1u << hdr.rpos[4]);
+            if (i < p.k - 9 && ((warp >> i) & 1)) {
+                slot_rest ^= hdr->wslot[i];
+                ctx |= 1ull << hdr->wphys[i];
+            }
+        const uint32_t slot_t = slot_rest ^ (l1 ? hdr->qslot : 0u);
+        const uint32_t r0 = hdr->rslot[0], r1 = hdr->rslot[1], r2 = hdr->rslot[2], r3 = hdr->rslot[3], r4 = hdr->rslot[4];
 #pragma unroll
-            for (int r = 0; r < NR; ++r) a[r] = ampd[2 * (slot_t ^ TQ_SEL5(r, r0, r1, r2, r3, r4)) + comp];
-        }
-        if (!read_only) __syncthreads();   // everyone holds its entry data: the tile may be overwritten from here on
+        for (int r = 0; r < NR; ++r) a[r] = ampd[2 * (slot_t ^ TQ_SEL5(r, r0, r1, r2, r3, r4)) + comp];
+        return hdr;
+    };
 
-        for (int o = op_begin - staged_begin; o < op_end - staged_begin; ++o) {
-            const WinOp wo = s_wops[o];
+    // ---- 2a. gate windows ----
+    for (int w = 0; w < p.n_gate_windows; ++w) {
+        const MmaWindowDev* hdr = enter(w);
+        if (hdr->flags & kWinFlagReadOnly) continue;   // layout-only window of an expectation-only pass
+        __syncthreads();   // everyone holds its entry data: the tile may be overwritten from here on
+        const int o_end = hdr->op_end - staged_begin;
+        for (int o = hdr->op_begin - staged_begin; o < o_end; ++o) {
+            const uint32_t w0 = s_wops[o].w0;
             const double2* m = s_mat + o * kMatStride;
-            const int fc = wo.w0 & 0xff;
-            const int qsel = (wo.w0 >> 16) & 0xff;
+            const int fc = w0 & 0xff;
+            const int qsel = (w0 >> 16) & 0xff;
             if (fc <= FM_SCAL) {
                 double2 u0, u1;
                 if (fc == FM_SCAL) {
@@ -900,8 +891,9 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
                     u0 = m[brow * 4 + bcol];
                     u1 = m[brow * 4 + bcol + 2];
                 }
-                const double b0 = bsame ? u0.x : (bco ? u0.y : -u0.y);
-                const double b1 = bsame ? u1.x : (bco ? u1.y : -u1.y);
+                // real 8x8 form: same component -> Re, re<-im -> -Im, im<-re -> +Im (sign flipped on the integer pipe)
+                const double b0 = bsame ? u0.x : __longlong_as_double(__double_as_longlong(u0.y) ^ bneg);
+                const double b1 = bsame ? u1.x : __longlong_as_double(__double_as_longlong(u1.y) ^ bneg);
                 switch (fc) {
                 case FM_U2 + 1: m_u2<1>(a, b0, b1); break;
                 case FM_U2 + 2: m_u2<2>(a, b0, b1); break;
@@ -921,8 +913,37 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
                 case FM_CXO + 2: m_cx_out<2>(a, (bool)((ctx >> qsel) & 1ull)); break;
                 case FM_CXO + 3: m_cx_out<3>(a, (bool)((ctx >> qsel) & 1ull)); break;
                 case FM_CXO + 4: m_cx_out<4>(a, (bool)((ctx >> qsel) & 1ull)); break;
-                case FM_CXRR: exec_m_cx_rr(a, (wo.w0 >> 8) & 0xf, (wo.w0 >> 12) & 0xf); break;
-                case FM_EXPC: {
+                default: break;
+                }
+            }
+        }
+        {
+            const uint32_t slot_t = slot_rest ^ (l1 ? hdr->qslot_out : 0u);
+            const uint32_t r0 = hdr->rslot_out[0], r1 = hdr->rslot_out[1], r2 = hdr->rslot_out[2],
+                           r3 = hdr->rslot_out[3], r4 = hdr->rslot_out[4];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) ampd[2 * (slot_t ^ TQ_SEL5(r, r0, r1, r2, r3, r4)) + comp] = a[r];
+        }
+        __syncthreads();   // the tile is complete in shared memory again
+    }
+
+    // ---- write back (shared memory holds the final tile) ----
+    if (p.dst) {
+        double2* dst = p.dst + elem_off + tile_base;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dst[TQ_IO_GOFF(i)] = amp[TQ_IO_SLOT(i)];
+    }
+
+    // ---- 2b. expectation windows (read-only: no barriers between them) ----
+    if (p.exp_mode == 1) {
+        for (int w = p.n_gate_windows; w < p.n_windows; ++w) {
+            const MmaWindowDev* hdr = enter(w);
+            const int o_end = hdr->op_end - staged_begin;
+            for (int o = hdr->op_begin - staged_begin; o < o_end; ++o) {
+                const WinOp wo = s_wops[o];
+                const double2* m = s_mat + o * kMatStride;
+                const int qsel = (wo.w0 >> 16) & 0xff;
+                if ((wo.w0 & 0xff) == FM_EXPC) {
                     const double* cA = reinterpret_cast<const double*>(m + 1);
                     const double* cB = ((wo.w0 >> 12) & 1)
                                            ? reinterpret_cast<const double*>(reinterpret_cast<const double2*>(p.eterms) + wo.t + 9)
@@ -930,28 +951,14 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
                     const double sum = exec_m_expc(a, (int)(wo.w0 >> 24), cA, cB, comp != 0);
                     const uint64_t zphys = (uint64_t)__double_as_longlong(m[0].x);
                     acc += (__popcll(ctx & zphys) & 1) ? -sum : sum;
-                    break;
-                }
-                default: {  // FM_EXPD: register bit 4 is treated as a bit outside the window (physical bit qsel)
+                } else {  // FM_EXPD: register bit 4 is treated as a bit outside the window (physical bit qsel)
                     const double2* terms = reinterpret_cast<const double2*>(p.eterms) + wo.t + 2;
                     acc += m_expd_half<0>(a, ctx, m, terms);
                     acc += m_expd_half<1>(a, ctx | (1ull << qsel), m, terms);
-                    break;
-                }
                 }
             }
         }
-        if (!read_only) {
-            const uint32_t slot_t = swz(jrest | ((uint32_t)l1 << hdr.qlpos_out));
-            const uint32_t r0 = swz(1u << hdr.rpos_out[0]), r1 = swz(1u << hdr.rpos_out[1]),
-                           r2 = swz(1u << hdr.rpos_out[2]), r3 = swz(1u << hdr.rpos_out[3]),
-                           r4 = swz(1u << hdr.rpos_out[4]);
-#pragma unroll
-            for (int r = 0; r < NR; ++r) ampd[2 * (slot_t ^ TQ_SEL5(r, r0, r1, r2, r3, r4)) + comp] = a[r];
-            __syncthreads();   // the tile is complete in shared memory again
-        }
     }
-    write_back();
 
     // ---- 3. Hamiltonian terms evaluated from shared memory (flip masks wider than a window / sparse entries) ----
     if (p.exp_mode != 0) {
@@ -1106,7 +1113,7 @@ __global__ void __launch_bounds__(kMaxThreads) dm_expect_kernel(const double2* _
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead) {
     const size_t n_hi = (size_t)1 << (k - lead);
     return ((size_t)16 << k_eff) + kOpSlots * (kMatStride * sizeof(double2) + sizeof(WinOp)) + 32 * sizeof(double) +
-           kWinSlots * sizeof(MmaWindow) + n_hi * sizeof(uint32_t);   // MmaWindow (32 B) >= Window (24 B)
+           kWinSlots * sizeof(MmaWindowDev) + n_hi * sizeof(uint32_t);   // MmaWindowDev (64 B) >= Window (24 B)
 }
 
 cudaError_t tile_pass_configure() {

@@ -45,7 +45,7 @@ struct PassParams {
     int src_mode;  // 0: |0...0>, 1: one shared initial vector, 2: per-element state buffer
     double2* dst;  // nullptr: tile is not written back
     const Window* windows;
-    const MmaWindow* mwindows;   // non-null: tensor-core pass (tile_pass_mma_kernel), `windows` unused
+    const MmaWindowDev* mwindows;   // non-null: tensor-core pass (tile_pass_mma_kernel), `windows` unused
     int n_windows, n_gate_windows;   // expectation windows follow the gate windows
     const EUnit* eterms;
     const WinOp* wops;

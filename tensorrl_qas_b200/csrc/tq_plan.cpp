@@ -532,6 +532,7 @@ void schedule_windows_mma(Pass& p) {
             const DevOp& d = tops[mine[j]].d;
             if (d.op == OP_U2) return ql == d.a || ql == d.b;
             if ((d.op == OP_CNOT && !((W >> d.a) & 1)) || d.op == OP_CNOT_NL) return ql != d.b;
+            if (d.op == OP_CNOT) return ql == d.a || ql == d.b;   // inside the window: runs as a dense block with QL
             return true;
         };
 
@@ -582,7 +583,7 @@ void schedule_windows_mma(Pass& p) {
                 if (pick < 0) pick = ready.front();
                 const DevOp& d = tops[mine[pick]].d;
                 int want;
-                if (d.op == OP_U2) {
+                if (d.op == OP_U2 || (d.op == OP_CNOT && ((W >> d.a) & 1))) {
                     done[pick] = 1;  // count the uses AFTER this block
                     want = better_ql(d.a, d.b);
                     done[pick] = 0;
@@ -617,12 +618,15 @@ void schedule_windows_mma(Pass& p) {
                     // the CNOT's constant matrix has index bit 0 = the physically lower qubit = the lower position
                     const int lo = std::min(d.a, d.b), other = (ql == d.a) ? d.b : d.a;
                     o.w0 = winop_pack(M_U2, rb_of(other), ql == lo ? 0 : 1, 0, 0);
-                } else o.w0 = winop_pack(M_CX_RR, rb_of(d.a), rb_of(d.b), 0, 0);
-                break;
+                }
+                break;   // (fits() guarantees QL is one of the two qubits of an in-window CNOT)
             case OP_CNOT_NL: o.w0 = winop_pack(M_CX_OUT, rb_of(d.b), 0, d.a, 0); break;
             default: break;  // density-matrix ops never reach a DMMA pass
             }
             out.push_back(o);
+            // a dense block on register bit x != 0 leaves its register qubit on bit 0 and the former bit-0 qubit on
+            // bit x (the tensor-core results always land in adjacent register pairs)
+            if ((o.w0 & 0xff) == M_U2 && ((o.w0 >> 8) & 0xf) != 0) std::swap(rp[0], rp[(o.w0 >> 8) & 0xf]);
             done[pick] = 1;
         }
         if (!have_layout) fix_layout(act[0]);
@@ -643,6 +647,7 @@ void schedule_windows_mma(Pass& p) {
             for (size_t i = lo; i < hi; ++i) {
                 p.wops.push_back(out[i]);
                 if ((out[i].w0 & 0xff) == M_SWAPQL) std::swap(cql, crp[(out[i].w0 >> 8) & 0xf]);
+                else if ((out[i].w0 & 0xff) == M_U2 && ((out[i].w0 >> 8) & 0xf) != 0) std::swap(crp[0], crp[(out[i].w0 >> 8) & 0xf]);
             }
             cur.op_end = (int32_t)p.wops.size();
             for (int r = 0; r < kMmaRegBits; ++r) cur.rpos_out[r] = (uint8_t)crp[r];
@@ -923,6 +928,23 @@ void append_expectation_windows(Pass& p, const std::vector<ExpGroupIn>& groups, 
             if (lo + kMaxWindowOps >= ops.size()) break;
         }
     }
+}
+
+MmaWindowDev resolve_window(const MmaWindow& w, const Pass& p) {
+    MmaWindowDev d{};
+    const int k = (int)p.local.size();
+    auto slot = [](int pos) { return (uint16_t)swizzle_slot(1u << pos); };
+    for (int r = 0; r < kMmaRegBits; ++r) { d.rslot[r] = slot(w.rpos[r]); d.rslot_out[r] = slot(w.rpos_out[r]); }
+    d.qslot = slot(w.qlpos);
+    d.qslot_out = slot(w.qlpos_out);
+    d.qlphys = (uint8_t)p.local[w.qlpos];
+    for (int i = 0; i < 3; ++i) { d.gslot[i] = slot(w.gpos[i]); d.gphys[i] = (uint8_t)p.local[w.gpos[i]]; }
+    for (int i = 0; i < 3; ++i)
+        if (i < k - 9) { d.wslot[i] = slot(w.wpos[i]); d.wphys[i] = (uint8_t)p.local[w.wpos[i]]; }
+    d.flags = w.flags;
+    d.op_begin = w.op_begin;
+    d.op_end = w.op_end;
+    return d;
 }
 
 bool mask_is_local(const Pass& p, uint64_t mask) {

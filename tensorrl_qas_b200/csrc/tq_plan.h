@@ -107,6 +107,12 @@ struct Window {     // 24 bytes, read by the kernel from global memory
 // bank swizzle of the shared-memory tile: amplitude j lives in slot j ^ fold(j >> 3), a GF(2)-linear map that
 // spreads any three independent tile positions over the eight 16-byte bank groups
 constexpr uint8_t kSwizzleVec[13] = {1, 2, 4, 3, 5, 6, 7, 1, 2, 4, 3, 5, 6};
+inline uint32_t swizzle_slot(uint32_t j) {
+    uint32_t s = j;
+    for (int p = 3; p < 13; ++p)
+        if ((j >> p) & 1) s ^= kSwizzleVec[p];
+    return s;
+}
 
 // ---- tensor-core (DMMA) windows -----------------------------------------------------------------------------------
 // Pure-state passes with tiles of >= 2^9 amplitudes run their blocks on the FP64 tensor cores (mma.sync m8n8k4.f64).
@@ -122,13 +128,14 @@ constexpr int kMmaRegBits = 5;
 constexpr int kMmaWinBits = kMmaRegBits + 1;   // qubits a window can act on
 constexpr int kMmaMinTileBits = 9;             // one warp
 enum : int32_t {    // WinOp codes of DMMA windows; rb / rb2 are 4-bit fields, qsel and flags 8-bit fields
-    M_U2 = 16,      // dense block: rb = x (register bit paired with QL), rb2 = mode:
+    M_U2 = 16,      // dense block: rb = x (register bit paired with QL; for x != 0 the block also exchanges the roles of
+                    // register bits 0 and x -- its results land in adjacent registers), rb2 = mode:
                     //   0: 4x4, matrix index bit 0 = QL, bit 1 = Rx     1: 4x4, index bit 0 = Rx, bit 1 = QL
                     //   2: 2x2 on Rx (identity on QL)                   3: 2x2 on QL (identity on Rx)
                     //   4: scalar m[0] / m[3] selected by physical bit qsel (diagonal block outside the window)
     M_SWAPQL = 17,  // rb = x: exchange the roles of QL and Rx
     M_CX_OUT = 18,  // rb = target register bit, qsel = physical control bit (outside the window)
-    M_CX_RR = 19,   // rb = control register bit, rb2 = target register bit
+                    // (a CNOT with both qubits inside the window runs as an M_U2 with its constant matrix)
     M_EXPC = 20,    // expectation class: flags = flip mask over the register bits (!= 0), rb2 bit 0 = has imaginary
                     // coefficients.  Data at eterms[t]: unit 0 = Z/Y mask outside the window; units 1..8 = cA[16]
                     // (one per register pair r < r ^ flip); units 9..16 = cB[16]
@@ -146,6 +153,22 @@ struct MmaWindow {  // 32 bytes
     int32_t op_begin, op_end;
 };
 static_assert(sizeof(MmaWindow) == 32, "MmaWindow layout");
+// What the kernel reads: the same window with every tile position resolved to its swizzled shared-memory slot offset
+// (the bank swizzle is GF(2)-linear, so a thread's slot is the XOR of the offsets of its set bits) and to its physical
+// qubit (for the control / sign bits a thread reads from its own index).
+struct MmaWindowDev {  // 64 bytes
+    uint16_t rslot[kMmaRegBits], rslot_out[kMmaRegBits];
+    uint16_t qslot, qslot_out;
+    uint16_t gslot[3], wslot[3];
+    uint8_t gphys[3], wphys[3], qlphys, flags;
+    int32_t op_begin, op_end;
+    uint8_t pad[12];
+};
+static_assert(sizeof(MmaWindowDev) == 64, "MmaWindowDev layout");
+MmaWindowDev resolve_window(const MmaWindow& w, const struct Pass& p);
+
+struct Pass;
+inline uint32_t swizzle_slot(uint32_t j);   // slot of tile index j (defined below kSwizzleVec)
 
 struct Pass {
     bool mma = false;           // windows are MmaWindow (tensor-core kernel) instead of Window

@@ -194,14 +194,13 @@ def _run_mma_window(vec, nbits, loc, w, mats):
             else:             # diagonal block on a bit outside the window
                 assert rb2 == 4 and M.shape == (2, 2) and M[0, 1] == 0 and M[1, 0] == 0 and qsel not in inside
                 vec = apply_1q(vec, nbits, qsel, M)
+            if rb != 0:       # results land in adjacent registers: register bits 0 and rb trade qubits
+                r[0], r[rb] = r[rb], r[0]
         elif code == M_SWAPQL:
             r[rb], ql = ql, r[rb]
         elif code == M_CX_OUT:
             assert qsel not in inside
             vec = apply_cnot(vec, nbits, qsel, loc[r[rb]])
-        elif code == M_CX_RR:
-            assert rb != rb2
-            vec = apply_cnot(vec, nbits, loc[r[rb]], loc[r[rb2]])
         else:
             raise ValueError(code)
     assert r == w["rout"] and ql == w["qlout"], "exit layout does not match the swaps"
