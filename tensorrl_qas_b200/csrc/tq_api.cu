@@ -287,6 +287,10 @@ int compile_plan(tq_handle h, int which) {
     std::vector<Offsets> offs(passes.size());
     const size_t off_descs = append(cc.mats.data(), cc.mats.size() * sizeof(MatDesc));
     const size_t off_prog = append(cc.prog.data(), cc.prog.size() * sizeof(MatGate));
+    std::vector<ExpTermIn> diag_pool;   // diagonal terms still to be evaluated (tensor-core passes share them)
+    size_t last_eval_pass = 0;
+    for (size_t i = 0; i < passes.size(); ++i)
+        if (!groups_of_pass[i].empty()) last_eval_pass = i;
     for (size_t i = 0; i < passes.size(); ++i) {
         Pass& p = passes[i];
         // groups whose flips fit a register window are evaluated there; wider ones through shared memory
@@ -299,7 +303,7 @@ int compile_plan(tq_handle h, int which) {
         }
         std::vector<int> wide;
         if (!gin.empty()) {
-            if (p.mma) append_expectation_windows_mma(p, gin, &wide);
+            if (p.mma) append_expectation_windows_mma(p, gin, &wide, &diag_pool, i == last_eval_pass);
             else append_expectation_windows(p, gin, &wide);
         }
         std::vector<int> wide_groups;

@@ -718,7 +718,7 @@ __device__ __forceinline__ double m_expd_half(const Regs& a, uint64_t ctx, const
     return total;
 }
 
-enum : int { FM_U2 = 0, FM_SCAL = 5, FM_SWAP = 6, FM_CXO = 11, FM_EXPC = 17, FM_EXPD = 18 };
+enum : int { FM_U2 = 0, FM_SCAL = 5, FM_SWAP = 6, FM_CXO = 11, FM_EXPC = 17, FM_EXPD = 18, FM_EXPT = 19 };
 
 __device__ __forceinline__ int flat_code_mma(uint32_t w0) {
     const int code = w0 & 0xff, rb = (w0 >> 8) & 0xf, rb2 = (w0 >> 12) & 0xf;
@@ -727,6 +727,7 @@ __device__ __forceinline__ int flat_code_mma(uint32_t w0) {
     case M_SWAPQL: return FM_SWAP + rb;
     case M_CX_OUT: return FM_CXO + rb;
     case M_EXPC: return FM_EXPC;
+    case M_EXPT: return FM_EXPT;
     default: return FM_EXPD;
     }
 }
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
                 s_wops[oi] = wo;
             }
             if (code >= M_EXPC) {
-                if (e < (code == M_EXPC ? 9 : 2))   // class header + cA[16] | the 16 class counts
+                if (e < (code == M_EXPC ? 9 : code == M_EXPT ? 16 : 2))   // header + cA[16] | D[32] | 16 class counts
                     s_mat[oi * kMatStride + e] = reinterpret_cast<const double2*>(p.eterms)[(size_t)wo.t + e];
             } else if (code == M_U2) {
                 // expand to a 4x4 with index bit 0 = QL, bit 1 = RX
@@ -951,6 +952,12 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
                     const double sum = exec_m_expc(a, (int)(wo.w0 >> 24), cA, cB, comp != 0);
                     const uint64_t zphys = (uint64_t)__double_as_longlong(m[0].x);
                     acc += (__popcll(ctx & zphys) & 1) ? -sum : sum;
+                } else if ((wo.w0 & 0xff) == FM_EXPT) {   // diagonal terms inside the window: signed-weight table
+                    const double* D = reinterpret_cast<const double*>(m);
+                    double sum = 0.0;
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) sum = fma(a[r] * a[r], D[r], sum);
+                    acc += sum;
                 } else {  // FM_EXPD: register bit 4 is treated as a bit outside the window (physical bit qsel)
                     const double2* terms = reinterpret_cast<const double2*>(p.eterms) + wo.t + 2;
                     acc += m_expd_half<0>(a, ctx, m, terms);

@@ -685,7 +685,8 @@ void schedule_windows_mma(Pass& p) {
     p.n_gate_windows = (int)p.mwindows.size();
 }
 
-void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover) {
+void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover,
+                                    std::vector<ExpTermIn>* diag_pool, bool final_pass) {
     const int k = (int)p.local.size();
     constexpr int NR = 1 << kMmaRegBits;
     std::vector<uint32_t> xl(groups.size());
@@ -693,16 +694,17 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
     size_t left = 0;
     for (size_t g = 0; g < groups.size(); ++g) {
         xl[g] = mask_to_local(p, groups[g].x);
-        if (popc32(xl[g]) > kMmaRegBits) { leftover->push_back((int)g); done[g] = 1; }
+        if (groups[g].x == 0) {   // diagonal terms go to the shared pool: every window takes those it fully contains
+            for (const ExpTermIn& t : groups[g].terms) diag_pool->push_back(t);
+            done[g] = 1;
+        } else if (popc32(xl[g]) > kMmaRegBits) { leftover->push_back((int)g); done[g] = 1; }
         else ++left;
     }
-    while (left > 0) {
-        uint32_t W = 0;
-        std::vector<int> mine;
-        for (size_t g = 0; g < groups.size(); ++g) {
-            if (done[g]) continue;
-            if (popc32(W | xl[g]) <= kMmaRegBits) { W |= xl[g]; mine.push_back((int)g); done[g] = 1; --left; }
-        }
+
+    // one read-only window with register positions W: the off-diagonal groups `mine`, the pool's diagonal terms that
+    // live entirely on its register qubits (a 32-entry sign-weight table, M_EXPT), and optionally `generic`: diagonal
+    // terms evaluated with signs from the thread's index (M_EXPD)
+    auto make_window = [&](uint32_t W, const std::vector<int>& mine, const std::vector<ExpTermIn>& generic) {
         for (int q = 0; q < k && popc32(W) < kMmaRegBits; ++q) W |= 1u << q;
         MmaWindow w{};
         std::vector<int> rest;
@@ -726,38 +728,59 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
             return zr;
         };
         std::vector<WinOp> ops;
+        // --- diagonal terms contained in the window: E += sum_r |psi_r|^2 D[r] ---
+        {
+            double D[NR] = {};
+            bool any = false;
+            for (auto it = diag_pool->begin(); it != diag_pool->end();) {
+                if ((it->z & ~wphys) == 0) {
+                    const uint32_t zr = zr_of(it->z);
+                    for (uint32_t r = 0; r < (uint32_t)NR; ++r) D[r] += __builtin_parity(r & zr) ? -it->wre : it->wre;
+                    any = true;
+                    it = diag_pool->erase(it);
+                } else ++it;
+            }
+            if (any) {
+                WinOp o{};
+                o.w0 = winop_pack(M_EXPT, 0, 0, 0, 0);
+                o.t = (int32_t)p.eterms.size();
+                for (int i = 0; i < NR; i += 2) { EUnit u; memcpy(&u.w[0], &D[i], 8); memcpy(&u.w[1], &D[i + 1], 8); p.eterms.push_back(u); }
+                ops.push_back(o);
+            }
+        }
+        // --- diagonal terms that reach outside the window (signs from the thread's index) ---
+        if (!generic.empty()) {
+            // classes over register bits 0..3 only; register bit 4 counts as an outside bit (the kernel evaluates the
+            // two halves separately to stay within its register budget)
+            const int r4phys = p.local[w.rpos[4]];
+            const uint64_t wphys4 = wphys & ~bit(r4phys);
+            std::vector<std::vector<const ExpTermIn*>> cls(16);
+            for (const ExpTermIn& in : generic) cls[zr_of(in.z) & 15].push_back(&in);
+            WinOp o{};
+            o.w0 = winop_pack(M_EXPD, 0, 0, r4phys, 0);
+            o.t = (int32_t)p.eterms.size();
+            EUnit cnt[2] = {};
+            for (uint32_t zr = 0; zr < 16; ++zr) {
+                const uint64_t c = std::min<size_t>(cls[zr].size(), 0xffff);
+                cnt[zr / 8].w[(zr % 8) / 4] |= c << (16 * (zr % 4));
+            }
+            p.eterms.push_back(cnt[0]);
+            p.eterms.push_back(cnt[1]);
+            for (uint32_t zr = 0; zr < 16; ++zr)
+                for (size_t i = 0; i < std::min<size_t>(cls[zr].size(), 0xffff); ++i) {
+                    EUnit u;
+                    u.w[0] = cls[zr][i]->z & ~wphys4;
+                    memcpy(&u.w[1], &cls[zr][i]->wre, 8);
+                    p.eterms.push_back(u);
+                }
+            ops.push_back(o);
+        }
+        // --- off-diagonal groups ---
         for (int g : mine) {
             uint32_t xr = 0;
             for (int r = 0; r < kMmaRegBits; ++r)
                 if ((xl[g] >> w.rpos[r]) & 1) xr |= 1u << r;
             const auto& terms = groups[g].terms;
-            if (xr == 0) {
-                // diagonal terms: classes over register bits 0..3 only; register bit 4 counts as an outside bit (the
-                // kernel evaluates the two halves separately to stay within its register budget)
-                const int r4phys = p.local[w.rpos[4]];
-                const uint64_t wphys4 = wphys & ~bit(r4phys);
-                std::vector<std::vector<const ExpTermIn*>> cls(16);
-                for (const ExpTermIn& in : terms) cls[zr_of(in.z) & 15].push_back(&in);
-                WinOp o{};
-                o.w0 = winop_pack(M_EXPD, 0, 0, r4phys, 0);
-                o.t = (int32_t)p.eterms.size();
-                EUnit cnt[2] = {};
-                for (uint32_t zr = 0; zr < 16; ++zr) {
-                    const uint64_t c = std::min<size_t>(cls[zr].size(), 0xffff);
-                    cnt[zr / 8].w[(zr % 8) / 4] |= c << (16 * (zr % 4));
-                }
-                p.eterms.push_back(cnt[0]);
-                p.eterms.push_back(cnt[1]);
-                for (uint32_t zr = 0; zr < 16; ++zr)
-                    for (size_t i = 0; i < std::min<size_t>(cls[zr].size(), 0xffff); ++i) {
-                        EUnit u;
-                        u.w[0] = cls[zr][i]->z & ~wphys4;
-                        memcpy(&u.w[1], &cls[zr][i]->wre, 8);
-                        p.eterms.push_back(u);
-                    }
-                ops.push_back(o);
-                continue;
-            }
             std::vector<uint64_t> keys;
             for (const ExpTermIn& in : terms) {
                 const uint64_t key = in.z & ~wphys;
@@ -803,6 +826,42 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
             p.mwindows.push_back(part);
             if (lo + kMaxWindowOps >= ops.size()) break;
         }
+    };
+
+    // 1. windows for the off-diagonal groups
+    while (left > 0) {
+        uint32_t W = 0;
+        std::vector<int> mine;
+        for (size_t g = 0; g < groups.size(); ++g) {
+            if (done[g]) continue;
+            if (popc32(W | xl[g]) <= kMmaRegBits) { W |= xl[g]; mine.push_back((int)g); done[g] = 1; --left; }
+        }
+        make_window(W, mine, {});
+    }
+    if (!final_pass) return;
+    // 2. the last pass that evaluates anything also takes what is left of the diagonal pool: windows for the terms
+    //    whose qubits are local here and fit a window ...
+    uint64_t lmask = 0;
+    for (int q : p.local) lmask |= bit(q);
+    for (;;) {
+        uint32_t W = 0;
+        for (const ExpTermIn& t : *diag_pool) {
+            if (t.z & ~lmask) continue;
+            const uint32_t zl = mask_to_local(p, t.z);
+            if (popc32(W | zl) <= kMmaRegBits) W |= zl;
+        }
+        if (W == 0) {   // nothing coverable is left (a term with z == 0, the identity, is taken by any window)
+            bool identity_left = false;
+            for (const ExpTermIn& t : *diag_pool) identity_left = identity_left || t.z == 0;
+            if (!identity_left) break;
+        }
+        make_window(W, {}, {});
+    }
+    // 3. ... and one window with index-dependent signs for the rest (long Z strings, qubits outside the tile)
+    if (!diag_pool->empty()) {
+        std::vector<ExpTermIn> rest;
+        rest.swap(*diag_pool);
+        make_window(0, {}, rest);
     }
 }
 

@@ -139,7 +139,11 @@ enum : int32_t {    // WinOp codes of DMMA windows; rb / rb2 are 4-bit fields, q
     M_EXPC = 20,    // expectation class: flags = flip mask over the register bits (!= 0), rb2 bit 0 = has imaginary
                     // coefficients.  Data at eterms[t]: unit 0 = Z/Y mask outside the window; units 1..8 = cA[16]
                     // (one per register pair r < r ^ flip); units 9..16 = cB[16]
-    M_EXPD = 21,    // all diagonal terms: units 0..3 at eterms[t] = 32 uint16 class counts, then one unit per term
+    M_EXPD = 21,    // diagonal terms with Z bits outside the window: classes over register bits 0..3 (units 0..1 at
+                    // eterms[t] = 16 uint16 class counts, then one unit (outside Z mask incl. register bit 4, weight)
+                    // per term); qsel = physical bit of register bit 4
+    M_EXPT = 22,    // diagonal terms that live on the window's register qubits: E += sum_r |psi_r|^2 D[r], D[32] at
+                    // eterms[t] (16 units)
 };
 struct MmaWindow {  // 32 bytes
     uint8_t rpos[kMmaRegBits];      // tile position of register bit r when the window is entered
@@ -212,7 +216,10 @@ std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const Pla
 
 void schedule_windows(Pass& p);
 void schedule_windows_mma(Pass& p);   // needs >= kMmaMinTileBits local qubits, no density-matrix ops
-void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover);
+// diag_pool: diagonal terms not evaluated yet (shared by the passes of a plan, consumed window by window); the final
+// pass of the plan takes whatever is left.
+void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover,
+                                    std::vector<ExpTermIn>* diag_pool, bool final_pass);
 // Appends read-only windows that evaluate the given Hamiltonian groups (flip masks must be local to the pass) on
 // registers; groups that flip more than kRegBits qubits are returned in `leftover` (shared-memory fallback).
 void append_expectation_windows(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover);
