@@ -49,6 +49,7 @@ struct Plan {
 }  // namespace
 
 struct tq_context {
+    int skew_ns = 0, n_sms = 0;
     int n = 0, device = 0;
     std::string err;
     PlanOptions opt;
@@ -283,7 +284,7 @@ int compile_plan(tq_handle h, int which) {
         if (bytes) memcpy(blob.data() + off, data, bytes);
         return off;
     };
-    struct Offsets { size_t windows, wops, groups, terms, eterms; int n_groups, n_terms; };
+    struct Offsets { size_t windows, wops, groups, terms, eterms, io_goff; int n_groups, n_terms; };
     std::vector<Offsets> offs(passes.size());
     const size_t off_descs = append(cc.mats.data(), cc.mats.size() * sizeof(MatDesc));
     const size_t off_prog = append(cc.prog.data(), cc.prog.size() * sizeof(MatGate));
@@ -309,6 +310,15 @@ int compile_plan(tq_handle h, int which) {
         std::vector<int> wide_groups;
         for (int wi : wide) wide_groups.push_back(groups_of_pass[i][wi]);
         if (p.mma) {
+            // physical offset of tile index j: tile position i -> physical bit local[i]
+            const int threads = threads_for((int)p.local.size());
+            std::vector<uint32_t> goff(threads);
+            for (int j = 0; j < threads; ++j) {
+                uint32_t off = 0;
+                for (size_t q = 0; q < p.local.size(); ++q) off |= ((uint32_t)(j >> q) & 1u) << p.local[q];
+                goff[j] = off;
+            }
+            offs[i].io_goff = append(goff.data(), goff.size() * sizeof(uint32_t));
             std::vector<MmaWindowDev> dev;
             for (const MmaWindow& w : p.mwindows) dev.push_back(resolve_window(w, p));
             offs[i].windows = append(dev.data(), dev.size() * sizeof(MmaWindowDev));
@@ -362,6 +372,11 @@ int compile_plan(tq_handle h, int which) {
         dp.gate_pass = (int)i < n_gate_passes;
         if (passes[i].mma) {
             dp.proto.mwindows = (const MmaWindowDev*)(base + offs[i].windows);
+            dp.proto.io_goff = (const uint32_t*)(base + offs[i].io_goff);
+            for (int s = 0; s < 4; ++s) {   // tile index threads << s is the single tile position log2(threads) + s
+                const int pos = (dp.proto.k_eff - kRegBits) + s;
+                dp.proto.io_stride[s] = 1u << passes[i].local[pos];
+            }
             dp.proto.n_windows = (int)passes[i].mwindows.size();
         } else {
             dp.proto.windows = (const Window*)(base + offs[i].windows);
@@ -503,6 +518,11 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 if (plan.slots == 1) { pp.partial = out + b0; pp.partial_ld = 1; pp.partial_off = 0; }
                 else { pp.partial = h->d_partial; pp.partial_ld = plan.slots; }
             }
+            if (pp.mwindows) {
+                pp.skew_ns = h->skew_ns;
+                pp.skew_lo = h->n_sms;
+                pp.skew_hi = 2 * h->n_sms;
+            }
             launch_tile_pass(pp, bc, dp.threads, dm, stream);
             ++h->launches;
             rc = check_launch(h, "tile_pass_kernel");
@@ -612,6 +632,8 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->opt.tile_bits = std::max(8, std::min(kMaxTileBits, env_int("TQ_TILE_BITS", 12)));  // kMaxTileBits = 12
     h->opt.low_bits = std::max(0, std::min(h->opt.tile_bits - 4, env_int("TQ_LOW_BITS", 3)));
     h->max_scratch = (size_t)std::max(64, env_int("TQ_MAX_SCRATCH_MB", 16384)) << 20;
+    h->skew_ns = std::max(0, env_int("TQ_SKEW_NS", 0));
+    h->n_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);
         delete h;

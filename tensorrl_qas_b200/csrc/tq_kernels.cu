@@ -743,7 +743,6 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     WinOp* s_wops = reinterpret_cast<WinOp*>(s_mat + kOpSlots * kMatStride);
     double* s_red = reinterpret_cast<double*>(s_wops + kOpSlots);
     MmaWindowDev* s_win = reinterpret_cast<MmaWindowDev*>(s_red + 32);           // kWinSlots headers
-    uint32_t* hi_off = reinterpret_cast<uint32_t*>(s_win + kWinSlots);
 
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -755,22 +754,21 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
 
     uint64_t tile_base = 0;
     for (int i = 0; i < p.n_nl; ++i) tile_base |= (uint64_t)((tile >> i) & 1u) << p.nonlocal[i];
-
-    const int n_hi = 1 << (p.k - p.lead);
-    for (int h = tid; h < n_hi; h += nthreads) {
-        uint32_t off = 0;
-        for (int i = p.lead; i < p.k; ++i) off |= ((uint32_t)(h >> (i - p.lead)) & 1u) << p.local[i];
-        hi_off[h] = off;
+    if (p.skew_ns > 0 && (int)blockIdx.x >= p.skew_lo && (int)blockIdx.x < p.skew_hi) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < (unsigned long long)p.skew_ns);
     }
-    __syncthreads();
-    const uint32_t lead_mask = (1u << p.lead) - 1u;
 
-    // I/O layout as in tile_pass_kernel: amplitude i of thread t is tile index t + i * nthreads (16 per thread)
+    // I/O layout as in tile_pass_kernel: amplitude i of thread t is tile index t + i * nthreads (16 per thread); the
+    // physical offsets of the thread part and of the four per-bit strides come precomputed from the host
     const uint32_t io_slot = swz(tid);
     const uint32_t iw0 = swz(nthreads), iw1 = swz(nthreads << 1), iw2 = swz(nthreads << 2), iw3 = swz(nthreads << 3);
-    const uint32_t io_goff = TQ_PHYS(tid);
-    const uint32_t ig0 = TQ_PHYS(nthreads), ig1 = TQ_PHYS(nthreads << 1), ig2 = TQ_PHYS(nthreads << 2),
-                   ig3 = TQ_PHYS(nthreads << 3);
+    const uint32_t io_goff = __ldg(p.io_goff + tid);
+    const uint32_t ig0 = p.io_stride[0], ig1 = p.io_stride[1], ig2 = p.io_stride[2], ig3 = p.io_stride[3];
     const uint64_t elem_off = (uint64_t)b << p.nbits;
     const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
     const int n_run = (p.exp_mode == 1) ? p.n_windows : p.n_gate_windows;
@@ -807,7 +805,9 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
                 else if (mode == 2) { if ((r & 1) == (c & 1)) v = M[(r >> 1) * 2 + (c >> 1)]; }
                 else if (mode == 3) { if ((r >> 1) == (c >> 1)) v = M[(r & 1) * 2 + (c & 1)]; }
                 else { if (e == 0 || e == 3) v = M[e]; }
-                s_mat[oi * kMatStride + e] = v;
+                // kMmaFlagSwapOut: the outputs trade places -> row r goes to the row with its two index bits swapped
+                const int dst = ((wo.w0 >> 24) & kMmaFlagSwapOut) ? (((((r & 1) << 1) | (r >> 1)) << 2) | c) : e;
+                s_mat[oi * kMatStride + dst] = v;
             }
         }
     };
@@ -863,45 +863,65 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
                 slot_rest ^= hdr->wslot[i];
                 ctx |= 1ull << hdr->wphys[i];
             }
-        const uint32_t slot_t = slot_rest ^ (l1 ? hdr->qslot : 0u);
-        const uint32_t r0 = hdr->rslot[0], r1 = hdr->rslot[1], r2 = hdr->rslot[2], r3 = hdr->rslot[3], r4 = hdr->rslot[4];
+        // byte offset of register r's double: ((slot_t ^ xor of its bits' slots) << 4) | comp << 3, as three-input XORs
+        const uint32_t t = ((slot_rest ^ (l1 ? hdr->qslot : 0u)) << 4) | ((uint32_t)comp << 3);
+        const uint32_t x0 = (uint32_t)hdr->rslot[0] << 4, x1 = (uint32_t)hdr->rslot[1] << 4, x2 = (uint32_t)hdr->rslot[2] << 4,
+                       x3 = (uint32_t)hdr->rslot[3] << 4, x4 = (uint32_t)hdr->rslot[4] << 4;
+        const uint32_t lo[4] = {0u, x0, x1, x0 ^ x1};
+        const uint32_t hi[8] = {t, t ^ x2, t ^ x3, t ^ x2 ^ x3, t ^ x4, t ^ x4 ^ x2, t ^ x4 ^ x3, t ^ x4 ^ x3 ^ x2};
 #pragma unroll
-        for (int r = 0; r < NR; ++r) a[r] = ampd[2 * (slot_t ^ TQ_SEL5(r, r0, r1, r2, r3, r4)) + comp];
+        for (int r = 0; r < NR; ++r)
+            a[r] = *reinterpret_cast<const double*>(smem_raw + (hi[r >> 2] ^ lo[r & 3]));
         return hdr;
     };
 
+#ifdef TQ_TRACE
+    __shared__ unsigned long long s_tr[40];
+    int n_tr = 0;
+    unsigned smid_; asm("mov.u32 %0, %%smid;" : "=r"(smid_));
+#define TQ_TR() do { if (tid == 0 && n_tr < 40) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); s_tr[n_tr++] = t_; } } while (0)
+#else
+#define TQ_TR() do {} while (0)
+#endif
+    TQ_TR();
     // ---- 2a. gate windows ----
     for (int w = 0; w < p.n_gate_windows; ++w) {
         const MmaWindowDev* hdr = enter(w);
         if (hdr->flags & kWinFlagReadOnly) continue;   // layout-only window of an expectation-only pass
         __syncthreads();   // everyone holds its entry data: the tile may be overwritten from here on
+        TQ_TR();
         const int o_end = hdr->op_end - staged_begin;
-        for (int o = hdr->op_begin - staged_begin; o < o_end; ++o) {
-            const uint32_t w0 = s_wops[o].w0;
+        // op word and B fragment of op o (prefetched one op ahead, so the loads run under the previous block's DMMAs)
+        auto fetch = [&](int o, uint32_t& w0, double& b0, double& b1) {
+            w0 = s_wops[o].w0;
             const double2* m = s_mat + o * kMatStride;
+            double2 u0 = m[brow * 4 + bcol], u1 = m[brow * 4 + bcol + 2];
+            if ((w0 & 0xff) == FM_SCAL) {
+                const double2 d = ((ctx >> ((w0 >> 16) & 0xff)) & 1ull) ? m[3] : m[0];
+                const double2 z = make_double2(0.0, 0.0);
+                u0 = (brow == bcol) ? d : z;
+                u1 = (brow == (bcol | 2)) ? d : z;
+            }
+            // real 8x8 form: same component -> Re, re<-im -> -Im, im<-re -> +Im (sign flipped on the integer pipe)
+            b0 = bsame ? u0.x : __longlong_as_double(__double_as_longlong(u0.y) ^ bneg);
+            b1 = bsame ? u1.x : __longlong_as_double(__double_as_longlong(u1.y) ^ bneg);
+        };
+        uint32_t w0n = 0;
+        double b0n = 0.0, b1n = 0.0;
+        int o = hdr->op_begin - staged_begin;
+        if (o < o_end) fetch(o, w0n, b0n, b1n);
+        for (; o < o_end; ++o) {
+            const uint32_t w0 = w0n;
+            const double b0 = b0n, b1 = b1n;
+            if (o + 1 < o_end) fetch(o + 1, w0n, b0n, b1n);
             const int fc = w0 & 0xff;
             const int qsel = (w0 >> 16) & 0xff;
-            if (fc <= FM_SCAL) {
-                double2 u0, u1;
-                if (fc == FM_SCAL) {
-                    const double2 d = ((ctx >> qsel) & 1ull) ? m[3] : m[0];
-                    const double2 z = make_double2(0.0, 0.0);
-                    u0 = (brow == bcol) ? d : z;
-                    u1 = (brow == (bcol | 2)) ? d : z;
-                } else {
-                    u0 = m[brow * 4 + bcol];
-                    u1 = m[brow * 4 + bcol + 2];
-                }
-                // real 8x8 form: same component -> Re, re<-im -> -Im, im<-re -> +Im (sign flipped on the integer pipe)
-                const double b0 = bsame ? u0.x : __longlong_as_double(__double_as_longlong(u0.y) ^ bneg);
-                const double b1 = bsame ? u1.x : __longlong_as_double(__double_as_longlong(u1.y) ^ bneg);
-                switch (fc) {
-                case FM_U2 + 1: m_u2<1>(a, b0, b1); break;
-                case FM_U2 + 2: m_u2<2>(a, b0, b1); break;
-                case FM_U2 + 3: m_u2<3>(a, b0, b1); break;
-                case FM_U2 + 4: m_u2<4>(a, b0, b1); break;
-                default: m_u2<0>(a, b0, b1); break;   // FM_U2 + 0 and FM_SCAL
-                }
+            if (fc <= FM_SCAL) {   // compare chain (CTA-uniform), cheaper than an indirect branch per block
+                if (fc == FM_U2 + 1) m_u2<1>(a, b0, b1);
+                else if (fc == FM_U2 + 2) m_u2<2>(a, b0, b1);
+                else if (fc == FM_U2 + 3) m_u2<3>(a, b0, b1);
+                else if (fc == FM_U2 + 4) m_u2<4>(a, b0, b1);
+                else m_u2<0>(a, b0, b1);   // FM_U2 + 0 and FM_SCAL
             } else {
                 switch (fc) {
                 case FM_SWAP + 0: m_swapql<0>(a, l1); break;
@@ -918,14 +938,19 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
                 }
             }
         }
+        TQ_TR();
         {
-            const uint32_t slot_t = slot_rest ^ (l1 ? hdr->qslot_out : 0u);
-            const uint32_t r0 = hdr->rslot_out[0], r1 = hdr->rslot_out[1], r2 = hdr->rslot_out[2],
-                           r3 = hdr->rslot_out[3], r4 = hdr->rslot_out[4];
+            const uint32_t t = ((slot_rest ^ (l1 ? hdr->qslot_out : 0u)) << 4) | ((uint32_t)comp << 3);
+            const uint32_t x0 = (uint32_t)hdr->rslot_out[0] << 4, x1 = (uint32_t)hdr->rslot_out[1] << 4,
+                           x2 = (uint32_t)hdr->rslot_out[2] << 4, x3 = (uint32_t)hdr->rslot_out[3] << 4,
+                           x4 = (uint32_t)hdr->rslot_out[4] << 4;
+            const uint32_t lo[4] = {0u, x0, x1, x0 ^ x1};
+            const uint32_t hi[8] = {t, t ^ x2, t ^ x3, t ^ x2 ^ x3, t ^ x4, t ^ x4 ^ x2, t ^ x4 ^ x3, t ^ x4 ^ x3 ^ x2};
 #pragma unroll
-            for (int r = 0; r < NR; ++r) ampd[2 * (slot_t ^ TQ_SEL5(r, r0, r1, r2, r3, r4)) + comp] = a[r];
+            for (int r = 0; r < NR; ++r) *reinterpret_cast<double*>(smem_raw + (hi[r >> 2] ^ lo[r & 3])) = a[r];
         }
         __syncthreads();   // the tile is complete in shared memory again
+        TQ_TR();
     }
 
     // ---- write back (shared memory holds the final tile) ----
@@ -967,6 +992,14 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
         }
     }
 
+#ifdef TQ_TRACE
+    TQ_TR();
+    if (tid == 0 && smid_ == 0 && p.src_mode == 0 && b >= 40 && b < 46) {
+        printf("TRACE cta %d b %d:", (int)blockIdx.x, (int)b);
+        for (int i = 0; i < n_tr; ++i) printf(" %llu", s_tr[i] - s_tr[0] + (s_tr[0] % 100000000ull));
+        printf("\n");
+    }
+#endif
     // ---- 3. Hamiltonian terms evaluated from shared memory (flip masks wider than a window / sparse entries) ----
     if (p.exp_mode != 0) {
         if (p.exp_mode == 1) {

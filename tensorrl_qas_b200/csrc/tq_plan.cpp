@@ -576,6 +576,37 @@ void schedule_windows_mma(Pass& p) {
             if (have_layout)
                 for (int j : ready)
                     if (fits(j, ql)) { pick = j; break; }
+            if (pick < 0 && have_layout && !out.empty() && (out.back().w0 & 0xff) == M_U2 &&
+                ((out.back().w0 >> 12) & 0xf) <= 3 && !((out.back().w0 >> 24) & kMmaFlagSwapOut)) {
+                // the block just emitted can hand QL over to its register qubit for free (its matrix rows are
+                // permuted so that the two outputs trade places): do that if it makes a ready op fit
+                const int cand = rp[0];   // where that register qubit sits after the block
+                for (int j : ready)
+                    if (tops[mine[j]].d.op == OP_U2 && fits(j, cand)) { pick = j; break; }
+                if (pick < 0)
+                    for (int j : ready)
+                        if (tops[mine[j]].d.op == OP_CNOT && ((W >> tops[mine[j]].d.a) & 1) && fits(j, cand)) { pick = j; break; }
+                if (pick >= 0) {
+                    out.back().w0 |= (uint32_t)kMmaFlagSwapOut << 24;
+                    std::swap(ql, rp[0]);
+                } else if (((out.back().w0 >> 12) & 0xf) == 3) {
+                    // a one-qubit block on QL pairs with ANY register bit: pair it with the qubit a ready dense block
+                    // needs and hand QL over to that one
+                    for (int j : ready) {
+                        const DevOp& d = tops[mine[j]].d;
+                        if (d.op != OP_U2) continue;
+                        done[j] = 1;
+                        const int want = better_ql(d.a, d.b);
+                        done[j] = 0;
+                        const int x = rb_of(want);
+                        out.back().w0 = (out.back().w0 & ~0xf00u) | ((uint32_t)x << 8) | ((uint32_t)kMmaFlagSwapOut << 24);
+                        if (x != 0) std::swap(rp[0], rp[x]);
+                        std::swap(ql, rp[0]);
+                        pick = j;
+                        break;
+                    }
+                }
+            }
             if (pick < 0) {
                 // prefer a dense block: it decides where QL should sit
                 for (int j : ready)
@@ -647,7 +678,10 @@ void schedule_windows_mma(Pass& p) {
             for (size_t i = lo; i < hi; ++i) {
                 p.wops.push_back(out[i]);
                 if ((out[i].w0 & 0xff) == M_SWAPQL) std::swap(cql, crp[(out[i].w0 >> 8) & 0xf]);
-                else if ((out[i].w0 & 0xff) == M_U2 && ((out[i].w0 >> 8) & 0xf) != 0) std::swap(crp[0], crp[(out[i].w0 >> 8) & 0xf]);
+                else if ((out[i].w0 & 0xff) == M_U2) {
+                    if (((out[i].w0 >> 8) & 0xf) != 0) std::swap(crp[0], crp[(out[i].w0 >> 8) & 0xf]);
+                    if ((out[i].w0 >> 24) & kMmaFlagSwapOut) std::swap(cql, crp[0]);
+                }
             }
             cur.op_end = (int32_t)p.wops.size();
             for (int r = 0; r < kMmaRegBits; ++r) cur.rpos_out[r] = (uint8_t)crp[r];

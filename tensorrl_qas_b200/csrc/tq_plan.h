@@ -127,13 +127,16 @@ inline uint32_t swizzle_slot(uint32_t j) {
 constexpr int kMmaRegBits = 5;
 constexpr int kMmaWinBits = kMmaRegBits + 1;   // qubits a window can act on
 constexpr int kMmaMinTileBits = 9;             // one warp
+constexpr int kMmaFlagSwapOut = 1;
 enum : int32_t {    // WinOp codes of DMMA windows; rb / rb2 are 4-bit fields, qsel and flags 8-bit fields
     M_U2 = 16,      // dense block: rb = x (register bit paired with QL; for x != 0 the block also exchanges the roles of
                     // register bits 0 and x -- its results land in adjacent registers), rb2 = mode:
                     //   0: 4x4, matrix index bit 0 = QL, bit 1 = Rx     1: 4x4, index bit 0 = Rx, bit 1 = QL
                     //   2: 2x2 on Rx (identity on QL)                   3: 2x2 on QL (identity on Rx)
                     //   4: scalar m[0] / m[3] selected by physical bit qsel (diagonal block outside the window)
-    M_SWAPQL = 17,  // rb = x: exchange the roles of QL and Rx
+                    // flags bit kMmaFlagSwapOut (modes 0..3): the block's two output qubits trade places (matrix rows
+                    // permuted when it is staged): afterwards QL holds the register qubit and register bit 0 the old QL
+    M_SWAPQL = 17,  // rb = x: exchange the roles of QL and Rx (data crosses lanes by shuffle)
     M_CX_OUT = 18,  // rb = target register bit, qsel = physical control bit (outside the window)
                     // (a CNOT with both qubits inside the window runs as an M_U2 with its constant matrix)
     M_EXPC = 20,    // expectation class: flags = flip mask over the register bits (!= 0), rb2 bit 0 = has imaginary

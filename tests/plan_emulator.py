@@ -196,6 +196,9 @@ def _run_mma_window(vec, nbits, loc, w, mats):
                 vec = apply_1q(vec, nbits, qsel, M)
             if rb != 0:       # results land in adjacent registers: register bits 0 and rb trade qubits
                 r[0], r[rb] = r[rb], r[0]
+            if flags & 1:     # output roles exchanged (row-permuted matrix): QL <-> register bit 0
+                assert rb2 <= 3
+                r[0], ql = ql, r[0]
         elif code == M_SWAPQL:
             r[rb], ql = ql, r[rb]
         elif code == M_CX_OUT:
