@@ -25,6 +25,7 @@ struct HamGroup {
 };
 
 struct DevPass {
+    bool direct = false;
     PassParams proto;  // geometry + device pointers filled at compile time
     int threads = 0;
     int n_tiles = 1;
@@ -370,6 +371,7 @@ int compile_plan(tq_handle h, int which) {
         dp.threads = threads_for(dp.proto.k_eff);
         dp.n_tiles = 1 << dp.proto.n_nl;
         dp.gate_pass = (int)i < n_gate_passes;
+        dp.direct = passes[i].direct;
         if (passes[i].mma) {
             dp.proto.mwindows = (const MmaWindowDev*)(base + offs[i].windows);
             dp.proto.io_goff = (const uint32_t*)(base + offs[i].io_goff);
@@ -406,6 +408,18 @@ int compile_plan(tq_handle h, int which) {
         if (tile_pass_smem_bytes(dp.proto.k_eff, dp.proto.k, dp.proto.lead) > 100 * 1024)
             return fail(h, TQ_EINVAL, "tile does not fit shared memory (lower TQ_TILE_BITS)");
         plan.passes.push_back(dp);
+    }
+    if (env_int("TQ_DEBUG_PLAN", 0)) {
+        for (size_t i = 0; i < passes.size(); ++i) {
+            const Pass& p = passes[i];
+            fprintf(stderr, "[tqsim] pass %zu: mma=%d direct=%d ops=%zu gate_windows=%d windows=%zu groups=%zu wide=%d local=", i,
+                    (int)p.mma, (int)p.direct, p.ops.size(), p.n_gate_windows, p.mma ? p.mwindows.size() : p.windows.size(),
+                    groups_of_pass[i].size(), offs[i].n_groups);
+            for (int q : p.local) fprintf(stderr, "%d,", q);
+            fprintf(stderr, " wflags=");
+            for (const MmaWindow& w : p.mwindows) fprintf(stderr, "%d", (int)w.flags);
+            fprintf(stderr, "\n");
+        }
     }
     plan.n_unitary = plan.n_rot = 0;
     for (const Gate& g : h->gates) {
@@ -519,6 +533,9 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 else { pp.partial = h->d_partial; pp.partial_ld = plan.slots; }
             }
             if (pp.mwindows) {
+                // expectation-only pass whose windows all read the state straight from global memory (needs the
+                // per-element state buffer and no leftover shared-memory groups)
+                pp.direct = (dp.direct && pp.src_mode == 2 && pp.exp_mode == 1 && pp.n_groups == 0 && !pp.dst) ? 1 : 0;
                 pp.skew_ns = h->skew_ns;
                 pp.skew_lo = h->n_sms;
                 pp.skew_hi = 2 * h->n_sms;

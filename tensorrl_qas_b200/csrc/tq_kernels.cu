@@ -815,7 +815,9 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     // ---- 1. stage the tile, the window headers and the first ops ----
     {
         double2 v[16];
-        if (p.src_mode != 0) {
+        if (p.direct) {
+            // nothing to stage: every window of this pass reads the state itself
+        } else if (p.src_mode != 0) {
             const double2* src = p.src + (p.src_mode == 2 ? elem_off : 0ull) + tile_base;
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __ldcs(src + TQ_IO_GOFF(i));
@@ -826,8 +828,10 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
         for (int i = tid; i < 4 * min(n_run, kWinSlots); i += nthreads)
             reinterpret_cast<uint4*>(s_win)[i] = __ldg(reinterpret_cast<const uint4*>(p.mwindows) + i);
         stage_ops(0);
+        if (!p.direct) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) amp[TQ_IO_SLOT(i)] = v[i];
+            for (int i = 0; i < 16; ++i) amp[TQ_IO_SLOT(i)] = v[i];
+        }
     }
     __syncthreads();
 
@@ -863,6 +867,19 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
                 slot_rest ^= hdr->wslot[i];
                 ctx |= 1ull << hdr->wphys[i];
             }
+        if (p.direct) {
+            // straight from global memory: amplitude index = ctx | the register bits' physical bits; lanes 2i, 2i+1
+            // read the two halves of one amplitude and lane bits 1..3 are qubits 0..2 -> 256 contiguous bytes per load
+            const unsigned char* base = reinterpret_cast<const unsigned char*>(p.src + elem_off);
+            const uint32_t t = ((uint32_t)ctx << 4) | ((uint32_t)comp << 3);
+            const uint32_t x0 = 16u << hdr->rphys[0], x1 = 16u << hdr->rphys[1], x2 = 16u << hdr->rphys[2],
+                           x3 = 16u << hdr->rphys[3], x4 = 16u << hdr->rphys[4];
+            const uint32_t lo[4] = {0u, x0, x1, x0 ^ x1};
+            const uint32_t hi[8] = {t, t ^ x2, t ^ x3, t ^ x2 ^ x3, t ^ x4, t ^ x4 ^ x2, t ^ x4 ^ x3, t ^ x4 ^ x3 ^ x2};
+#pragma unroll
+            for (int r = 0; r < NR; ++r) a[r] = __ldg(reinterpret_cast<const double*>(base + (hi[r >> 2] ^ lo[r & 3])));
+            return hdr;
+        }
         // byte offset of register r's double: ((slot_t ^ xor of its bits' slots) << 4) | comp << 3, as three-input XORs
         const uint32_t t = ((slot_rest ^ (l1 ? hdr->qslot : 0u)) << 4) | ((uint32_t)comp << 3);
         const uint32_t x0 = (uint32_t)hdr->rslot[0] << 4, x1 = (uint32_t)hdr->rslot[1] << 4, x2 = (uint32_t)hdr->rslot[2] << 4,
@@ -886,8 +903,9 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     TQ_TR();
     // ---- 2a. gate windows ----
     for (int w = 0; w < p.n_gate_windows; ++w) {
+        if (w < kWinSlots && (s_win[w].flags & kWinFlagReadOnly)) continue;   // layout-only window (expectation-only pass)
         const MmaWindowDev* hdr = enter(w);
-        if (hdr->flags & kWinFlagReadOnly) continue;   // layout-only window of an expectation-only pass
+        if (hdr->flags & kWinFlagReadOnly) continue;
         __syncthreads();   // everyone holds its entry data: the tile may be overwritten from here on
         TQ_TR();
         const int o_end = hdr->op_end - staged_begin;

@@ -739,6 +739,8 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
     // live entirely on its register qubits (a 32-entry sign-weight table, M_EXPT), and optionally `generic`: diagonal
     // terms evaluated with signs from the thread's index (M_EXPD)
     auto make_window = [&](uint32_t W, const std::vector<int>& mine, const std::vector<ExpTermIn>& generic) {
+        // fill up with unused positions, the three lowest last (keeping them free allows direct global loads)
+        for (int q = 3; q < k && popc32(W) < kMmaRegBits; ++q) W |= 1u << q;
         for (int q = 0; q < k && popc32(W) < kMmaRegBits; ++q) W |= 1u << q;
         MmaWindow w{};
         std::vector<int> rest;
@@ -747,12 +749,26 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
             if ((W >> q) & 1) w.rpos[nb++] = (uint8_t)q;
             else rest.push_back(q);
         }
-        w.qlpos = (uint8_t)rest.back();   // any position outside the flip masks
-        rest.pop_back();
-        split_rest(rest, w.gpos, w.wpos);
+        w.flags = kWinFlagReadOnly;
+        if (p.lead >= 3 && !(W & 7u)) {
+            // the three lowest qubits are free: put them on lane bits 1..3 (QL, g0, g1), so that a warp's 8-byte loads
+            // of one register cover 256 contiguous bytes of the state
+            w.qlpos = 0;
+            w.gpos[0] = 1;
+            w.gpos[1] = 2;
+            std::vector<int> others;
+            for (int q : rest)
+                if (q > 2) others.push_back(q);
+            w.gpos[2] = (uint8_t)others[0];
+            for (int i = 0; i < 3; ++i) w.wpos[i] = (uint8_t)(1 + i < (int)others.size() ? others[1 + i] : 0);
+            w.flags |= kWinFlagDirect;
+        } else {
+            w.qlpos = (uint8_t)rest.back();   // any position outside the flip masks
+            rest.pop_back();
+            split_rest(rest, w.gpos, w.wpos);
+        }
         for (int r = 0; r < kMmaRegBits; ++r) w.rpos_out[r] = w.rpos[r];
         w.qlpos_out = w.qlpos;
-        w.flags = kWinFlagReadOnly;
         uint64_t wphys = 0;
         for (int r = 0; r < kMmaRegBits; ++r) wphys |= bit(p.local[w.rpos[r]]);
         auto zr_of = [&](uint64_t z) {
@@ -872,6 +888,12 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
         }
         make_window(W, mine, {});
     }
+    auto mark_direct = [&]() {
+        bool all = p.ops.empty() && (int)p.mwindows.size() > p.n_gate_windows;
+        for (size_t i = (size_t)p.n_gate_windows; i < p.mwindows.size(); ++i) all = all && (p.mwindows[i].flags & kWinFlagDirect);
+        p.direct = all;
+    };
+    mark_direct();
     if (!final_pass) return;
     // 2. the last pass that evaluates anything also takes what is left of the diagonal pool: windows for the terms
     //    whose qubits are local here and fit a window ...
@@ -897,6 +919,7 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
         rest.swap(*diag_pool);
         make_window(0, {}, rest);
     }
+    mark_direct();
 }
 
 void append_expectation_windows(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover) {
@@ -1034,6 +1057,7 @@ MmaWindowDev resolve_window(const MmaWindow& w, const Pass& p) {
     for (int i = 0; i < 3; ++i) { d.gslot[i] = slot(w.gpos[i]); d.gphys[i] = (uint8_t)p.local[w.gpos[i]]; }
     for (int i = 0; i < 3; ++i)
         if (i < k - 9) { d.wslot[i] = slot(w.wpos[i]); d.wphys[i] = (uint8_t)p.local[w.wpos[i]]; }
+    for (int r = 0; r < kMmaRegBits; ++r) d.rphys[r] = (uint8_t)p.local[w.rpos[r]];
     d.flags = w.flags;
     d.op_begin = w.op_begin;
     d.op_end = w.op_end;

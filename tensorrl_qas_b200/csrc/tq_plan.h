@@ -85,6 +85,8 @@ enum : int32_t {    // WinOp code; rb / rb2 are register-bit indices inside the 
                     // sorted by class:  E += sum_zr WHT(|psi|^2)[zr] * sum_{t in zr} w_t sign_t(ctx)
 };
 constexpr int kWinFlagReadOnly = 1;  // Window::tpos[11]: the window does not change the amplitudes
+constexpr int kWinFlagDirect = 2;    // MmaWindow (read-only): lane bits 1..3 are the three lowest qubits, so the thread
+                                     // can load its registers straight from global memory, fully coalesced
 
 struct EUnit { uint64_t w[2]; };   // 16 bytes of expectation data (bit patterns of masks / doubles)
 struct ExpTermIn { uint64_t z; double wre, wim; };
@@ -169,7 +171,8 @@ struct MmaWindowDev {  // 64 bytes
     uint16_t gslot[3], wslot[3];
     uint8_t gphys[3], wphys[3], qlphys, flags;
     int32_t op_begin, op_end;
-    uint8_t pad[12];
+    uint8_t rphys[kMmaRegBits];   // physical qubits of the register bits on entry (direct global loads)
+    uint8_t pad[7];
 };
 static_assert(sizeof(MmaWindowDev) == 64, "MmaWindowDev layout");
 MmaWindowDev resolve_window(const MmaWindow& w, const struct Pass& p);
@@ -179,6 +182,7 @@ inline uint32_t swizzle_slot(uint32_t j);   // slot of tile index j (defined bel
 
 struct Pass {
     bool mma = false;           // windows are MmaWindow (tensor-core kernel) instead of Window
+    bool direct = false;        // expectation-only tensor-core pass whose windows all load straight from global memory
     std::vector<MmaWindow> mwindows;
     std::vector<int> local;     // physical bits of the tile, ascending; local[p] = physical bit of tile position p
     std::vector<int> nonlocal;  // remaining physical bits, ascending
