@@ -30,6 +30,7 @@ GATES_PER_BRICK = 21
 AGENT_GATES = 41
 CIRCUIT_SEED = 5
 BATCH_PER_GPU = 64
+FP64_DMMA_PEAK_TFLOPS = 37.2   # profiles/microbench/fp64_peak.cu on this pool's B200
 METRIC = "energy_evals_per_sec"
 UNIT = "evals/s"
 
@@ -268,15 +269,26 @@ def main():
         tj = json.load(open(tpath))
         if tj.get("batch") == B:
             traffic = tj.get("dram_bytes_per_step")
+    counts = sim.plan_counts(0)
+    # FP64 tensor-core work: every dense block is an 8x8 real DMMA product = 16 FMA per amplitude
+    dmma_flop_eval = 2.0 * 16.0 * counts["tensor_core_blocks"] * (1 << N_QUBITS)
+    dmma_tflops = dmma_flop_eval * per_gpu_evals_s / 1e12
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-        "peak_source": peak_src, "kernel": "tile_pass_kernel (5 launches per step, 99.5 % of the step; per-step totals)",
+        "peak_source": peak_src,
+        "kernel": f"tile_pass_mma_kernel ({passes_rw + passes_ro} launches per step, > 99 % of the step; per-step totals)",
         "algorithmic_bytes_per_eval": bytes_eval, "algorithmic_bytes_per_step": bytes_eval * B,
-        "note": "algorithmic bytes = qulacs' unfused model 16*2^n*(2G+M); the fused passes move far fewer real bytes, "
-                "so frac > 1 is expected -- see hbm_actual",
+        "note": "algorithmic bytes = qulacs' unfused model 16*2^n*(2G+M) (SURVEY.md 8d); the fused passes move far "
+                "fewer real bytes, so frac > 1 is expected -- hbm_actual has the real traffic, fp64_tensor the bound "
+                "the fused kernel actually runs against",
         "hbm_actual": {"bytes_per_eval_model": moved, "gbs_model": moved * per_gpu_evals_s / 1e9,
                        "frac_of_peak_model": moved * per_gpu_evals_s / 1e9 / peak,
                        "gate_passes": passes_rw, "expectation_passes": passes_ro},
+        "fp64_tensor": {"achieved": dmma_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                        "frac": dmma_tflops / FP64_DMMA_PEAK_TFLOPS, "blocks_per_eval": counts["tensor_core_blocks"],
+                        "flop_per_eval": dmma_flop_eval,
+                        "peak_source": "measured: profiles/microbench/fp64_peak.cu, mma.sync.m8n8k4.f64 on this pool's "
+                                       "B200 (63.9 FMA/clk/SM x 148 SMs x 1.965 GHz); MEASURED_PEAKS.json has no FP64 figure"},
     }
 
     # ---------------- CPU baseline beside it: the oracle port on the host cores, bounded sample -------------------
@@ -298,7 +310,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params.nbytes),
                 "d2h_bytes_per_step": int(8 * B)},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "plan": info,
+        "plan": dict(info, **counts),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -132,6 +132,14 @@ int tq_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_p
  * which: 0 = pure-state plan, 1 = density-matrix plan, 2 = pure-state plan with trajectory-noise slots. */
 int tq_plan_info(tq_handle h, int which, int64_t* info8);
 
+/* Work counts of the compiled plan (bench.py's FP64 tensor-core accounting):
+ *   counts[0] dense blocks executed on the FP64 tensor cores (each = 16 FMA per amplitude: a 4x4 complex block as an
+ *             8x8 real DMMA product), counts[1] lane<->register qubit exchanges by shuffle, counts[2] gate windows,
+ *             counts[3] expectation windows, counts[4] FP64-pipe register windows (tiles below 2^9 amplitudes and
+ *             density matrices), counts[5] expectation-only passes that stream the state straight from HBM,
+ *             counts[6..7] reserved (0). */
+int tq_plan_counts(tq_handle h, int which, int64_t* counts8);
+
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t tq_launch_count(tq_handle h);
 

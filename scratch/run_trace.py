@@ -1,7 +1,7 @@
 import os, sys, shutil
 sys.path.insert(0, '.')
 import tensorrl_qas_b200._lib as L
-L.LIB_PATH = os.path.abspath('scratch/libtqsim_trace.so')
+L.LIB_PATH = os.path.abspath('scratch/libtqsim_trace'+os.environ.get('TRW','3')+'.so')
 import numpy as np, torch
 from tensorrl_qas_b200 import Simulator, loaders
 from tensorrl_qas_b200.circuit import brickwork_circuit, parameter_batch

@@ -47,6 +47,7 @@ SIGNATURES = {
     "tq_state_batch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_dbl_p, ctypes.c_int, c_dbl_p]),
     "tq_dm_batch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_dbl_p, ctypes.c_int, c_dbl_p]),
     "tq_plan_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p]),
+    "tq_plan_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p]),
     "tq_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "tq_plan_dump": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_u64_p]),

@@ -40,6 +40,7 @@ struct Plan {
     int n_gate_passes = 0;
     int slots = 0;        // partial sums per element
     int n_unitary = 0, n_rot = 0;
+    int64_t counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // see tq_plan_counts
     void* arena = nullptr;  // device blob holding windows / ops / groups / terms of all passes + matrix programs
     size_t arena_cap = 0;
     int n_mats = 0;
@@ -419,6 +420,21 @@ int compile_plan(tq_handle h, int which) {
             fprintf(stderr, " wflags=");
             for (const MmaWindow& w : p.mwindows) fprintf(stderr, "%d", (int)w.flags);
             fprintf(stderr, "\n");
+        }
+    }
+    for (int64_t& c : plan.counts) c = 0;
+    for (size_t i = 0; i < passes.size(); ++i) {
+        const Pass& p = passes[i];
+        if (!p.mma) {
+            plan.counts[4] += (int64_t)p.windows.size();
+            continue;
+        }
+        plan.counts[2] += p.n_gate_windows - ((p.ops.empty() && p.n_gate_windows == 1) ? 1 : 0);
+        plan.counts[3] += (int64_t)p.mwindows.size() - p.n_gate_windows;
+        plan.counts[5] += p.direct ? 1 : 0;
+        for (const WinOp& o : p.wops) {
+            if ((o.w0 & 0xff) == M_U2) ++plan.counts[0];
+            if ((o.w0 & 0xff) == M_SWAPQL) ++plan.counts[1];
         }
     }
     plan.n_unitary = plan.n_rot = 0;
@@ -836,6 +852,16 @@ int tq_plan_info(tq_handle h, int which, int64_t* info8) {
     info8[5] = (int64_t)h->hent.size();
     info8[6] = plan.n_unitary;
     info8[7] = plan.n_rot;
+    return TQ_OK;
+}
+
+int tq_plan_counts(tq_handle h, int which, int64_t* counts8) {
+    if (!h || !counts8 || which < 0 || which > 2) return TQ_EINVAL;
+    TQ_CUDA(cudaSetDevice(h->device));
+    int rc = compile_plan(h, which);
+    if (rc) return rc;
+    const Plan& plan = which == 1 ? h->plan_dm : (which == 2 ? h->plan_traj : h->plan_sv);
+    for (int i = 0; i < 8; ++i) counts8[i] = plan.counts[i];
     return TQ_OK;
 }
 

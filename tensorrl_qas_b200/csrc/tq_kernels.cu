@@ -745,6 +745,15 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     MmaWindowDev* s_win = reinterpret_cast<MmaWindowDev*>(s_red + 32);           // kWinSlots headers
 
     const int tid = threadIdx.x, nthreads = blockDim.x;
+#ifdef TQ_TRACE   // debugging aid: phase timestamps of a few CTAs (scratch builds only)
+    __shared__ unsigned long long s_tr[40];
+    int n_tr = 0;
+    unsigned smid_; asm("mov.u32 %0, %%smid;" : "=r"(smid_));
+#define TQ_TR() do { if (tid == 0 && n_tr < 40) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); s_tr[n_tr++] = t_; } } while (0)
+#else
+#define TQ_TR() do {} while (0)
+#endif
+    TQ_TR();
     const int lane = tid & 31, warp = tid >> 5;
     const int comp = lane & 1;
     const bool l1 = (lane >> 1) & 1;
@@ -892,14 +901,6 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
         return hdr;
     };
 
-#ifdef TQ_TRACE
-    __shared__ unsigned long long s_tr[40];
-    int n_tr = 0;
-    unsigned smid_; asm("mov.u32 %0, %%smid;" : "=r"(smid_));
-#define TQ_TR() do { if (tid == 0 && n_tr < 40) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); s_tr[n_tr++] = t_; } } while (0)
-#else
-#define TQ_TR() do {} while (0)
-#endif
     TQ_TR();
     // ---- 2a. gate windows ----
     for (int w = 0; w < p.n_gate_windows; ++w) {
@@ -1012,7 +1013,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
 
 #ifdef TQ_TRACE
     TQ_TR();
-    if (tid == 0 && smid_ == 0 && p.src_mode == 0 && b >= 40 && b < 46) {
+    if (tid == 0 && smid_ == 0 && p.n_gate_windows == TQ_TRACE && b >= 40 && b < 46) {
         printf("TRACE cta %d b %d:", (int)blockIdx.x, (int)b);
         for (int i = 0; i < n_tr; ++i) printf(" %llu", s_tr[i] - s_tr[0] + (s_tr[0] % 100000000ull));
         printf("\n");

@@ -169,6 +169,13 @@ class Simulator:
                 "rotation_gates")
         return dict(zip(keys, [int(v) for v in info]))
 
+    def plan_counts(self, which=0):
+        c = (ctypes.c_int64 * 8)()
+        self._check(self._L.tq_plan_counts(self._h, which, c))
+        keys = ("tensor_core_blocks", "lane_register_swaps", "gate_windows", "expectation_windows",
+                "fp64_pipe_windows", "direct_expectation_passes")
+        return dict(zip(keys, [int(v) for v in c]))
+
     @property
     def launch_count(self):
         return int(self._L.tq_launch_count(self._h))
