@@ -293,7 +293,7 @@ def main():
 
     # ---------------- CPU baseline beside it: the oracle port on the host cores, bounded sample -------------------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only (task contract)
         from oracle import c_oracle
         cores = c_oracle.max_threads()
         sample = max(cores, 1)
