@@ -97,10 +97,16 @@ def bind(n_qubits, circuit, op, tn_state=None, use_tn=False):
 
 
 def apply_angles(circuit, angles, which_angles):
-    """The set_parameter loop of get_energy_qulacs (VQE_qulacs.py:66-74)."""
+    """The set_parameter loop of get_energy_qulacs (VQE_qulacs.py:66-74): parameter j <- angles[i] for the i-th entry j
+    of which_angles (all parameters in order when which_angles is empty).  Same assignments, done as one array write
+    (any float dtype is promoted exactly); like the reference it raises when angles is too short."""
     count = circuit.get_parameter_count()
+    a = np.asarray(angles)
     if not list(which_angles):
-        which_angles = np.arange(count)
+        if a.shape[0] < count:
+            raise IndexError(f"index {a.shape[0]} is out of bounds for angles of size {a.shape[0]}")
+        circuit.params[:count] = a[:count]
+        return
     for i, j in enumerate(which_angles):
         circuit.set_parameter(j, angles[i])
 

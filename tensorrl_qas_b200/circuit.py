@@ -79,17 +79,32 @@ def decode_state_tensor(state, n_qubits, noise=None):
     arr = np.asarray(state.detach().cpu().numpy() if hasattr(state, "detach") else state)
     n = int(n_qubits)
     gl = GateList(n)
-    for layer in arr:
-        targ, ctrl = np.nonzero(layer[:n] == 1)
-        for t, c in zip(targ, ctrl):
-            gl.add_cnot(int(c), int(t))
-            if noise is not None:
-                gl.add_depol2(int(c), int(t), noise[1])
-        axis, qubit = np.nonzero(layer[n:n + 3] == 1)
-        for a, q in zip(axis, qubit):
-            gl.add_rotation(int(a), int(q), float(layer[n + 3 + a][q]))
-            if noise is not None:
-                gl.add_depol1(int(q), noise[0])
+    # one nonzero() over the whole tensor instead of two per layer: row-major order of (layer, row, column) is exactly
+    # the per-layer row-major order the reference walks
+    cl, ct, cc = np.nonzero(arr[:, :n, :] == 1)
+    rl, ra, rq = np.nonzero(arr[:, n:n + 3, :] == 1)
+    angles = arr[rl, n + 3 + ra, rq].astype(np.float64)   # float32 -> float64, exact
+    n_c, n_r = len(cl), len(rl)
+    # merge the two streams: within a layer all CNOTs come before the rotations (stable sort on 2 * layer + is_rotation)
+    order = np.argsort(np.concatenate([2 * cl, 2 * rl + 1]), kind="stable")
+    kind = np.concatenate([np.full(n_c, KIND["CNOT"]), ra])[order]
+    q0 = np.concatenate([cc, rq])[order]
+    q1 = np.concatenate([ct, np.zeros(n_r, dtype=np.int64)])[order]
+    pidx = np.concatenate([np.full(n_c, -1), np.arange(n_r)])[order]
+    fixed = np.concatenate([np.zeros(n_c), angles])[order]
+    if noise is not None:   # every gate is followed by its depolarising channel; noise slots count gates in order
+        is_c = kind == KIND["CNOT"]
+        total = n_c + n_r
+        slots = np.arange(total)
+        kind = np.stack([kind, np.where(is_c, KIND["DEPOL2"], KIND["DEPOL1"])], axis=1).reshape(-1)
+        q0 = np.repeat(q0, 2)
+        q1 = np.repeat(q1, 2)
+        pidx = np.stack([pidx, slots], axis=1).reshape(-1)
+        fixed = np.stack([fixed, np.where(is_c, noise[1], noise[0])], axis=1).reshape(-1)
+        gl.n_slots = total
+    gl.kind, gl.q0, gl.q1, gl.pidx, gl.fixed = kind.tolist(), q0.tolist(), q1.tolist(), pidx.tolist(), fixed.tolist()
+    gl.n_params = n_r
+    gl.initial_angles = angles.tolist()
     return gl
 
 

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,6 +53,9 @@ struct Plan {
 
 struct tq_context {
     int skew_ns = 0, n_sms = 0;
+    bool fuse_prep = true;      // TQ_FUSE_PREP
+    bool spin_wait = true;      // TQ_SPIN: poll the pinned result slots instead of cudaStreamSynchronize (latency path)
+    bool zero_copy = true;      // TQ_ZERO_COPY: small host-buffer calls read angles / write energies in pinned host memory
     int n = 0, device = 0;
     std::string err;
     PlanOptions opt;
@@ -525,7 +529,9 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
     for (int b0 = 0; b0 < batch; b0 += chunk) {
         const int bc = std::min(chunk, batch - b0);
         double2* buf = states_out ? states_out + ((size_t)b0 << plan.nbits) : h->d_state;
-        if (plan.n_mats > 0) {
+        // single-tile plans (one CTA per element): the pass kernel evaluates the block matrices itself -> one launch
+        const bool fuse_prep = plan.n_mats > 0 && total_passes == 1 && plan.passes[0].proto.n_nl == 0 && h->fuse_prep;
+        if (plan.n_mats > 0 && !fuse_prep) {
             launch_prep_matrices(plan.d_descs, plan.d_prog, plan.n_mats, bc, params ? params + (size_t)b0 * ld : nullptr, ld,
                                  codes ? codes + (size_t)b0 * ldc : nullptr, ldc, h->d_mats, stream);
             ++h->launches;
@@ -536,6 +542,15 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
             const DevPass& dp = plan.passes[i];
             PassParams pp = dp.proto;
             pp.mats = h->d_mats;
+            if (fuse_prep) {
+                pp.fused_prep = 1;
+                pp.descs = plan.d_descs;
+                pp.prog = plan.d_prog;
+                pp.params = params ? params + (size_t)b0 * ld : nullptr;
+                pp.ld_params = ld;
+                pp.codes = codes ? codes + (size_t)b0 * ldc : nullptr;
+                pp.ld_codes = ldc;
+            }
             if (i == 0) {
                 if (h->have_init) { pp.src_mode = 1; pp.src = dm ? h->d_init_rho : h->d_init; }
                 else { pp.src_mode = 0; pp.src = nullptr; }
@@ -605,6 +620,35 @@ int run_host(tq_handle h, int which, int batch, const double* params_host, int l
     if (rc) return rc;
     unsigned char* hp = (unsigned char*)h->h_pin;
     unsigned char* dp = (unsigned char*)h->d_stage;
+    // Latency path (the reference's own workload: one COBYLA cost evaluation at a time on a 5-12 qubit circuit): the
+    // kernels read the angles from and write the energies to the pinned staging buffer directly (unified addressing),
+    // so the call is one memcpy-free launch sequence + one synchronisation.
+    if (h->zero_copy && !states_host && pbytes + cbytes <= (64u << 10) && batch <= 1024) {
+        if (pbytes) memcpy(hp + p_off, params_host, pbytes);
+        if (cbytes) memcpy(hp + c_off, codes_host, (size_t)batch * ldc);
+        // every energy slot starts as a marker NaN; the host polls the (host-resident) slots instead of paying a driver
+        // synchronisation, and falls back to cudaStreamSynchronize if the results do not show up in time
+        volatile uint64_t* slots = (volatile uint64_t*)(hp + o_off);
+        const uint64_t kPending = 0x7ff8dead5eed0001ull;
+        for (int i = 0; i < batch; ++i) slots[i] = kPending;
+        rc = run_plan(h, which, batch, pbytes ? (const double*)(hp + p_off) : nullptr, ld,
+                      cbytes ? (const uint8_t*)(hp + c_off) : nullptr, ldc, (double*)(hp + o_off), nullptr, h->stream);
+        if (rc) return rc;
+        bool done = false;
+        if (h->spin_wait) {
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int it = 0; !done; ++it) {
+                done = true;
+                for (int i = batch - 1; i >= 0 && done; --i) done = slots[i] != kPending;
+                if (!done && (it & 1023) == 1023 &&
+                    std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2))
+                    break;
+            }
+        }
+        if (!done) TQ_CUDA(cudaStreamSynchronize(h->stream));
+        memcpy(out_host, hp + o_off, obytes);
+        return TQ_OK;
+    }
     if (pbytes) {
         memcpy(hp + p_off, params_host, pbytes);
         TQ_CUDA(cudaMemcpyAsync(dp + p_off, hp + p_off, pbytes, cudaMemcpyHostToDevice, h->stream));
@@ -666,6 +710,9 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->opt.low_bits = std::max(0, std::min(h->opt.tile_bits - 4, env_int("TQ_LOW_BITS", 3)));
     h->max_scratch = (size_t)std::max(64, env_int("TQ_MAX_SCRATCH_MB", 16384)) << 20;
     h->skew_ns = std::max(0, env_int("TQ_SKEW_NS", 0));
+    h->fuse_prep = env_int("TQ_FUSE_PREP", 1) != 0;
+    h->zero_copy = env_int("TQ_ZERO_COPY", 1) != 0;
+    h->spin_wait = env_int("TQ_SPIN", 1) != 0;
     h->n_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);

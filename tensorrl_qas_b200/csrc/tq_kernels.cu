@@ -299,6 +299,79 @@ __device__ __forceinline__ double block_sum(double v, double* s_red, int tid, in
     return total;
 }
 
+// ---- block matrices: the matrix program of one fused block for one batch element -------------------------------
+__device__ __forceinline__ void eval_block_matrix(const MatDesc md, const MatGate* __restrict__ prog,
+                                                  const double* __restrict__ params, size_t b, int ld_params,
+                                                  const uint8_t* __restrict__ codes, int ld_codes,
+                                                  double2* __restrict__ out) {
+    double2 M[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) M[r][c] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+    for (int gi = md.begin; gi < md.end; ++gi) {
+        const MatGate g = prog[gi];
+        int kind = g.kind;
+        if (kind == MG_CX) {  // control = lq: swap the two rows with the control bit set
+            if (g.lq == 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { const double2 t = M[1][c]; M[1][c] = M[3][c]; M[3][c] = t; }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { const double2 t = M[2][c]; M[2][c] = M[3][c]; M[3][c] = t; }
+            }
+            continue;
+        }
+        if (kind == MG_PAULI_SLOT) {
+            const int code = (codes[(size_t)b * ld_codes + g.pidx] >> (int)g.fixed) & 3;
+            if (code == 0) continue;
+            kind = MG_X + code - 1;
+        }
+        double2 g00 = make_double2(0.0, 0.0), g01 = g00, g10 = g00, g11 = g00;
+        if (kind <= MG_RZ) {
+            const double theta = g.pidx >= 0 ? params[(size_t)b * ld_params + g.pidx] : g.fixed;
+            double s, c;
+            sincos(0.5 * theta, &s, &c);
+            if (kind == MG_RX) { g00.x = c; g01.y = s; g10.y = s; g11.x = c; }            // cos I + i sin X
+            else if (kind == MG_RY) { g00.x = c; g01.x = s; g10.x = -s; g11.x = c; }      // cos I + i sin Y
+            else { g00.x = c; g00.y = s; g11.x = c; g11.y = -s; }                         // diag(e^{+it/2}, e^{-it/2})
+        } else if (kind == MG_X) { g01.x = 1.0; g10.x = 1.0; }
+        else if (kind == MG_Y) { g01.y = -1.0; g10.y = 1.0; }
+        else { g00.x = 1.0; g11.x = -1.0; }
+        // M <- (G on block qubit lq) * M : mixes row pairs that differ in bit lq
+        if (g.lq == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; r += 2) {
+                    const double2 x0 = M[r][c], x1 = M[r + 1][c];
+                    M[r][c] = cfma(g01, x1, cmul(g00, x0));
+                    M[r + 1][c] = cfma(g11, x1, cmul(g10, x0));
+                }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const double2 x0 = M[r][c], x1 = M[r + 2][c];
+                    M[r][c] = cfma(g01, x1, cmul(g00, x0));
+                    M[r + 2][c] = cfma(g11, x1, cmul(g10, x0));
+                }
+        }
+    }
+    if (md.nq == 2) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) out[r * 4 + c] = M[r][c];
+    } else {  // one-qubit block: the 2x2 matrix in entries 0..3
+        out[0] = M[0][0];
+        out[1] = M[0][1];
+        out[2] = M[1][0];
+        out[3] = M[1][1];
+    }
+}
+
 #define TQ_SEL4(i, v0, v1, v2, v3, OP) ((((i) & 1) ? (v0) : 0u) OP (((i) & 2) ? (v1) : 0u) OP (((i) & 4) ? (v2) : 0u) OP (((i) & 8) ? (v3) : 0u))
 #define TQ_SLOT(r) (slot_t ^ TQ_SEL4(r, ws0, ws1, ws2, ws3, ^))
 #define TQ_IO_SLOT(i) (io_slot ^ TQ_SEL4(i, iw0, iw1, iw2, iw3, ^))
@@ -367,6 +440,21 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
     const uint64_t elem_off = (uint64_t)b << p.nbits;
 
     const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
+    if (p.fused_prep) {   // single-tile plans: this CTA is the only one of its element and evaluates its block matrices itself
+        // the element's angles first, in one coalesced sweep (they may live in pinned HOST memory on the latency path)
+        const double* par = p.params ? p.params + (size_t)b * p.ld_params : nullptr;
+        const uint8_t* cod = p.codes ? p.codes + (size_t)b * p.ld_codes : nullptr;
+        if (par && p.ld_params <= kOpSlots * kMatStride * 2) {
+            double* s_par = reinterpret_cast<double*>(s_mat);
+            for (int i = tid; i < p.ld_params; i += nthreads) s_par[i] = par[i];
+            __syncthreads();
+            par = s_par;
+        }
+        for (int mi = tid; mi < p.n_mats; mi += nthreads)
+            eval_block_matrix(p.descs[mi], p.prog, par, 0, p.ld_params, cod, p.ld_codes,
+                              const_cast<double2*>(my_mats) + (size_t)mi * kMatStride);
+        __syncthreads();
+    }
     const bool active = tid < (tile_amps >> kRegBits);
     const int n_tbits = p.k_eff - kRegBits;
     const int n_run = (!DM && p.exp_mode == 1) ? p.n_windows : p.n_gate_windows;
@@ -795,6 +883,21 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     const uint32_t ig0 = p.io_stride[0], ig1 = p.io_stride[1], ig2 = p.io_stride[2], ig3 = p.io_stride[3];
     const uint64_t elem_off = (uint64_t)b << p.nbits;
     const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
+    if (p.fused_prep) {   // single-tile plans: this CTA is the only one of its element and evaluates its block matrices itself
+        // the element's angles first, in one coalesced sweep (they may live in pinned HOST memory on the latency path)
+        const double* par = p.params ? p.params + (size_t)b * p.ld_params : nullptr;
+        const uint8_t* cod = p.codes ? p.codes + (size_t)b * p.ld_codes : nullptr;
+        if (par && p.ld_params <= kOpSlots * kMatStride * 2) {
+            double* s_par = reinterpret_cast<double*>(s_mat);
+            for (int i = tid; i < p.ld_params; i += nthreads) s_par[i] = par[i];
+            __syncthreads();
+            par = s_par;
+        }
+        for (int mi = tid; mi < p.n_mats; mi += nthreads)
+            eval_block_matrix(p.descs[mi], p.prog, par, 0, p.ld_params, cod, p.ld_codes,
+                              const_cast<double2*>(my_mats) + (size_t)mi * kMatStride);
+        __syncthreads();
+    }
     const int n_run = (p.exp_mode == 1) ? p.n_windows : p.n_gate_windows;
 
     // B-fragment coordinates of this lane: B[k = lane & 3][n = lane >> 2]; n = (QL', c', RX'), k = (QL, c)
@@ -1082,7 +1185,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     }
 }
 
-// ---- block matrices: one thread per (batch element, fused block) evaluates the block's matrix program ---------
+// one thread per (batch element, fused block)
 __global__ void __launch_bounds__(128) prep_matrices_kernel(const MatDesc* __restrict__ descs, const MatGate* __restrict__ prog,
                                                             int n_mats, int batch, const double* __restrict__ params,
                                                             int ld_params, const uint8_t* __restrict__ codes,
@@ -1090,74 +1193,7 @@ __global__ void __launch_bounds__(128) prep_matrices_kernel(const MatDesc* __res
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_mats * batch) return;
     const int b = idx / n_mats, mi = idx - b * n_mats;
-    const MatDesc md = descs[mi];
-    double2 M[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) M[r][c] = make_double2(r == c ? 1.0 : 0.0, 0.0);
-    for (int gi = md.begin; gi < md.end; ++gi) {
-        const MatGate g = prog[gi];
-        int kind = g.kind;
-        if (kind == MG_CX) {  // control = lq: swap the two rows with the control bit set
-            if (g.lq == 0) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { const double2 t = M[1][c]; M[1][c] = M[3][c]; M[3][c] = t; }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { const double2 t = M[2][c]; M[2][c] = M[3][c]; M[3][c] = t; }
-            }
-            continue;
-        }
-        if (kind == MG_PAULI_SLOT) {
-            const int code = (codes[(size_t)b * ld_codes + g.pidx] >> (int)g.fixed) & 3;
-            if (code == 0) continue;
-            kind = MG_X + code - 1;
-        }
-        double2 g00 = make_double2(0.0, 0.0), g01 = g00, g10 = g00, g11 = g00;
-        if (kind <= MG_RZ) {
-            const double theta = g.pidx >= 0 ? params[(size_t)b * ld_params + g.pidx] : g.fixed;
-            double s, c;
-            sincos(0.5 * theta, &s, &c);
-            if (kind == MG_RX) { g00.x = c; g01.y = s; g10.y = s; g11.x = c; }            // cos I + i sin X
-            else if (kind == MG_RY) { g00.x = c; g01.x = s; g10.x = -s; g11.x = c; }      // cos I + i sin Y
-            else { g00.x = c; g00.y = s; g11.x = c; g11.y = -s; }                         // diag(e^{+it/2}, e^{-it/2})
-        } else if (kind == MG_X) { g01.x = 1.0; g10.x = 1.0; }
-        else if (kind == MG_Y) { g01.y = -1.0; g10.y = 1.0; }
-        else { g00.x = 1.0; g11.x = -1.0; }
-        // M <- (G on block qubit lq) * M : mixes row pairs that differ in bit lq
-        if (g.lq == 0) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int r = 0; r < 4; r += 2) {
-                    const double2 x0 = M[r][c], x1 = M[r + 1][c];
-                    M[r][c] = cfma(g01, x1, cmul(g00, x0));
-                    M[r + 1][c] = cfma(g11, x1, cmul(g10, x0));
-                }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const double2 x0 = M[r][c], x1 = M[r + 2][c];
-                    M[r][c] = cfma(g01, x1, cmul(g00, x0));
-                    M[r + 2][c] = cfma(g11, x1, cmul(g10, x0));
-                }
-        }
-    }
-    double2* out = mats + (size_t)idx * kMatStride;
-    if (md.nq == 2) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) out[r * 4 + c] = M[r][c];
-    } else {  // one-qubit block: the 2x2 matrix in entries 0..3
-        out[0] = M[0][0];
-        out[1] = M[0][1];
-        out[2] = M[1][0];
-        out[3] = M[1][1];
-    }
+    eval_block_matrix(descs[mi], prog, params, (size_t)b, ld_params, codes, ld_codes, mats + (size_t)idx * kMatStride);
 }
 
 __global__ void reduce_partials_kernel(const double* __restrict__ partial, int ld, int n, double* __restrict__ out,

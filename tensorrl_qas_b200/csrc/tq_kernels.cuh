@@ -48,6 +48,14 @@ struct PassParams {
     const MmaWindowDev* mwindows;   // non-null: tensor-core pass (tile_pass_mma_kernel), `windows` unused
     const uint32_t* io_goff;        // tensor-core pass: physical offset of tile index t, t < threads (global table)
     uint32_t io_stride[4];          // ... and of tile indices threads << i
+    // single-tile plans may fold prep_matrices_kernel into the pass (one launch per energy call): the CTA of element b
+    // evaluates its own block matrices into mats[b] first
+    int fused_prep;
+    const MatDesc* descs;
+    const MatGate* prog;
+    const double* params;
+    const uint8_t* codes;
+    int ld_params, ld_codes;
     int direct;                     // expectation-only pass: no tile staging, windows load from `src` directly
     int skew_ns, skew_lo, skew_hi;  // CTAs [skew_lo, skew_hi) (the second resident CTA of every SM in the first wave)
                                     // start skew_ns late, so that the two CTAs of an SM alternate between their
