@@ -1107,10 +1107,29 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
 #endif
             TQ_TR();
             const int o_end = hdr->op_end - staged_begin;
+            if (hdr->flags & kWinFlagGenericDiag) {
+                // diagonal terms with signs from the thread's index: a window of its own, so that this code (and the
+                // registers of its Walsh-Hadamard transform) stays out of the loop below
+                for (int o = hdr->op_begin - staged_begin; o < o_end; ++o) {
+                    const WinOp wo = s_wops[o];
+                    const double2* m = s_mat + o * kMatStride;
+                    if ((wo.w0 & 0xff) == FM_EXPD) {   // register bit 4 counts as a bit outside the window (qsel)
+                        const double2* terms = reinterpret_cast<const double2*>(p.eterms) + wo.t + 2;
+                        acc += m_expd_half<0>(a, ctx, m, terms);
+                        acc += m_expd_half<1>(a, ctx | (1ull << ((wo.w0 >> 16) & 0xff)), m, terms);
+                    } else if ((wo.w0 & 0xff) == FM_EXPT) {
+                        const double* D = reinterpret_cast<const double*>(m);
+                        double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) s4[r & 3] = fma(a[r] * a[r], D[r], s4[r & 3]);
+                        acc += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                    }
+                }
+                continue;
+            }
             for (int o = hdr->op_begin - staged_begin; o < o_end; ++o) {
                 const WinOp wo = s_wops[o];
                 const double2* m = s_mat + o * kMatStride;
-                const int qsel = (wo.w0 >> 16) & 0xff;
                 if ((wo.w0 & 0xff) == FM_EXPC) {
                     const double* cA = reinterpret_cast<const double*>(m + 1);
                     const double* cB = ((wo.w0 >> 12) & 1)
@@ -1119,29 +1138,17 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
                     const double sum = exec_m_expc(a, (int)(wo.w0 >> 24), cA, cB, comp != 0);
                     const uint64_t zphys = (uint64_t)__double_as_longlong(m[0].x);
                     acc += (__popcll(ctx & zphys) & 1) ? -sum : sum;
-                } else if ((wo.w0 & 0xff) == FM_EXPT) {   // diagonal terms inside the window: signed-weight table
+                } else {   // FM_EXPT: diagonal terms inside the window, signed-weight table
                     const double* D = reinterpret_cast<const double*>(m);
                     double s4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                     for (int r = 0; r < NR; ++r) s4[r & 3] = fma(a[r] * a[r], D[r], s4[r & 3]);
                     acc += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-                } else {  // FM_EXPD: register bit 4 is treated as a bit outside the window (physical bit qsel)
-                    const double2* terms = reinterpret_cast<const double2*>(p.eterms) + wo.t + 2;
-                    acc += m_expd_half<0>(a, ctx, m, terms);
-                    acc += m_expd_half<1>(a, ctx | (1ull << qsel), m, terms);
                 }
             }
         }
     }
 
-#ifdef TQ_TRACE
-    TQ_TR();
-    if (tid == 0 && smid_ == 0 && p.n_windows - p.n_gate_windows == TQ_TRACE && b >= 40 && b < 44) {
-        printf("TRACE cta %d b %d:", (int)blockIdx.x, (int)b);
-        for (int i = 0; i < n_tr; ++i) printf(" %llu", s_tr[i] - s_tr[0] + (s_tr[0] % 100000000ull));
-        printf("\n");
-    }
-#endif
     // ---- 3. Hamiltonian terms evaluated from shared memory (flip masks wider than a window / sparse entries) ----
     if (p.exp_mode != 0) {
         if (p.exp_mode == 1) {

@@ -800,6 +800,7 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
         }
         // --- diagonal terms that reach outside the window (signs from the thread's index) ---
         if (!generic.empty()) {
+            w.flags |= kWinFlagGenericDiag;   // (such windows never carry off-diagonal groups: `mine` is empty)
             // classes over register bits 0..3 only; register bit 4 counts as an outside bit (the kernel evaluates the
             // two halves separately to stay within its register budget)
             const int r4phys = p.local[w.rpos[4]];

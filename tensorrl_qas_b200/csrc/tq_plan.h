@@ -85,6 +85,8 @@ enum : int32_t {    // WinOp code; rb / rb2 are register-bit indices inside the 
                     // sorted by class:  E += sum_zr WHT(|psi|^2)[zr] * sum_{t in zr} w_t sign_t(ctx)
 };
 constexpr int kWinFlagReadOnly = 1;  // Window::tpos[11]: the window does not change the amplitudes
+constexpr int kWinFlagGenericDiag = 4;  // MmaWindow (read-only): holds an M_EXPD op (and no M_EXPC): the kernel keeps that code
+                                        // path out of the ordinary expectation loop
 constexpr int kWinFlagDirect = 2;    // MmaWindow (read-only): lane bits 1..3 are the three lowest qubits, so the thread
                                      // can load its registers straight from global memory, fully coalesced
 
