@@ -52,7 +52,7 @@ struct Plan {
 }  // namespace
 
 struct tq_context {
-    int skew_ns = 0, n_sms = 0;
+    int n_sms = 0;
     bool fuse_prep = true;      // TQ_FUSE_PREP
     bool spin_wait = true;      // TQ_SPIN: poll the pinned result slots instead of cudaStreamSynchronize (latency path)
     bool zero_copy = true;      // TQ_ZERO_COPY: small host-buffer calls read angles / write energies in pinned host memory
@@ -567,9 +567,6 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 // expectation-only pass whose windows all read the state straight from global memory (needs the
                 // per-element state buffer and no leftover shared-memory groups)
                 pp.direct = (dp.direct && pp.src_mode == 2 && pp.exp_mode == 1 && pp.n_groups == 0 && !pp.dst) ? 1 : 0;
-                pp.skew_ns = h->skew_ns;
-                pp.skew_lo = h->n_sms;
-                pp.skew_hi = 2 * h->n_sms;
             }
             launch_tile_pass(pp, bc, dp.threads, dm, stream);
             ++h->launches;
@@ -709,7 +706,6 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->opt.tile_bits = std::max(8, std::min(kMaxTileBits, env_int("TQ_TILE_BITS", 12)));  // kMaxTileBits = 12
     h->opt.low_bits = std::max(0, std::min(h->opt.tile_bits - 4, env_int("TQ_LOW_BITS", 3)));
     h->max_scratch = (size_t)std::max(64, env_int("TQ_MAX_SCRATCH_MB", 16384)) << 20;
-    h->skew_ns = std::max(0, env_int("TQ_SKEW_NS", 0));
     h->fuse_prep = env_int("TQ_FUSE_PREP", 1) != 0;
     h->zero_copy = env_int("TQ_ZERO_COPY", 1) != 0;
     h->spin_wait = env_int("TQ_SPIN", 1) != 0;

@@ -866,15 +866,6 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
 
     uint64_t tile_base = 0;
     for (int i = 0; i < p.n_nl; ++i) tile_base |= (uint64_t)((tile >> i) & 1u) << p.nonlocal[i];
-    if (p.skew_ns > 0 && (int)blockIdx.x >= p.skew_lo && (int)blockIdx.x < p.skew_hi) {
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        do {
-            __nanosleep(200);
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        } while (t1 - t0 < (unsigned long long)p.skew_ns);
-    }
-
     // I/O layout as in tile_pass_kernel: amplitude i of thread t is tile index t + i * nthreads (16 per thread); the
     // physical offsets of the thread part and of the four per-bit strides come precomputed from the host
     const uint32_t io_slot = swz(tid);

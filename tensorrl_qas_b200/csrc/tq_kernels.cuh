@@ -57,9 +57,6 @@ struct PassParams {
     const uint8_t* codes;
     int ld_params, ld_codes;
     int direct;                     // expectation-only pass: no tile staging, windows load from `src` directly
-    int skew_ns, skew_lo, skew_hi;  // CTAs [skew_lo, skew_hi) (the second resident CTA of every SM in the first wave)
-                                    // start skew_ns late, so that the two CTAs of an SM alternate between their
-                                    // tensor-core and data-movement phases instead of running them in lockstep
     int n_windows, n_gate_windows;   // expectation windows follow the gate windows
     const EUnit* eterms;
     const WinOp* wops;
