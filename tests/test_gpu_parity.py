@@ -303,3 +303,51 @@ def test_vqa_shims_mirror_reference_calls(built_lib, key):
         assert abs(es.mean() - e_dm) < 5 * es.std() / np.sqrt(len(es))
         assert c.eig_min - 1e-9 < e_dm < 0
     _backend.reset_backends()
+
+
+@pytest.mark.parametrize("n,gates", [(9, 1500), (12, 2500), (14, 1200)])
+def test_long_circuits_many_windows_per_pass(built_lib, oracle, n, gates):
+    """Passes with more windows than the kernel keeps headers for in shared memory (32) and more ops than it stages at
+    once (48): the header and op restaging paths of the tensor-core kernel."""
+    from tensorrl_qas_b200.simulator import plan_dump
+    gl = synthetic_circuit(n, gates, 77 + n)
+    plan = plan_dump(gl, 0, 12, 3)
+    if n <= 12:
+        assert max(len(p["windows"]) for p in plan) > 32
+    else:
+        assert len(plan) > 10   # many passes instead
+    params = parameter_batch(gl, 2)
+    paulis, w = loaders.heisenberg_terms(n)
+    x, z = loaders.pauli_masks(paulis, n)
+    sim = Simulator(n)
+    sim.set_circuit(gl)
+    sim.set_pauli_hamiltonian(x, z, w)
+    st = sim.states(params[:1])[0]
+    assert np.abs(st - oracle.state(gl, params[0])).max() < 1e-11
+    assert np.abs(sim.energies(params) - oracle.energies(gl, params, pauli=(x, z, w))).max() < TOL
+    sim.close()
+
+
+def test_tensor_core_path_with_loaded_state_trajectories_and_imaginary_terms(built_lib, oracle):
+    """13 qubits (two tiles per state): loaded initial state, sampled-Pauli trajectories, and a Hamiltonian whose terms
+    have odd numbers of Y factors (imaginary class coefficients in the expectation windows)."""
+    from tensorrl_qas_b200.VQAs._backend import sample_noise_codes
+    n = 13
+    base = synthetic_circuit(n, 70, 5)
+    init = oracle.state(synthetic_circuit(n, 40, 6), parameter_batch(synthetic_circuit(n, 40, 6), 1)[0])
+    x, z, w = random_pauli_sum(n, 40, 9, max_flips=4)
+    sim = Simulator(n)
+    sim.set_init_state(init)
+    sim.set_pauli_hamiltonian(x, z, w)
+    sim.set_circuit(base)
+    p = parameter_batch(base, 3)
+    assert np.abs(sim.energies(p) - oracle.energies(base, p, pauli=(x, z, w), init=init)).max() < TOL
+    noisy = noisy_copy(base, 0.05, 0.1)
+    sim.set_circuit(noisy)
+    pn = parameter_batch(noisy, 4)
+    codes = sample_noise_codes(noisy, np.random.default_rng(4), 4)
+    assert codes.any()
+    got = sim.energies_traj(pn, codes)
+    want = oracle.energies(noisy, pn, pauli=(x, z, w), init=init, codes=codes)
+    assert np.abs(got - want).max() < TOL
+    sim.close()
