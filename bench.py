@@ -271,7 +271,9 @@ def main():
             traffic = tj.get("dram_bytes_per_step")
     counts = sim.plan_counts(0)
     # FP64 tensor-core work: every dense block is an 8x8 real DMMA product = 16 FMA per amplitude
-    dmma_flop_eval = 2.0 * 16.0 * counts["tensor_core_blocks"] * (1 << N_QUBITS)
+    # (block-tile pairs actually executed: tiles that are still all-zero early in a run from |0...0> are skipped)
+    tile_amps = 1 << info["tile_bits"]
+    dmma_flop_eval = 2.0 * 16.0 * counts["tensor_core_block_tiles"] * tile_amps
     dmma_tflops = dmma_flop_eval * per_gpu_evals_s / 1e12
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -286,6 +288,8 @@ def main():
                        "gate_passes": passes_rw, "expectation_passes": passes_ro},
         "fp64_tensor": {"achieved": dmma_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                         "frac": dmma_tflops / FP64_DMMA_PEAK_TFLOPS, "blocks_per_eval": counts["tensor_core_blocks"],
+                        "block_tiles_per_eval": counts["tensor_core_block_tiles"],
+                        "dense_block_tiles_per_eval": counts["tensor_core_blocks"] * ((1 << N_QUBITS) // tile_amps),
                         "flop_per_eval": dmma_flop_eval,
                         "peak_source": "measured: profiles/microbench/fp64_peak.cu, mma.sync.m8n8k4.f64 on this pool's "
                                        "B200 (63.9 FMA/clk/SM x 148 SMs x 1.965 GHz); MEASURED_PEAKS.json has no FP64 figure"},

@@ -137,7 +137,8 @@ int tq_plan_info(tq_handle h, int which, int64_t* info8);
  *             8x8 real DMMA product), counts[1] lane<->register qubit exchanges by shuffle, counts[2] gate windows,
  *             counts[3] expectation windows, counts[4] FP64-pipe register windows (tiles below 2^9 amplitudes and
  *             density matrices), counts[5] expectation-only passes that stream the state straight from HBM,
- *             counts[6..7] reserved (0). */
+ *             counts[6] (dense block, tile) pairs executed per batch element with the current initial state (a run
+ *             from |0...0> skips the tiles and amplitudes nothing has populated yet), counts[7] reserved (0). */
 int tq_plan_counts(tq_handle h, int which, int64_t* counts8);
 
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */

@@ -27,6 +27,8 @@ struct HamGroup {
 
 struct DevPass {
     bool direct = false;
+    uint64_t mix_mask = 0;   // physical qubits the pass's ops mix (can turn from 0 to 1)
+    int n_blocks = 0;        // dense tensor-core blocks of the pass
     PassParams proto;  // geometry + device pointers filled at compile time
     int threads = 0;
     int n_tiles = 1;
@@ -54,6 +56,7 @@ struct Plan {
 struct tq_context {
     int n_sms = 0;
     bool fuse_prep = true;      // TQ_FUSE_PREP
+    bool sparse_init = true;    // TQ_SPARSE_INIT: skip the known zeros of states grown from |0...0> (tensor-core passes)
     bool spin_wait = true;      // TQ_SPIN: poll the pinned result slots instead of cudaStreamSynchronize (latency path)
     bool zero_copy = true;      // TQ_ZERO_COPY: small host-buffer calls read angles / write energies in pinned host memory
     int n = 0, device = 0;
@@ -377,6 +380,16 @@ int compile_plan(tq_handle h, int which) {
         dp.n_tiles = 1 << dp.proto.n_nl;
         dp.gate_pass = (int)i < n_gate_passes;
         dp.direct = passes[i].direct;
+        for (const DevOp& d : passes[i].ops) {
+            const std::vector<int>& loc = passes[i].local;
+            if (d.op == OP_U2) dp.mix_mask |= (1ull << loc[d.a]) | (1ull << loc[d.b]);
+            else if (d.op == OP_U1) dp.mix_mask |= 1ull << loc[d.a];
+            else if (d.op == OP_CNOT || d.op == OP_CNOT_NL) dp.mix_mask |= 1ull << loc[d.b];
+            else if (d.op == OP_DEPOL1_DM || d.op == OP_DEPOL2_DM) dp.mix_mask = ~0ull;
+        }
+        if (passes[i].mma)
+            for (const WinOp& o : passes[i].wops)
+                if ((o.w0 & 0xff) == M_U2) ++dp.n_blocks;
         if (passes[i].mma) {
             dp.proto.mwindows = (const MmaWindowDev*)(base + offs[i].windows);
             dp.proto.io_goff = (const uint32_t*)(base + offs[i].io_goff);
@@ -526,7 +539,10 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
     if (rc) return rc;
 
     h->last_stream = stream;
+    // qubits that can be 1 so far: a run that starts from |0...0> (no loaded state) only populates what its gates touch
+    const bool track_support = h->sparse_init && !h->have_init && !dm;
     for (int b0 = 0; b0 < batch; b0 += chunk) {
+        uint64_t support = track_support ? 0ull : ~0ull;
         const int bc = std::min(chunk, batch - b0);
         double2* buf = states_out ? states_out + ((size_t)b0 << plan.nbits) : h->d_state;
         // single-tile plans (one CTA per element): the pass kernel evaluates the block matrices itself -> one launch
@@ -563,6 +579,19 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 if (plan.slots == 1) { pp.partial = out + b0; pp.partial_ld = 1; pp.partial_off = 0; }
                 else { pp.partial = h->d_partial; pp.partial_ld = plan.slots; }
             }
+            pp.in_mask = ~0ull;
+            if (pp.mwindows && dp.gate_pass && support != ~0ull) {
+                pp.in_mask = support;
+                // every pass but the last gate pass may skip the tiles that are entirely zero (a non-local qubit set
+                // that nothing has populated yet): the next pass knows not to read them
+                if (i + 1 < plan.n_gate_passes) {
+                    int kept = 0;
+                    for (int q = 0; q < pp.n_nl; ++q)
+                        if ((support >> pp.nonlocal[q]) & 1ull) pp.nonlocal[kept++] = pp.nonlocal[q];
+                    pp.n_nl = kept;
+                }
+            }
+            if (dp.gate_pass && support != ~0ull) support |= dp.mix_mask;
             if (pp.mwindows) {
                 // expectation-only pass whose windows all read the state straight from global memory (needs the
                 // per-element state buffer and no leftover shared-memory groups)
@@ -709,6 +738,7 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->fuse_prep = env_int("TQ_FUSE_PREP", 1) != 0;
     h->zero_copy = env_int("TQ_ZERO_COPY", 1) != 0;
     h->spin_wait = env_int("TQ_SPIN", 1) != 0;
+    h->sparse_init = env_int("TQ_SPARSE_INIT", 1) != 0;
     h->n_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);
@@ -905,6 +935,20 @@ int tq_plan_counts(tq_handle h, int which, int64_t* counts8) {
     if (rc) return rc;
     const Plan& plan = which == 1 ? h->plan_dm : (which == 2 ? h->plan_traj : h->plan_sv);
     for (int i = 0; i < 8; ++i) counts8[i] = plan.counts[i];
+    // counts[6]: (dense block, tile) pairs executed per batch element with the current initial state
+    uint64_t support = (h->sparse_init && !h->have_init && which != 1) ? 0ull : ~0ull;
+    counts8[6] = 0;
+    for (int i = 0; i < plan.n_gate_passes; ++i) {
+        const DevPass& dp = plan.passes[i];
+        int n_nl = dp.proto.n_nl;
+        if (dp.proto.mwindows && support != ~0ull && i + 1 < plan.n_gate_passes) {
+            n_nl = 0;
+            for (int q = 0; q < dp.proto.n_nl; ++q)
+                if ((support >> dp.proto.nonlocal[q]) & 1ull) ++n_nl;
+        }
+        counts8[6] += (int64_t)dp.n_blocks << n_nl;
+        if (support != ~0ull) support |= dp.mix_mask;
+    }
     return TQ_OK;
 }
 

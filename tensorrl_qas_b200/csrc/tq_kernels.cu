@@ -937,8 +937,16 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
             // nothing to stage: every window of this pass reads the state itself
         } else if (p.src_mode != 0) {
             const double2* src = p.src + (p.src_mode == 2 ? elem_off : 0ull) + tile_base;
+            if (p.in_mask == ~0ull) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __ldcs(src + TQ_IO_GOFF(i));
+                for (int i = 0; i < 16; ++i) v[i] = __ldcs(src + TQ_IO_GOFF(i));
+            } else {   // known zeros of a state grown from |0...0> are not read
+                const bool tile_dead = (tile_base & ~p.in_mask) != 0;
+                const uint32_t dead = (uint32_t)~p.in_mask;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    v[i] = (tile_dead || (TQ_IO_GOFF(i) & dead)) ? make_double2(0.0, 0.0) : __ldcs(src + TQ_IO_GOFF(i));
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = make_double2((tile_base == 0 && tid == 0 && i == 0) ? 1.0 : 0.0, 0.0);

@@ -56,6 +56,10 @@ struct PassParams {
     const double* params;
     const uint8_t* codes;
     int ld_params, ld_codes;
+    uint64_t in_mask;               // tensor-core pass: qubits that can be 1 in the input state (~0: any).  A circuit
+                                    // started from |0...0> only populates the qubits its gates have touched so far:
+                                    // amplitudes with another bit set are known zeros and are not read (nor were
+                                    // they written by the pass before)
     int direct;                     // expectation-only pass: no tile staging, windows load from `src` directly
     int n_windows, n_gate_windows;   // expectation windows follow the gate windows
     const EUnit* eterms;

@@ -173,7 +173,7 @@ class Simulator:
         c = (ctypes.c_int64 * 8)()
         self._check(self._L.tq_plan_counts(self._h, which, c))
         keys = ("tensor_core_blocks", "lane_register_swaps", "gate_windows", "expectation_windows",
-                "fp64_pipe_windows", "direct_expectation_passes")
+                "fp64_pipe_windows", "direct_expectation_passes", "tensor_core_block_tiles")
         return dict(zip(keys, [int(v) for v in c]))
 
     @property

@@ -351,3 +351,42 @@ def test_tensor_core_path_with_loaded_state_trajectories_and_imaginary_terms(bui
     want = oracle.energies(noisy, pn, pauli=(x, z, w), init=init, codes=codes)
     assert np.abs(got - want).max() < TOL
     sim.close()
+
+
+def test_zero_skipping_from_the_all_zero_state(built_lib, oracle, monkeypatch):
+    """A run from |0...0> skips the tiles / amplitudes no gate has populated yet (TQ_SPARSE_INIT): same energies and
+    states, bit for bit, as with the skipping switched off, and equal to the oracle -- including circuits whose first
+    passes touch only a few (high) qubits, CNOTs controlled by untouched qubits, and back-to-back calls that leave stale
+    data in the skipped regions of the scratch buffer."""
+    n = 16
+    rng = np.random.default_rng(123)
+    circuits = []
+    gl = GateList(n)                      # (a) only high qubits at first, then a CNOT fan-out, then everything
+    from tensorrl_qas_b200.circuit import append_random_gates
+    append_random_gates(gl, 30, rng, (13, 14, 15))
+    gl.add_cnot(2, 9)                     # control never populated: must stay a no-op
+    gl.add_cnot(15, 3)
+    append_random_gates(gl, 60, rng, (3, 4, 5, 15))
+    append_random_gates(gl, 80, rng)
+    circuits.append(gl)
+    circuits.append(synthetic_circuit(n, 25, 5, qubits=(0, 1)))            # (b) most of the register untouched at the end
+    circuits.append(brickwork_circuit(n, 21, 30, 8))                        # (c) the bench shape
+    paulis, w = loaders.heisenberg_terms(n)
+    x, z = loaders.pauli_masks(paulis, n)
+    results = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TQ_SPARSE_INIT", flag)
+        sim = Simulator(n)
+        sim.set_pauli_hamiltonian(x, z, w)
+        out = []
+        for gl in circuits + circuits[:1]:          # the first circuit again at the end: stale scratch contents
+            sim.set_circuit(gl)
+            p = parameter_batch(gl, 3)
+            out.append((sim.energies(p), sim.states(p[:1])[0]))
+        results[flag] = out
+        sim.close()
+    for (e1, s1), (e0, s0), gl in zip(results["1"], results["0"], circuits + circuits[:1]):
+        assert np.array_equal(e1, e0) and np.array_equal(s1, s0)
+        p = parameter_batch(gl, 3)
+        assert np.abs(e1 - oracle.energies(gl, p, pauli=(x, z, w))).max() < TOL
+        assert np.abs(s1 - oracle.state(gl, p[0])).max() < 1e-12
