@@ -580,6 +580,7 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 else { pp.partial = h->d_partial; pp.partial_ld = plan.slots; }
             }
             pp.in_mask = ~0ull;
+            pp.use_dead = (pp.mwindows && track_support) ? 1 : 0;
             if (pp.mwindows && dp.gate_pass && support != ~0ull) {
                 pp.in_mask = support;
                 // every pass but the last gate pass may skip the tiles that are entirely zero (a non-local qubit set
@@ -987,7 +988,7 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
     for (const Pass& p : cc.passes) {
         out += "PASS lead=" + std::to_string(p.lead) + " local=";
         for (size_t i = 0; i < p.local.size(); ++i) out += (i ? "," : "") + std::to_string(p.local[i]);
-        out += "\n";
+        out += " support=" + std::to_string((unsigned long long)p.support_in) + "\n";
         for (const DevOp& d : p.ops) {
             snprintf(line, sizeof line, "OP %d %d %d %d %d %.17g\n", d.op, d.a, d.b, d.t, d.flags, d.fixed);
             out += line;
@@ -1001,7 +1002,8 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
             };
             out += "MWIN r=" + list(w.rpos, kMmaRegBits) + " ql=" + std::to_string(w.qlpos) + " g=" + list(w.gpos, 3) +
                    " w=" + list(w.wpos, std::max(0, (int)p.local.size() - 9)) + " rout=" + list(w.rpos_out, kMmaRegBits) +
-                   " qlout=" + std::to_string(w.qlpos_out) + " flags=" + std::to_string(w.flags) + "\n";
+                   " qlout=" + std::to_string(w.qlpos_out) + " flags=" + std::to_string(w.flags) + " dead=" +
+                   std::to_string(w.dead_wbits) + "\n";
             for (int i = w.op_begin; i < w.op_end; ++i) {
                 const WinOp& o = p.wops[i];
                 snprintf(line, sizeof line, "WOP %u %u %u %u %u %d %.17g\n", o.w0 & 0xff, (o.w0 >> 8) & 0xf,

@@ -1006,6 +1006,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
             for (int r = 0; r < NR; ++r) a[r] = __ldg(reinterpret_cast<const double*>(base + (hi[r >> 2] ^ lo[r & 3])));
             return hdr;
         }
+        if (p.use_dead && (warp & hdr->dead_wbits)) return hdr;   // this warp's share of the tile is all zeros
         // byte offset of register r's double: ((slot_t ^ xor of its bits' slots) << 4) | comp << 3, as three-input XORs
         const uint32_t t = ((slot_rest ^ (l1 ? hdr->qslot : 0u)) << 4) | ((uint32_t)comp << 3);
         const uint32_t x0 = (uint32_t)hdr->rslot[0] << 4, x1 = (uint32_t)hdr->rslot[1] << 4, x2 = (uint32_t)hdr->rslot[2] << 4,
@@ -1026,7 +1027,11 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
         if (hdr->flags & kWinFlagReadOnly) continue;
         __syncthreads();   // everyone holds its entry data: the tile may be overwritten from here on
         TQ_TR();
-        const int o_end = hdr->op_end - staged_begin;
+        // a circuit started from |0...0>: warps whose warp-index bits select a qubit nothing has touched yet hold zeros,
+        // stay zeros through the window (it does not act on that qubit) and own a region of the tile that is all zeros
+        // before and after: they only keep the barriers company
+        const bool idle = p.use_dead && (warp & hdr->dead_wbits);
+        const int o_end = idle ? 0 : hdr->op_end - staged_begin;
         // op word and B fragment of op o (prefetched one op ahead, so the loads run under the previous block's DMMAs)
         auto fetch = [&](int o, uint32_t& w0, double& b0, double& b1) {
             w0 = s_wops[o].w0;
@@ -1075,7 +1080,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
             }
         }
         TQ_TR();
-        {
+        if (!idle) {
             const uint32_t t = ((slot_rest ^ (l1 ? hdr->qslot_out : 0u)) << 4) | ((uint32_t)comp << 3);
             const uint32_t x0 = (uint32_t)hdr->rslot_out[0] << 4, x1 = (uint32_t)hdr->rslot_out[1] << 4,
                            x2 = (uint32_t)hdr->rslot_out[2] << 4, x3 = (uint32_t)hdr->rslot_out[3] << 4,

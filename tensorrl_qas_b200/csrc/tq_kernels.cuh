@@ -60,6 +60,7 @@ struct PassParams {
                                     // started from |0...0> only populates the qubits its gates have touched so far:
                                     // amplitudes with another bit set are known zeros and are not read (nor were
                                     // they written by the pass before)
+    int use_dead;                   // honour MmaWindowDev::dead_wbits (the run started from |0...0>)
     int direct;                     // expectation-only pass: no tile staging, windows load from `src` directly
     int n_windows, n_gate_windows;   // expectation windows follow the gate windows
     const EUnit* eterms;

@@ -207,6 +207,7 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
     std::vector<int> remaining(ops.size());
     for (size_t i = 0; i < ops.size(); ++i) remaining[i] = int(i);
 
+    uint64_t support = mma ? 0ull : ~0ull;   // qubits mixed so far (tensor-core plans only use it)
     while (!remaining.empty()) {
         uint64_t L = (nbits <= k) ? all : (bit(std::min(opt.low_bits, k)) - 1);
         uint64_t blocked_mix = 0, blocked_diag = 0;
@@ -236,6 +237,8 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
         Pass p;
         finish_pass(p, nbits, L);
         for (int idx : mine) p.ops.push_back(emit(p, ops[idx]));
+        p.support_in = support;
+        for (int idx : mine) support |= ops[idx].mix;
         if (mma && (int)p.local.size() >= kMmaMinTileBits) schedule_windows_mma(p);
         else schedule_windows(p);
         passes.push_back(std::move(p));
@@ -474,12 +477,22 @@ namespace {
 
 // tile positions outside the window -> three lane-group positions (independent bank-swizzle vectors when possible,
 // so the sixteen amplitudes a warp touches per shared-memory access spread over all bank groups) + warp positions
-void split_rest(const std::vector<int>& rest_in, uint8_t gpos[3], uint8_t wpos[3]) {
+void split_rest(const std::vector<int>& rest_in, uint8_t gpos[3], uint8_t wpos[3], uint32_t prefer_warp = 0) {
     std::vector<int> rest = rest_in;
+    // positions in prefer_warp (still-untouched qubits) should end up on the warp index: keep up to n_warp of them out
+    // of the lane-group choice by moving them to the back
+    const int n_warp = (int)rest.size() - 3;
+    if (prefer_warp && n_warp > 0) {
+        std::vector<int> front, back;
+        for (int q : rest) (((prefer_warp >> q) & 1) && (int)back.size() < n_warp ? back : front).push_back(q);
+        front.insert(front.end(), back.begin(), back.end());
+        rest.swap(front);
+    }
+    const size_t n_lane_cand = prefer_warp ? std::max<size_t>(3, rest.size() - (size_t)std::min<int>(n_warp, popc32(prefer_warp))) : rest.size();
     bool found = false;
-    for (size_t a = 0; a < rest.size() && !found; ++a)
-        for (size_t b = a + 1; b < rest.size() && !found; ++b)
-            for (size_t c = b + 1; c < rest.size() && !found; ++c)
+    for (size_t a = 0; a < n_lane_cand && !found; ++a)
+        for (size_t b = a + 1; b < n_lane_cand && !found; ++b)
+            for (size_t c = b + 1; c < n_lane_cand && !found; ++c)
                 if (independent3(rest[a], rest[b], rest[c])) {
                     std::vector<int> order = {rest[a], rest[b], rest[c]};
                     for (size_t i = 0; i < rest.size(); ++i)
@@ -505,6 +518,9 @@ void schedule_windows_mma(Pass& p) {
         tile_masks(tops[i]);
     }
     auto phys = [&](int pos) { return p.local[pos]; };
+    uint32_t populated = 0;   // tile positions some gate has mixed so far (circuit started from |0...0>)
+    for (int q = 0; q < k; ++q)
+        if ((p.support_in >> p.local[q]) & 1ull) populated |= 1u << q;
 
     auto emit_window = [&](uint32_t W, const std::vector<int>& mine) {
         for (int q = 0; q < k && popc32(W) < kMmaWinBits; ++q) W |= 1u << q;
@@ -661,7 +677,10 @@ void schedule_windows_mma(Pass& p) {
             done[pick] = 1;
         }
         if (!have_layout) fix_layout(act[0]);
-        split_rest(rest, w.gpos, w.wpos);
+        split_rest(rest, w.gpos, w.wpos, ~populated & ((1u << k) - 1u));
+        for (int i = 0; i < 3 && i < k - 9; ++i)
+            if (!((populated >> w.wpos[i]) & 1)) w.dead_wbits |= (uint8_t)(1u << i);
+        for (int idx : mine) populated |= tops[idx].mix;   // what this window's gates may populate
         if (out.empty()) w.flags = kWinFlagReadOnly;   // layout-only window (expectation-only passes)
 
         // emit, splitting at kMaxWindowOps (a continuation window re-enters with the layout the previous part left)
@@ -1059,6 +1078,7 @@ MmaWindowDev resolve_window(const MmaWindow& w, const Pass& p) {
     for (int i = 0; i < 3; ++i)
         if (i < k - 9) { d.wslot[i] = slot(w.wpos[i]); d.wphys[i] = (uint8_t)p.local[w.wpos[i]]; }
     for (int r = 0; r < kMmaRegBits; ++r) d.rphys[r] = (uint8_t)p.local[w.rpos[r]];
+    d.dead_wbits = w.dead_wbits;
     d.flags = w.flags;
     d.op_begin = w.op_begin;
     d.op_end = w.op_end;

@@ -160,7 +160,9 @@ struct MmaWindow {  // 32 bytes
     uint8_t rpos_out[kMmaRegBits];  // the same after the window's M_SWAPQL ops (layout written back)
     uint8_t qlpos_out;
     uint8_t flags;                  // kWinFlagReadOnly
-    uint8_t pad[5];
+    uint8_t dead_wbits;             // warp-index bits whose qubit nothing has populated yet when the circuit starts from
+                                    // |0...0>: warps with such a bit set hold only zeros and skip the window
+    uint8_t pad[4];
     int32_t op_begin, op_end;
 };
 static_assert(sizeof(MmaWindow) == 32, "MmaWindow layout");
@@ -174,7 +176,8 @@ struct MmaWindowDev {  // 64 bytes
     uint8_t gphys[3], wphys[3], qlphys, flags;
     int32_t op_begin, op_end;
     uint8_t rphys[kMmaRegBits];   // physical qubits of the register bits on entry (direct global loads)
-    uint8_t pad[7];
+    uint8_t dead_wbits;           // see MmaWindow
+    uint8_t pad[6];
 };
 static_assert(sizeof(MmaWindowDev) == 64, "MmaWindowDev layout");
 MmaWindowDev resolve_window(const MmaWindow& w, const struct Pass& p);
@@ -183,6 +186,8 @@ struct Pass;
 inline uint32_t swizzle_slot(uint32_t j);   // slot of tile index j (defined below kSwizzleVec)
 
 struct Pass {
+    uint64_t support_in = ~0ull;  // qubits some earlier gate has mixed, for a circuit started from |0...0> (tensor-core
+                                  // windows put still-untouched qubits on the warp index so those warps can idle)
     bool mma = false;           // windows are MmaWindow (tensor-core kernel) instead of Window
     bool direct = false;        // expectation-only tensor-core pass whose windows all load straight from global memory
     std::vector<MmaWindow> mwindows;

@@ -207,7 +207,8 @@ def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=(), w
         elif tok[0] == "PASS":
             lead = int(tok[1].split("=")[1])
             local = [int(v) for v in tok[2].split("=")[1].split(",") if v != ""]
-            passes.append({"lead": lead, "local": local, "ops": [], "windows": []})
+            support = int(tok[3].split("=")[1]) if len(tok) > 3 else (1 << 64) - 1
+            passes.append({"lead": lead, "local": local, "support": support, "ops": [], "windows": []})
         elif tok[0] == "OP":
             passes[-1]["ops"].append((int(tok[1]), int(tok[2]), int(tok[3]), int(tok[4]), int(tok[5]), float(tok[6])))
         elif tok[0] == "WIN":
@@ -219,7 +220,7 @@ def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=(), w
             ints = lambda v: [int(x) for x in v.split(",") if x != ""]  # noqa: E731
             passes[-1]["windows"].append({"mma": True, "r": ints(kv["r"]), "ql": int(kv["ql"]), "g": ints(kv["g"]),
                                           "w": ints(kv["w"]), "rout": ints(kv["rout"]), "qlout": int(kv["qlout"]),
-                                          "flags": int(kv["flags"]), "ops": []})
+                                          "flags": int(kv["flags"]), "dead": int(kv.get("dead", 0)), "ops": []})
         elif tok[0] == "WOP":  # (code, rb, rb2, qsel, flags, t, fixed)
             passes[-1]["windows"][-1]["ops"].append(tuple(int(v) for v in tok[1:7]) + (float(tok[7]),))
     return {"passes": passes, "mats": mats} if with_mats else passes

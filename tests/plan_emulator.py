@@ -126,6 +126,15 @@ def run_plan_windows(plan, nbits, params, init=None, codes=None):
         k_eff = max(len(loc), 4)
         for w in p["windows"]:
             if w.get("mma"):
+                if init is None:
+                    # warps the kernel lets idle (dead warp-index bits) must really hold zeros: every amplitude whose
+                    # index has such a qubit set is zero on entry (the run started from |0...0>)
+                    idx = np.arange(1 << nbits)
+                    for i, pos in enumerate(w["w"]):
+                        if (w["dead"] >> i) & 1:
+                            assert not np.any(vec[((idx >> loc[pos]) & 1) == 1]), "idle warp holds non-zero amplitudes"
+                else:
+                    pass  # with a loaded state the kernel ignores the dead bits
                 vec = _run_mma_window(vec, nbits, loc, w, mats)
                 continue
             assert len(w["wpos"]) == 4 and len(set(w["wpos"])) == 4
