@@ -29,6 +29,8 @@ struct DevPass {
     bool direct = false;
     uint64_t mix_mask = 0;   // physical qubits the pass's ops mix (can turn from 0 to 1)
     int n_blocks = 0;        // dense tensor-core blocks of the pass
+    double live_blocks = 0;  // the same weighted by the share of register pairs / warps that are not known zeros when the
+                             // run starts from |0...0>
     PassParams proto;  // geometry + device pointers filled at compile time
     int threads = 0;
     int n_tiles = 1;
@@ -388,8 +390,19 @@ int compile_plan(tq_handle h, int which) {
             else if (d.op == OP_DEPOL1_DM || d.op == OP_DEPOL2_DM) dp.mix_mask = ~0ull;
         }
         if (passes[i].mma)
-            for (const WinOp& o : passes[i].wops)
-                if ((o.w0 & 0xff) == M_U2) ++dp.n_blocks;
+            for (const MmaWindow& w : passes[i].mwindows) {
+                const double warp_share = 1.0 / (double)(1 << __builtin_popcount(w.dead_wbits));
+                for (int oi = w.op_begin; oi < w.op_end; ++oi) {
+                    const WinOp& o = passes[i].wops[oi];
+                    if ((o.w0 & 0xff) != M_U2) continue;
+                    ++dp.n_blocks;
+                    const uint32_t x = (o.w0 >> 8) & 0xf, dead = (o.w0 >> (24 + kMmaDeadShift)) & 0x1f;
+                    const uint32_t others = dead & ~(1u | (1u << x));
+                    double share = 1.0 / (double)(1 << __builtin_popcount(others));
+                    if ((dead >> x) & 1) share *= 0.5;
+                    dp.live_blocks += share * warp_share;
+                }
+            }
         if (passes[i].mma) {
             dp.proto.mwindows = (const MmaWindowDev*)(base + offs[i].windows);
             dp.proto.io_goff = (const uint32_t*)(base + offs[i].io_goff);
@@ -939,6 +952,7 @@ int tq_plan_counts(tq_handle h, int which, int64_t* counts8) {
     // counts[6]: (dense block, tile) pairs executed per batch element with the current initial state
     uint64_t support = (h->sparse_init && !h->have_init && which != 1) ? 0ull : ~0ull;
     counts8[6] = 0;
+    double work = 0.0;
     for (int i = 0; i < plan.n_gate_passes; ++i) {
         const DevPass& dp = plan.passes[i];
         int n_nl = dp.proto.n_nl;
@@ -947,9 +961,11 @@ int tq_plan_counts(tq_handle h, int which, int64_t* counts8) {
             for (int q = 0; q < dp.proto.n_nl; ++q)
                 if ((support >> dp.proto.nonlocal[q]) & 1ull) ++n_nl;
         }
-        counts8[6] += (int64_t)dp.n_blocks << n_nl;
+        work += ((support != ~0ull || (h->sparse_init && !h->have_init && which != 1)) ? dp.live_blocks : (double)dp.n_blocks) *
+                (double)(1 << n_nl);
         if (support != ~0ull) support |= dp.mix_mask;
     }
+    counts8[6] = (int64_t)(work + 0.5);
     return TQ_OK;
 }
 

@@ -693,28 +693,67 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // D = the new pair, which the instruction delivers in two ADJACENT registers.  With RX on register bit 0 that is the
 // pair itself.  With RX on bit X != 0 the four registers of (bit X, bit 0) are processed together and written back
 // with the two bits' roles exchanged -- still in place, no register moves; the planner tracks the relabelling.
+// `dead`: register bits whose qubit no gate has populated yet (runs from |0...0>, CTA-uniform): register pairs with such
+// a bit set hold zeros and are skipped; if RX itself is dead its RX = 1 inputs are zeros and one DMMA per pair suffices.
 template <int X>
-__device__ __forceinline__ void m_u2(Regs& a, double b0, double b1) {
-    if (X == 0) {
+__device__ __forceinline__ void m_u2(Regs& a, double b0, double b1, uint32_t dead) {
+    if (dead == 0) {   // the common case: a straight run of 64 DMMAs
+        if (X == 0) {
 #pragma unroll
-        for (int p = 0; p < NR; p += 4) {   // two independent chains in flight
-            double t0, t1, u0, u1;
-            dmma884(t0, t1, a[p], b0, 0.0, 0.0);
-            dmma884(u0, u1, a[p + 2], b0, 0.0, 0.0);
-            dmma884(a[p], a[p + 1], a[p + 1], b1, t0, t1);
-            dmma884(a[p + 2], a[p + 3], a[p + 3], b1, u0, u1);
+            for (int p = 0; p < NR; p += 4) {   // two independent chains in flight
+                double t0, t1, u0, u1;
+                dmma884(t0, t1, a[p], b0, 0.0, 0.0);
+                dmma884(u0, u1, a[p + 2], b0, 0.0, 0.0);
+                dmma884(a[p], a[p + 1], a[p + 1], b1, t0, t1);
+                dmma884(a[p + 2], a[p + 3], a[p + 3], b1, u0, u1);
+            }
+        } else {
+#pragma unroll
+            for (int o = 0; o < NR / 4; ++o) {
+                // o enumerates the register bits other than 0 and X
+                const int lo = o & ((1 << (X - 1)) - 1), hi = o >> (X - 1);
+                const int p00 = (hi << (X + 1)) | (lo << 1), p01 = p00 | 1, p10 = p00 | (1 << X), p11 = p10 | 1;
+                double t0, t1, u0, u1;
+                dmma884(t0, t1, a[p00], b0, 0.0, 0.0);   // bit-0 qubit = 0: inputs RX = 0 / 1 are p00 / p10
+                dmma884(u0, u1, a[p01], b0, 0.0, 0.0);   // bit-0 qubit = 1: inputs p01 / p11
+                dmma884(a[p00], a[p01], a[p10], b1, t0, t1);   // -> (bit X = 0; bit 0 = RX')
+                dmma884(a[p10], a[p11], a[p11], b1, u0, u1);   // -> (bit X = 1; bit 0 = RX')
+            }
+        }
+        return;
+    }
+    // early in a run from |0...0>: skip the register pairs that are known zeros
+    if (X == 0) {
+        const bool x_dead = dead & 1u;
+#pragma unroll
+        for (int p = 0; p < NR; p += 2) {
+            if (p & dead) continue;
+            if (x_dead) {
+                dmma884(a[p], a[p + 1], a[p], b0, 0.0, 0.0);
+            } else {
+                double t0, t1;
+                dmma884(t0, t1, a[p], b0, 0.0, 0.0);
+                dmma884(a[p], a[p + 1], a[p + 1], b1, t0, t1);
+            }
         }
     } else {
+        const bool x_dead = (dead >> X) & 1u;
+        const uint32_t others = dead & ~(1u | (1u << X));
 #pragma unroll
         for (int o = 0; o < NR / 4; ++o) {
-            // o enumerates the register bits other than 0 and X
             const int lo = o & ((1 << (X - 1)) - 1), hi = o >> (X - 1);
             const int p00 = (hi << (X + 1)) | (lo << 1), p01 = p00 | 1, p10 = p00 | (1 << X), p11 = p10 | 1;
-            double t0, t1, u0, u1;
-            dmma884(t0, t1, a[p00], b0, 0.0, 0.0);   // bit-0 qubit = 0: inputs RX = 0 / 1 are p00 / p10
-            dmma884(u0, u1, a[p01], b0, 0.0, 0.0);   // bit-0 qubit = 1: inputs p01 / p11
-            dmma884(a[p00], a[p01], a[p10], b1, t0, t1);   // -> (bit X = 0; bit 0 = RX')
-            dmma884(a[p10], a[p11], a[p11], b1, u0, u1);   // -> (bit X = 1; bit 0 = RX')
+            if (p00 & others) continue;
+            if (x_dead) {   // inputs with RX = 1 (p10, p11) are zeros: one DMMA per chain, the second chain first (it reads p01)
+                dmma884(a[p10], a[p11], a[p01], b0, 0.0, 0.0);
+                dmma884(a[p00], a[p01], a[p00], b0, 0.0, 0.0);
+            } else {
+                double t0, t1, u0, u1;
+                dmma884(t0, t1, a[p00], b0, 0.0, 0.0);
+                dmma884(u0, u1, a[p01], b0, 0.0, 0.0);
+                dmma884(a[p00], a[p01], a[p10], b1, t0, t1);
+                dmma884(a[p10], a[p11], a[p11], b1, u0, u1);
+            }
         }
     }
 }
@@ -1058,11 +1097,12 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
             const int fc = w0 & 0xff;
             const int qsel = (w0 >> 16) & 0xff;
             if (fc <= FM_SCAL) {   // compare chain (CTA-uniform), cheaper than an indirect branch per block
-                if (fc == FM_U2 + 1) m_u2<1>(a, b0, b1);
-                else if (fc == FM_U2 + 2) m_u2<2>(a, b0, b1);
-                else if (fc == FM_U2 + 3) m_u2<3>(a, b0, b1);
-                else if (fc == FM_U2 + 4) m_u2<4>(a, b0, b1);
-                else m_u2<0>(a, b0, b1);   // FM_U2 + 0 and FM_SCAL
+                const uint32_t dead = p.use_dead ? ((w0 >> 25) & 0x1fu) : 0u;   // flags bits 1..5
+                if (fc == FM_U2 + 1) m_u2<1>(a, b0, b1, dead);
+                else if (fc == FM_U2 + 2) m_u2<2>(a, b0, b1, dead);
+                else if (fc == FM_U2 + 3) m_u2<3>(a, b0, b1, dead);
+                else if (fc == FM_U2 + 4) m_u2<4>(a, b0, b1, dead);
+                else m_u2<0>(a, b0, b1, dead);   // FM_U2 + 0 and FM_SCAL
             } else {
                 switch (fc) {
                 case FM_SWAP + 0: m_swapql<0>(a, l1); break;

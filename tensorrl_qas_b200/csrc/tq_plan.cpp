@@ -553,6 +553,7 @@ void schedule_windows_mma(Pass& p) {
         };
 
         int ql = -1;
+        uint32_t live = populated;   // positions populated so far, op by op
         int rp[kMmaRegBits];
         struct Emit { WinOp o; };
         std::vector<WinOp> out;
@@ -670,6 +671,14 @@ void schedule_windows_mma(Pass& p) {
             case OP_CNOT_NL: o.w0 = winop_pack(M_CX_OUT, rb_of(d.b), 0, d.a, 0); break;
             default: break;  // density-matrix ops never reach a DMMA pass
             }
+            if ((o.w0 & 0xff) == M_U2 && ((o.w0 >> 12) & 0xf) <= 3) {
+                // register bits whose qubit is still untouched right before this block (runs from |0...0>)
+                uint32_t dead = 0;
+                for (int r = 0; r < kMmaRegBits; ++r)
+                    if (!((live >> rp[r]) & 1)) dead |= 1u << r;
+                o.w0 |= dead << (24 + kMmaDeadShift);
+            }
+            live |= tops[mine[pick]].mix;
             out.push_back(o);
             // a dense block on register bit x != 0 leaves its register qubit on bit 0 and the former bit-0 qubit on
             // bit x (the tensor-core results always land in adjacent register pairs)

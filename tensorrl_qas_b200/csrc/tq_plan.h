@@ -132,6 +132,7 @@ constexpr int kMmaRegBits = 5;
 constexpr int kMmaWinBits = kMmaRegBits + 1;   // qubits a window can act on
 constexpr int kMmaMinTileBits = 9;             // one warp
 constexpr int kMmaFlagSwapOut = 1;
+constexpr int kMmaDeadShift = 1;
 enum : int32_t {    // WinOp codes of DMMA windows; rb / rb2 are 4-bit fields, qsel and flags 8-bit fields
     M_U2 = 16,      // dense block: rb = x (register bit paired with QL; for x != 0 the block also exchanges the roles of
                     // register bits 0 and x -- its results land in adjacent registers), rb2 = mode:
@@ -140,6 +141,8 @@ enum : int32_t {    // WinOp codes of DMMA windows; rb / rb2 are 4-bit fields, q
                     //   4: scalar m[0] / m[3] selected by physical bit qsel (diagonal block outside the window)
                     // flags bit kMmaFlagSwapOut (modes 0..3): the block's two output qubits trade places (matrix rows
                     // permuted when it is staged): afterwards QL holds the register qubit and register bit 0 the old QL
+                    // flags bits 1..5 (kMmaDeadShift): register bits (as they sit BEFORE the block) whose qubit no gate
+                    // has populated yet when the circuit starts from |0...0> -- those register pairs are zeros
     M_SWAPQL = 17,  // rb = x: exchange the roles of QL and Rx (data crosses lanes by shuffle)
     M_CX_OUT = 18,  // rb = target register bit, qsel = physical control bit (outside the window)
                     // (a CNOT with both qubits inside the window runs as an M_U2 with its constant matrix)

@@ -135,7 +135,7 @@ def run_plan_windows(plan, nbits, params, init=None, codes=None):
                             assert not np.any(vec[((idx >> loc[pos]) & 1) == 1]), "idle warp holds non-zero amplitudes"
                 else:
                     pass  # with a loaded state the kernel ignores the dead bits
-                vec = _run_mma_window(vec, nbits, loc, w, mats)
+                vec = _run_mma_window(vec, nbits, loc, w, mats, from_zero=init is None)
                 continue
             assert len(w["wpos"]) == 4 and len(set(w["wpos"])) == 4
             assert sorted(w["wpos"] + w["tpos"]) == list(range(k_eff))
@@ -175,7 +175,7 @@ def run_plan_windows(plan, nbits, params, init=None, codes=None):
     return vec
 
 
-def _run_mma_window(vec, nbits, loc, w, mats):
+def _run_mma_window(vec, nbits, loc, w, mats, from_zero=False):
     """Tensor-core window (tq_plan.h "DMMA windows"): ops act on (QL, register bit) pairs; M_SWAPQL only relabels."""
     k = len(loc)
     assert k >= 9 and len(w["r"]) == 5 and len(w["g"]) == 3 and len(w["w"]) == k - 9
@@ -188,6 +188,12 @@ def _run_mma_window(vec, nbits, loc, w, mats):
         if code == M_U2:
             M = mats[t]
             pq, px = loc[ql], loc[r[rb]]
+            if from_zero and rb2 <= 3:
+                # flags bits 1..5: register bits the kernel treats as all-zero before this block
+                idx = np.arange(1 << nbits)
+                for bit_r in range(5):
+                    if (flags >> (1 + bit_r)) & 1:
+                        assert not np.any(vec[((idx >> loc[r[bit_r]]) & 1) == 1]), "dead register bit holds amplitudes"
             if rb2 == 0:      # 4x4, index bit 0 = QL
                 assert M.shape == (4, 4)
                 vec = apply_2q(vec, nbits, pq, px, M)
