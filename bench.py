@@ -285,7 +285,13 @@ def main():
                 "the fused kernel actually runs against",
         "hbm_actual": {"bytes_per_eval_model": moved, "gbs_model": moved * per_gpu_evals_s / 1e9,
                        "frac_of_peak_model": moved * per_gpu_evals_s / 1e9 / peak,
-                       "gate_passes": passes_rw, "expectation_passes": passes_ro},
+                       "bytes_per_eval_ncu": (traffic / B) if traffic else None,
+                       "gbs_ncu": (traffic / B * per_gpu_evals_s / 1e9) if traffic else None,
+                       "frac_of_peak_ncu": (traffic / B * per_gpu_evals_s / 1e9 / peak) if traffic else None,
+                       "gate_passes": passes_rw, "expectation_passes": passes_ro,
+                       "note": "model = one read + one write of the state per gate pass, one read per expectation pass; "
+                               "ncu = measured DRAM bytes of one step (profiles/traffic.json): the first gate pass of a "
+                               "run from |0...0> only touches the tiles that are not all-zero yet"},
         "fp64_tensor": {"achieved": dmma_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                         "frac": dmma_tflops / FP64_DMMA_PEAK_TFLOPS, "blocks_per_eval": counts["tensor_core_blocks"],
                         "block_tiles_per_eval": counts["tensor_core_block_tiles"],
