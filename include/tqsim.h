@@ -102,6 +102,15 @@ int tq_energy_batch(tq_handle h, int batch, const double* params_dev, int ld_par
                     void* stream);
 int tq_energy_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* out_host);
 
+/* Energies of n_problems DIFFERENT problems in one launch: problem i is handles[i] -- its own circuit, Hamiltonian and
+ * initial state -- evaluated at params_host[i] (n_params doubles of that handle; the pointer may be NULL when the circuit
+ * has no parameters) and, when codes_host and codes_host[i] are non-NULL, with that trajectory-noise code row.  All
+ * handles share the device and n_qubits, and every problem must fit one tile (n_qubits <= 12).  out_host[i] receives
+ * energy i.  Replaces B independent environments each calling get_energy_qulacs once (one COBYLA round of a lock-step
+ * multi-environment driver; environments/environment_qulacs.py:429-433 called from B environments at a time). */
+int tq_energy_multi_host(int n_problems, tq_handle* handles, const double* const* params_host,
+                         const uint8_t* const* codes_host, double* out_host);
+
 /* Pauli-trajectory noise on the pure-state path (what the reference's noise environments actually run:
  * one sampled Pauli per noise gate and per evaluation, VQE_qulacs_noise.py:31-33,44-54).
  * codes is [B][ld_codes] uint8: for a TQ_DEPOL1 gate with slot s, codes[b][s] in {0:I,1:X,2:Y,3:Z} acts on q0;

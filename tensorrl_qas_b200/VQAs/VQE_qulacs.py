@@ -30,7 +30,7 @@ def get_energy_qulacs(angles, observable, circuit, n_qubits, n_shots, phys_noise
 def get_exp_val(n_qubits, circuit, op):
     """reference: VQE_qulacs.py:79-86 -- returns numpy float64 like `(np.conj(psi).T @ op @ psi).real`."""
     sim = _backend.bind(n_qubits, circuit, op)
-    return sim.energies(circuit.params.reshape(1, -1))[0]
+    return _backend.evaluate(sim, circuit.params.reshape(1, -1))
 
 
 def get_energy_qulacs_batch(angles, observable, circuit, n_qubits):

@@ -26,7 +26,7 @@ def get_energy_qulacs(angles, observable, circuit, n_qubits, TN_state, n_shots, 
 def get_exp_val(n_qubits, circuit, op, TN_state):
     """reference: VQE_qulacs_TN_notin_RL.py:80-87"""
     sim = _backend.bind(n_qubits, circuit, op, TN_state, use_tn=True)
-    return sim.energies(circuit.params.reshape(1, -1))[0]
+    return _backend.evaluate(sim, circuit.params.reshape(1, -1))
 
 
 def get_energy_qulacs_batch(angles, observable, circuit, n_qubits, TN_state):

@@ -40,8 +40,8 @@ def get_exp_val(n_qubits, circuit, op, TN_state, n_shots, weights):
     p = circuit.params.reshape(1, -1)
     if NOISE_MODE == "density_matrix":
         return sim.energies_dm(p)[0]
-    codes = _backend.sample_noise_codes(circuit.gates, rng, 1)
-    return sim.energies_traj(p, codes)[0]
+    codes = _backend.sample_noise_codes(circuit.gates, _backend.noise_rng(rng), 1)
+    return _backend.evaluate(sim, p, codes)
 
 
 if __name__ == "__main__":

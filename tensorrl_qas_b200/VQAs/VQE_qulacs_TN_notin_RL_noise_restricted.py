@@ -29,7 +29,7 @@ def get_energy_qulacs(angles, observable, circuit, weights, n_qubits, TN_state, 
 
 def get_exp_val(n_qubits, circuit, op, TN_state, n_shots, weights):
     sim = _backend.bind(n_qubits, circuit, op, TN_state, use_tn=True)
-    expval = sim.energies(circuit.params.reshape(1, -1))[0]
+    expval = _backend.evaluate(sim, circuit.params.reshape(1, -1))
     if n_shots != 0:
         sigma = (n_shots) ** (-0.5)
         shot_noise = shot_noise_np(weights, sigma)

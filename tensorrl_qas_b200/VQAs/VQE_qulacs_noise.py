@@ -48,8 +48,8 @@ def get_exp_val(n_qubits, circuit, op, n_shots, weights):
     p = circuit.params.reshape(1, -1)
     if NOISE_MODE == "density_matrix":
         return sim.energies_dm(p)[0]
-    codes = _backend.sample_noise_codes(circuit.gates, rng, 1)
-    return sim.energies_traj(p, codes)[0]
+    codes = _backend.sample_noise_codes(circuit.gates, _backend.noise_rng(rng), 1)
+    return _backend.evaluate(sim, p, codes)
 
 
 def get_energy_qulacs_batch(angles, observable, circuit, n_qubits, codes=None):

@@ -2,6 +2,7 @@
 so that the COBYLA loop (up to 1000 `get_energy_qulacs` calls on the same circuit / Hamiltonian objects,
 environments/environment_qulacs.py:429-445) uploads the circuit and the Hamiltonian once."""
 import os
+import threading
 
 import numpy as np
 
@@ -9,6 +10,7 @@ from ..circuit import decode_state_tensor
 from ..simulator import Simulator
 
 _sims = {}
+_ctx = threading.local()   # per-thread evaluation context, set by tensorrl_qas_b200.lockstep for its worker threads
 
 
 def default_device():
@@ -31,10 +33,29 @@ class _Slot:
 
 
 def _slot(n, device=None):
-    key = (int(n), default_device() if device is None else int(device))
+    """One handle per (n_qubits, device) -- and per lock-step worker, whose environments hold different circuits."""
+    key = (int(n), default_device() if device is None else int(device), getattr(_ctx, "slot_key", None))
     if key not in _sims:
-        _sims[key] = _Slot(*key)
+        _sims[key] = _Slot(key[0], key[1])
     return _sims[key]
+
+
+def evaluate(sim, params, codes=None):
+    """One energy of the problem bound to `sim`.  Directly (tq_energy_batch_host / tq_energy_traj_batch_host), or, inside
+    a lock-step worker thread, through the group's coordinator: the evaluations of all workers of a round become ONE
+    tq_energy_multi_host launch."""
+    group = getattr(_ctx, "group", None)
+    if group is not None:
+        return group.submit(_ctx.worker, sim, params, codes)
+    if codes is not None:
+        return sim.energies_traj(params, codes)[0]
+    return sim.energies(params)[0]
+
+
+def noise_rng(module_rng):
+    """The generator the noise shims sample their Pauli codes from: the module-level one, or the worker's own inside a
+    lock-step thread (so that every environment keeps a reproducible stream whatever the thread interleaving)."""
+    return getattr(_ctx, "rng", None) or module_rng
 
 
 def reset_backends():

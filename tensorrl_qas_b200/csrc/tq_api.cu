@@ -123,6 +123,14 @@ int fail(tq_handle h, int code, const std::string& msg) {
                         std::string(#call) + ": " + cudaGetErrorString(e_));                            \
     } while (0)
 
+#define TQ_CUDA_H(hh, call)                                                                             \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(hh, e_ == cudaErrorMemoryAllocation ? TQ_ENOMEM : TQ_ECUDA,                     \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                            \
+    } while (0)
+
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
@@ -880,6 +888,101 @@ int tq_energy_batch(tq_handle h, int batch, const double* params_dev, int ld_par
 int tq_energy_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* out_host) {
     if (!h || !out_host) return TQ_EINVAL;
     return run_host(h, 0, batch, params_host, ld_params, nullptr, 0, out_host, nullptr, 0);
+}
+
+// One launch for n DIFFERENT problems (lock-step drivers: B environments, one cost evaluation each per COBYLA round).
+int tq_energy_multi_host(int n_problems, tq_handle* handles, const double* const* params_host,
+                         const uint8_t* const* codes_host, double* out_host) {
+    if (n_problems <= 0) return n_problems == 0 ? TQ_OK : TQ_EINVAL;
+    if (!handles || !out_host || !handles[0]) return TQ_EINVAL;
+    tq_handle m = handles[0];   // its stream and pinned staging buffer carry the call
+    TQ_CUDA_H(m, cudaSetDevice(m->device));
+    // staging layout: [PassParams table][angle rows][code rows][energies]
+    size_t p_doubles = 0, c_bytes = 0;
+    for (int i = 0; i < n_problems; ++i) {
+        tq_handle h = handles[i];
+        if (!h) return fail(m, TQ_EINVAL, "tq_energy_multi_host: NULL handle");
+        if (h->device != m->device || h->n != m->n)
+            return fail(m, TQ_EINVAL, "tq_energy_multi_host: all handles must share the device and n_qubits");
+        p_doubles += (size_t)std::max(h->n_params, 1);
+        c_bytes += ((size_t)std::max(h->n_slots, 1) + 15) / 16 * 16;
+    }
+    const size_t t_off = 0, p_off = ((size_t)n_problems * sizeof(PassParams) + 15) / 16 * 16;
+    const size_t c_off = p_off + p_doubles * sizeof(double), o_off = c_off + c_bytes;
+    int rc = ensure_staging(m, o_off + (size_t)n_problems * sizeof(double) + 16);
+    if (rc) return rc;
+    unsigned char* hp = (unsigned char*)m->h_pin;
+    PassParams* table = (PassParams*)(hp + t_off);
+    volatile uint64_t* slots = (volatile uint64_t*)(hp + o_off);
+    const uint64_t kPending = 0x7ff8dead5eed0001ull;
+    size_t pcur = p_off, ccur = c_off, smem = 0;
+    int threads = 0;
+    bool mma = false;
+    for (int i = 0; i < n_problems; ++i) {
+        tq_handle h = handles[i];
+        const bool traj = codes_host && codes_host[i] && h->n_slots > 0;
+        const int which = traj ? 2 : 0;
+        rc = compile_plan(h, which);
+        if (rc) return fail(m, rc, std::string("problem ") + std::to_string(i) + ": " + h->err);
+        Plan& plan = which == 2 ? h->plan_traj : h->plan_sv;
+        if (plan.passes.size() != 1 || plan.passes[0].proto.n_nl != 0 || plan.slots != 1)
+            return fail(m, TQ_EINVAL, "tq_energy_multi_host: needs single-tile problems (n_qubits <= tile bits)");
+        if (!h->have_pauli && !h->have_dense) return fail(m, TQ_ESTATE, "tq_energy_multi_host: a handle has no Hamiltonian");
+        if (plan.n_rot > 0 && h->n_params > 0 && (!params_host || !params_host[i]))
+            return fail(m, TQ_EINVAL, "tq_energy_multi_host: missing angles");
+        rc = upload_entries(h);
+        if (rc) return fail(m, rc, h->err);
+        rc = grow(h, (void**)&h->d_mats, &h->mats_cap, std::max<size_t>(16, (size_t)plan.n_mats * kMatStride * 16));
+        if (rc) return fail(m, rc, h->err);
+        const DevPass& dp = plan.passes[0];
+        PassParams pp = dp.proto;
+        pp.table = nullptr;
+        pp.mats = h->d_mats;
+        if (h->have_init) { pp.src_mode = 1; pp.src = h->d_init; }
+        else { pp.src_mode = 0; pp.src = nullptr; }
+        pp.dst = nullptr;
+        pp.hent = h->d_hent;
+        pp.n_hent = (int)h->hent.size();
+        pp.partial = (double*)(hp + o_off) + i;
+        pp.partial_ld = 1;
+        pp.partial_off = 0;
+        pp.in_mask = ~0ull;
+        pp.use_dead = (pp.mwindows && h->sparse_init && !h->have_init) ? 1 : 0;
+        pp.direct = 0;
+        pp.fused_prep = plan.n_mats > 0 ? 1 : 0;
+        pp.descs = plan.d_descs;
+        pp.prog = plan.d_prog;
+        pp.ld_params = std::max(h->n_params, 1);
+        pp.params = (const double*)(hp + pcur);
+        if (h->n_params > 0 && params_host && params_host[i]) memcpy(hp + pcur, params_host[i], (size_t)h->n_params * sizeof(double));
+        pcur += (size_t)pp.ld_params * sizeof(double);
+        pp.ld_codes = std::max(h->n_slots, 1);
+        pp.codes = traj ? (const uint8_t*)(hp + ccur) : nullptr;
+        if (traj) memcpy(hp + ccur, codes_host[i], (size_t)h->n_slots);
+        ccur += ((size_t)pp.ld_codes + 15) / 16 * 16;
+        memcpy(&table[i], &pp, sizeof(PassParams));
+        slots[i] = kPending;
+        smem = std::max(smem, tile_pass_smem_bytes(pp.k_eff, pp.k, pp.lead));
+        threads = std::max(threads, dp.threads);
+        mma = pp.mwindows != nullptr;
+        h->last_stream = m->stream;
+    }
+    launch_tile_pass_table(table, n_problems, threads, smem, mma, m->stream);
+    ++m->launches;
+    rc = check_launch(m, "tile_pass_kernel (table launch)");
+    if (rc) return rc;
+    bool done = false;
+    if (m->spin_wait) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int it = 0; !done; ++it) {
+            done = true;
+            for (int i = n_problems - 1; i >= 0 && done; --i) done = slots[i] != kPending;
+            if (!done && (it & 1023) == 1023 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(5)) break;
+        }
+    }
+    if (!done) TQ_CUDA_H(m, cudaStreamSynchronize(m->stream));
+    memcpy(out_host, hp + o_off, (size_t)n_problems * sizeof(double));
+    return TQ_OK;
 }
 
 int tq_energy_traj_batch(tq_handle h, int batch, const double* params_dev, int ld_params, const uint8_t* codes_dev,

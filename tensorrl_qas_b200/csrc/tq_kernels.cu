@@ -395,8 +395,14 @@ __device__ __forceinline__ int flat_code(uint32_t w0) {
     }
 }
 
-template <bool DM>
-__global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(const PassParams p) {
+// TABLE = true: every CTA runs its OWN single-tile problem (circuit, block matrices, Hamiltonian, initial state): CTA i
+// takes its parameters from p_in.table[i] -- B different environments evaluated by one launch.
+template <bool DM, bool TABLE>
+__global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(const PassParams p_in) {
+    PassParams p_own;
+    if (TABLE) p_own = p_in.table[blockIdx.x];
+    const PassParams& p = TABLE ? p_own : p_in;
+    const uint32_t cta = TABLE ? 0u : blockIdx.x;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tile_amps = 1 << p.k_eff;
     const int valid_amps = 1 << p.k;
@@ -409,8 +415,8 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
 
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const uint32_t ntiles = 1u << p.n_nl;
-    const uint32_t tile = blockIdx.x & (ntiles - 1u);
-    const uint32_t b = blockIdx.x >> p.n_nl;
+    const uint32_t tile = cta & (ntiles - 1u);
+    const uint32_t b = cta >> p.n_nl;
 
     uint64_t tile_base = 0;
     for (int i = 0; i < p.n_nl; ++i) tile_base |= (uint64_t)((tile >> i) & 1u) << p.nonlocal[i];
@@ -876,7 +882,12 @@ __device__ __forceinline__ int flat_code_mma(uint32_t w0) {
 
 #define TQ_SEL5(i, v0, v1, v2, v3, v4) ((((i) & 1) ? (v0) : 0u) ^ (((i) & 2) ? (v1) : 0u) ^ (((i) & 4) ? (v2) : 0u) ^ (((i) & 8) ? (v3) : 0u) ^ (((i) & 16) ? (v4) : 0u))
 
-__global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kernel(const PassParams p) {
+template <bool TABLE>
+__global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kernel(const PassParams p_in) {
+    PassParams p_own;
+    if (TABLE) p_own = p_in.table[blockIdx.x];
+    const PassParams& p = TABLE ? p_own : p_in;
+    const uint32_t cta = TABLE ? 0u : blockIdx.x;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tile_amps = 1 << p.k;   // k >= 9: k_eff == k, every thread of every warp is active
     double2* amp = reinterpret_cast<double2*>(smem_raw);
@@ -900,8 +911,8 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     const int comp = lane & 1;
     const bool l1 = (lane >> 1) & 1;
     const uint32_t ntiles = 1u << p.n_nl;
-    const uint32_t tile = blockIdx.x & (ntiles - 1u);
-    const uint32_t b = blockIdx.x >> p.n_nl;
+    const uint32_t tile = cta & (ntiles - 1u);
+    const uint32_t b = cta >> p.n_nl;
 
     uint64_t tile_base = 0;
     for (int i = 0; i < p.n_nl; ++i) tile_base |= (uint64_t)((tile >> i) & 1u) << p.nonlocal[i];
@@ -1283,19 +1294,29 @@ size_t tile_pass_smem_bytes(int k_eff, int k, int lead) {
 }
 
 cudaError_t tile_pass_configure() {
-    cudaError_t e = cudaFuncSetAttribute(tile_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tile_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tile_pass_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    const void* kernels[] = {(const void*)tile_pass_kernel<false, false>, (const void*)tile_pass_kernel<true, false>,
+                             (const void*)tile_pass_kernel<false, true>, (const void*)tile_pass_mma_kernel<false>,
+                             (const void*)tile_pass_mma_kernel<true>};
+    for (const void* k : kernels) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 void launch_tile_pass(const PassParams& p, int batch, int threads, bool density, cudaStream_t stream) {
     const unsigned grid = (unsigned)batch << p.n_nl;
     const size_t smem = tile_pass_smem_bytes(p.k_eff, p.k, p.lead);
-    if (p.mwindows) tile_pass_mma_kernel<<<grid, threads, smem, stream>>>(p);
-    else if (density) tile_pass_kernel<true><<<grid, threads, smem, stream>>>(p);
-    else tile_pass_kernel<false><<<grid, threads, smem, stream>>>(p);
+    if (p.mwindows) tile_pass_mma_kernel<false><<<grid, threads, smem, stream>>>(p);
+    else if (density) tile_pass_kernel<true, false><<<grid, threads, smem, stream>>>(p);
+    else tile_pass_kernel<false, false><<<grid, threads, smem, stream>>>(p);
+}
+
+void launch_tile_pass_table(const PassParams* table_dev, int n, int threads, size_t smem, bool mma, cudaStream_t stream) {
+    PassParams head{};
+    head.table = table_dev;
+    if (mma) tile_pass_mma_kernel<true><<<n, threads, smem, stream>>>(head);
+    else tile_pass_kernel<false, true><<<n, threads, smem, stream>>>(head);
 }
 
 void launch_prep_matrices(const MatDesc* descs, const MatGate* prog, int n_mats, int batch, const double* params,

@@ -38,6 +38,7 @@ struct HEntry {     // non-zero of the symmetrised Hamiltonian, upper triangle, 
 };
 
 struct PassParams {
+    const PassParams* table;   // table launches (launch_tile_pass_table): per-CTA parameters, everything else unused
     int nbits, k, k_eff, lead, n_nl;   // k = real tile bits, k_eff = max(k, kRegBits)
     uint8_t local[16];
     uint8_t nonlocal[32];
@@ -82,6 +83,8 @@ struct PassParams {
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead);
 cudaError_t tile_pass_configure();  // opt in to > 48 KiB dynamic shared memory
 void launch_tile_pass(const PassParams& p, int batch, int threads, bool density, cudaStream_t stream);
+// n CTAs, CTA i runs the single-tile pure-state problem table_dev[i] (one element each): B different circuits per launch
+void launch_tile_pass_table(const PassParams* table_dev, int n, int threads, size_t smem, bool mma, cudaStream_t stream);
 
 // block matrices of every (element, fused block): mats[(b * n_mats + m) * kMatStride ...]
 void launch_prep_matrices(const MatDesc* descs, const MatGate* prog, int n_mats, int batch, const double* params,

@@ -181,6 +181,32 @@ class Simulator:
         return int(self._L.tq_launch_count(self._h))
 
 
+def energies_multi(sims, params, codes=None):
+    """One launch for len(sims) DIFFERENT problems (tq_energy_multi_host): sims[i] is a Simulator with its own circuit /
+    Hamiltonian / initial state (same n_qubits, same device, n_qubits <= 12), params[i] its angle vector (any float
+    dtype, promoted exactly), codes[i] an optional trajectory-noise code row.  Returns a float64 array of energies."""
+    n = len(sims)
+    if n == 0:
+        return np.zeros(0)
+    L = sims[0]._L
+    handles = (ctypes.c_void_p * n)(*[s._h for s in sims])
+    rows = [np.ascontiguousarray(np.asarray(p, dtype=np.float64).reshape(-1)) for p in params]
+    for s, r in zip(sims, rows):
+        if r.shape[0] < s.n_params:
+            raise ValueError("angle vector shorter than the circuit's parameter count")
+    prow = (_lib.c_dbl_p * n)(*[r.ctypes.data_as(_lib.c_dbl_p) if r.shape[0] else None for r in rows])
+    crow = None
+    keep = []
+    if codes is not None:
+        keep = [None if c is None else np.ascontiguousarray(np.asarray(c, dtype=np.uint8).reshape(-1)) for c in codes]
+        crow = (_lib.c_u8_p * n)(*[None if c is None or c.shape[0] == 0 else c.ctypes.data_as(_lib.c_u8_p) for c in keep])
+    out = np.empty(n, dtype=np.float64)
+    rc = L.tq_energy_multi_host(n, handles, prow, crow, _dptr(out))
+    if rc != 0:
+        raise TqError(rc, L.tq_last_error(sims[0]._h).decode())
+    return out
+
+
 def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=(), with_mats=False):
     """Planner dry run (no GPU): list of passes, each {'lead', 'local', 'ops': [(op, a, b, t, flags, fixed)],
     'windows': [{'wpos', 'tpos', 'ops': [(code, rb, rb2, qsel, flags, t, fixed)]}]}.  with_mats=True also returns the

@@ -1,0 +1,160 @@
+"""Lock-step multi-environment evaluation (tensorrl_qas_b200/lockstep.py, tq_energy_multi_host)."""
+import importlib
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import env_fixture as fx
+
+
+def test_lockstep_group_batches_rounds_and_handles_uneven_workers():
+    """Workers with different numbers of evaluations: every round holds one request per still-running worker, results
+    go back to the right worker, a finished worker no longer blocks the others."""
+    from tensorrl_qas_b200.VQAs import _backend
+    from tensorrl_qas_b200.lockstep import run_lockstep
+    sizes = []
+
+    def evaluate_round(items):
+        sizes.append(len(items))
+        return [float(np.sum(p)) + 1000.0 * sim for sim, p, _ in items]
+
+    def make_task(i, n_evals):
+        def task():
+            out = []
+            for k in range(n_evals):
+                out.append(_backend.evaluate(i, np.array([k, 0.5 * i])))   # `sim` is just a tag here
+            return out
+        return task
+
+    counts = [5, 2, 7, 1]
+    results, group = run_lockstep([make_task(i, c) for i, c in enumerate(counts)], evaluate_round=evaluate_round)
+    for i, c in enumerate(counts):
+        assert results[i] == [k + 0.5 * i + 1000.0 * i for k in range(c)]
+    assert sizes == [4, 3, 2, 2, 2, 1, 1] and group.evaluations == sum(counts) and group.rounds == 7
+    # outside a lock-step thread the hook is inert
+    assert getattr(_backend._ctx, "group", None) is None
+
+
+def test_lockstep_propagates_errors_without_deadlock():
+    from tensorrl_qas_b200.VQAs import _backend
+    from tensorrl_qas_b200.lockstep import run_lockstep
+
+    def bad_round(items):
+        raise RuntimeError("device lost")
+
+    with pytest.raises(RuntimeError, match="device lost"):
+        run_lockstep([lambda: _backend.evaluate(0, np.zeros(1)), lambda: _backend.evaluate(1, np.zeros(1))],
+                     evaluate_round=bad_round)
+
+    def task_raises():
+        raise ValueError("boom")
+
+    with pytest.raises(ValueError, match="boom"):
+        run_lockstep([task_raises, lambda: _backend.evaluate(1, np.ones(1))], evaluate_round=lambda it: [0.0] * len(it))
+
+
+@pytest.mark.gpu
+def test_multi_problem_launch_matches_individual_calls(built_lib, oracle):
+    """tq_energy_multi_host: B different circuits / Hamiltonians / initial states in one launch, bit-identical to B
+    separate calls; both kernel families (n = 6: FP64-pipe windows, n = 10: tensor-core windows)."""
+    from tensorrl_qas_b200 import Simulator, loaders
+    from tensorrl_qas_b200.circuit import parameter_batch, synthetic_circuit
+    from tensorrl_qas_b200.simulator import energies_multi
+    for n in (6, 10):
+        sims, params, want = [], [], []
+        for i in range(9):
+            gl = synthetic_circuit(n, 10 + 7 * i, 100 + i)
+            rng = np.random.default_rng(i)
+            A = rng.normal(size=(1 << n, 1 << n))
+            H = A + A.T
+            s = Simulator(n)
+            s.set_circuit(gl)
+            s.set_dense_hamiltonian(H)
+            init = None
+            if i % 3 == 1:
+                init = oracle.state(synthetic_circuit(n, 12, 7 + i), parameter_batch(synthetic_circuit(n, 12, 7 + i), 1)[0])
+                s.set_init_state(init)
+            p = parameter_batch(gl, 1)[0]
+            sims.append(s)
+            params.append(p.astype(np.float32) if i % 2 else p)      # float32 angle vectors are promoted exactly
+            want.append(oracle.energies(gl, np.asarray(params[-1], dtype=np.float64).reshape(1, -1), dense=H, init=init)[0])
+        got = energies_multi(sims, params)
+        single = np.array([s.energies(np.asarray(p, dtype=np.float64).reshape(1, -1))[0] for s, p in zip(sims, params)])
+        assert np.array_equal(got, single)
+        assert np.abs(got - np.array(want)).max() < 1e-10
+        for s in sims:
+            s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("module_name,key", [("environment_qulacs_TN_notin_agent", "fixed_beh2"),
+                                              ("environment_qulacs", "trainable_beh2"),
+                                              ("environment_qulacs_noise", "noise_trainable_h2o8")])
+def test_lockstep_envs_reproduce_serial_trajectories(module_name, key, tmp_path, monkeypatch):
+    """B environments stepped in lock-step (one launch per COBYLA round) follow exactly the trajectories of the same
+    environments stepped one after the other."""
+    from tensorrl_qas_b200.VQAs import _backend
+    from tensorrl_qas_b200.environments.utils import utils
+    from tensorrl_qas_b200.lockstep import LockstepEnvs
+    ep = fx.Episode(key)
+    fx.materialize(str(tmp_path), ep)
+    monkeypatch.setenv("TQ_DATA_ROOT", str(tmp_path))
+    mod = importlib.import_module(f"tensorrl_qas_b200.environments.{module_name}")
+    conf = ep.conf
+    conf["non_local_opt"]["global_iters"] = 60
+    B, steps = 4, 4
+    table = utils.dictionary_of_actions(conf["env"]["num_qubits"])
+    rng = np.random.default_rng(5)
+    plans = [[int(rng.integers(len(table))) for _ in range(steps)] for _ in range(B)]
+    noisy = "noise" in module_name
+
+    def fresh():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return [mod.CircuitEnv(conf, device=torch.device("cpu")) for _ in range(B)]
+
+    # serial reference: each environment with its own noise stream
+    _backend.reset_backends()
+    serial = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for b, env in enumerate(fresh()):
+            if noisy:
+                mod.CircuitEnv.vc.seed(100 + b)
+            env.reset()
+            rec = []
+            for a in plans[b]:
+                obs, rwd, done = env.step(list(table[a]))
+                rec.append((obs.numpy().copy(), float(rwd), done, float(env.energy), int(env.nfev)))
+                if done:
+                    break
+            serial.append(rec)
+    _backend.reset_backends()
+    envs = fresh()
+    ls = LockstepEnvs(envs, seeds=[100 + b for b in range(B)] if noisy else None)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ls.reset_all()
+        got = [[] for _ in range(B)]
+        alive = list(range(B))
+        for t in range(steps):
+            out = LockstepEnvs([envs[b] for b in alive], seeds=None)   # (sub-group of the still-running environments)
+            out._rngs = None if ls._rngs is None else [ls._rngs[b] for b in alive]
+            out._tag = ls._tag
+            res = out.step_all([list(table[plans[b][t]]) for b in alive])
+            assert out.last_group.rounds < out.last_group.evaluations or len(alive) == 1
+            nxt = []
+            for b, (obs, rwd, done) in zip(alive, res):
+                got[b].append((obs.numpy().copy(), float(rwd), done, float(envs[b].energy), int(envs[b].nfev)))
+                if not done:
+                    nxt.append(b)
+            alive = nxt
+            if not alive:
+                break
+    for b in range(B):
+        assert len(got[b]) == len(serial[b])
+        for (o1, r1, d1, e1, n1), (o0, r0, d0, e0, n0) in zip(got[b], serial[b]):
+            assert np.array_equal(o1, o0) and r1 == r0 and d1 == d0 and e1 == e0 and n1 == n0
+    _backend.reset_backends()
