@@ -176,7 +176,13 @@ def main():
         raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch N>1 with torchrun")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # NCCL announces itself on STDOUT ("NCCL version ...") when the communicator is created; the contract is ONE JSON
+    # line on stdout, so file descriptor 1 points at stderr until the warm-up (first collective) is over
+    saved_stdout = None
     if world > 1:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     gl, ham, parameter_batch = workload()
@@ -206,6 +212,10 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     # ---------------- timed region: device time with CUDA events on the launch stream, max over ranks ----------
     sampler = ClockSampler(local_rank) if rank == 0 else None
