@@ -490,6 +490,18 @@ void split_rest(const std::vector<int>& rest_in, uint8_t gpos[3], uint8_t wpos[3
     }
     const size_t n_lane_cand = prefer_warp ? std::max<size_t>(3, rest.size() - (size_t)std::min<int>(n_warp, popc32(prefer_warp))) : rest.size();
     bool found = false;
+    {   // the three lowest tile positions make a conflict-free lane group (swizzle vectors 1, 2, 4): take them when free
+        size_t at[3] = {rest.size(), rest.size(), rest.size()};
+        for (size_t i = 0; i < n_lane_cand; ++i)
+            if (rest[i] < 3) at[rest[i]] = i;
+        if (at[0] < rest.size() && at[1] < rest.size() && at[2] < rest.size()) {
+            std::vector<int> order = {0, 1, 2};
+            for (size_t i = 0; i < rest.size(); ++i)
+                if (rest[i] > 2) order.push_back(rest[i]);
+            rest.swap(order);
+            found = true;
+        }
+    }
     for (size_t a = 0; a < n_lane_cand && !found; ++a)
         for (size_t b = a + 1; b < n_lane_cand && !found; ++b)
             for (size_t c = b + 1; c < n_lane_cand && !found; ++c)
