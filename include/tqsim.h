@@ -131,6 +131,17 @@ int tq_energy_dm_batch_host(tq_handle h, int batch, const double* params_host, i
 int tq_state_batch(tq_handle h, int batch, const double* params_dev, int ld_params, double* states_dev,
                    void* stream);
 int tq_state_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* states_host);
+
+/* Device-resident states evolved IN PLACE: states_dev is [B][2^n] complex128 and every element starts from what the
+ * buffer holds (not from the handle's initial state; the states need not be normalised -- every kernel is linear).  The
+ * handle's circuit is applied (a gate-free circuit leaves the buffer untouched) and, when energies_dev is non-NULL,
+ * energies_dev[b] = <psi_b| H |psi_b> of the evolved state.  This is the building block of single-state sharding
+ * (tensorrl_qas_b200/sharded.py): each rank evolves its 2^(n-g)-amplitude shard through the
+ * gates that are local in the current qubit layout and evaluates its part of the Pauli sum; the qubit exchange between
+ * layouts is one all-to-all.  Replaces circuit.update_quantum_state(state) on a state that already holds amplitudes
+ * (environments/VQAs/VQE_qulacs_TN_notin_RL.py:82-84) for registers too large for one GPU's share of the batch. */
+int tq_evolve_states(tq_handle h, int batch, const double* params_dev, int ld_params, double* states_dev,
+                     double* energies_dev, void* stream);
 /* Final density matrices, [B][4^n] complex128, entry rho[r][c] at index r + (c << n). */
 int tq_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* rho_host);
 

@@ -46,6 +46,8 @@ SIGNATURES = {
     "tq_energy_dm_batch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_dbl_p, ctypes.c_int, c_dbl_p]),
     "tq_state_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_void_p]),
+    "tq_evolve_states": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
     "tq_state_batch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_dbl_p, ctypes.c_int, c_dbl_p]),
     "tq_dm_batch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_dbl_p, ctypes.c_int, c_dbl_p]),
     "tq_plan_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p]),

@@ -36,6 +36,7 @@ struct DevPass {
     int n_tiles = 1;
     int n_groups = 0;
     bool gate_pass = true;
+    bool no_ops = false;     // the single pass of a gate-free circuit: it only stages the state
 };
 
 struct Plan {
@@ -389,6 +390,7 @@ int compile_plan(tq_handle h, int which) {
         dp.threads = threads_for(dp.proto.k_eff);
         dp.n_tiles = 1 << dp.proto.n_nl;
         dp.gate_pass = (int)i < n_gate_passes;
+        dp.no_ops = passes[i].ops.empty();
         dp.direct = passes[i].direct;
         for (const DevOp& d : passes[i].ops) {
             const std::vector<int>& loc = passes[i].local;
@@ -517,9 +519,11 @@ int ensure_init_rho(tq_handle h) {
     return TQ_OK;
 }
 
-// Run the plan for `batch` elements.  mode: 0 energies, 1 final states into `states_out` (gate passes only).
+// Run the plan for `batch` elements: energies into `out` and / or final states into `states_out`.  from_states: the
+// elements start from the states already in `states_out` (device-resident, evolved in place) instead of the handle's
+// initial state.
 int run_plan(tq_handle h, int which, int batch, const double* params, int ld, const uint8_t* codes, int ldc,
-             double* out, double2* states_out, cudaStream_t stream) {
+             double* out, double2* states_out, cudaStream_t stream, bool from_states = false) {
     if (batch <= 0) return TQ_OK;
     int rc = compile_plan(h, which);
     if (rc) return rc;
@@ -528,7 +532,7 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
         return fail(h, TQ_EINVAL, "params is NULL or ld_params < n_params");
     if (which == 2 && h->n_slots > 0 && (!codes || ldc < h->n_slots))
         return fail(h, TQ_EINVAL, "codes is NULL or ld_codes < number of noise slots");
-    const bool want_energy = states_out == nullptr;
+    const bool want_energy = out != nullptr;
     const bool dm = which == 1;
     const bool single_tile = plan.nbits <= h->opt.tile_bits;
     if (want_energy) {
@@ -561,7 +565,7 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
 
     h->last_stream = stream;
     // qubits that can be 1 so far: a run that starts from |0...0> (no loaded state) only populates what its gates touch
-    const bool track_support = h->sparse_init && !h->have_init && !dm;
+    const bool track_support = h->sparse_init && !h->have_init && !dm && !from_states;
     for (int b0 = 0; b0 < batch; b0 += chunk) {
         uint64_t support = track_support ? 0ull : ~0ull;
         const int bc = std::min(chunk, batch - b0);
@@ -588,12 +592,13 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 pp.codes = codes ? codes + (size_t)b0 * ldc : nullptr;
                 pp.ld_codes = ldc;
             }
-            if (i == 0) {
+            if (i == 0 && !from_states) {
                 if (h->have_init) { pp.src_mode = 1; pp.src = dm ? h->d_init_rho : h->d_init; }
                 else { pp.src_mode = 0; pp.src = nullptr; }
             } else { pp.src_mode = 2; pp.src = buf; }
             const bool is_last = (i == total_passes - 1);
             pp.dst = (states_out || dm || !is_last) && dp.gate_pass ? buf : nullptr;
+            if (from_states && dp.no_ops) pp.dst = nullptr;   // gate-free circuit: the states stay as they are
             if (!want_energy || dm) pp.exp_mode = 0;
             if (pp.exp_mode == 2) { pp.hent = h->d_hent; pp.n_hent = (int)h->hent.size(); }
             if (pp.exp_mode) {
@@ -1015,6 +1020,14 @@ int tq_state_batch(tq_handle h, int batch, const double* params_dev, int ld_para
     if (!h || !states_dev) return TQ_EINVAL;
     TQ_CUDA(cudaSetDevice(h->device));
     return run_plan(h, 0, batch, params_dev, ld_params, nullptr, 0, nullptr, (double2*)states_dev, (cudaStream_t)stream);
+}
+
+int tq_evolve_states(tq_handle h, int batch, const double* params_dev, int ld_params, double* states_dev,
+                     double* energies_dev, void* stream) {
+    if (!h || !states_dev) return TQ_EINVAL;
+    TQ_CUDA(cudaSetDevice(h->device));
+    return run_plan(h, 0, batch, params_dev, ld_params, nullptr, 0, energies_dev, (double2*)states_dev,
+                    (cudaStream_t)stream, /*from_states=*/true);
 }
 
 int tq_state_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* states_host) {

@@ -161,6 +161,30 @@ class Simulator:
         self._check(rc)
         return out
 
+    def evolve_states(self, states, params=None, energies=False, stream=None):
+        """states: torch CUDA tensor holding [B][2^n] complex128 (dtype complex128, or float64 with a trailing 2),
+        evolved IN PLACE through the handle's circuit from whatever they hold (tq_evolve_states).  params: float64 CUDA
+        tensor [B][ld] or None for a circuit without parameters.  energies=True also returns <psi_b|H|psi_b> of the
+        evolved states as a float64 CUDA tensor [B].  No synchronisation."""
+        import torch
+        if not states.is_cuda or not states.is_contiguous() or states.dtype not in (torch.complex128, torch.float64):
+            raise ValueError("states must be a contiguous complex128 / float64 CUDA tensor")
+        amps = states.numel() // (1 if states.dtype == torch.complex128 else 2)
+        batch, rem = divmod(amps, 1 << self.n_qubits)
+        if rem or batch == 0:
+            raise ValueError("states does not hold a whole number of 2^n-amplitude vectors")
+        ld = 0
+        if params is not None:
+            if not params.is_cuda or params.dtype != torch.float64 or not params.is_contiguous():
+                raise ValueError("params must be a contiguous float64 CUDA tensor")
+            params = params.reshape(batch, -1)
+            ld = params.shape[1]
+        out = torch.empty(batch, dtype=torch.float64, device=states.device) if energies else None
+        s = stream if stream is not None else torch.cuda.current_stream(states.device).cuda_stream
+        self._check(self._L.tq_evolve_states(self._h, batch, params.data_ptr() if params is not None else None, ld,
+                                             states.data_ptr(), out.data_ptr() if energies else None, s))
+        return out
+
     # ------------------------------------------------------------------ introspection
     def plan_info(self, which=0):
         info = (ctypes.c_int64 * 8)()

@@ -1,0 +1,117 @@
+"""Single-state sharding on the GPU (-m gpu): tq_evolve_states against the oracle, the sharded driver with R virtual ranks
+on one device (real kernels, transposed-tensor all-to-all) against the oracle, and -- when the box has two GPUs -- two
+NCCL ranks.  Tolerance 1e-10 Ha (BASELINE.json north_star)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tensorrl_qas_b200 import Simulator, loaders
+from tensorrl_qas_b200.circuit import GateList, brickwork_circuit, synthetic_circuit
+from tensorrl_qas_b200.sharded import LocalComm, ShardedSimulator
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _random_pauli_sum(n, n_terms, seed, max_weight=4):
+    rng = np.random.default_rng(seed)
+    xs, zs, cs = [0], [0], [0.75]    # identity term first: shards are not normalised one by one
+    for _ in range(n_terms):
+        x = 0
+        for q in rng.choice(n, size=int(rng.integers(0, max_weight + 1)), replace=False):
+            x |= 1 << int(q)
+        xs.append(x)
+        zs.append(int(rng.integers(0, 1 << n)))
+        cs.append(float(rng.normal()))
+    return np.asarray(xs, dtype=np.uint64), np.asarray(zs, dtype=np.uint64), np.asarray(cs)
+
+
+@pytest.mark.parametrize("n,tile_bits", [(10, 12), (13, 12), (13, 9), (16, 12)])
+def test_evolve_states_in_place(built_lib, oracle, monkeypatch, n, tile_bits):
+    import torch
+    monkeypatch.setenv("TQ_TILE_BITS", str(tile_bits))
+    rng = np.random.default_rng(n)
+    gl = synthetic_circuit(n, 90, 7 + n)
+    B = 3
+    params = np.asarray(gl.initial_angles)[None, :] + rng.uniform(-0.1, 0.1, (B, gl.n_params))
+    init = rng.normal(size=(B, 1 << n)) + 1j * rng.normal(size=(B, 1 << n))
+    init *= 0.5                                              # deliberately not normalised
+    x, z, w = _random_pauli_sum(n, 12, n)
+    sim = Simulator(n, 0)
+    sim.set_circuit(gl)
+    sim.set_pauli_hamiltonian(x, z, w)
+    states = torch.from_numpy(init.copy()).cuda()
+    e = sim.evolve_states(states, torch.from_numpy(params).cuda(), energies=True)
+    torch.cuda.synchronize()
+    got = states.cpu().numpy()
+    for b in range(B):
+        ref = oracle.state(gl, params[b], init=init[b])
+        assert np.abs(got[b] - ref).max() < 1e-12
+        assert abs(float(e[b]) - oracle.expect_pauli(ref, x, z, w)) < TOL
+    # a gate-free circuit evaluates the states without touching them
+    sim.set_circuit(GateList(n))
+    before = states.clone()
+    e2 = sim.evolve_states(states, None, energies=True)
+    torch.cuda.synchronize()
+    assert torch.equal(before, states)
+    assert np.abs(e2.cpu().numpy() - e.cpu().numpy()).max() < TOL
+    sim.close()
+
+
+@pytest.mark.parametrize("n,ranks,tile_bits,seed", [(13, 2, 12, 0), (14, 4, 12, 1), (15, 8, 12, 2), (13, 4, 9, 3),
+                                                     (16, 8, 10, 4), (16, 2, 12, 5)])
+def test_virtual_ranks_match_the_oracle(built_lib, oracle, monkeypatch, n, ranks, tile_bits, seed):
+    monkeypatch.setenv("TQ_TILE_BITS", str(tile_bits))
+    gl = synthetic_circuit(n, 120, 40 + seed)
+    x, z, w = _random_pauli_sum(n, 20, seed)
+    rng = np.random.default_rng(seed)
+    params = np.asarray(gl.initial_angles) + rng.uniform(-0.1, 0.1, gl.n_params)
+    sim = ShardedSimulator(n, LocalComm(ranks), device=0)
+    sim.set_circuit(gl)
+    sim.set_pauli_hamiltonian(x, z, w)
+    ref = oracle.energies(gl, params[None, :], pauli=(x, z, w))[0]
+    assert abs(sim.energy(params) - ref) < TOL
+    assert sim.n_exchanges >= 1
+    params2 = params + 0.03
+    assert abs(sim.energy(params2) - oracle.energies(gl, params2[None, :], pauli=(x, z, w))[0]) < TOL
+
+
+def test_sharded_heisenberg_brickwork_matches_unsharded_kernels(built_lib, oracle):
+    n = 18
+    gl = brickwork_circuit(n, 21, 41, 5)
+    paulis, w = loaders.heisenberg_terms(n)
+    x, z = loaders.pauli_masks(paulis, n)
+    p = np.asarray(gl.initial_angles)
+    one = Simulator(n, 0)
+    one.set_circuit(gl)
+    one.set_pauli_hamiltonian(x, z, w)
+    e1 = one.energies(p[None, :])[0]
+    one.close()
+    for ranks in (2, 8):
+        sim = ShardedSimulator(n, LocalComm(ranks), device=0)
+        sim.set_circuit(gl)
+        sim.set_pauli_hamiltonian(x, z, w)
+        assert abs(sim.energy(p) - e1) < TOL
+        sim.set_circuit(GateList(n))
+        assert abs(sim.energy() - (2 * n - 1)) < TOL     # |0...0>: every ZZ and Z term is +1
+
+
+def test_two_nccl_ranks(built_lib, oracle):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "profiles", "bench_state_sharding.py"), "--qubits", "18",
+           "--check-oracle"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert '"oracle_abs_err"' in res.stdout
