@@ -711,7 +711,7 @@ int run_host(tq_handle h, int which, int batch, const double* params_host, int l
         TQ_CUDA(cudaMemcpyAsync(dp + c_off, hp + c_off, cbytes, cudaMemcpyHostToDevice, h->stream));
     }
     rc = run_plan(h, which, batch, pbytes ? (const double*)(dp + p_off) : nullptr, ld,
-                  cbytes ? (const uint8_t*)(dp + c_off) : nullptr, ldc, (double*)(dp + o_off),
+                  cbytes ? (const uint8_t*)(dp + c_off) : nullptr, ldc, states_host ? nullptr : (double*)(dp + o_off),
                   states_host ? (double2*)(dp + s_off) : nullptr, h->stream);
     if (rc) return rc;
     if (states_host) {

@@ -739,8 +739,10 @@ void schedule_windows_mma(Pass& p) {
         for (int idx : remaining) {
             const TOp& t = tops[idx];
             bool take = !((t.mix & (blocked_mix | blocked_diag)) || (t.diag & blocked_mix));
-            // a CNOT whose control is inside the window must have it among the window's positions: count it
-            const uint32_t need = t.mix;
+            // a CNOT whose control is inside the window must have it among the window's positions: count it.  A diagonal
+            // one-qubit block on a tile position joins the window as well: outside it the position could land on a lane
+            // bit, where the phase would differ between the rows of one DMMA (B is shared by all rows of a warp).
+            const uint32_t need = t.mix | (t.d.op == OP_D1 ? t.diag : 0u);
             if (take) {
                 if (popc32(W | need) <= kMmaWinBits) W |= need;
                 else take = false;

@@ -208,6 +208,9 @@ def _run_mma_window(vec, nbits, loc, w, mats, from_zero=False):
                 vec = apply_1q(vec, nbits, pq, M)
             else:             # diagonal block on a bit outside the window
                 assert rb2 == 4 and M.shape == (2, 2) and M[0, 1] == 0 and M[1, 0] == 0 and qsel not in inside
+                # the phase is part of the B fragment, which all rows (lane bits 2..4) of a DMMA share
+                assert qsel not in [loc[q] for q in w["g"]], "diagonal block on a lane-group qubit"
+
                 vec = apply_1q(vec, nbits, qsel, M)
             if rb != 0:       # results land in adjacent registers: register bits 0 and rb trade qubits
                 r[0], r[rb] = r[rb], r[0]

@@ -40,7 +40,7 @@ def test_evolve_states_in_place(built_lib, oracle, monkeypatch, n, tile_bits):
     B = 3
     params = np.asarray(gl.initial_angles)[None, :] + rng.uniform(-0.1, 0.1, (B, gl.n_params))
     init = rng.normal(size=(B, 1 << n)) + 1j * rng.normal(size=(B, 1 << n))
-    init *= 0.5                                              # deliberately not normalised
+    init *= 1.5 / np.linalg.norm(init, axis=1, keepdims=True)    # deliberately not normalised: <psi|psi> = 2.25
     x, z, w = _random_pauli_sum(n, 12, n)
     sim = Simulator(n, 0)
     sim.set_circuit(gl)

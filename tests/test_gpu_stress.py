@@ -72,3 +72,43 @@ def test_random_problem_matches_oracle(built_lib, oracle, monkeypatch, seed):
     assert np.abs(st - oracle.state(gl, p[0], init=init)).max() < 1e-12
     assert np.array_equal(sim.energies(p), e)   # deterministic
     sim.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_sparse_circuits_with_lone_diagonal_gates(built_lib, oracle, monkeypatch, seed):
+    """Few gates on many qubits: lone RZ / Z gates whose qubit nothing else in the window touches, CNOT triples (SWAPs),
+    loaded states.  Regression for [CNOT(11,9), RX(11), RZ(7)] on 12 qubits (a phase applied per thread inside a DMMA whose
+    B fragment all rows share)."""
+    rng = np.random.default_rng(7000 + seed)
+    n = 12 if seed == 0 else int(rng.integers(9, 16))
+    gl = GateList(n)
+    if seed == 0:
+        gl.add_cnot(11, 9)
+        gl.add_rotation(0, 11, 0.3)
+        gl.add_rotation(2, 7, 0.7)
+    else:
+        for _ in range(int(rng.integers(3, 40))):
+            u = rng.random()
+            if u < 0.45:
+                gl.add_rotation(2, int(rng.integers(n)), float(rng.uniform(-3, 3)))
+            elif u < 0.55:
+                gl.add_pauli("Z", int(rng.integers(n)))
+            elif u < 0.75:
+                gl.add_rotation(int(rng.integers(2)), int(rng.integers(n)), float(rng.uniform(-3, 3)))
+            elif u < 0.9:
+                c, t = rng.choice(n, size=2, replace=False)
+                gl.add_cnot(int(c), int(t))
+            else:
+                a, b = (int(v) for v in rng.choice(n, size=2, replace=False))
+                gl.add_cnot(a, b), gl.add_cnot(b, a), gl.add_cnot(a, b)
+    monkeypatch.setenv("TQ_TILE_BITS", str(int(rng.choice([9, 10, 12]))))
+    init = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    init /= np.linalg.norm(init)
+    p = parameter_batch(gl, 2)
+    sim = Simulator(n)
+    sim.set_circuit(gl)
+    for ini in (None, init):
+        sim.set_init_state(ini)
+        st = sim.states(p[:1])[0]
+        assert np.abs(st - oracle.state(gl, p[0], init=ini)).max() < 1e-12
+    sim.close()

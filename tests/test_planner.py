@@ -161,3 +161,37 @@ def test_bad_gate_is_reported(built_lib):
     gl.add_rotation(0, 7, 0.1)
     with pytest.raises(ValueError):
         plan_dump(gl, 0, 12, 4)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_lone_diagonal_gates_never_sit_on_lane_bits(built_lib, oracle, seed):
+    """A diagonal one-qubit block whose qubit no other gate of the window touches (a lone RZ / Z) must not be applied as
+    a per-thread phase inside a DMMA on a lane-group position: the B fragment is shared by all rows of the product.
+    (Regression: [CNOT(11,9), RX(11), RZ(7)] on 12 qubits came out wrong on the GPU; the emulator now asserts it.)"""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(9, 15))
+    gl = GateList(n)
+    if seed == 0:
+        n = 12
+        gl = GateList(n)
+        gl.add_cnot(11, 9)
+        gl.add_rotation(0, 11, 0.3)
+        gl.add_rotation(2, 7, 0.7)
+    else:
+        for _ in range(int(rng.integers(3, 30))):
+            u = rng.random()
+            if u < 0.5:
+                gl.add_rotation(2, int(rng.integers(n)), float(rng.uniform(-3, 3)))      # lone RZ gates, many qubits
+            elif u < 0.6:
+                gl.add_pauli("Z", int(rng.integers(n)))
+            elif u < 0.8:
+                gl.add_rotation(int(rng.integers(2)), int(rng.integers(n)), float(rng.uniform(-3, 3)))
+            else:
+                c, t = rng.choice(n, size=2, replace=False)
+                gl.add_cnot(int(c), int(t))
+    params = parameter_batch(gl, 1)[0]
+    tile_bits = int(rng.choice([9, 10, 12]))
+    plan = plan_dump(gl, 0, tile_bits, 3, with_mats=True)
+    init = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    want = oracle.state(gl, params, init=init)
+    assert np.abs(run_plan_windows(plan, n, params, init=init) - want).max() < 1e-12
