@@ -622,7 +622,8 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
             if (pp.mwindows) {
                 // expectation-only pass whose windows all read the state straight from global memory (needs the
                 // per-element state buffer and no leftover shared-memory groups)
-                pp.direct = (dp.direct && pp.src_mode == 2 && pp.exp_mode == 1 && pp.n_groups == 0 && !pp.dst) ? 1 : 0;
+                pp.direct = (dp.direct && pp.src_mode == 2 && pp.exp_mode == 1 && pp.n_groups == 0 && !pp.dst &&
+                             plan.nbits <= 27 /* 32-bit byte offsets inside an element */) ? 1 : 0;
             }
             launch_tile_pass(pp, bc, dp.threads, dm, stream);
             ++h->launches;
