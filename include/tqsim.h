@@ -142,6 +142,25 @@ int tq_state_batch_host(tq_handle h, int batch, const double* params_host, int l
  * (environments/VQAs/VQE_qulacs_TN_notin_RL.py:82-84) for registers too large for one GPU's share of the batch. */
 int tq_evolve_states(tq_handle h, int batch, const double* params_dev, int ld_params, double* states_dev,
                      double* energies_dev, void* stream);
+/* Evolution of one shard with the qubit exchange fused into the write-back (single-state sharding over n_ranks = 2, 4 or
+ * 8 GPUs of one NVSwitch box).  shard_dev holds this rank's 2^n amplitudes (n = the handle's qubit count = local qubits);
+ * the circuit is applied and the LAST tile pass stores every amplitude where it lives after the rank bits have been
+ * swapped with the top log2(n_ranks) local qubits: amplitude idx goes to rank c = idx >> (n - g), at index
+ * (rank << (n - g)) | (idx & (2^(n-g) - 1)) of recv_ptrs[c] -- rank c's receive buffer (device pointers valid on this
+ * device: peer memory opened with tq_ipc_open, or local buffers; recv_ptrs is a HOST array of n_ranks addresses and must
+ * not alias shard_dev).  That replaces the all-to-all between two segments (tensorrl_qas_b200/sharded.py): the NVLink
+ * transfer runs tile by tile under the tensor-core work of the same kernel.  The caller synchronises the ranks (any
+ * stream-ordered collective) before the receive buffers are read.  Needs tensor-core passes (n >= 9). */
+int tq_evolve_states_exchange(tq_handle h, const double* params_dev, int ld_params, double* shard_dev, int n_ranks,
+                              int rank, const uint64_t* recv_ptrs, void* stream);
+/* Plumbing for the above: shard buffers as plain cudaMalloc allocations (base pointers, so that they can be exported), and
+ * CUDA IPC handles (64 bytes) to map a peer rank's buffer into this process. */
+int tq_device_alloc(int device, uint64_t bytes, void** out);
+int tq_device_free(int device, void* p);
+int tq_ipc_export(int device, void* base, unsigned char* handle64);
+int tq_ipc_open(int device, const unsigned char* handle64, void** out);
+int tq_ipc_close(int device, void* p);
+
 /* Final density matrices, [B][4^n] complex128, entry rho[r][c] at index r + (c << n). */
 int tq_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* rho_host);
 

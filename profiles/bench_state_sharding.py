@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--virtual", type=int, default=0)
     ap.add_argument("--check-oracle", action="store_true")
     ap.add_argument("--check-unsharded", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="NCCL all-to-all between segments instead of the fused write-back")
     args = ap.parse_args()
 
     import torch
@@ -50,7 +51,7 @@ def main():
     paulis, w = loaders.heisenberg_terms(n)
     x, z = loaders.pauli_masks(paulis, n)
     p = np.asarray(gl.initial_angles)
-    sim = ShardedSimulator(n, comm, device=local_rank)
+    sim = ShardedSimulator(n, comm, device=local_rank, fused_exchange=not args.no_fused)
     sim.set_circuit(gl)
     sim.set_pauli_hamiltonian(x, z, w)
 
@@ -74,7 +75,7 @@ def main():
 
     out = {"metric": "energy evals/sec (one fp64 statevector sharded over the ranks)", "qubits": n,
            "ranks": comm.size, "virtual_ranks": world == 1, "gates": len(gl), "pauli_terms": len(w),
-           "exchanges_per_eval": sim.n_exchanges, "shard_bytes": 16 << sim.n_local,
+           "exchanges_per_eval": sim.n_exchanges, "fused_exchange": sim.fused_exchange, "shard_bytes": 16 << sim.n_local,
            "exchange_bytes_per_rank_per_eval": sim.n_exchanges * (16 << sim.n_local) * (comm.size - 1) // comm.size,
            "ms_per_eval": ms, "value": 1e3 / ms, "unit": "evals/s", "steps": args.steps, "warmup": args.warmup,
            "energy": e}

@@ -48,6 +48,13 @@ SIGNATURES = {
                                       ctypes.c_void_p]),
     "tq_evolve_states": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p]),
+    "tq_evolve_states_exchange": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.c_int, ctypes.c_int, c_u64_p, ctypes.c_void_p]),
+    "tq_device_alloc": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]),
+    "tq_device_free": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
+    "tq_ipc_export": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, c_u8_p]),
+    "tq_ipc_open": (ctypes.c_int, [ctypes.c_int, c_u8_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "tq_ipc_close": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
     "tq_state_batch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_dbl_p, ctypes.c_int, c_dbl_p]),
     "tq_dm_batch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_dbl_p, ctypes.c_int, c_dbl_p]),
     "tq_plan_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p]),

@@ -522,8 +522,14 @@ int ensure_init_rho(tq_handle h) {
 // Run the plan for `batch` elements: energies into `out` and / or final states into `states_out`.  from_states: the
 // elements start from the states already in `states_out` (device-resident, evolved in place) instead of the handle's
 // initial state.
+struct XchgSpec {   // tq_evolve_states_exchange: the last gate pass writes into the ranks' receive buffers
+    int n_ranks, rank;
+    double2* peer[kMaxShardRanks];
+};
+
 int run_plan(tq_handle h, int which, int batch, const double* params, int ld, const uint8_t* codes, int ldc,
-             double* out, double2* states_out, cudaStream_t stream, bool from_states = false) {
+             double* out, double2* states_out, cudaStream_t stream, bool from_states = false,
+             const XchgSpec* xchg = nullptr) {
     if (batch <= 0) return TQ_OK;
     int rc = compile_plan(h, which);
     if (rc) return rc;
@@ -598,7 +604,15 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
             } else { pp.src_mode = 2; pp.src = buf; }
             const bool is_last = (i == total_passes - 1);
             pp.dst = (states_out || dm || !is_last) && dp.gate_pass ? buf : nullptr;
-            if (from_states && dp.no_ops) pp.dst = nullptr;   // gate-free circuit: the states stay as they are
+            if (from_states && dp.no_ops && !xchg) pp.dst = nullptr;   // gate-free circuit: the states stay as they are
+            if (xchg && i == plan.n_gate_passes - 1) {
+                if (!pp.mwindows) return fail(h, TQ_EINVAL, "the exchange write-back needs tensor-core passes (shards of >= 2^9 amplitudes, TQ_MMA=1)");
+                int g = 0;
+                while ((1 << g) < xchg->n_ranks) ++g;
+                pp.xchg_shift = plan.nbits - g;
+                pp.xchg_self = (uint32_t)xchg->rank << pp.xchg_shift;
+                for (int r = 0; r < xchg->n_ranks; ++r) pp.xchg_peer[r] = xchg->peer[r];
+            }
             if (!want_energy || dm) pp.exp_mode = 0;
             if (pp.exp_mode == 2) { pp.hent = h->d_hent; pp.n_hent = (int)h->hent.size(); }
             if (pp.exp_mode) {
@@ -1029,6 +1043,64 @@ int tq_evolve_states(tq_handle h, int batch, const double* params_dev, int ld_pa
     TQ_CUDA(cudaSetDevice(h->device));
     return run_plan(h, 0, batch, params_dev, ld_params, nullptr, 0, energies_dev, (double2*)states_dev,
                     (cudaStream_t)stream, /*from_states=*/true);
+}
+
+int tq_evolve_states_exchange(tq_handle h, const double* params_dev, int ld_params, double* shard_dev, int n_ranks,
+                              int rank, const uint64_t* recv_ptrs, void* stream) {
+    if (!h || !shard_dev || !recv_ptrs) return TQ_EINVAL;
+    if (n_ranks < 2 || n_ranks > kMaxShardRanks || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks)
+        return fail(h, TQ_EINVAL, "n_ranks must be 2, 4 or 8 and 0 <= rank < n_ranks");
+    if (h->n > 28 || (1 << h->n) < n_ranks * n_ranks)
+        return fail(h, TQ_EINVAL, "shard size out of range for the exchange write-back");
+    XchgSpec x{};
+    x.n_ranks = n_ranks;
+    x.rank = rank;
+    for (int r = 0; r < n_ranks; ++r) {
+        if (!recv_ptrs[r]) return fail(h, TQ_EINVAL, "NULL receive buffer");
+        x.peer[r] = reinterpret_cast<double2*>(recv_ptrs[r]);
+    }
+    TQ_CUDA(cudaSetDevice(h->device));
+    return run_plan(h, 0, 1, params_dev, ld_params, nullptr, 0, nullptr, (double2*)shard_dev, (cudaStream_t)stream,
+                    /*from_states=*/true, &x);
+}
+
+int tq_device_alloc(int device, uint64_t bytes, void** out) {
+    if (!out || bytes == 0) return TQ_EINVAL;
+    *out = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return TQ_ECUDA;
+    return cudaMalloc(out, bytes) == cudaSuccess ? TQ_OK : TQ_ENOMEM;
+}
+
+int tq_device_free(int device, void* p) {
+    if (!p) return TQ_OK;
+    if (cudaSetDevice(device) != cudaSuccess) return TQ_ECUDA;
+    return cudaFree(p) == cudaSuccess ? TQ_OK : TQ_ECUDA;
+}
+
+int tq_ipc_export(int device, void* base, unsigned char* handle64) {
+    if (!base || !handle64) return TQ_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (cudaSetDevice(device) != cudaSuccess) return TQ_ECUDA;
+    cudaIpcMemHandle_t hd;
+    if (cudaIpcGetMemHandle(&hd, base) != cudaSuccess) { cudaGetLastError(); return TQ_ECUDA; }
+    memcpy(handle64, &hd, 64);
+    return TQ_OK;
+}
+
+int tq_ipc_open(int device, const unsigned char* handle64, void** out) {
+    if (!handle64 || !out) return TQ_EINVAL;
+    *out = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return TQ_ECUDA;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    if (cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return TQ_ECUDA; }
+    return TQ_OK;
+}
+
+int tq_ipc_close(int device, void* p) {
+    if (!p) return TQ_OK;
+    if (cudaSetDevice(device) != cudaSuccess) return TQ_ECUDA;
+    return cudaIpcCloseMemHandle(p) == cudaSuccess ? TQ_OK : TQ_ECUDA;
 }
 
 int tq_state_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* states_host) {

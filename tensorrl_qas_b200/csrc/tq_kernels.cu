@@ -882,7 +882,8 @@ __device__ __forceinline__ int flat_code_mma(uint32_t w0) {
 
 #define TQ_SEL5(i, v0, v1, v2, v3, v4) ((((i) & 1) ? (v0) : 0u) ^ (((i) & 2) ? (v1) : 0u) ^ (((i) & 4) ? (v2) : 0u) ^ (((i) & 8) ? (v3) : 0u) ^ (((i) & 16) ? (v4) : 0u))
 
-template <bool TABLE>
+template <bool TABLE, bool XCHG>   // XCHG: the write-back is the qubit exchange of a sharded state (own instantiation,
+                                   // so that the ordinary kernel's register allocation stays as it is)
 __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kernel(const PassParams p_in) {
     PassParams p_own;
     if (TABLE) p_own = p_in.table[blockIdx.x];
@@ -1146,7 +1147,16 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     }
 
     // ---- write back (shared memory holds the final tile) ----
-    if (p.dst) {
+    if (XCHG && p.dst && p.xchg_shift) {
+        // sharded state: the top bits of the shard index name the rank that owns the amplitude after the exchange -- the
+        // tile goes straight into the peers' buffers (16-byte stores over NVLink), no separate all-to-all pass
+        const uint32_t low = (1u << p.xchg_shift) - 1u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t idx = (uint32_t)tile_base | TQ_IO_GOFF(i);
+            p.xchg_peer[idx >> p.xchg_shift][p.xchg_self | (idx & low)] = amp[TQ_IO_SLOT(i)];
+        }
+    } else if (p.dst) {
         double2* dst = p.dst + elem_off + tile_base;
 #pragma unroll
         for (int i = 0; i < 16; ++i) dst[TQ_IO_GOFF(i)] = amp[TQ_IO_SLOT(i)];
@@ -1295,8 +1305,8 @@ size_t tile_pass_smem_bytes(int k_eff, int k, int lead) {
 
 cudaError_t tile_pass_configure() {
     const void* kernels[] = {(const void*)tile_pass_kernel<false, false>, (const void*)tile_pass_kernel<true, false>,
-                             (const void*)tile_pass_kernel<false, true>, (const void*)tile_pass_mma_kernel<false>,
-                             (const void*)tile_pass_mma_kernel<true>};
+                             (const void*)tile_pass_kernel<false, true>, (const void*)tile_pass_mma_kernel<false, false>,
+                             (const void*)tile_pass_mma_kernel<true, false>, (const void*)tile_pass_mma_kernel<false, true>};
     for (const void* k : kernels) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return e;
@@ -1307,7 +1317,8 @@ cudaError_t tile_pass_configure() {
 void launch_tile_pass(const PassParams& p, int batch, int threads, bool density, cudaStream_t stream) {
     const unsigned grid = (unsigned)batch << p.n_nl;
     const size_t smem = tile_pass_smem_bytes(p.k_eff, p.k, p.lead);
-    if (p.mwindows) tile_pass_mma_kernel<false><<<grid, threads, smem, stream>>>(p);
+    if (p.mwindows && p.xchg_shift) tile_pass_mma_kernel<false, true><<<grid, threads, smem, stream>>>(p);
+    else if (p.mwindows) tile_pass_mma_kernel<false, false><<<grid, threads, smem, stream>>>(p);
     else if (density) tile_pass_kernel<true, false><<<grid, threads, smem, stream>>>(p);
     else tile_pass_kernel<false, false><<<grid, threads, smem, stream>>>(p);
 }
@@ -1315,7 +1326,7 @@ void launch_tile_pass(const PassParams& p, int batch, int threads, bool density,
 void launch_tile_pass_table(const PassParams* table_dev, int n, int threads, size_t smem, bool mma, cudaStream_t stream) {
     PassParams head{};
     head.table = table_dev;
-    if (mma) tile_pass_mma_kernel<true><<<n, threads, smem, stream>>>(head);
+    if (mma) tile_pass_mma_kernel<true, false><<<n, threads, smem, stream>>>(head);
     else tile_pass_kernel<false, true><<<n, threads, smem, stream>>>(head);
 }
 

@@ -19,6 +19,7 @@
 namespace tq {
 
 constexpr int kMaxTileBits = 12;
+constexpr int kMaxShardRanks = 8;   // ranks one state can be sharded over (one NVSwitch box)
 constexpr int kMaxThreads = 256; // 2^(kMaxTileBits - kRegBits)
 
 struct ExpGroup {   // one X/Y flip mask of the Hamiltonian, local to the pass
@@ -78,6 +79,12 @@ struct PassParams {
     int n_hent;
     double* partial;  // partial[b * partial_ld + partial_off + tile]
     int partial_ld, partial_off;
+    // single-state sharding (tensor-core passes, one element): the write-back IS the qubit exchange.  Amplitude idx of this
+    // rank's shard goes to rank idx >> xchg_shift, at (xchg_self | (idx & low bits)) of that rank's buffer xchg_peer[...]
+    // (peer memory over NVLink, or this rank's own second buffer).  xchg_shift == 0: ordinary write-back to `dst`.
+    int xchg_shift;
+    uint32_t xchg_self;             // this rank's number << xchg_shift
+    double2* xchg_peer[kMaxShardRanks];
 };
 
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead);

@@ -22,11 +22,19 @@ Schedule (host logic, identical on all ranks, `plan_state_sharding`):
     first evaluation is fused with the last segment (energy and evolution in one call); the partial energies of all ranks
     and evaluations are added with one all-reduce.
 
+Fused exchange.  With the GPU engine the all-to-all is not a separate pass: the last tile pass of a segment stores every
+amplitude straight into the receive buffer of the rank that owns it after the exchange (`tq_evolve_states_exchange`: peer
+memory mapped over CUDA IPC, 16-byte stores over NVLink issued tile by tile under the tensor-core work of the same
+kernel); the ranks then meet in a one-element all-reduce.  Every rank keeps two shard buffers and alternates between
+them.  `fused_exchange=False` keeps the NCCL all-to-all (the baseline the fused path is measured against).
+
 `comm` is either `TorchComm` (one rank per process, torch.distributed: NCCL on GPUs, gloo in the CPU tests) or
 `LocalComm` (R virtual ranks inside one process: the same schedule with the all-to-all done as a tensor transpose --
 used to test the whole path on a single GPU).  The engine is libtqsim (`GpuEngine`); there is no CPU engine in the
 product -- the CPU tests plug in a numpy stand-in of their own.
 """
+import ctypes
+
 import numpy as np
 
 from .circuit import KIND, GateList
@@ -198,6 +206,40 @@ class TorchComm:
         self._dist.all_reduce(t, group=self.group)
         return t
 
+    # fused exchange: two shard buffers per rank, every rank maps all peers' buffers (CUDA IPC)
+    def setup_exchange(self, engine):
+        import torch
+        lib, dev = engine.lib, engine.index
+        mine = [engine.alloc_shard() for _ in range(2)]
+        handles = torch.zeros(2, 64, dtype=torch.uint8)
+        for s in range(2):
+            buf = (ctypes.c_uint8 * 64)()
+            if lib.tq_ipc_export(dev, ctypes.c_void_p(mine[s][1]), buf) != 0:
+                raise RuntimeError("cudaIpcGetMemHandle failed")
+            handles[s] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
+        mine_dev = handles.to(engine.device)
+        everyone = torch.empty(self.size, 2, 64, dtype=torch.uint8, device=engine.device)
+        self._dist.all_gather_into_tensor(everyone, mine_dev, group=self.group)
+        everyone = everyone.cpu()
+        tables, self._opened = [[0] * self.size for _ in range(2)], []
+        for r in range(self.size):
+            for s in range(2):
+                if r == self.rank:
+                    tables[s][r] = mine[s][1]
+                    continue
+                raw = (ctypes.c_uint8 * 64)(*everyone[r, s].tolist())
+                out = ctypes.c_void_p()
+                if lib.tq_ipc_open(dev, raw, ctypes.byref(out)) != 0:
+                    raise RuntimeError("cudaIpcOpenMemHandle failed (peer access between the GPUs of this job?)")
+                tables[s][r] = out.value
+                self._opened.append(out.value)
+        self._token = torch.zeros(1, dtype=torch.float32, device=engine.device)
+        return [[mine[0][0]], [mine[1][0]]], tables
+
+    def meet(self):
+        """stream-ordered rendezvous: returns (on the stream) once every rank's preceding kernels have finished"""
+        self._dist.all_reduce(self._token, group=self.group)
+
 
 class LocalComm:
     """R virtual ranks in one process (one device): the all-to-all is a transpose of the [rank][chunk] grid."""
@@ -219,10 +261,32 @@ class LocalComm:
             t = t + p
         return t
 
+    def setup_exchange(self, engine):
+        bufs = [[engine.alloc_shard() for _ in self.ranks] for _ in range(2)]
+        return [[b[0] for b in bufs[s]] for s in range(2)], [[b[1] for b in bufs[s]] for s in range(2)]
+
+    def meet(self):
+        pass   # one process, one stream: launches are already ordered
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # engine
 # ---------------------------------------------------------------------------------------------------------------
+class _DeviceBuffer:
+    """float64 view of a tq_device_alloc allocation for torch.as_tensor (CUDA array interface); frees it when dropped"""
+
+    def __init__(self, address, n_doubles, lib, device):
+        self._address, self._lib, self._device = address, lib, device
+        self.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8", "data": (int(address), False),
+                                         "version": 2, "strides": None}
+
+    def __del__(self):
+        try:
+            self._lib.tq_device_free(self._device, ctypes.c_void_p(self._address))
+        except Exception:
+            pass
+
+
 class GpuEngine:
     """libtqsim on one device: every (rank, step) owns a handle whose compiled plan is reused across evaluations."""
 
@@ -231,10 +295,28 @@ class GpuEngine:
         self.n_local = int(n_local)
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        from . import _lib
+        self.lib = _lib.lib()
+
+    supports_fused_exchange = True
 
     def zeros(self):
         import torch
         return torch.zeros(2 << self.n_local, dtype=torch.float64, device=self.device)   # interleaved (re, im)
+
+    def alloc_shard(self):
+        """(tensor, address) of a shard buffer that is a cudaMalloc allocation of its own (exportable over CUDA IPC)"""
+        import torch
+        out = ctypes.c_void_p()
+        if self.lib.tq_device_alloc(self.index, 16 << self.n_local, ctypes.byref(out)) != 0:
+            raise MemoryError("tq_device_alloc failed")
+        view = _DeviceBuffer(out.value, 2 << self.n_local, self.lib, self.index)
+        t = torch.as_tensor(view, device=self.device)
+        t._tq_owner = view     # keeps the allocation alive as long as the tensor
+        return t, out.value
+
+    def run_exchange(self, step, shard, params, recv_ptrs, rank, n_ranks):
+        step.evolve_states_exchange(shard, params if step.n_params > 0 else None, n_ranks, rank, recv_ptrs)
 
     def params(self, values):
         import torch
@@ -259,7 +341,7 @@ class ShardedSimulator:
     """Energy of one n-qubit circuit whose state is sharded over comm.size = 2^g ranks.  Mirrors `Simulator`'s problem
     definition calls (set_circuit / set_pauli_hamiltonian) and evaluates one parameter vector per `energy()` call."""
 
-    def __init__(self, n_qubits, comm, device=0, engine=None):
+    def __init__(self, n_qubits, comm, device=0, engine=None, fused_exchange=True):
         self.n_qubits = int(n_qubits)
         self.comm = comm
         g = int(comm.size).bit_length() - 1
@@ -271,6 +353,10 @@ class ShardedSimulator:
         self._pauli = None
         self._program = None
         self.n_exchanges = 0
+        # the exchange as the write-back of the segment's last tile pass (tensor-core passes: shards of >= 2^9 amplitudes)
+        self.fused_exchange = bool(fused_exchange and getattr(self.engine, "supports_fused_exchange", False) and
+                                   2 <= comm.size <= 8 and 9 <= self.n_local <= 28)
+        self._xbufs = self._xtables = self._copy_steps = None
 
     def set_circuit(self, gl):
         if gl.n_qubits != self.n_qubits:
@@ -323,6 +409,8 @@ class ShardedSimulator:
         """<psi(params)|H|psi(params)> from |0...0>; every rank returns the same float."""
         if self._program is None:
             self._compile()
+        if self.fused_exchange:
+            return self._energy_fused(params)
         eng = self.engine
         shards = [eng.zeros() for _ in self.comm.ranks]
         if 0 in self.comm.ranks:
@@ -342,4 +430,51 @@ class ShardedSimulator:
                     partials[k] = e if partials[k] is None else partials[k] + e
         zero = eng.params([0.0]).reshape(-1)[:1] * 0.0
         total = self.comm.total([zero if e is None else e.reshape(-1)[:1] for e in partials])
+        return float(total.reshape(-1)[0].item())
+
+    def _energy_fused(self, params):
+        eng, comm = self.engine, self.comm
+        if self._xbufs is None:
+            self._xbufs, self._xtables = comm.setup_exchange(eng)
+            self._copy_steps = {}
+        p = eng.params(params if params is not None else np.zeros(max(1, self._gl.n_params)))
+        cur = 0
+        for k, r in enumerate(comm.ranks):
+            self._xbufs[0][k].zero_()
+            if r == 0:
+                self._xbufs[0][k][0] = 1.0
+        partials = [None] * len(comm.ranks)
+
+        def send(per_rank):
+            # every local rank pushes its shard (evolved through its part of the segment, if any) into the receive buffers
+            nonlocal cur
+            for k, r in enumerate(comm.ranks):
+                step = per_rank.get(r)
+                if step is None:   # nothing to apply on this rank: a gate-free pass that only moves the shard
+                    if r not in self._copy_steps:
+                        self._copy_steps[r] = eng.make_step(GateList(self.n_local), None)
+                    step = self._copy_steps[r]
+                eng.run_exchange(step, self._xbufs[cur][k], p, self._xtables[1 - cur], r, comm.size)
+            comm.meet()
+            cur = 1 - cur
+
+        prog, i = self._program, 0
+        while i < len(prog):
+            st = prog[i]
+            if st[0] == "exchange":
+                send({})
+            elif not st[2] and i + 1 < len(prog) and prog[i + 1][0] == "exchange":
+                send(st[1])
+                i += 1
+            else:
+                for k, r in enumerate(comm.ranks):
+                    step = st[1].get(r)
+                    if step is None:
+                        continue
+                    e = eng.run(step, self._xbufs[cur][k], p, st[2])
+                    if st[2]:
+                        partials[k] = e if partials[k] is None else partials[k] + e
+            i += 1
+        zero = eng.params([0.0]).reshape(-1)[:1] * 0.0
+        total = comm.total([zero if e is None else e.reshape(-1)[:1] for e in partials])
         return float(total.reshape(-1)[0].item())

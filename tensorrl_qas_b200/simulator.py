@@ -185,6 +185,24 @@ class Simulator:
                                              states.data_ptr(), out.data_ptr() if energies else None, s))
         return out
 
+    def evolve_states_exchange(self, shard, params, n_ranks, rank, recv_ptrs, stream=None):
+        """tq_evolve_states_exchange: apply the circuit to this rank's shard (torch CUDA tensor, 2^n complex128) and store
+        the result straight into the ranks' receive buffers (`recv_ptrs`: n_ranks device addresses) in the layout after
+        the rank bits have been swapped with the top local qubits.  No synchronisation."""
+        import torch
+        if not shard.is_cuda or not shard.is_contiguous() or shard.dtype not in (torch.complex128, torch.float64):
+            raise ValueError("shard must be a contiguous complex128 / float64 CUDA tensor")
+        if shard.numel() // (1 if shard.dtype == torch.complex128 else 2) != 1 << self.n_qubits:
+            raise ValueError("shard does not hold 2^n amplitudes")
+        ld = 0
+        if params is not None:
+            params = params.reshape(1, -1)
+            ld = params.shape[1]
+        ptrs = (ctypes.c_uint64 * int(n_ranks))(*[int(v) for v in recv_ptrs])
+        s = stream if stream is not None else torch.cuda.current_stream(shard.device).cuda_stream
+        self._check(self._L.tq_evolve_states_exchange(self._h, params.data_ptr() if params is not None else None, ld,
+                                                      shard.data_ptr(), int(n_ranks), int(rank), ptrs, s))
+
     # ------------------------------------------------------------------ introspection
     def plan_info(self, which=0):
         info = (ctypes.c_int64 * 8)()

@@ -63,15 +63,19 @@ def test_evolve_states_in_place(built_lib, oracle, monkeypatch, n, tile_bits):
     sim.close()
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("n,ranks,tile_bits,seed", [(13, 2, 12, 0), (14, 4, 12, 1), (15, 8, 12, 2), (13, 4, 9, 3),
-                                                     (16, 8, 10, 4), (16, 2, 12, 5)])
-def test_virtual_ranks_match_the_oracle(built_lib, oracle, monkeypatch, n, ranks, tile_bits, seed):
+                                                     (16, 8, 10, 4), (16, 2, 12, 5), (12, 8, 12, 6)])
+def test_virtual_ranks_match_the_oracle(built_lib, oracle, monkeypatch, n, ranks, tile_bits, seed, fused):
+    """fused: the exchange is the write-back of the segment's last tile pass (tq_evolve_states_exchange); otherwise a
+    separate all-to-all.  (12 qubits over 8 ranks: shards of 2^9 amplitudes, the smallest tensor-core tile.)"""
     monkeypatch.setenv("TQ_TILE_BITS", str(tile_bits))
     gl = synthetic_circuit(n, 120, 40 + seed)
     x, z, w = _random_pauli_sum(n, 20, seed)
     rng = np.random.default_rng(seed)
     params = np.asarray(gl.initial_angles) + rng.uniform(-0.1, 0.1, gl.n_params)
-    sim = ShardedSimulator(n, LocalComm(ranks), device=0)
+    sim = ShardedSimulator(n, LocalComm(ranks), device=0, fused_exchange=fused)
+    assert sim.fused_exchange == fused
     sim.set_circuit(gl)
     sim.set_pauli_hamiltonian(x, z, w)
     ref = oracle.energies(gl, params[None, :], pauli=(x, z, w))[0]
@@ -92,8 +96,8 @@ def test_sharded_heisenberg_brickwork_matches_unsharded_kernels(built_lib, oracl
     one.set_pauli_hamiltonian(x, z, w)
     e1 = one.energies(p[None, :])[0]
     one.close()
-    for ranks in (2, 8):
-        sim = ShardedSimulator(n, LocalComm(ranks), device=0)
+    for ranks, fused in ((2, True), (8, True), (4, False)):
+        sim = ShardedSimulator(n, LocalComm(ranks), device=0, fused_exchange=fused)
         sim.set_circuit(gl)
         sim.set_pauli_hamiltonian(x, z, w)
         assert abs(sim.energy(p) - e1) < TOL
@@ -112,6 +116,8 @@ def test_two_nccl_ranks(built_lib, oracle):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "profiles", "bench_state_sharding.py"), "--qubits", "18",
            "--check-oracle"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert res.returncode == 0, res.stdout + res.stderr
-    assert '"oracle_abs_err"' in res.stdout
+    for extra in ([], ["--no-fused"]):     # exchange fused into the last tile pass (CUDA IPC peer stores) / NCCL all-to-all
+        res = subprocess.run(cmd + extra, capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert '"oracle_abs_err"' in res.stdout
+        assert ('"fused_exchange": true' in res.stdout) == (not extra)
