@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--check-oracle", action="store_true")
     ap.add_argument("--check-unsharded", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="NCCL all-to-all between segments instead of the fused write-back")
+    ap.add_argument("--fused", action="store_true", help="force the fused write-back (default: up to four ranks)")
     args = ap.parse_args()
 
     import torch
@@ -51,7 +52,7 @@ def main():
     paulis, w = loaders.heisenberg_terms(n)
     x, z = loaders.pauli_masks(paulis, n)
     p = np.asarray(gl.initial_angles)
-    sim = ShardedSimulator(n, comm, device=local_rank, fused_exchange=not args.no_fused)
+    sim = ShardedSimulator(n, comm, device=local_rank, fused_exchange=False if args.no_fused else (True if args.fused else None))
     sim.set_circuit(gl)
     sim.set_pauli_hamiltonian(x, z, w)
 
