@@ -59,6 +59,7 @@ struct Plan {
 struct tq_context {
     int n_sms = 0;
     bool fuse_prep = true;      // TQ_FUSE_PREP
+    bool direct_kernel = true;  // TQ_DIRECT_KERNEL: the streaming expectation-only passes of a plan in one persistent launch
     bool sparse_init = true;    // TQ_SPARSE_INIT: skip the known zeros of states grown from |0...0> (tensor-core passes)
     bool spin_wait = true;      // TQ_SPIN: poll the pinned result slots instead of cudaStreamSynchronize (latency path)
     bool zero_copy = true;      // TQ_ZERO_COPY: small host-buffer calls read angles / write energies in pinned host memory
@@ -585,6 +586,8 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
             rc = check_launch(h, "prep_matrices_kernel");
             if (rc) return rc;
         }
+        DirectParams direct{};
+        int direct_windows = 0, direct_ops = 0, direct_threads = 0;
         for (int i = 0; i < total_passes; ++i) {
             const DevPass& dp = plan.passes[i];
             PassParams pp = dp.proto;
@@ -639,9 +642,27 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 pp.direct = (dp.direct && pp.src_mode == 2 && pp.exp_mode == 1 && pp.n_groups == 0 && !pp.dst &&
                              plan.nbits <= 27 /* 32-bit byte offsets inside an element */) ? 1 : 0;
             }
+            if (pp.direct && h->direct_kernel && direct.n_sub < kMaxDirectSub &&
+                direct_windows + (pp.n_windows - pp.n_gate_windows) <= kDirectWinSlots &&
+                direct_ops + pp.n_wops <= kDirectOpSlots) {
+                // expectation-only pass that streams the state: a sub-pass of the one persistent launch below
+                direct_windows += pp.n_windows - pp.n_gate_windows;
+                direct_ops += pp.n_wops;
+                direct_threads = dp.threads;
+                direct.sub[direct.n_sub++] = pp;
+                continue;
+            }
             launch_tile_pass(pp, bc, dp.threads, dm, stream);
             ++h->launches;
             rc = check_launch(h, "tile_pass_kernel");
+            if (rc) return rc;
+        }
+        if (direct.n_sub > 0) {
+            direct.batch = bc;
+            const long long tiles = (long long)bc << direct.sub[0].n_nl;
+            launch_expect_direct(direct, (int)std::min<long long>(tiles, (long long)h->n_sms * 2), direct_threads, stream);
+            ++h->launches;
+            rc = check_launch(h, "expect_direct_kernel");
             if (rc) return rc;
         }
         if (want_energy) {
@@ -781,6 +802,7 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->zero_copy = env_int("TQ_ZERO_COPY", 1) != 0;
     h->spin_wait = env_int("TQ_SPIN", 1) != 0;
     h->sparse_init = env_int("TQ_SPARSE_INIT", 1) != 0;
+    h->direct_kernel = env_int("TQ_DIRECT_KERNEL", 1) != 0;
     h->n_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);

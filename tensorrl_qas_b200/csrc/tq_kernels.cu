@@ -1257,6 +1257,152 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     }
 }
 
+// =================================================================================================================
+// Expectation-only passes in ONE persistent launch.  Every "direct" expectation-only pass of a plan (windows whose lane bits
+// 1..3 are qubits 0..2: registers loaded straight from the state, no tile staging) becomes a sub-pass of this kernel:
+//   * window headers, op words and coefficient tables of all sub-passes are staged in shared memory once per CTA, not
+//     once per tile;
+//   * a CTA walks the (element, tile) pairs t = blockIdx.x, blockIdx.x + gridDim.x, ... and, for each, runs every
+//     sub-pass on ITS tile number t (each sub-pass has its own tiling of the state).  The resident CTAs therefore work
+//     on one or two batch elements at a time: the element is read from HBM once and the other sub-passes find it in L2
+//     (separate launches would stream the whole batch once per pass);
+//   * no barriers except the per-tile sum (double-buffered reduction slots).
+// Same arithmetic, same per-(element, pass, tile) partial sums in the same slots as tile_pass_mma_kernel's expectation
+// windows: results are bit-identical to the one-launch-per-pass path (TQ_DIRECT_KERNEL=0).
+// =================================================================================================================
+__global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) expect_direct_kernel(const __grid_constant__ DirectParams dp) {
+    __shared__ double2 s_mat[kOpSlots * kMatStride];
+    __shared__ WinOp s_wops[kOpSlots];
+    __shared__ MmaWindowDev s_win[kWinSlots];
+    __shared__ double s_red[32];
+    __shared__ int s_wbase[kMaxDirectSub + 1], s_obase[kMaxDirectSub + 1];
+
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int comp = lane & 1;
+    const bool l1 = (lane >> 1) & 1;
+
+    // ---- stage every sub-pass once ----
+    if (tid == 0) {
+        int wb = 0, ob = 0;
+        for (int s = 0; s < dp.n_sub; ++s) {
+            s_wbase[s] = wb;
+            s_obase[s] = ob;
+            wb += dp.sub[s].n_windows - dp.sub[s].n_gate_windows;
+            ob += dp.sub[s].n_wops;
+        }
+        s_wbase[dp.n_sub] = wb;
+        s_obase[dp.n_sub] = ob;
+    }
+    __syncthreads();
+    for (int s = 0; s < dp.n_sub; ++s) {
+        const PassParams& p = dp.sub[s];
+        const int nw = p.n_windows - p.n_gate_windows;
+        for (int i = tid; i < 4 * nw; i += nthreads)
+            reinterpret_cast<uint4*>(s_win + s_wbase[s])[i] =
+                __ldg(reinterpret_cast<const uint4*>(p.mwindows + p.n_gate_windows) + i);
+        for (int i = tid; i < p.n_wops * kMatStride; i += nthreads) {
+            const int oi = i >> 4, e = i & 15;
+            WinOp wo = p.wops[oi];
+            const int code = wo.w0 & 0xff;
+            if (e == 0) {
+                wo.w0 = (wo.w0 & ~0xffu) | (uint32_t)flat_code_mma(wo.w0);
+                s_wops[s_obase[s] + oi] = wo;
+            }
+            if (code >= M_EXPC && e < (code == M_EXPC ? 9 : code == M_EXPT ? 16 : 2))
+                s_mat[(s_obase[s] + oi) * kMatStride + e] = reinterpret_cast<const double2*>(p.eterms)[(size_t)wo.t + e];
+        }
+    }
+    __syncthreads();
+
+    const int n_nl = dp.sub[0].n_nl, nbits = dp.sub[0].nbits, k = dp.sub[0].k;
+    const uint32_t ntiles = 1u << n_nl;
+    const uint32_t total = (uint32_t)dp.batch << n_nl;
+    int flip = 0;
+    for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const uint32_t tile = t & (ntiles - 1u), b = t >> n_nl;
+        const uint64_t elem_off = (uint64_t)b << nbits;
+        for (int s = 0; s < dp.n_sub; ++s) {
+            const PassParams& p = dp.sub[s];
+            uint64_t tile_base = 0;
+            for (int i = 0; i < n_nl; ++i) tile_base |= (uint64_t)((tile >> i) & 1u) << p.nonlocal[i];
+            const unsigned char* base = reinterpret_cast<const unsigned char*>(p.src + elem_off);
+            double acc = 0.0;
+            for (int w = s_wbase[s]; w < s_wbase[s + 1]; ++w) {
+                const MmaWindowDev* hdr = s_win + w;
+                uint64_t ctx = tile_base | ((uint64_t)((lane >> 2) & 1) << hdr->gphys[0]) |
+                               ((uint64_t)((lane >> 3) & 1) << hdr->gphys[1]) | ((uint64_t)((lane >> 4) & 1) << hdr->gphys[2]) |
+                               ((uint64_t)l1 << hdr->qlphys);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (i < k - 9 && ((warp >> i) & 1)) ctx |= 1ull << hdr->wphys[i];
+                Regs a;
+                {
+                    const uint32_t tt = ((uint32_t)ctx << 4) | ((uint32_t)comp << 3);
+                    const uint32_t x0 = 16u << hdr->rphys[0], x1 = 16u << hdr->rphys[1], x2 = 16u << hdr->rphys[2],
+                                   x3 = 16u << hdr->rphys[3], x4 = 16u << hdr->rphys[4];
+                    const uint32_t lo[4] = {0u, x0, x1, x0 ^ x1};
+                    const uint32_t hi[8] = {tt, tt ^ x2, tt ^ x3, tt ^ x2 ^ x3, tt ^ x4, tt ^ x4 ^ x2, tt ^ x4 ^ x3, tt ^ x4 ^ x3 ^ x2};
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) a[r] = __ldg(reinterpret_cast<const double*>(base + (hi[r >> 2] ^ lo[r & 3])));
+                }
+                const int o_begin = s_obase[s] + hdr->op_begin, o_end = s_obase[s] + hdr->op_end;
+                if (hdr->flags & kWinFlagGenericDiag) {
+                    for (int o = o_begin; o < o_end; ++o) {
+                        const WinOp wo = s_wops[o];
+                        const double2* m = s_mat + o * kMatStride;
+                        if ((wo.w0 & 0xff) == FM_EXPD) {
+                            const double2* terms = reinterpret_cast<const double2*>(p.eterms) + wo.t + 2;
+                            acc += m_expd_half<0>(a, ctx, m, terms);
+                            acc += m_expd_half<1>(a, ctx | (1ull << ((wo.w0 >> 16) & 0xff)), m, terms);
+                        } else if ((wo.w0 & 0xff) == FM_EXPT) {
+                            const double* D = reinterpret_cast<const double*>(m);
+                            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) s4[r & 3] = fma(a[r] * a[r], D[r], s4[r & 3]);
+                            acc += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                        }
+                    }
+                    continue;
+                }
+                for (int o = o_begin; o < o_end; ++o) {
+                    const WinOp wo = s_wops[o];
+                    const double2* m = s_mat + o * kMatStride;
+                    if ((wo.w0 & 0xff) == FM_EXPC) {
+                        const double* cA = reinterpret_cast<const double*>(m + 1);
+                        const double* cB = ((wo.w0 >> 12) & 1)
+                                               ? reinterpret_cast<const double*>(reinterpret_cast<const double2*>(p.eterms) + wo.t + 9)
+                                               : nullptr;
+                        const double sum = exec_m_expc(a, (int)(wo.w0 >> 24), cA, cB, comp != 0);
+                        const uint64_t zphys = (uint64_t)__double_as_longlong(m[0].x);
+                        acc += (__popcll(ctx & zphys) & 1) ? -sum : sum;
+                    } else {   // FM_EXPT
+                        const double* D = reinterpret_cast<const double*>(m);
+                        double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) s4[r & 3] = fma(a[r] * a[r], D[r], s4[r & 3]);
+                        acc += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                    }
+                }
+            }
+            // deterministic CTA sum (same tree as block_sum); two sets of slots alternate so that a fast warp cannot
+            // overwrite what thread 0 is still adding up
+            double* red = s_red + (flip ? 16 : 0);
+            flip ^= 1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+            if (lane == 0) red[warp] = acc;
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+                const int nwarps = (nthreads + 31) >> 5;
+                for (int w = 0; w < nwarps; ++w) tot += red[w];
+                p.partial[(size_t)b * p.partial_ld + p.partial_off + tile] = tot;
+            }
+        }
+    }
+}
+
 // one thread per (batch element, fused block)
 __global__ void __launch_bounds__(128) prep_matrices_kernel(const MatDesc* __restrict__ descs, const MatGate* __restrict__ prog,
                                                             int n_mats, int batch, const double* __restrict__ params,
@@ -1328,6 +1474,10 @@ void launch_tile_pass_table(const PassParams* table_dev, int n, int threads, siz
     head.table = table_dev;
     if (mma) tile_pass_mma_kernel<true, false><<<n, threads, smem, stream>>>(head);
     else tile_pass_kernel<false, true><<<n, threads, smem, stream>>>(head);
+}
+
+void launch_expect_direct(const DirectParams& dp, int n_ctas, int threads, cudaStream_t stream) {
+    expect_direct_kernel<<<n_ctas, threads, 0, stream>>>(dp);
 }
 
 void launch_prep_matrices(const MatDesc* descs, const MatGate* prog, int n_mats, int batch, const double* params,

@@ -87,6 +87,15 @@ struct PassParams {
     double2* xchg_peer[kMaxShardRanks];
 };
 
+// the direct expectation-only passes of a plan as sub-passes of one persistent launch (expect_direct_kernel)
+constexpr int kMaxDirectSub = 4;
+constexpr int kDirectOpSlots = 48, kDirectWinSlots = 32;   // = kOpSlots / kWinSlots of tq_kernels.cu: totals over the sub-passes
+struct DirectParams {
+    int n_sub, batch;
+    PassParams sub[kMaxDirectSub];
+};
+void launch_expect_direct(const DirectParams& dp, int n_ctas, int threads, cudaStream_t stream);
+
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead);
 cudaError_t tile_pass_configure();  // opt in to > 48 KiB dynamic shared memory
 void launch_tile_pass(const PassParams& p, int batch, int threads, bool density, cudaStream_t stream);
