@@ -288,7 +288,8 @@ def main():
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": peak_src,
-        "kernel": f"tile_pass_mma_kernel ({passes_rw + passes_ro} launches per step, > 99 % of the step; per-step totals)",
+        "kernel": f"tile_pass_mma_kernel ({passes_rw} gate-pass launches per step, 78 % of the step) + expect_direct_kernel "
+                  f"(the {passes_ro} expectation-only passes in one persistent launch, 21 %); per-step totals",
         "algorithmic_bytes_per_eval": bytes_eval, "algorithmic_bytes_per_step": bytes_eval * B,
         "note": "algorithmic bytes = qulacs' unfused model 16*2^n*(2G+M) (SURVEY.md 8d); the fused passes move far "
                 "fewer real bytes, so frac > 1 is expected -- hbm_actual has the real traffic, fp64_tensor the bound "
