@@ -121,3 +121,24 @@ def test_two_nccl_ranks(built_lib, oracle):
         assert res.returncode == 0, res.stdout + res.stderr
         assert '"oracle_abs_err"' in res.stdout
         assert ('"fused_exchange": true' in res.stdout) == (not extra)
+
+
+@pytest.mark.parametrize("chunk", range(3))
+def test_fuzz_virtual_ranks(built_lib, oracle, monkeypatch, chunk):
+    """Random circuit lengths (5-150 gates: few or many exchanges, rank-bit controls, lone gates), rank counts, tile sizes,
+    fused and NCCL-style exchange, against the oracle."""
+    for it in range(12):
+        seed = 900 + 12 * chunk + it
+        rng = np.random.default_rng(seed)
+        ranks = int(rng.choice([2, 4, 8]))
+        n = int(rng.integers(12, 17))
+        monkeypatch.setenv("TQ_TILE_BITS", str(int(rng.choice([9, 10, 12]))))
+        gl = synthetic_circuit(n, int(rng.choice([5, 15, 40, 90, 150])), seed)
+        x, z, w = _random_pauli_sum(n, int(rng.integers(1, 20)), seed, max_weight=3)
+        params = np.asarray(gl.initial_angles) + rng.uniform(-0.1, 0.1, gl.n_params)
+        fused = bool(rng.random() < 0.6)
+        sim = ShardedSimulator(n, LocalComm(ranks), device=0, fused_exchange=fused)
+        sim.set_circuit(gl)
+        sim.set_pauli_hamiltonian(x, z, w)
+        ref = oracle.energies(gl, params[None, :] if gl.n_params else np.zeros((1, 1)), pauli=(x, z, w))[0]
+        assert abs(sim.energy(params if gl.n_params else None) - ref) < TOL, (seed, n, ranks, fused, len(gl))
