@@ -164,6 +164,21 @@ int tq_ipc_close(int device, void* p);
 /* Final density matrices, [B][4^n] complex128, entry rho[r][c] at index r + (c << n). */
 int tq_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* rho_host);
 
+/* Ask/tell COBYLA for the path's unconstrained problems (tensorrl_qas_b200/csrc/tq_cobyla.cpp; host only, no GPU).
+ * Optional replacement for scipy.optimize.minimize(cost, x0, method="COBYLA", options={"maxiter": maxfun}) as the
+ * reference calls it (environments/environment_qulacs.py:436-441: no constraints; scipy's defaults rhobeg = 1.0,
+ * rhoend = tol = 1e-4).  Powell's COBYLA restated for m = 0; NOT trajectory-identical to scipy >= 1.16 (PRIMA), so the
+ * drop-in environments keep scipy unless asked (TQ_OPTIMIZER=native).
+ *   create: the first point to evaluate is x0.   ask: 0 = x_out holds the next point, 1 = finished.
+ *   tell: value at the point last asked; returns 0 = ask again, 1 = finished.   result: best point, its value, number of
+ *   evaluations, status (1 = rho reached rhoend, 2 = maxfun evaluations used, 3 = rounding errors in the simplex). */
+typedef struct tq_cobyla* tq_cobyla_handle;
+int tq_cobyla_create(int n, const double* x0, double rhobeg, double rhoend, int maxfun, tq_cobyla_handle* out);
+int tq_cobyla_destroy(tq_cobyla_handle h);
+int tq_cobyla_ask(tq_cobyla_handle h, double* x_out);
+int tq_cobyla_tell(tq_cobyla_handle h, double f);
+int tq_cobyla_result(tq_cobyla_handle h, double* x_out, double* f_out, int* nfev_out, int* status_out);
+
 /* Introspection of the compiled plan of the current circuit (for DESIGN/bench accounting):
  *   info[0] gate passes over the state, info[1] expectation-only passes, info[2] tile qubits k,
  *   info[3] kernel launches per energy call, info[4] Hamiltonian flip-mask groups M, info[5] non-zeros kept

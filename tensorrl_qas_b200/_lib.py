@@ -7,7 +7,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtqsim.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["tq_api.cu", "tq_kernels.cu", "tq_plan.cpp"]
+SOURCES = ["tq_api.cu", "tq_kernels.cu", "tq_plan.cpp", "tq_cobyla.cpp"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
@@ -57,6 +57,12 @@ SIGNATURES = {
     "tq_ipc_close": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
     "tq_state_batch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_dbl_p, ctypes.c_int, c_dbl_p]),
     "tq_dm_batch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_dbl_p, ctypes.c_int, c_dbl_p]),
+    "tq_cobyla_create": (ctypes.c_int, [ctypes.c_int, c_dbl_p, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_void_p)]),
+    "tq_cobyla_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "tq_cobyla_ask": (ctypes.c_int, [ctypes.c_void_p, c_dbl_p]),
+    "tq_cobyla_tell": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double]),
+    "tq_cobyla_result": (ctypes.c_int, [ctypes.c_void_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p]),
     "tq_plan_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p]),
     "tq_plan_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p]),
     "tq_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),

@@ -356,7 +356,15 @@ class CircuitEnvBase:
             cost(start)
             x, nfev = np.zeros(0, dtype=np.float64), 1
         else:
-            res = scipy.optimize.minimize(cost, x0=start, method=method, options={"maxiter": self.global_iters})
+            if getattr(self, "optimizer", None) is None:
+                self.optimizer = os.environ.get("TQ_OPTIMIZER", "scipy")
+            if self.optimizer == "native" and method == "COBYLA":
+                # optional: the library's own ask/tell COBYLA (microseconds per iteration instead of scipy >= 1.16's
+                # pure-Python milliseconds).  Not scipy's trajectory: off unless asked for.
+                from .. import cobyla
+                res = cobyla.minimize(cost, start, maxiter=self.global_iters)
+            else:
+                res = scipy.optimize.minimize(cost, x0=start, method=method, options={"maxiter": self.global_iters})
             x, nfev = res["x"], res["nfev"]
         if picked:
             x0[which_angles] = x
