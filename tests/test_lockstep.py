@@ -89,12 +89,14 @@ def test_multi_problem_launch_matches_individual_calls(built_lib, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("optimizer", ["scipy", "native"])
 @pytest.mark.parametrize("module_name,key", [("environment_qulacs_TN_notin_agent", "fixed_beh2"),
                                               ("environment_qulacs", "trainable_beh2"),
                                               ("environment_qulacs_noise", "noise_trainable_h2o8")])
-def test_lockstep_envs_reproduce_serial_trajectories(module_name, key, tmp_path, monkeypatch):
+def test_lockstep_envs_reproduce_serial_trajectories(module_name, key, optimizer, tmp_path, monkeypatch):
     """B environments stepped in lock-step (one launch per COBYLA round) follow exactly the trajectories of the same
-    environments stepped one after the other."""
+    environments stepped one after the other -- with scipy's COBYLA and with the library's own (TQ_OPTIMIZER=native)."""
+    monkeypatch.setenv("TQ_OPTIMIZER", optimizer)
     from tensorrl_qas_b200.VQAs import _backend
     from tensorrl_qas_b200.environments.utils import utils
     from tensorrl_qas_b200.lockstep import LockstepEnvs
