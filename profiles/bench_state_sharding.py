@@ -97,6 +97,7 @@ def main():
         out["unsharded_ms_per_eval"] = (time.perf_counter() - t0) * 1e3
         out["unsharded_abs_diff"] = abs(e - float(e1[0].item()))
         one.close()
+    sim.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -241,6 +241,18 @@ class TorchComm:
         """stream-ordered rendezvous: returns (on the stream) once every rank's preceding kernels have finished"""
         self._dist.all_reduce(self._token, group=self.group)
 
+    def release_exchange(self, engine):
+        """unmap the peers' buffers (collective: every rank must have stopped storing into them)"""
+        import torch
+        opened = getattr(self, "_opened", None)
+        if not opened:
+            return
+        torch.cuda.synchronize(engine.device)
+        self._dist.barrier(group=self.group)
+        for ptr in opened:
+            engine.lib.tq_ipc_close(engine.index, ctypes.c_void_p(ptr))
+        self._opened = []
+
 
 class LocalComm:
     """R virtual ranks in one process (one device): the all-to-all is a transpose of the [rank][chunk] grid."""
@@ -268,6 +280,9 @@ class LocalComm:
 
     def meet(self):
         pass   # one process, one stream: launches are already ordered
+
+    def release_exchange(self, engine):
+        pass
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -362,6 +377,21 @@ class ShardedSimulator:
         self.fused_exchange = bool(fused_exchange and getattr(self.engine, "supports_fused_exchange", False) and
                                    2 <= comm.size <= 8 and 9 <= self.n_local <= 28)
         self._xbufs = self._xtables = self._copy_steps = None
+
+    def close(self):
+        """Release the handles of the compiled schedule and the exchange buffers (collective under TorchComm)."""
+        for st in self._program or []:
+            if st[0] == "run":
+                for step in st[1].values():
+                    if hasattr(step, "close"):
+                        step.close()
+        for step in (self._copy_steps or {}).values():
+            if hasattr(step, "close"):
+                step.close()
+        self._program = self._copy_steps = None
+        if self._xbufs is not None:
+            self.comm.release_exchange(self.engine)
+            self._xbufs = self._xtables = None
 
     def set_circuit(self, gl):
         if gl.n_qubits != self.n_qubits:

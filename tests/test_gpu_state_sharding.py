@@ -142,3 +142,41 @@ def test_fuzz_virtual_ranks(built_lib, oracle, monkeypatch, chunk):
         sim.set_pauli_hamiltonian(x, z, w)
         ref = oracle.energies(gl, params[None, :] if gl.n_params else np.zeros((1, 1)), pauli=(x, z, w))[0]
         assert abs(sim.energy(params if gl.n_params else None) - ref) < TOL, (seed, n, ranks, fused, len(gl))
+
+
+def test_exchange_entry_point_rejects_bad_arguments(built_lib):
+    import ctypes
+    import torch
+    from tensorrl_qas_b200 import _lib
+    from tensorrl_qas_b200.simulator import TqError
+    L = _lib.lib()
+    sim = Simulator(10, 0)
+    sim.set_circuit(synthetic_circuit(10, 20, 1))
+    shard = torch.zeros(2 << 10, dtype=torch.float64, device="cuda")
+    recv = [torch.zeros(2 << 10, dtype=torch.float64, device="cuda") for _ in range(2)]
+    params = torch.zeros(1, max(1, sim.n_params), dtype=torch.float64, device="cuda")
+    ptrs = [r.data_ptr() for r in recv]
+    sim.evolve_states_exchange(shard, params, 2, 1, ptrs)                 # fine
+    for n_ranks, rank, bad in ((3, 0, ptrs + [ptrs[0]]), (2, 2, ptrs), (16, 0, ptrs * 8), (2, 0, [ptrs[0], 0])):
+        with pytest.raises(TqError) as err:
+            sim.evolve_states_exchange(shard, params, n_ranks, rank, bad)
+        assert err.value.code == -1
+    with pytest.raises(ValueError):
+        sim.evolve_states_exchange(shard[:64], params, 2, 0, ptrs)       # not 2^n amplitudes
+    with pytest.raises(ValueError):
+        sim.evolve_states(shard.cpu(), params)                           # host tensor
+    small = Simulator(6, 0)                                              # below a tensor-core tile: no fused write-back
+    small.set_circuit(synthetic_circuit(6, 10, 2))
+    s6 = torch.zeros(2 << 6, dtype=torch.float64, device="cuda")
+    with pytest.raises(TqError):
+        small.evolve_states_exchange(s6, torch.zeros(1, max(1, small.n_params), dtype=torch.float64, device="cuda"), 2, 0,
+                                     [s6.data_ptr(), s6.data_ptr()])
+    # device buffers + IPC export of the library's own allocator
+    out = ctypes.c_void_p()
+    assert L.tq_device_alloc(0, 1 << 20, ctypes.byref(out)) == 0 and out.value
+    handle = (ctypes.c_uint8 * 64)()
+    assert L.tq_ipc_export(0, out, handle) == 0 and any(handle)
+    assert L.tq_device_free(0, out) == 0
+    assert L.tq_device_alloc(0, 0, ctypes.byref(out)) == -1
+    sim.close()
+    small.close()
