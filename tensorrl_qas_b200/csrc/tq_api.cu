@@ -59,6 +59,7 @@ struct Plan {
 struct tq_context {
     int n_sms = 0;
     bool fuse_prep = true;      // TQ_FUSE_PREP
+    int direct_ctas_per_sm = 2; // TQ_DIRECT_CTAS: persistent CTAs per SM of that launch (128 registers: two fit)
     bool direct_kernel = true;  // TQ_DIRECT_KERNEL: the streaming expectation-only passes of a plan in one persistent launch
     bool sparse_init = true;    // TQ_SPARSE_INIT: skip the known zeros of states grown from |0...0> (tensor-core passes)
     bool spin_wait = true;      // TQ_SPIN: poll the pinned result slots instead of cudaStreamSynchronize (latency path)
@@ -660,7 +661,8 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
         if (direct.n_sub > 0) {
             direct.batch = bc;
             const long long tiles = (long long)bc << direct.sub[0].n_nl;
-            launch_expect_direct(direct, (int)std::min<long long>(tiles, (long long)h->n_sms * 2), direct_threads, stream);
+            launch_expect_direct(direct, (int)std::min<long long>(tiles, (long long)h->n_sms * h->direct_ctas_per_sm),
+                                 direct_threads, stream);
             ++h->launches;
             rc = check_launch(h, "expect_direct_kernel");
             if (rc) return rc;
@@ -803,6 +805,7 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->spin_wait = env_int("TQ_SPIN", 1) != 0;
     h->sparse_init = env_int("TQ_SPARSE_INIT", 1) != 0;
     h->direct_kernel = env_int("TQ_DIRECT_KERNEL", 1) != 0;
+    h->direct_ctas_per_sm = std::max(1, std::min(8, env_int("TQ_DIRECT_CTAS", 2)));
     h->n_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);
