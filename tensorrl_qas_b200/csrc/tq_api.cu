@@ -281,8 +281,14 @@ int compile_plan(tq_handle h, int which) {
     if (which != 1 && !single_tile && h->have_pauli) {
         std::vector<uint64_t> todo;
         std::vector<int> todo_group;
+        // TQ_EXPECT_IN_PASS=0: when some group needs an expectation-only pass anyway, evaluate ALL off-diagonal groups in
+        // those passes (the last gate pass then carries no expectation windows)
+        bool any_outside = false;
+        for (size_t g = 0; g < h->groups.size(); ++g) any_outside = any_outside || !mask_is_local(passes.back(), h->groups[g].x);
+        const bool in_pass = env_int("TQ_EXPECT_IN_PASS", 1) != 0 || !any_outside;
         for (size_t g = 0; g < h->groups.size(); ++g) {
-            if (mask_is_local(passes.back(), h->groups[g].x)) groups_of_pass[n_gate_passes - 1].push_back((int)g);
+            if (mask_is_local(passes.back(), h->groups[g].x) && (in_pass || h->groups[g].x == 0))
+                groups_of_pass[n_gate_passes - 1].push_back((int)g);
             else { todo.push_back(h->groups[g].x); todo_group.push_back((int)g); }
         }
         if (!todo.empty()) {
