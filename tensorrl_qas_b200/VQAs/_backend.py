@@ -44,6 +44,12 @@ def evaluate(sim, params, codes=None):
     """One energy of the problem bound to `sim`.  Directly (tq_energy_batch_host / tq_energy_traj_batch_host), or, inside
     a lock-step worker thread, through the group's coordinator: the evaluations of all workers of a round become ONE
     tq_energy_multi_host launch."""
+    capture = getattr(_ctx, "capture", None)
+    if capture is not None:
+        # the lock-step coordinator is probing a cost closure for its (handle, angles, noise codes): nothing is evaluated
+        # here, the whole round goes to the GPU as one launch afterwards
+        capture.append((sim, np.array(params, dtype=np.float64).reshape(-1), codes))
+        return np.float64(0.0)
     group = getattr(_ctx, "group", None)
     if group is not None:
         return group.submit(_ctx.worker, sim, params, codes)

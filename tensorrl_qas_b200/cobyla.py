@@ -83,7 +83,8 @@ def minimize_many(batch_fun, x0s, maxiter=1000, rhobeg=1.0, tol=1e-4):
     """Lock-step optimisation of B independent problems: every round asks all running optimisers for their next point and
     calls `batch_fun(indices, points)` ONCE (-> one value per point; e.g. `energies_multi`, one launch for B different
     circuits), then tells them.  Returns the list of result dicts and the number of rounds."""
-    opts = [NativeCobyla(x0, rhobeg, tol, maxiter) for x0 in x0s]
+    budgets = list(maxiter) if hasattr(maxiter, "__len__") else [maxiter] * len(x0s)   # one budget, or one per problem
+    opts = [NativeCobyla(x0, rhobeg, tol, m) for x0, m in zip(x0s, budgets)]
     running = list(range(len(opts)))
     rounds = 0
     while running:

@@ -362,7 +362,15 @@ class CircuitEnvBase:
                 # optional: the library's own ask/tell COBYLA (microseconds per iteration instead of scipy >= 1.16's
                 # pure-Python milliseconds).  Not scipy's trajectory: off unless asked for.
                 from .. import cobyla
-                res = cobyla.minimize(cost, start, maxiter=self.global_iters)
+                from ..VQAs import _backend
+                group = getattr(_backend._ctx, "group", None)
+                raw_energy = not (self.shot_args and int(self.n_shots) != 0)   # (shot noise is added after the evaluation)
+                if group is not None and hasattr(group, "optimise") and raw_energy:
+                    # lock-step worker: hand the whole problem to the group -- the optimisers of all environments then
+                    # run in ONE host loop, one launch per round (no thread hand-over per evaluation)
+                    res = group.optimise(_backend._ctx.worker, cost, start, self.global_iters)
+                else:
+                    res = cobyla.minimize(cost, start, maxiter=self.global_iters)
             else:
                 res = scipy.optimize.minimize(cost, x0=start, method=method, options={"maxiter": self.global_iters})
             x, nfev = res["x"], res["nfev"]

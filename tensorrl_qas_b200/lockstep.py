@@ -28,6 +28,7 @@ class LockstepGroup:
         self.n_active = int(n_workers)
         self.cv = threading.Condition()
         self.pending = {}
+        self.opt_pending = {}   # whole optimisation problems (native COBYLA): worker -> (cost, x0, maxiter, slot_key, rng)
         self.results = {}
         self.rounds = 0
         self.evaluations = 0
@@ -41,7 +42,15 @@ class LockstepGroup:
         codes = [it[2] for it in items]
         return energies_multi(sims, params, codes if any(c is not None for c in codes) else None)
 
+    def _waiting(self):
+        return len(self.pending) + len(self.opt_pending)
+
     def _flush(self):
+        if self.opt_pending:
+            self._optimise_round()
+        if not self.pending:
+            self.cv.notify_all()
+            return
         order = sorted(self.pending)
         try:
             energies = self.evaluate_round([self.pending[w] for w in order])
@@ -56,10 +65,67 @@ class LockstepGroup:
         self.pending.clear()
         self.cv.notify_all()
 
+    def _optimise_round(self):
+        """Every waiting optimisation problem in one host loop (`cobyla.minimize_many`): per round the coordinator probes
+        each running cost closure for its (handle, angles, noise codes) -- in that environment's evaluation context, so
+        handles and noise streams are the ones the environment would use itself -- and evaluates the round as one launch.
+        Each optimiser sees exactly the evaluations of its serial run."""
+        from . import cobyla
+        order = sorted(self.opt_pending)
+        problems = [self.opt_pending[w] for w in order]
+        ctx = _backend._ctx
+        saved = (getattr(ctx, "slot_key", None), getattr(ctx, "rng", None))
+
+        def batch(indices, points):
+            items = []
+            for i, x in zip(indices, points):
+                cost, _, _, slot_key, rng = problems[i]
+                ctx.slot_key, ctx.rng, ctx.capture = slot_key, rng, []
+                try:
+                    probe = cost(x)
+                    got = ctx.capture
+                finally:
+                    ctx.capture = None
+                if len(got) != 1 or float(probe) != 0.0:   # the probe must hand back the placeholder energy untouched
+                    raise RuntimeError("lock-step optimisation needs a cost that is exactly one energy evaluation")
+                items.append(got[0])
+            self.rounds += 1
+            self.evaluations += len(items)
+            return self.evaluate_round(items)
+
+        try:
+            results, _ = cobyla.minimize_many(batch, [p[1] for p in problems], maxiter=[p[2] for p in problems])
+            for w, r in zip(order, results):
+                self.results[w] = r
+        except BaseException as exc:
+            self.failure = exc
+            for w in order:
+                self.results[w] = exc
+        finally:
+            ctx.slot_key, ctx.rng = saved
+        self.opt_pending.clear()
+
+    def optimise(self, worker, cost, x0, maxiter):
+        """COBYLA (the library's own) of `cost` from `x0`, run together with the other workers' problems; blocks until
+        this worker's result dict (x, fun, nfev, ...) is ready."""
+        ctx = _backend._ctx
+        with self.cv:
+            self.opt_pending[worker] = (cost, np.array(x0, dtype=np.float64).reshape(-1), int(maxiter),
+                                        getattr(ctx, "slot_key", None), getattr(ctx, "rng", None))
+            if self._waiting() >= self.n_active:
+                self._flush()
+            else:
+                while worker not in self.results:
+                    self.cv.wait()
+            out = self.results.pop(worker)
+        if isinstance(out, BaseException):
+            raise out
+        return out
+
     def submit(self, worker, sim, params, codes=None):
         with self.cv:
             self.pending[worker] = (sim, np.array(params, dtype=np.float64).reshape(-1), codes)
-            if len(self.pending) >= self.n_active:
+            if self._waiting() >= self.n_active:
                 self._flush()
             else:
                 while worker not in self.results:
@@ -73,7 +139,7 @@ class LockstepGroup:
         """The worker will not submit again (its step finished or failed)."""
         with self.cv:
             self.n_active -= 1
-            if self.pending and len(self.pending) >= self.n_active:
+            if self._waiting() and self._waiting() >= self.n_active:
                 self._flush()
 
 

@@ -88,6 +88,53 @@ def test_multi_problem_launch_matches_individual_calls(built_lib, oracle):
             s.close()
 
 
+def test_group_optimise_runs_whole_problems_in_one_host_loop(built_lib):
+    """Native-optimiser lock-step: each worker hands its WHOLE problem to the group (one thread hand-over per
+    optimisation, not per evaluation); the coordinator probes the cost closures for their requests and evaluates every
+    round as one batch.  Results equal stand-alone runs bit for bit; workers that only need single evaluations, or finish
+    early, mix in."""
+    from tensorrl_qas_b200 import cobyla
+    from tensorrl_qas_b200.VQAs import _backend
+    from tensorrl_qas_b200.lockstep import run_lockstep
+    shifts = [np.linspace(-1, 1, n) * (i + 1) for i, n in enumerate((3, 5, 8))]
+    sizes = []
+
+    def f(i, p):
+        return float(np.sum((p - shifts[i]) ** 2) + np.sum(np.cos(p)))
+
+    def evaluate_round(items):
+        sizes.append(len(items))
+        return [f(tag, p) for tag, p, _ in items]
+
+    def make_task(i):
+        def task():
+            first = _backend.evaluate(i, np.zeros(len(shifts[i])))               # a plain evaluation first (get_energy)
+            res = _backend._ctx.group.optimise(i, lambda x: _backend.evaluate(i, x), np.zeros(len(shifts[i])), 1000)
+            last = _backend.evaluate(i, res["x"])                               # ... and one after (the step's energy)
+            return first, res, last
+        return task
+
+    def lone_task():
+        return [_backend.evaluate(0, np.full(3, 0.1 * k)) for k in range(4)]
+
+    results, group = run_lockstep([make_task(i) for i in range(3)] + [lone_task], evaluate_round=evaluate_round)
+    for i in range(3):
+        first, res, last = results[i]
+        single = cobyla.minimize(lambda x: f(i, x), np.zeros(len(shifts[i])))
+        assert first == f(i, np.zeros(len(shifts[i])))
+        assert res["nfev"] == single["nfev"] and np.array_equal(res["x"], single["x"]) and res["fun"] == single["fun"]
+        assert last == res["fun"]
+    assert results[3] == [f(0, np.full(3, 0.1 * k)) for k in range(4)]
+    assert max(sizes) >= 3 and group.evaluations == sum(sizes)
+
+    # a cost that post-processes the energy cannot be probed: loud failure, no dead-lock
+    def bad_task():
+        return _backend._ctx.group.optimise(0, lambda x: _backend.evaluate(0, x) + 1.0, np.zeros(2), 50)
+
+    with pytest.raises(RuntimeError, match="exactly one energy evaluation"):
+        run_lockstep([bad_task], evaluate_round=evaluate_round)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("optimizer", ["scipy", "native"])
 @pytest.mark.parametrize("module_name,key", [("environment_qulacs_TN_notin_agent", "fixed_beh2"),
