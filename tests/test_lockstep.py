@@ -204,6 +204,8 @@ def test_lockstep_envs_reproduce_serial_trajectories(module_name, key, optimizer
                 break
     for b in range(B):
         assert len(got[b]) == len(serial[b])
-        for (o1, r1, d1, e1, n1), (o0, r0, d0, e0, n0) in zip(got[b], serial[b]):
-            assert np.array_equal(o1, o0) and r1 == r0 and d1 == d0 and e1 == e0 and n1 == n0
+        for t, ((o1, r1, d1, e1, n1), (o0, r0, d0, e0, n0)) in enumerate(zip(got[b], serial[b])):
+            assert (e1, n1, r1, d1) == (e0, n0, r0, d0), f"environment {b}, step {t}: (energy, nfev, reward, done)"
+            assert np.array_equal(o1, o0), f"environment {b}, step {t}: observation"
+
     _backend.reset_backends()
