@@ -134,6 +134,12 @@ int fail(tq_handle h, int code, const std::string& msg) {
                         std::string(#call) + ": " + cudaGetErrorString(e_));                            \
     } while (0)
 
+// Host -> device upload of plan / Hamiltonian / initial-state data that kernels on ANY stream may read right afterwards.
+// A plain cudaMemcpy from pageable memory may return while the DMA from the driver's staging buffer is still in flight
+// (it is only ordered with the legacy default stream), and the handles' streams are non-blocking: a kernel launched a few
+// microseconds later could read the old contents.  Copy on the handle's stream and wait for it.
+cudaError_t upload_sync(tq_handle h, void* dst, const void* src, size_t bytes);
+
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
@@ -141,6 +147,12 @@ int env_int(const char* name, int dflt) {
 
 void invalidate_plans(tq_handle h) {
     h->plan_sv.valid = h->plan_traj.valid = h->plan_dm.valid = false;
+}
+
+cudaError_t upload_sync(tq_handle h, void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(h->stream);
 }
 
 int grow(tq_handle h, void** ptr, size_t* cap, size_t need) {
@@ -224,7 +236,7 @@ int upload_entries(tq_handle h) {
     int rc = grow(h, (void**)&h->d_hent, &h->d_hent_cap, bytes);
     if (rc) return rc;
     if (!h->hent.empty())
-        TQ_CUDA(cudaMemcpy(h->d_hent, h->hent.data(), h->hent.size() * sizeof(HEntry), cudaMemcpyHostToDevice));
+        TQ_CUDA(upload_sync(h, h->d_hent, h->hent.data(), h->hent.size() * sizeof(HEntry)));
     h->hent_uploaded = true;
     return TQ_OK;
 }
@@ -382,7 +394,7 @@ int compile_plan(tq_handle h, int which) {
     if (h->last_stream) TQ_CUDA(cudaStreamSynchronize(h->last_stream));
     int rc = grow(h, &plan.arena, &plan.arena_cap, std::max<size_t>(blob.size(), 16));
     if (rc) return rc;
-    if (!blob.empty()) TQ_CUDA(cudaMemcpy(plan.arena, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    if (!blob.empty()) TQ_CUDA(upload_sync(h, plan.arena, blob.data(), blob.size()));
 
     plan.passes.clear();
     plan.nbits = nbits;
@@ -522,7 +534,7 @@ int ensure_init_rho(tq_handle h) {
     if (h->d_init_rho) TQ_CUDA(cudaFree(h->d_init_rho));
     h->d_init_rho = nullptr;
     TQ_CUDA(cudaMalloc((void**)&h->d_init_rho, rho.size() * sizeof(double)));
-    TQ_CUDA(cudaMemcpy(h->d_init_rho, rho.data(), rho.size() * sizeof(double), cudaMemcpyHostToDevice));
+    TQ_CUDA(upload_sync(h, h->d_init_rho, rho.data(), rho.size() * sizeof(double)));
     h->init_rho_valid = true;
     return TQ_OK;
 }
@@ -897,7 +909,7 @@ int tq_set_init_state(tq_handle h, const double* psi) {
     const size_t dim = (size_t)1 << h->n;
     h->init_host.assign(psi, psi + 2 * dim);
     if (!h->d_init) TQ_CUDA(cudaMalloc((void**)&h->d_init, dim * 16));
-    TQ_CUDA(cudaMemcpy(h->d_init, psi, dim * 16, cudaMemcpyHostToDevice));
+    TQ_CUDA(upload_sync(h, h->d_init, psi, dim * 16));
     h->have_init = true;
     return TQ_OK;
 }
