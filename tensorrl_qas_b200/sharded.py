@@ -41,7 +41,6 @@ import numpy as np
 from .circuit import KIND, GateList
 
 _CNOT = KIND["CNOT"]
-_ROT = (KIND["RX"], KIND["RY"], KIND["RZ"])
 
 
 # ---------------------------------------------------------------------------------------------------------------
