@@ -1166,7 +1166,9 @@ int tq_plan_info(tq_handle h, int which, int64_t* info8) {
     info8[0] = plan.n_gate_passes;
     info8[1] = (int64_t)plan.passes.size() - plan.n_gate_passes;
     info8[2] = plan.passes.empty() ? 0 : plan.passes[0].proto.k;
-    info8[3] = (int64_t)plan.passes.size() + ((which == 1) ? 1 : (plan.slots > 1 ? 1 : 0)) + (plan.n_mats > 0 ? 1 : 0);
+    // (the streaming expectation-only passes share one persistent launch: expect_direct_kernel)
+    const int64_t merged = (h->direct_kernel && plan.counts[5] > 1) ? std::min<int64_t>(plan.counts[5], kMaxDirectSub) - 1 : 0;
+    info8[3] = (int64_t)plan.passes.size() - merged + ((which == 1) ? 1 : (plan.slots > 1 ? 1 : 0)) + (plan.n_mats > 0 ? 1 : 0);
     info8[4] = (int64_t)h->groups.size();
     info8[5] = (int64_t)h->hent.size();
     info8[6] = plan.n_unitary;
