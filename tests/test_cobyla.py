@@ -140,3 +140,22 @@ def test_environment_switch(key, tmp_path, monkeypatch):
             if done:
                 break
     assert optimised >= 5
+
+
+def test_pinned_trajectories(built_lib):
+    """Regression pins of the optimiser's own path (round 1 values; plain double arithmetic, no fused multiply-adds on the
+    host side): evaluation counts are exact, values to 1e-12."""
+    def quad(x):
+        return float(np.sum((x - np.arange(len(x))) ** 2) + 0.5 * x[0] * x[1])
+
+    r = cobyla.minimize(quad, np.zeros(12))
+    assert (r["nfev"], r["status"]) == (293, 1)
+    assert abs(r["fun"] - (-0.06666665549933619)) < 1e-12
+    assert abs(r["x"][0] - (-0.2666608162230507)) < 1e-9 and abs(r["x"][-1] - 10.999971975379118) < 1e-9
+
+    def wells(x):
+        return float(np.sum(np.cos(x)) + 0.1 * np.sum(x * x))
+
+    r = cobyla.minimize(wells, np.linspace(-1, 1, 7))
+    assert (r["nfev"], r["status"]) == (150, 1)
+    assert abs(r["fun"] - (-1.2662883372511278)) < 1e-12
