@@ -155,3 +155,17 @@ def test_two_gloo_ranks_match_the_oracle(tmp_path):
         e, n_ex, ref = np.load(tmp_path / f"rank{r}.npy")
         assert n_ex >= 1
         assert abs(e - ref) < 1e-12
+
+
+def test_schedule_quality_on_the_benchmark_shape():
+    """The C5-shaped brickwork circuit + Heisenberg chain at the sizes measured in round 1 (profiles/state_sharding_r01.json):
+    two qubit exchanges per evaluation, whatever the rank count (pure planning, no state is touched)."""
+    for n, g in ((24, 2), (28, 1), (28, 3), (31, 3)):
+        gl = brickwork_circuit(n, 21, 41, 5)
+        paulis, _ = loaders.heisenberg_terms(n)
+        x, _ = loaders.pauli_masks(paulis, n)
+        steps = plan_state_sharding(gl.tuples(), n, g, sorted(set(int(v) for v in x)))
+        assert sum(1 for s in steps if s[0] == "exchange") <= 2, (n, g)
+        # every original gate appears exactly once; the only additions are the SWAP triples in front of an exchange
+        n_ops = sum(len(s[1]) for s in steps if s[0] == "evolve")
+        assert n_ops >= len(gl) and (n_ops - len(gl)) % 3 == 0 and n_ops - len(gl) <= 3 * g * 2
