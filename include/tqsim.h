@@ -192,7 +192,8 @@ int tq_plan_info(tq_handle h, int which, int64_t* info8);
  *             counts[3] expectation windows, counts[4] FP64-pipe register windows (tiles below 2^9 amplitudes and
  *             density matrices), counts[5] expectation-only passes that stream the state straight from HBM,
  *             counts[6] (dense block, tile) pairs executed per batch element with the current initial state (a run
- *             from |0...0> skips the tiles and amplitudes nothing has populated yet), counts[7] reserved (0). */
+ *             from |0...0> skips the tiles and amplitudes nothing has populated yet), counts[7] launches of the streaming
+ *             pass kernel (persistent CTAs, TMA tile I/O; tq_stream.cu) issued by this handle so far. */
 int tq_plan_counts(tq_handle h, int which, int64_t* counts8);
 
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
@@ -200,7 +201,9 @@ int64_t tq_launch_count(tq_handle h);
 
 /* Diagnostics -- planner dry run, needs no GPU: text dump ("PASS lead=.. local=a,b,.." / "OP op a b t flags fixed"
  * lines) of the tile passes the circuit compiler produces for a gate list.  which as in tq_plan_info (2 =
- * trajectory-noise plan).  The caller releases the string with tq_free. */
+ * trajectory-noise plan); which | 16 additionally assigns a synthetic Hamiltonian built from cover_masks to the passes and
+ * reports the streaming-kernel layouts ("STREAMABLE", "STREAM", "STREAMCHECK" lines).  The caller releases the string
+ * with tq_free. */
 char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t* q0, const int32_t* q1,
                    const int32_t* param_idx, const double* fixed, int which, int tile_bits, int low_bits,
                    int n_cover, const uint64_t* cover_masks);

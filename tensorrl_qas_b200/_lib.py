@@ -7,7 +7,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtqsim.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["tq_api.cu", "tq_kernels.cu", "tq_plan.cpp", "tq_cobyla.cpp"]
+SOURCES = ["tq_api.cu", "tq_kernels.cu", "tq_stream.cu", "tq_plan.cpp", "tq_cobyla.cpp"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -37,6 +38,13 @@ struct DevPass {
     int n_groups = 0;
     bool gate_pass = true;
     bool no_ops = false;     // the single pass of a gate-free circuit: it only stages the state
+    // streaming kernel (tq_stream.cu): layouts chosen by the planner, window headers resolved for them
+    bool stream = false;
+    bool sparse_ok = false;  // the known-zero bookkeeping of run_plan matches what the planner assumed (support_in)
+    uint64_t support_in = ~0ull;
+    StreamLayout lin_dense, lin_sparse, lout;
+    const MmaWindowDev* swin_dense = nullptr;
+    const MmaWindowDev* swin_sparse = nullptr;
 };
 
 struct Plan {
@@ -62,6 +70,8 @@ struct tq_context {
     int direct_ctas_per_sm = 2; // TQ_DIRECT_CTAS: persistent CTAs per SM of that launch (128 registers: two fit)
     bool direct_kernel = true;  // TQ_DIRECT_KERNEL: the streaming expectation-only passes of a plan in one persistent launch
     bool sparse_init = true;    // TQ_SPARSE_INIT: skip the known zeros of states grown from |0...0> (tensor-core passes)
+    bool stream_kernel = true;  // TQ_STREAM: multi-tile tensor-core passes run on the persistent TMA kernel (tq_stream.cu)
+    int64_t stream_launches = 0;
     bool spin_wait = true;      // TQ_SPIN: poll the pinned result slots instead of cudaStreamSynchronize (latency path)
     bool zero_copy = true;      // TQ_ZERO_COPY: small host-buffer calls read angles / write energies in pinned host memory
     int n = 0, device = 0;
@@ -288,33 +298,24 @@ int compile_plan(tq_handle h, int which) {
         if (p.ops.empty() && passes.size() > 1) return fail(h, TQ_EINVAL, "planner produced an empty pass");
     const int n_gate_passes = (int)passes.size();
 
-    // expectation assignment (pure paths with more than one tile): group -> pass
-    std::vector<std::vector<int>> groups_of_pass(passes.size());
-    if (which != 1 && !single_tile && h->have_pauli) {
-        std::vector<uint64_t> todo;
-        std::vector<int> todo_group;
-        // TQ_EXPECT_IN_PASS=0: when some group needs an expectation-only pass anyway, evaluate ALL off-diagonal groups in
-        // those passes (the last gate pass then carries no expectation windows)
-        bool any_outside = false;
-        for (size_t g = 0; g < h->groups.size(); ++g) any_outside = any_outside || !mask_is_local(passes.back(), h->groups[g].x);
-        const bool in_pass = env_int("TQ_EXPECT_IN_PASS", 1) != 0 || !any_outside;
-        for (size_t g = 0; g < h->groups.size(); ++g) {
-            if (mask_is_local(passes.back(), h->groups[g].x) && (in_pass || h->groups[g].x == 0))
-                groups_of_pass[n_gate_passes - 1].push_back((int)g);
-            else { todo.push_back(h->groups[g].x); todo_group.push_back((int)g); }
+    // expectation assignment (pure paths with more than one tile): group -> pass; expectation windows appended
+    std::vector<ExpGroupIn> gin_all;
+    if (which != 1 && !single_tile && h->have_pauli)
+        for (const HamGroup& g : h->groups) {
+            ExpGroupIn x;
+            x.x = g.x;
+            for (int t : g.terms) x.terms.push_back(ExpTermIn{h->pz[t], h->pre[t], h->pim[t]});
+            gin_all.push_back(std::move(x));
         }
-        if (!todo.empty()) {
-            std::vector<int> assign;
-            std::vector<Pass> extra = plan_cover(n, todo, opt, &assign);
-            for (size_t i = 0; i < todo.size(); ++i) {
-                if (assign[i] < 0) return fail(h, TQ_EINVAL, "Hamiltonian term flips more qubits than a tile holds");
-            }
-            const size_t base = passes.size();
-            groups_of_pass.resize(base + extra.size());
-            for (size_t i = 0; i < todo.size(); ++i) groups_of_pass[base + assign[i]].push_back(todo_group[i]);
-            for (Pass& p : extra) passes.push_back(std::move(p));
+    const bool want_stream = h->stream_kernel && which != 1 && !single_tile;
+    ExpPlan ep = attach_expectation(passes, gin_all, opt, n, env_int("TQ_EXPECT_IN_PASS", 1) != 0, want_stream);
+    if (!ep.err.empty()) return fail(h, TQ_EINVAL, ep.err);
+    const std::vector<std::vector<int>>& groups_of_pass = ep.groups_of_pass;
+    if (want_stream && env_int("TQ_VALIDATE_PLAN", 0))
+        for (const Pass& p : passes) {
+            const std::string verr = validate_stream(p);
+            if (!verr.empty()) return fail(h, TQ_EINVAL, verr);
         }
-    }
 
     // ---- serialise ops / groups / terms of every pass into one device blob ----
     std::vector<unsigned char> blob;
@@ -324,31 +325,13 @@ int compile_plan(tq_handle h, int which) {
         if (bytes) memcpy(blob.data() + off, data, bytes);
         return off;
     };
-    struct Offsets { size_t windows, wops, groups, terms, eterms, io_goff; int n_groups, n_terms; };
+    struct Offsets { size_t windows, wops, groups, terms, eterms, io_goff, swin_dense, swin_sparse; int n_groups, n_terms; };
     std::vector<Offsets> offs(passes.size());
     const size_t off_descs = append(cc.mats.data(), cc.mats.size() * sizeof(MatDesc));
     const size_t off_prog = append(cc.prog.data(), cc.prog.size() * sizeof(MatGate));
-    std::vector<ExpTermIn> diag_pool;   // diagonal terms still to be evaluated (tensor-core passes share them)
-    size_t last_eval_pass = 0;
-    for (size_t i = 0; i < passes.size(); ++i)
-        if (!groups_of_pass[i].empty()) last_eval_pass = i;
     for (size_t i = 0; i < passes.size(); ++i) {
         Pass& p = passes[i];
-        // groups whose flips fit a register window are evaluated there; wider ones through shared memory
-        std::vector<ExpGroupIn> gin;
-        for (int g : groups_of_pass[i]) {
-            ExpGroupIn x;
-            x.x = h->groups[g].x;
-            for (int t : h->groups[g].terms) x.terms.push_back(ExpTermIn{h->pz[t], h->pre[t], h->pim[t]});
-            gin.push_back(std::move(x));
-        }
-        std::vector<int> wide;
-        if (!gin.empty()) {
-            if (p.mma) append_expectation_windows_mma(p, gin, &wide, &diag_pool, i == last_eval_pass);
-            else append_expectation_windows(p, gin, &wide);
-        }
-        std::vector<int> wide_groups;
-        for (int wi : wide) wide_groups.push_back(groups_of_pass[i][wi]);
+        const std::vector<int>& wide_groups = ep.wide_of_pass[i];
         if (p.mma) {
             // physical offset of tile index j: tile position i -> physical bit local[i]
             const int threads = threads_for((int)p.local.size());
@@ -362,6 +345,15 @@ int compile_plan(tq_handle h, int which) {
             std::vector<MmaWindowDev> dev;
             for (const MmaWindow& w : p.mwindows) dev.push_back(resolve_window(w, p));
             offs[i].windows = append(dev.data(), dev.size() * sizeof(MmaWindowDev));
+            if (p.stream) {
+                std::vector<MmaWindowDev> sd, ss;
+                for (int wi = 0; wi < (int)p.mwindows.size(); ++wi) {
+                    sd.push_back(resolve_window_stream(p, wi, false));
+                    ss.push_back(resolve_window_stream(p, wi, true));
+                }
+                offs[i].swin_dense = append(sd.data(), sd.size() * sizeof(MmaWindowDev));
+                offs[i].swin_sparse = append(ss.data(), ss.size() * sizeof(MmaWindowDev));
+            }
         } else {
             offs[i].windows = append(p.windows.data(), p.windows.size() * sizeof(Window));
         }
@@ -412,6 +404,15 @@ int compile_plan(tq_handle h, int which) {
         dp.gate_pass = (int)i < n_gate_passes;
         dp.no_ops = passes[i].ops.empty();
         dp.direct = passes[i].direct;
+        if (passes[i].mma && passes[i].stream) {
+            dp.stream = true;
+            dp.support_in = passes[i].support_in;
+            dp.lin_dense = passes[i].lin_dense;
+            dp.lin_sparse = passes[i].lin_sparse;
+            dp.lout = passes[i].lout;
+            dp.swin_dense = (const MmaWindowDev*)(base + offs[i].swin_dense);
+            dp.swin_sparse = (const MmaWindowDev*)(base + offs[i].swin_sparse);
+        }
         for (const DevOp& d : passes[i].ops) {
             const std::vector<int>& loc = passes[i].local;
             if (d.op == OP_U2) dp.mix_mask |= (1ull << loc[d.a]) | (1ull << loc[d.b]);
@@ -470,6 +471,13 @@ int compile_plan(tq_handle h, int which) {
             return fail(h, TQ_EINVAL, "tile does not fit shared memory (lower TQ_TILE_BITS)");
         plan.passes.push_back(dp);
     }
+    {   // run_plan tracks the populated qubits pass by pass; the streaming layouts were built from the planner's own record
+        uint64_t sup = 0;
+        for (int i = 0; i < n_gate_passes; ++i) {
+            plan.passes[i].sparse_ok = plan.passes[i].support_in == sup;
+            sup |= plan.passes[i].mix_mask;
+        }
+    }
     if (env_int("TQ_DEBUG_PLAN", 0)) {
         for (size_t i = 0; i < passes.size(); ++i) {
             const Pass& p = passes[i];
@@ -477,6 +485,10 @@ int compile_plan(tq_handle h, int which) {
                     (int)p.mma, (int)p.direct, p.ops.size(), p.n_gate_windows, p.mma ? p.mwindows.size() : p.windows.size(),
                     groups_of_pass[i].size(), offs[i].n_groups);
             for (int q : p.local) fprintf(stderr, "%d,", q);
+            fprintf(stderr, " stream=%d", (int)p.stream);
+            if (p.stream)
+                fprintf(stderr, " in_ops=%d/%d out_ops=%d live_in=%d", p.lin_dense.n_ops, p.lin_sparse.n_ops, p.lout.n_ops,
+                        p.lin_sparse.n_live);
             fprintf(stderr, " wflags=");
             for (const MmaWindow& w : p.mwindows) fprintf(stderr, "%d", (int)w.flags);
             fprintf(stderr, "\n");
@@ -537,6 +549,55 @@ int ensure_init_rho(tq_handle h) {
     TQ_CUDA(upload_sync(h, h->d_init_rho, rho.data(), rho.size() * sizeof(double)));
     h->init_rho_valid = true;
     return TQ_OK;
+}
+
+// ---- streaming kernel plumbing: TMA descriptors -------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {   // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// Rank-5 view over doubles for one layout: dim 0 = the 128-byte row (16 doubles; its start coordinate carries the tile's
+// base offset, so it spans the whole buffer), dims 1..4 = the layout's runs of index bits (size = box = 2^len, stride
+// 16 << bit bytes), unused dims of size 1.  128-byte swizzle, as StreamLayout::slot assumes.
+bool encode_map(CUtensorMap* m, const void* base, uint64_t n_doubles, const StreamLayout& L, int nbits, std::string* err) {
+    EncodeTiledFn fn = tensor_map_encoder();
+    if (!fn) { *err = "cuTensorMapEncodeTiled is not available"; return false; }
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    gdim[0] = n_doubles;
+    box[0] = 16;
+    for (int d = 1; d < 5; ++d) {
+        if (d < L.n_dims) {
+            gdim[d] = box[d] = 1u << L.dim_len[d];
+            gstride[d - 1] = (cuuint64_t)16 << L.dim_bit[d];
+        } else {
+            gdim[d] = box[d] = 1;
+            gstride[d - 1] = (cuuint64_t)16 << nbits;
+        }
+    }
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r); return false; }
+    return true;
+}
+
+void fill_tma(StreamTma& t, const StreamLayout& L) {
+    t.n_ops = L.n_ops;
+    t.box_bytes = L.box_bytes;
+    t.tile_bytes = (uint32_t)L.n_ops * L.box_bytes;
+    for (int i = 0; i < L.n_ops; ++i) t.op_goff[i] = L.op_goff[i];
 }
 
 // Run the plan for `batch` elements: energies into `out` and / or final states into `states_out`.  from_states: the
@@ -607,6 +668,10 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
         }
         DirectParams direct{};
         int direct_windows = 0, direct_ops = 0, direct_threads = 0;
+        // streaming launches: one per gate pass, one for all expectation-only passes (sub-passes)
+        std::unique_ptr<StreamParams> gstream(new StreamParams), estream(new StreamParams);
+        memset(estream.get(), 0, sizeof(StreamParams));
+        int estream_windows = 0, estream_ops = 0;
         for (int i = 0; i < total_passes; ++i) {
             const DevPass& dp = plan.passes[i];
             PassParams pp = dp.proto;
@@ -661,6 +726,56 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 pp.direct = (dp.direct && pp.src_mode == 2 && pp.exp_mode == 1 && pp.n_groups == 0 && !pp.dst &&
                              plan.nbits <= 27 /* 32-bit byte offsets inside an element */) ? 1 : 0;
             }
+            // ---- streaming kernel (persistent CTAs, TMA tile I/O) for multi-tile tensor-core passes ----
+            const bool sparse_in = pp.in_mask != ~0ull;
+            const bool use_stream = h->stream_kernel && dp.stream && pp.mwindows && !xchg && !fuse_prep && pp.src_mode != 0 &&
+                                    pp.n_groups == 0 && pp.exp_mode != 2 && (!sparse_in || dp.sparse_ok) &&
+                                    ((uint64_t)bc << (plan.nbits + 1)) <= (1ull << 31);
+            if (use_stream) {
+                const bool exp_only = !dp.gate_pass;
+                StreamParams& sp = exp_only ? *estream : *gstream;
+                if (!exp_only) memset(&sp, 0, sizeof(sp));
+                const bool fits = !exp_only || (pp.src_mode == 2 && pp.exp_mode == 1 && !pp.dst && sp.n_sub < kStreamMaxSub &&
+                                                estream_windows + pp.n_windows <= kStreamWinSlots &&
+                                                estream_ops + pp.n_wops <= kStreamOpSlots);
+                if (fits) {
+                    StreamSub& S = sp.sub[sp.n_sub];
+                    S.pp = pp;
+                    S.pp.mwindows = sparse_in ? dp.swin_sparse : dp.swin_dense;
+                    S.pp.direct = 0;
+                    const StreamLayout& lin = sparse_in ? dp.lin_sparse : dp.lin_dense;
+                    fill_tma(S.in, lin);
+                    S.out.n_ops = 0;
+                    S.in_elem_stride = pp.src_mode == 2 ? ((uint64_t)1 << plan.nbits) : 0ull;
+                    std::string terr;
+                    bool ok = encode_map(&sp.map_in[sp.n_sub], pp.src, (uint64_t)(pp.src_mode == 2 ? bc : 1) << (plan.nbits + 1),
+                                         lin, plan.nbits, &terr);
+                    if (ok && pp.dst) {
+                        fill_tma(S.out, dp.lout);
+                        ok = encode_map(&sp.map_out, pp.dst, (uint64_t)bc << (plan.nbits + 1), dp.lout, plan.nbits, &terr);
+                    }
+                    if (!ok) {   // no TMA descriptors on this driver: say so once and stay on the register-staged kernels
+                        fprintf(stderr, "[tqsim] streaming kernel disabled: %s\n", terr.c_str());
+                        h->stream_kernel = false;
+                    } else if (exp_only) {
+                        ++sp.n_sub;
+                        estream_windows += pp.n_windows;
+                        estream_ops += pp.n_wops;
+                        continue;
+                    } else {
+                        sp.n_sub = 1;
+                        sp.batch = bc;
+                        sp.contiguous = 1;
+                        const long long tiles = (long long)bc << pp.n_nl;
+                        launch_tile_stream(sp, (int)std::min<long long>(tiles, h->n_sms), stream);
+                        ++h->launches;
+                        ++h->stream_launches;
+                        rc = check_launch(h, "tile_stream_kernel");
+                        if (rc) return rc;
+                        continue;
+                    }
+                }
+            }
             if (pp.direct && h->direct_kernel && direct.n_sub < kMaxDirectSub &&
                 direct_windows + (pp.n_windows - pp.n_gate_windows) <= kDirectWinSlots &&
                 direct_ops + pp.n_wops <= kDirectOpSlots) {
@@ -674,6 +789,16 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
             launch_tile_pass(pp, bc, dp.threads, dm, stream);
             ++h->launches;
             rc = check_launch(h, "tile_pass_kernel");
+            if (rc) return rc;
+        }
+        if (estream->n_sub > 0) {
+            estream->batch = bc;
+            estream->contiguous = 0;
+            const long long tiles = (long long)bc << estream->sub[0].pp.n_nl;
+            launch_tile_stream(*estream, (int)std::min<long long>(tiles, h->n_sms), stream);
+            ++h->launches;
+            ++h->stream_launches;
+            rc = check_launch(h, "tile_stream_kernel (expectation)");
             if (rc) return rc;
         }
         if (direct.n_sub > 0) {
@@ -808,6 +933,10 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
         return TQ_ENODEV;
     }
     if ((e = cudaSetDevice(device_id)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return TQ_ECUDA; }
+    if ((e = tile_stream_configure()) != cudaSuccess) {
+        g_create_error = std::string("cudaFuncSetAttribute (streaming kernel): ") + cudaGetErrorString(e);
+        return TQ_ECUDA;
+    }
     if ((e = tile_pass_configure()) != cudaSuccess) {
         g_create_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         return TQ_ECUDA;
@@ -823,6 +952,7 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->spin_wait = env_int("TQ_SPIN", 1) != 0;
     h->sparse_init = env_int("TQ_SPARSE_INIT", 1) != 0;
     h->direct_kernel = env_int("TQ_DIRECT_KERNEL", 1) != 0;
+    h->stream_kernel = env_int("TQ_STREAM", 1) != 0;
     h->direct_ctas_per_sm = std::max(1, std::min(8, env_int("TQ_DIRECT_CTAS", 2)));
     h->n_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -1200,6 +1330,7 @@ int tq_plan_counts(tq_handle h, int which, int64_t* counts8) {
         if (support != ~0ull) support |= dp.mix_mask;
     }
     counts8[6] = (int64_t)(work + 0.5);
+    counts8[7] = h->stream_launches;   // launches of the streaming kernel (persistent CTAs, TMA tile I/O) by this handle so far
     return TQ_OK;
 }
 
@@ -1214,6 +1345,10 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
                    int n_cover, const uint64_t* cover_masks) {
     std::vector<Gate> gates(n_gates);
     for (int g = 0; g < n_gates; ++g) gates[g] = Gate{kind[g], q0[g], q1[g], param_idx[g], fixed[g]};
+    // which & 16: also assign a synthetic Hamiltonian (one XX + YY-like group per cover mask and a ZZ-like diagonal group) to
+    // the passes, with the streaming layouts (tq_stream.cu) chosen first, and report validate_stream per pass
+    const bool with_stream = (which & 16) != 0;
+    which &= 15;
     PlanOptions opt;
     opt.tile_bits = tile_bits;
     opt.low_bits = low_bits;
@@ -1227,6 +1362,22 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
     std::string out;
     char line[256];
     if (!err.empty()) out = "ERROR " + err + "\n";
+    if (with_stream && err.empty() && which != 1 && !cc.passes.empty() && n_qubits > tile_bits) {
+        std::vector<ExpGroupIn> groups;
+        ExpGroupIn diag;
+        diag.x = 0;
+        for (uint64_t m : cover) {
+            ExpGroupIn g;
+            g.x = m;
+            g.terms.push_back(ExpTermIn{0ull, 0.25, 0.0});
+            g.terms.push_back(ExpTermIn{m, -0.25, 0.0});
+            groups.push_back(g);
+            diag.terms.push_back(ExpTermIn{m, 0.25, 0.0});
+        }
+        if (!diag.terms.empty()) groups.push_back(diag);
+        ExpPlan ep = attach_expectation(cc.passes, groups, opt, n_qubits, true, true);
+        if (!ep.err.empty()) out += "ERROR " + ep.err + "\n";
+    }
     for (const MatDesc& md : cc.mats) {
         out += "MAT " + std::to_string(md.nq) + " " + std::to_string(md.diag) + "\n";
         for (int g = md.begin; g < md.end; ++g) {
@@ -1239,6 +1390,22 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
         out += "PASS lead=" + std::to_string(p.lead) + " local=";
         for (size_t i = 0; i < p.local.size(); ++i) out += (i ? "," : "") + std::to_string(p.local[i]);
         out += " support=" + std::to_string((unsigned long long)p.support_in) + "\n";
+        if (with_stream) {
+            auto lay = [&](const char* name, const StreamLayout& L) {
+                std::string t = std::string("STREAM ") + name + " live=" + std::to_string(L.n_live) + " ops=" + std::to_string(L.n_ops) +
+                                " box_bytes=" + std::to_string(L.box_bytes) + " box_of=";
+                for (size_t i = 0; i < p.local.size(); ++i) t += (i ? "," : "") + std::to_string((int)L.box_of[i]);
+                t += " dims=";
+                for (int d = 1; d < L.n_dims; ++d) t += (d > 1 ? "," : "") + std::to_string((int)L.dim_bit[d]) + ":" + std::to_string((int)L.dim_len[d]);
+                return t + "\n";
+            };
+            out += std::string("STREAMABLE ") + (p.stream ? "1" : "0") + "\n";
+            if (p.stream) {
+                out += lay("in_dense", p.lin_dense) + lay("in_sparse", p.lin_sparse) + lay("out", p.lout);
+                const std::string v = validate_stream(p);
+                out += "STREAMCHECK " + (v.empty() ? std::string("ok") : v) + "\n";
+            }
+        }
         for (const DevOp& d : p.ops) {
             snprintf(line, sizeof line, "OP %d %d %d %d %d %.17g\n", d.op, d.a, d.b, d.t, d.flags, d.fixed);
             out += line;

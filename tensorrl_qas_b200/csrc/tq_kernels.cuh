@@ -11,6 +11,7 @@
 //   4. write the tile back.
 // HBM traffic per pass is one read + one write of the state no matter how many gates the pass fused.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -95,6 +96,32 @@ struct DirectParams {
     PassParams sub[kMaxDirectSub];
 };
 void launch_expect_direct(const DirectParams& dp, int n_ctas, int threads, cudaStream_t stream);
+
+// ---- streaming pass kernel (tq_stream.cu): persistent CTAs, tiles moved by TMA --------------------------------------
+constexpr int kStreamMaxSub = 4;      // sub-passes per launch (expectation-only passes share one launch)
+constexpr int kStreamThreads = 512;   // two groups of 256 threads, one tile each
+struct StreamTma {                    // one direction of one sub-pass (tq_plan.h StreamLayout, resolved)
+    int n_ops;                        // TMA operations per tile; 0 = direction unused
+    uint32_t box_bytes;               // bytes per operation = distance of the operations' shared-memory destinations
+    uint32_t tile_bytes;              // n_ops * box_bytes: the mbarrier transaction count of a tile load
+    uint32_t op_goff[kStreamMaxOps];  // physical amplitude offset of operation i inside the tile
+};
+struct StreamSub {
+    PassParams pp;             // geometry, windows (resolve_window_stream), ops, eterms, mats, partial: as for the pass kernels
+    StreamTma in, out;
+    uint64_t in_elem_stride;   // amplitudes between consecutive elements of the source (0: one shared initial vector)
+};
+struct alignas(64) StreamParams {
+    CUtensorMap map_in[kStreamMaxSub];   // rank-5 views over doubles; dim 0 = 16 doubles whose coordinate is the tile's base
+    CUtensorMap map_out;                 // gate passes (n_sub == 1) that write the tile back
+    StreamSub sub[kStreamMaxSub];
+    int n_sub, batch;
+    int contiguous;   // 1: CTA c takes a contiguous range of tiles (gate passes: block matrices are staged once per element);
+                      // 0: tiles c, c + grid, ... element-major (expectation sub-passes find the element in L2)
+};
+size_t tile_stream_smem_bytes();
+cudaError_t tile_stream_configure();   // opt in to the dynamic shared memory
+void launch_tile_stream(const StreamParams& sp, int n_ctas, cudaStream_t stream);
 
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead);
 cudaError_t tile_pass_configure();  // opt in to > 48 KiB dynamic shared memory

@@ -360,6 +360,11 @@ bool independent3(int a, int b, int c) {
     const int va = kSwizzleVec[a], vb = kSwizzleVec[b], vc = kSwizzleVec[c];
     return va != vb && va != vc && vb != vc && (va ^ vb) != vc;
 }
+// the same for an arbitrary bank-vector table (streaming layouts have positions without a vector)
+bool independent3v(const uint8_t* vec, int a, int b, int c) {
+    const int va = vec[a], vb = vec[b], vc = vec[c];
+    return va && vb && vc && va != vb && va != vc && vb != vc && (va ^ vb) != vc;
+}
 
 }  // namespace
 
@@ -475,9 +480,12 @@ void schedule_windows(Pass& p) {
 // ================================================================ 3b. DMMA windows ==============================
 namespace {
 
-// tile positions outside the window -> three lane-group positions (independent bank-swizzle vectors when possible,
-// so the sixteen amplitudes a warp touches per shared-memory access spread over all bank groups) + warp positions
-void split_rest(const std::vector<int>& rest_in, uint8_t gpos[3], uint8_t wpos[3], uint32_t prefer_warp = 0) {
+// tile positions outside the window -> three lane-group positions + warp positions.  A shared-memory access of a window
+// (8 bytes per lane) is served half-warp by half-warp: lanes 0..15 = (component, QL, g0, g1), so the bank vectors of QL,
+// g0 and g1 must be independent for the sixteen doubles to spread over all banks -- on entry (QL = ql_in) and on exit
+// (QL = ql_out).  vec: bank vector per tile position of the layout the accesses see.
+void split_rest(const std::vector<int>& rest_in, uint8_t gpos[3], uint8_t wpos[3], uint32_t prefer_warp, const uint8_t* vec,
+                int ql_in, int ql_out) {
     std::vector<int> rest = rest_in;
     // positions in prefer_warp (still-untouched qubits) should end up on the warp index: keep up to n_warp of them out
     // of the lane-group choice by moving them to the back
@@ -489,29 +497,18 @@ void split_rest(const std::vector<int>& rest_in, uint8_t gpos[3], uint8_t wpos[3
         rest.swap(front);
     }
     const size_t n_lane_cand = prefer_warp ? std::max<size_t>(3, rest.size() - (size_t)std::min<int>(n_warp, popc32(prefer_warp))) : rest.size();
-    bool found = false;
-    {   // the three lowest tile positions make a conflict-free lane group (swizzle vectors 1, 2, 4): take them when free
-        size_t at[3] = {rest.size(), rest.size(), rest.size()};
-        for (size_t i = 0; i < n_lane_cand; ++i)
-            if (rest[i] < 3) at[rest[i]] = i;
-        if (at[0] < rest.size() && at[1] < rest.size() && at[2] < rest.size()) {
-            std::vector<int> order = {0, 1, 2};
-            for (size_t i = 0; i < rest.size(); ++i)
-                if (rest[i] > 2) order.push_back(rest[i]);
-            rest.swap(order);
-            found = true;
+    int best_a = -1, best_b = -1, best_score = -1;
+    for (size_t a = 0; a < n_lane_cand && best_score < 2; ++a)
+        for (size_t b = a + 1; b < n_lane_cand && best_score < 2; ++b) {
+            const int score = (int)independent3v(vec, ql_in, rest[a], rest[b]) + (int)independent3v(vec, ql_out, rest[a], rest[b]);
+            if (score > best_score) { best_score = score; best_a = (int)a; best_b = (int)b; }
         }
+    if (best_a >= 0) {
+        std::vector<int> order = {rest[best_a], rest[best_b]};
+        for (size_t i = 0; i < rest.size(); ++i)
+            if ((int)i != best_a && (int)i != best_b) order.push_back(rest[i]);
+        rest.swap(order);
     }
-    for (size_t a = 0; a < n_lane_cand && !found; ++a)
-        for (size_t b = a + 1; b < n_lane_cand && !found; ++b)
-            for (size_t c = b + 1; c < n_lane_cand && !found; ++c)
-                if (independent3(rest[a], rest[b], rest[c])) {
-                    std::vector<int> order = {rest[a], rest[b], rest[c]};
-                    for (size_t i = 0; i < rest.size(); ++i)
-                        if (i != a && i != b && i != c) order.push_back(rest[i]);
-                    rest.swap(order);
-                    found = true;
-                }
     for (int i = 0; i < 3; ++i) gpos[i] = (uint8_t)rest[i];
     for (int i = 0; i < 3; ++i) wpos[i] = (uint8_t)(3 + i < (int)rest.size() ? rest[3 + i] : 0);
 }
@@ -698,7 +695,7 @@ void schedule_windows_mma(Pass& p) {
             done[pick] = 1;
         }
         if (!have_layout) fix_layout(act[0]);
-        split_rest(rest, w.gpos, w.wpos, ~populated & ((1u << k) - 1u));
+        split_rest(rest, w.gpos, w.wpos, ~populated & ((1u << k) - 1u), kSwizzleVec, w.qlpos, ql);
         for (int i = 0; i < 3 && i < k - 9; ++i)
             if (!((populated >> w.wpos[i]) & 1)) w.dead_wbits |= (uint8_t)(1u << i);
         for (int idx : mine) populated |= tops[idx].mix;   // what this window's gates may populate
@@ -782,6 +779,9 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
     // terms evaluated with signs from the thread's index (M_EXPD)
     auto make_window = [&](uint32_t W, const std::vector<int>& mine, const std::vector<ExpTermIn>& generic) {
         // fill up with unused positions, the three lowest last (keeping them free allows direct global loads)
+        // (positions without a bank vector first: they are of no use as lane qubits -- streaming layouts)
+        for (int q = 3; q < k && popc32(W) < kMmaRegBits; ++q)
+            if (!p.lane_vec[q]) W |= 1u << q;
         for (int q = 3; q < k && popc32(W) < kMmaRegBits; ++q) W |= 1u << q;
         for (int q = 0; q < k && popc32(W) < kMmaRegBits; ++q) W |= 1u << q;
         MmaWindow w{};
@@ -805,9 +805,16 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
             for (int i = 0; i < 3; ++i) w.wpos[i] = (uint8_t)(1 + i < (int)others.size() ? others[1 + i] : 0);
             w.flags |= kWinFlagDirect;
         } else {
-            w.qlpos = (uint8_t)rest.back();   // any position outside the flip masks
-            rest.pop_back();
-            split_rest(rest, w.gpos, w.wpos);
+            // QL = any position outside the flip masks; (QL, g0, g1) with independent bank vectors when there are such
+            size_t qi = rest.size() - 1;
+            bool found = false;
+            for (size_t a = 0; a < rest.size() && !found; ++a)
+                for (size_t b = 0; b < rest.size() && !found; ++b)
+                    for (size_t c = b + 1; c < rest.size() && !found; ++c)
+                        if (a != b && a != c && independent3v(p.lane_vec, rest[a], rest[b], rest[c])) { qi = a; found = true; }
+            w.qlpos = (uint8_t)rest[qi];
+            rest.erase(rest.begin() + (long)qi);
+            split_rest(rest, w.gpos, w.wpos, 0, p.lane_vec, w.qlpos, w.qlpos);
         }
         for (int r = 0; r < kMmaRegBits; ++r) w.rpos_out[r] = w.rpos[r];
         w.qlpos_out = w.qlpos;
@@ -1106,6 +1113,327 @@ MmaWindowDev resolve_window(const MmaWindow& w, const Pass& p) {
     d.op_begin = w.op_begin;
     d.op_end = w.op_end;
     return d;
+}
+
+// ================================================================ expectation assignment =========================
+ExpPlan attach_expectation(std::vector<Pass>& passes, const std::vector<ExpGroupIn>& groups, const PlanOptions& opt, int n,
+                           bool in_pass_pref, bool stream) {
+    ExpPlan ep;
+    ep.n_gate_passes = (int)passes.size();
+    ep.groups_of_pass.assign(passes.size(), {});
+    if (!groups.empty()) {
+        std::vector<uint64_t> todo;
+        std::vector<int> todo_group;
+        // in_pass_pref = false: when some group needs an expectation-only pass anyway, evaluate ALL off-diagonal groups in
+        // those passes (the last gate pass then carries no expectation windows)
+        bool any_outside = false;
+        for (const ExpGroupIn& g : groups) any_outside = any_outside || !mask_is_local(passes.back(), g.x);
+        const bool in_pass = in_pass_pref || !any_outside;
+        for (size_t g = 0; g < groups.size(); ++g) {
+            if (mask_is_local(passes.back(), groups[g].x) && (in_pass || groups[g].x == 0))
+                ep.groups_of_pass[ep.n_gate_passes - 1].push_back((int)g);
+            else { todo.push_back(groups[g].x); todo_group.push_back((int)g); }
+        }
+        if (!todo.empty()) {
+            std::vector<int> assign;
+            std::vector<Pass> extra = plan_cover(n, todo, opt, &assign);
+            for (size_t i = 0; i < todo.size(); ++i)
+                if (assign[i] < 0) { ep.err = "Hamiltonian term flips more qubits than a tile holds"; return ep; }
+            const size_t base = passes.size();
+            ep.groups_of_pass.resize(base + extra.size());
+            for (size_t i = 0; i < todo.size(); ++i) ep.groups_of_pass[base + assign[i]].push_back(todo_group[i]);
+            for (Pass& p : extra) passes.push_back(std::move(p));
+        }
+    }
+    ep.wide_of_pass.assign(passes.size(), {});
+    std::vector<ExpTermIn> diag_pool;   // diagonal terms still to be evaluated (tensor-core passes share them)
+    size_t last_eval_pass = 0;
+    for (size_t i = 0; i < passes.size(); ++i)
+        if (!ep.groups_of_pass[i].empty()) last_eval_pass = i;
+    for (size_t i = 0; i < passes.size(); ++i) {
+        Pass& p = passes[i];
+        // streaming kernel: the layouts are fixed before the expectation windows pick their lane qubits
+        if (stream && p.mma) plan_stream_layouts(p, n);
+        std::vector<ExpGroupIn> gin;
+        for (int g : ep.groups_of_pass[i]) gin.push_back(groups[g]);
+        std::vector<int> wide;
+        if (!gin.empty()) {
+            if (p.mma) append_expectation_windows_mma(p, gin, &wide, &diag_pool, i == last_eval_pass);
+            else append_expectation_windows(p, gin, &wide);
+        }
+        for (int wi : wide) ep.wide_of_pass[i].push_back(ep.groups_of_pass[i][wi]);
+        if (p.stream && (!wide.empty() || (int)p.wops.size() > kStreamOpSlots || (int)p.mwindows.size() > kStreamWinSlots))
+            p.stream = false;   // (the windows picked their lanes for the streaming layout: a few more bank conflicts)
+    }
+    return ep;
+}
+
+// ================================================================ streaming layouts ==============================
+namespace {
+
+// Box order of a tile for the TMA engine.  live: tile positions inside the box (must contain 0, 1, 2); lanes: tile positions
+// of (QL, g0, g1) of the access that should be conflict-free.  Box positions 0..2 are the tile positions 0..2 (physical
+// qubits 0..2, the 128-byte row); a lane qubit above them goes to box position 3 + c for a bank class c that no other lane
+// has; everything else is ordered so that runs of consecutive physical bits stay together (one TMA dimension per run).
+bool build_layout(const Pass& p, uint32_t live, const int lanes[3], StreamLayout& L) {
+    const int k = (int)p.local.size();
+    if ((live & 7u) != 7u) return false;
+    L = StreamLayout{};
+    memset(L.box_of, 0xff, sizeof(L.box_of));
+    memset(L.dim_bit, 0, sizeof(L.dim_bit));
+    memset(L.dim_len, 0, sizeof(L.dim_len));
+    L.n_live = popc32(live);
+    int forced[3] = {-1, -1, -1};   // tile position that wants box position 3 + c
+    bool class_used[3] = {false, false, false};
+    for (int i = 0; i < 3; ++i)
+        if (lanes[i] >= 0 && lanes[i] < 3) class_used[lanes[i]] = true;
+    for (int i = 0; i < 3; ++i) {
+        const int q = lanes[i];
+        if (q < 3 || !((live >> q) & 1)) continue;
+        for (int c = 0; c < 3; ++c)
+            if (!class_used[c]) { class_used[c] = true; forced[c] = q; break; }
+    }
+    std::vector<int> order = {0, 1, 2};
+    uint32_t placed = 7u;
+    auto is_forced = [&](int q) { return q == forced[0] || q == forced[1] || q == forced[2]; };
+    auto free_cand = [&](int q) { return ((live >> q) & 1) && !((placed >> q) & 1) && !is_forced(q); };
+    auto run_len_from = [&](int q) {   // unplaced free positions continuing upwards in physical bits from q
+        int len = 1;
+        for (int x = q; x + 1 < k && free_cand(x + 1) && p.local[x + 1] == p.local[x] + 1; ++x) ++len;
+        return len;
+    };
+    while ((int)order.size() < L.n_live) {
+        const int bp = (int)order.size();
+        int pick = -1;
+        if (bp < 6 && forced[bp - 3] >= 0) pick = forced[bp - 3];
+        if (pick < 0) {
+            const int prev = order.back();
+            // continue the current run
+            if (bp > 3)
+                for (int q = 0; q < k && pick < 0; ++q)
+                    if (free_cand(q) && p.local[q] == p.local[prev] + 1) pick = q;
+            // lead into the next forced position
+            if (pick < 0 && bp < 5 && forced[bp - 2] >= 0)
+                for (int q = 0; q < k && pick < 0; ++q)
+                    if (free_cand(q) && p.local[q] + 1 == p.local[forced[bp - 2]]) pick = q;
+            // start the longest remaining run (lowest bit on ties) whose start is not a continuation of a free position
+            if (pick < 0) {
+                int best_len = 0;
+                for (int q = 0; q < k; ++q) {
+                    if (!free_cand(q)) continue;
+                    if (q > 0 && free_cand(q - 1) && p.local[q - 1] + 1 == p.local[q]) continue;   // not a run start
+                    const int len = run_len_from(q);
+                    if (len > best_len) { best_len = len; pick = q; }
+                }
+            }
+            if (pick < 0)   // only forced positions are left (a box smaller than six positions): place them anyway
+                for (int c = 0; c < 3 && pick < 0; ++c)
+                    if (forced[c] >= 0 && !((placed >> forced[c]) & 1)) pick = forced[c];
+        }
+        if (pick < 0) return false;
+        for (int c = 0; c < 3; ++c)
+            if (forced[c] == pick) forced[c] = -1;
+        placed |= 1u << pick;
+        order.push_back(pick);
+    }
+    for (int bp = 0; bp < L.n_live; ++bp) L.box_of[order[bp]] = (uint8_t)bp;
+    // runs of consecutive ascending physical bits from box position 3 on -> TMA dims 1..4, the rest is enumerated
+    struct Run { int bp, bit, len; };
+    std::vector<Run> runs;
+    for (int bp = 3; bp < L.n_live; ++bp) {
+        const int bitq = p.local[order[bp]];
+        if (!runs.empty() && runs.back().bit + runs.back().len == bitq && runs.back().len < 8 &&
+            runs.back().bp + runs.back().len == bp)
+            ++runs.back().len;
+        else runs.push_back(Run{bp, bitq, 1});
+    }
+    L.n_dims = 1;
+    int first_enum_bp = L.n_live;
+    for (size_t i = 0; i < runs.size(); ++i) {
+        if (i < 4) {
+            L.dim_bit[L.n_dims] = (uint8_t)runs[i].bit;
+            L.dim_len[L.n_dims] = (uint8_t)runs[i].len;
+            ++L.n_dims;
+        } else { first_enum_bp = runs[i].bp; break; }
+    }
+    const int e = L.n_live - first_enum_bp;
+    if ((1 << e) > kStreamMaxOps) return false;
+    L.n_ops = 1 << e;
+    for (int i = 0; i < L.n_ops; ++i) {
+        uint32_t off = 0;
+        for (int j = 0; j < e; ++j)
+            if ((i >> j) & 1) off |= 1u << p.local[order[first_enum_bp + j]];
+        L.op_goff[i] = off;
+    }
+    L.box_bytes = 16u << first_enum_bp;
+    return true;
+}
+
+int first_gate_window(const Pass& p) {
+    for (int i = 0; i < p.n_gate_windows; ++i)
+        if (!(p.mwindows[i].flags & kWinFlagReadOnly)) return i;
+    return -1;
+}
+int last_gate_window(const Pass& p) {
+    for (int i = p.n_gate_windows - 1; i >= 0; --i)
+        if (!(p.mwindows[i].flags & kWinFlagReadOnly)) return i;
+    return -1;
+}
+uint32_t live_positions(const Pass& p) {
+    uint32_t live = 0;
+    for (size_t q = 0; q < p.local.size(); ++q)
+        if ((p.support_in >> p.local[q]) & 1ull) live |= 1u << q;
+    return live;
+}
+
+}  // namespace
+
+bool plan_stream_layouts(Pass& p, int nbits) {
+    p.stream = false;
+    p.sparse_differs = false;
+    const int k = (int)p.local.size();
+    if (!p.mma || k != kStreamTileBits || nbits <= k || p.lead < 3) return false;
+    const int first = first_gate_window(p), last = last_gate_window(p);
+    if (first < 0 && !p.ops.empty()) return false;
+    const uint32_t all = (1u << k) - 1u;
+    int lanes_in[3] = {0, 1, 2}, lanes_out[3] = {0, 1, 2};
+    if (first >= 0) {
+        const MmaWindow &wf = p.mwindows[first], &wl = p.mwindows[last];
+        lanes_in[0] = wf.qlpos; lanes_in[1] = wf.gpos[0]; lanes_in[2] = wf.gpos[1];
+        lanes_out[0] = wl.qlpos_out; lanes_out[1] = wl.gpos[0]; lanes_out[2] = wl.gpos[1];
+    }
+    if (!build_layout(p, all, lanes_in, p.lin_dense)) return false;
+    if (!build_layout(p, all, lanes_out, p.lout)) return false;
+    p.lin_sparse = p.lin_dense;
+    const uint32_t live = live_positions(p) & all;
+    if (first >= 0 && live != all && (live & 7u) == 7u) {
+        StreamLayout ls;
+        if (build_layout(p, live, lanes_in, ls)) { p.lin_sparse = ls; p.sparse_differs = true; }
+    }
+    // bank vectors of the layout the pass's expectation windows read: the store layout after gate windows, else the load
+    // layout
+    const StreamLayout& le = first >= 0 ? p.lout : p.lin_dense;
+    for (int q = 0; q < 16; ++q) p.lane_vec[q] = 0;
+    for (int q = 0; q < k; ++q) {
+        const int bp = le.box_of[q];
+        p.lane_vec[q] = (uint8_t)(bp < 3 ? (1 << bp) : bp < 6 ? (1 << (bp - 3)) : 0);
+    }
+    p.stream = true;
+    return true;
+}
+
+MmaWindowDev resolve_window_stream(const Pass& p, int widx, bool sparse) {
+    const MmaWindow& w = p.mwindows[widx];
+    MmaWindowDev d = resolve_window(w, p);   // kSwizzleVec layout everywhere, physical bits, op range, flags
+    const int k = (int)p.local.size();
+    const int first = first_gate_window(p), last = last_gate_window(p);
+    const bool is_exp = widx >= p.n_gate_windows;
+    const StreamLayout* lin = nullptr;   // nullptr: the kSwizzleVec layout
+    const StreamLayout* lex = nullptr;
+    if (is_exp || (w.flags & kWinFlagReadOnly)) lin = lex = (first >= 0 ? &p.lout : (sparse ? &p.lin_sparse : &p.lin_dense));
+    else {
+        if (widx == first) lin = sparse ? &p.lin_sparse : &p.lin_dense;
+        if (widx == last) lex = &p.lout;
+    }
+    auto slot_in = [&](int pos) -> uint16_t {
+        if (!lin) return (uint16_t)swizzle_slot(1u << pos);
+        return lin->box_of[pos] == 0xff ? (uint16_t)0 : lin->slot(pos);
+    };
+    auto slot_out = [&](int pos) -> uint16_t { return lex ? lex->slot(pos) : (uint16_t)swizzle_slot(1u << pos); };
+    for (int r = 0; r < kMmaRegBits; ++r) { d.rslot[r] = slot_in(w.rpos[r]); d.rslot_out[r] = slot_out(w.rpos_out[r]); }
+    d.qslot = slot_in(w.qlpos);
+    d.qslot_out = slot_out(w.qlpos_out);
+    for (int i = 0; i < 3; ++i) { d.gslot[i] = slot_in(w.gpos[i]); d.gslot_out[i] = slot_out(w.gpos[i]); }
+    for (int i = 0; i < 3; ++i)
+        if (i < k - 9) { d.wslot[i] = slot_in(w.wpos[i]); d.wslot_out[i] = slot_out(w.wpos[i]); }
+    d.flags2 = 0;
+    if (lin != lex) d.flags2 |= kWin2StoreAll;
+    if (sparse && widx == first) {
+        const uint32_t live = live_positions(p);
+        d.flags2 |= kWin2DeadEntry;
+        for (int r = 0; r < kMmaRegBits; ++r)
+            if (!((live >> w.rpos[r]) & 1)) d.dead_r |= (uint8_t)(1u << r);
+        if (!((live >> w.qlpos) & 1)) d.dead_l |= 1;
+        for (int i = 0; i < 3; ++i)
+            if (!((live >> w.gpos[i]) & 1)) d.dead_l |= (uint8_t)(2u << i);
+        d.dead_wbits = 0;
+        for (int i = 0; i < 3 && i < k - 9; ++i)
+            if (!((live >> w.wpos[i]) & 1)) d.dead_wbits |= (uint8_t)(1u << i);
+    }
+    return d;
+}
+
+std::string validate_stream(const Pass& p) {
+    if (!p.stream) return "";
+    const int k = (int)p.local.size();
+    auto fail = [](const std::string& m) { return std::string("stream layout: ") + m; };
+    // (1) TMA view of each layout: every box element's physical offset (dims + enumerated operations) is the one of
+    //     its tile index, each element exactly once
+    const StreamLayout* layouts[3] = {&p.lin_dense, &p.lin_sparse, &p.lout};
+    for (const StreamLayout* L : layouts) {
+        std::vector<int> order(L->n_live, -1);
+        for (int q = 0; q < k; ++q)
+            if (L->box_of[q] != 0xff) {
+                if (L->box_of[q] >= L->n_live || order[L->box_of[q]] >= 0) return fail("box positions are not a permutation");
+                order[L->box_of[q]] = q;
+            }
+        for (int bp = 0; bp < 3; ++bp)
+            if (order[bp] != bp || p.local[bp] != bp) return fail("box positions 0..2 must be qubits 0..2");
+        int dim_bits = 0;
+        for (int d = 1; d < L->n_dims; ++d) dim_bits += L->dim_len[d];
+        int e = 0;
+        while ((1 << e) < L->n_ops) ++e;
+        if (3 + dim_bits + e != L->n_live) return fail("dims + enumerated positions do not cover the box");
+        if (L->box_bytes != (16u << (3 + dim_bits))) return fail("box_bytes");
+        std::vector<char> seen((size_t)1 << L->n_live, 0);
+        for (int op = 0; op < L->n_ops; ++op)
+            for (uint32_t s = 0; s < (1u << (3 + dim_bits)); ++s) {   // element s of this operation's box, box order
+                uint32_t phys = L->op_goff[op] | (s & 7u);
+                int at = 3;
+                for (int d = 1; d < L->n_dims; ++d) {
+                    const uint32_t c = (s >> at) & ((1u << L->dim_len[d]) - 1u);
+                    phys |= c << L->dim_bit[d];
+                    at += L->dim_len[d];
+                }
+                const uint32_t boxidx = s | ((uint32_t)op << (3 + dim_bits));
+                uint32_t want = 0;
+                for (int bp = 0; bp < L->n_live; ++bp)
+                    if ((boxidx >> bp) & 1) want |= 1u << p.local[order[bp]];
+                if (phys != want) return fail("TMA dims do not reproduce the box order");
+                if (seen[boxidx]) return fail("box element visited twice");
+                seen[boxidx] = 1;
+            }
+    }
+    // (2) every window: the slot offsets of its twelve positions are linearly independent (distinct slot per (thread,
+    //     register)), on entry and on exit, and stay inside the box
+    for (int sparse = 0; sparse < 2; ++sparse)
+        for (int wi = 0; wi < (int)p.mwindows.size(); ++wi) {
+            const MmaWindowDev d = resolve_window_stream(p, wi, sparse != 0);
+            for (int side = 0; side < 2; ++side) {
+                std::vector<uint16_t> offs;
+                const bool dead_entry = side == 0 && (d.flags2 & kWin2DeadEntry);
+                for (int r = 0; r < kMmaRegBits; ++r)
+                    if (!(dead_entry && ((d.dead_r >> r) & 1))) offs.push_back(side ? d.rslot_out[r] : d.rslot[r]);
+                if (!(dead_entry && (d.dead_l & 1))) offs.push_back(side ? d.qslot_out : d.qslot);
+                for (int i = 0; i < 3; ++i)
+                    if (!(dead_entry && ((d.dead_l >> (1 + i)) & 1))) offs.push_back(side ? d.gslot_out[i] : d.gslot[i]);
+                for (int i = 0; i < 3 && i < k - 9; ++i)
+                    if (!(dead_entry && ((d.dead_wbits >> i) & 1))) offs.push_back(side ? d.wslot_out[i] : d.wslot[i]);
+                // Gaussian elimination over GF(2)
+                std::vector<uint16_t> basis;
+                for (uint16_t v : offs) {
+                    for (uint16_t b : basis) v = std::min<uint16_t>(v, v ^ b);
+                    if (v == 0) return fail("window " + std::to_string(wi) + ": slot offsets are dependent");
+                    basis.push_back(v);
+                }
+                uint32_t span = 0;
+                for (uint16_t v : offs) span |= v;
+                const int box_bits = (dead_entry && p.sparse_differs) ? p.lin_sparse.n_live : k;
+                if (span >= (1u << box_bits) || (int)offs.size() > box_bits)
+                    return fail("window " + std::to_string(wi) + ": slots leave the box");
+            }
+        }
+    return "";
 }
 
 bool mask_is_local(const Pass& p, uint64_t mask) {

@@ -172,21 +172,63 @@ static_assert(sizeof(MmaWindow) == 32, "MmaWindow layout");
 // What the kernel reads: the same window with every tile position resolved to its swizzled shared-memory slot offset
 // (the bank swizzle is GF(2)-linear, so a thread's slot is the XOR of the offsets of its set bits) and to its physical
 // qubit (for the control / sign bits a thread reads from its own index).
-struct MmaWindowDev {  // 64 bytes
+struct MmaWindowDev {  // 80 bytes
     uint16_t rslot[kMmaRegBits], rslot_out[kMmaRegBits];
     uint16_t qslot, qslot_out;
     uint16_t gslot[3], wslot[3];
+    uint16_t gslot_out[3], wslot_out[3];   // exit layout of the thread bits (differs from entry only in streaming passes)
     uint8_t gphys[3], wphys[3], qlphys, flags;
     int32_t op_begin, op_end;
     uint8_t rphys[kMmaRegBits];   // physical qubits of the register bits on entry (direct global loads)
     uint8_t dead_wbits;           // see MmaWindow
-    uint8_t pad[6];
+    // streaming passes, first window of a pass whose input holds known zeros: bits that are dead ON ENTRY -- register bits
+    // (dead_r) and lane bits QL, g0, g1, g2 (dead_l bits 0..3); such registers / threads start from 0.0 instead of a load
+    uint8_t dead_r, dead_l;
+    uint8_t flags2;               // kWin2*
+    uint8_t pad[7];
 };
-static_assert(sizeof(MmaWindowDev) == 64, "MmaWindowDev layout");
+static_assert(sizeof(MmaWindowDev) == 80, "MmaWindowDev layout");
+constexpr int kWinU4 = sizeof(MmaWindowDev) / 16;   // 16-byte units per header
+constexpr int kWin2StoreAll = 1;    // entry and exit layouts differ: every thread (idle warps too) writes its registers back
+constexpr int kWin2DeadEntry = 2;   // honour dead_r / dead_l / dead_wbits on entry (compact load layout)
 MmaWindowDev resolve_window(const MmaWindow& w, const struct Pass& p);
+// Streaming variant: window widx of a pass with p.stream set; sparse = the input has the known zeros of p.support_in
+MmaWindowDev resolve_window_stream(const struct Pass& p, int widx, bool sparse);
+// Choose the layouts of a pass for the streaming kernel (sets p.stream; false = the pass stays on tile_pass_mma_kernel).
+// Gate passes: call after schedule_windows_mma and BEFORE append_expectation_windows_mma (the expectation windows then
+// pick their lanes for the store layout); expectation-only passes: call after their windows exist.
+bool plan_stream_layouts(struct Pass& p, int nbits);
+// Consistency check of the layouts and resolved windows (every (thread, register) of every window must address a distinct
+// slot, the first entry / last exit must match the TMA box order); empty string = ok
+std::string validate_stream(const struct Pass& p);
 
 struct Pass;
 inline uint32_t swizzle_slot(uint32_t j);   // slot of tile index j (defined below kSwizzleVec)
+
+// ---- streaming passes (tq_stream.cu): tiles move between HBM and shared memory by TMA -----------------------------
+// The TMA engine writes a box densely in box order, 128-byte rows (8 amplitudes: physical qubits 0..2) with the hardware
+// 128-byte swizzle (16-byte chunk index ^= row index & 7).  Box position bp of a tile position therefore means the
+// shared-memory slot offset (1 << bp) ^ (3 <= bp <= 5 ? 1 << (bp - 3) : 0): box positions 3, 4, 5 carry the bank-swizzle
+// vectors 1, 2, 4 (like positions 0, 1, 2), everything above none.  The planner picks the box order per pass so that the
+// lane qubits (QL, g0, g1) of the FIRST window's entry (load layout) and of the LAST gate window's exit (store layout)
+// get three different vectors: those two accesses are conflict-free, all window exchanges in between keep the
+// kSwizzleVec layout.  Positions holding known zeros on input are not loaded at all (compact box).
+constexpr int kStreamMaxOps = 32;    // TMA operations per tile and direction
+constexpr int kStreamOpSlots = 48, kStreamWinSlots = 32;   // ops / window headers resident in shared memory (per launch)
+constexpr int kStreamTileBits = 12;  // the streaming kernel's tile (two groups of 256 threads, three 64 KiB buffers per SM)
+struct StreamLayout {
+    int n_live = 0;               // tile positions inside the box
+    uint8_t box_of[16];           // tile position -> box position, 0xff = not loaded (known zero)
+    int n_dims = 1;               // dims in use; dim 0 = 16 doubles, its coordinate carries the tile's base offset
+    uint8_t dim_bit[5], dim_len[5];   // dims 1..4: lowest physical bit and number of bits of the run
+    int n_ops = 1;                // operations per tile: box positions beyond the four run dims are enumerated
+    uint32_t op_goff[kStreamMaxOps];  // physical amplitude offset of operation i
+    uint32_t box_bytes = 0;       // bytes per operation (its shared-memory destination is i * box_bytes)
+    uint16_t slot(int pos) const {    // shared-memory slot offset of tile position pos
+        const int bp = box_of[pos];
+        return (uint16_t)((1u << bp) ^ ((bp >= 3 && bp <= 5) ? (1u << (bp - 3)) : 0u));
+    }
+};
 
 struct Pass {
     uint64_t support_in = ~0ull;  // qubits some earlier gate has mixed, for a circuit started from |0...0> (tensor-core
@@ -202,6 +244,12 @@ struct Pass {
     std::vector<WinOp> wops;
     int n_gate_windows = 0;       // windows [0, n_gate_windows) change the state, the rest only read it
     std::vector<EUnit> eterms;    // data of the expectation-window ops (see W_EXPC / W_EXPD)
+    // streaming kernel (plan_stream_layouts): load layouts for a dense input and for an input with the known zeros of
+    // support_in, store layout; lane_vec = bank-swizzle vector per tile position of the layout the expectation windows read
+    bool stream = false;
+    bool sparse_differs = false;  // lin_sparse is a proper sub-box of the tile
+    StreamLayout lin_dense, lin_sparse, lout;
+    uint8_t lane_vec[16] = {1, 2, 4, 3, 5, 6, 7, 1, 2, 4, 3, 5, 6, 0, 0, 0};
 };
 
 struct PlanOptions {
@@ -241,6 +289,17 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
 // registers; groups that flip more than kRegBits qubits are returned in `leftover` (shared-memory fallback).
 void append_expectation_windows(Pass& p, const std::vector<ExpGroupIn>& groups, std::vector<int>* leftover);
 bool mask_is_local(const Pass& p, uint64_t mask);
+// Hamiltonian groups -> passes: groups whose flips are local to the last gate pass are evaluated there, the rest in
+// expectation-only passes (plan_cover) appended to `passes`; the expectation windows of every pass are appended.
+// stream: choose streaming layouts (plan_stream_layouts) for the tensor-core passes first.
+struct ExpPlan {
+    int n_gate_passes = 0;
+    std::vector<std::vector<int>> groups_of_pass;   // indices into `groups`
+    std::vector<std::vector<int>> wide_of_pass;     // of those, the groups left to the shared-memory fallback
+    std::string err;
+};
+ExpPlan attach_expectation(std::vector<Pass>& passes, const std::vector<ExpGroupIn>& groups, const PlanOptions& opt, int n,
+                           bool in_pass_pref, bool stream);
 uint32_t mask_to_local(const Pass& p, uint64_t mask);
 
 }  // namespace tq

@@ -215,7 +215,7 @@ class Simulator:
         c = (ctypes.c_int64 * 8)()
         self._check(self._L.tq_plan_counts(self._h, which, c))
         keys = ("tensor_core_blocks", "lane_register_swaps", "gate_windows", "expectation_windows",
-                "fp64_pipe_windows", "direct_expectation_passes", "tensor_core_block_tiles")
+                "fp64_pipe_windows", "direct_expectation_passes", "tensor_core_block_tiles", "stream_launches")
         return dict(zip(keys, [int(v) for v in c]))
 
     @property
@@ -277,6 +277,16 @@ def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=(), w
             local = [int(v) for v in tok[2].split("=")[1].split(",") if v != ""]
             support = int(tok[3].split("=")[1]) if len(tok) > 3 else (1 << 64) - 1
             passes.append({"lead": lead, "local": local, "support": support, "ops": [], "windows": []})
+        elif tok[0] == "STREAMABLE":
+            passes[-1]["stream"] = tok[1] == "1"
+        elif tok[0] == "STREAM":
+            kv = dict(t.split("=") for t in tok[2:])
+            passes[-1].setdefault("layouts", {})[tok[1]] = {
+                "live": int(kv["live"]), "ops": int(kv["ops"]), "box_bytes": int(kv["box_bytes"]),
+                "box_of": [int(v) for v in kv["box_of"].split(",")],
+                "dims": [tuple(int(x) for x in d.split(":")) for d in kv["dims"].split(",") if d]}
+        elif tok[0] == "STREAMCHECK":
+            passes[-1]["streamcheck"] = " ".join(tok[1:])
         elif tok[0] == "OP":
             passes[-1]["ops"].append((int(tok[1]), int(tok[2]), int(tok[3]), int(tok[4]), int(tok[5]), float(tok[6])))
         elif tok[0] == "WIN":

@@ -1,0 +1,119 @@
+"""Streaming pass kernel (tq_stream.cu: persistent CTAs, TMA tile I/O, -m gpu): multi-tile problems against the oracle, with
+the kernel on and off.  Tolerances: 1e-10 Ha on energies (BASELINE.json north_star), 1e-12 on amplitudes."""
+import numpy as np
+import pytest
+
+from tensorrl_qas_b200 import Simulator, loaders
+from tensorrl_qas_b200.circuit import GateList, brickwork_circuit, parameter_batch, synthetic_circuit
+
+pytestmark = pytest.mark.gpu
+
+
+def heisenberg(n):
+    paulis, w = loaders.heisenberg_terms(n)
+    x, z = loaders.pauli_masks(paulis, n)
+    return x, z, w
+
+
+def make_sim(n, gl, ham, monkeypatch, stream, init=None):
+    monkeypatch.setenv("TQ_STREAM", "1" if stream else "0")
+    monkeypatch.setenv("TQ_VALIDATE_PLAN", "1")
+    sim = Simulator(n, 0)
+    sim.set_pauli_hamiltonian(*ham)
+    if init is not None:
+        sim.set_init_state(init)
+    sim.set_circuit(gl)
+    return sim
+
+
+@pytest.mark.parametrize("n,gates,seed,brick,batch", [(13, 150, 1, False, 5), (14, 300, 2, False, 3), (14, 120, 3, True, 4),
+                                                        (16, 400, 4, False, 2), (17, 420, 6, True, 2), (15, 40, 7, False, 3),
+                                                        (13, 12, 8, False, 2)])
+def test_stream_energies_match_oracle(built_lib, oracle, monkeypatch, n, gates, seed, brick, batch):
+    gl = brickwork_circuit(n, 21, max(0, gates - 21 * (n - 1)), seed) if brick else synthetic_circuit(n, gates, seed)
+    ham = heisenberg(n)
+    p = parameter_batch(gl, batch)
+    want = oracle.energies(gl, p, pauli=ham)
+    sim = make_sim(n, gl, ham, monkeypatch, True)
+    got = sim.energies(p)
+    again = sim.energies(p)
+    launches = sim.plan_counts()["stream_launches"]
+    sim.close()
+    ref = make_sim(n, gl, ham, monkeypatch, False)
+    off = ref.energies(p)
+    assert ref.plan_counts()["stream_launches"] == 0
+    ref.close()
+    assert launches > 0, "the streaming kernel did not run"
+    assert np.abs(got - want).max() < 1e-10
+    assert np.abs(off - want).max() < 1e-10
+    assert np.array_equal(got, again)   # deterministic
+
+
+@pytest.mark.parametrize("n,gates,seed", [(13, 200, 11), (14, 260, 12), (15, 90, 13)])
+def test_stream_states_match_oracle(built_lib, oracle, monkeypatch, n, gates, seed):
+    gl = synthetic_circuit(n, gates, seed)
+    p = parameter_batch(gl, 3)
+    sim = make_sim(n, gl, heisenberg(n), monkeypatch, True)
+    got = sim.states(p)
+    launches = sim.plan_counts()["stream_launches"]
+    sim.close()
+    assert launches > 0
+    for b in range(3):
+        assert np.abs(got[b] - oracle.state(gl, p[b])).max() < 1e-12
+
+
+def test_stream_loaded_initial_state(built_lib, oracle, monkeypatch):
+    """A loaded initial state (the fixed environments' TN state) switches the known-zero skipping off: dense loads."""
+    n = 14
+    rng = np.random.default_rng(5)
+    psi = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    psi /= np.linalg.norm(psi)
+    gl = synthetic_circuit(n, 220, 21)
+    ham = heisenberg(n)
+    p = parameter_batch(gl, 3)
+    sim = make_sim(n, gl, ham, monkeypatch, True, init=psi)
+    got = sim.energies(p)
+    st = sim.states(p[:1])[0]
+    launches = sim.plan_counts()["stream_launches"]
+    sim.close()
+    assert launches > 0
+    assert np.abs(got - oracle.energies(gl, p, pauli=ham, init=psi)).max() < 1e-10
+    assert np.abs(st - oracle.state(gl, p[0], init=psi)).max() < 1e-12
+
+
+def test_stream_untouched_qubits(built_lib, oracle, monkeypatch):
+    """Gates on a few qubits only: most tiles are known zeros (skipped, or zero-filled in the last gate pass)."""
+    n = 15
+    gl = GateList(n)
+    rng = np.random.default_rng(3)
+    for rep in range(3):
+        for q in (0, 1, 5, 13, 14):
+            gl.add_rotation(int(rng.integers(0, 3)), q, float(rng.uniform(-1, 1)))
+        gl.add_cnot(0, 13)
+        gl.add_cnot(14, 5)
+        gl.add_cnot(1, 0)
+    ham = heisenberg(n)
+    p = np.zeros((2, 1))
+    sim = make_sim(n, gl, ham, monkeypatch, True)
+    got = sim.energies(p)
+    st = sim.states(p[:1])[0]
+    sim.close()
+    assert np.abs(got - oracle.energies(gl, p, pauli=ham)).max() < 1e-10
+    assert np.abs(st - oracle.state(gl, p[0])).max() < 1e-12
+
+
+def test_stream_bench_shape_matches_oracle_sample(built_lib, oracle, monkeypatch):
+    """The bench workload (C5, 20 qubits): two elements against the oracle, the whole batch against the kernel switched off."""
+    import bench
+    gl, ham, parameter_batch_ = bench.workload()
+    p = parameter_batch_(gl, 8)
+    sim = make_sim(20, gl, ham, monkeypatch, True)
+    got = sim.energies(p)
+    launches = sim.plan_counts()["stream_launches"]
+    sim.close()
+    ref = make_sim(20, gl, ham, monkeypatch, False)
+    off = ref.energies(p)
+    ref.close()
+    assert launches >= 3
+    assert np.abs(got[:2] - oracle.energies(gl, p[:2], pauli=ham)).max() < 1e-10
+    assert np.abs(got - off).max() < 1e-11

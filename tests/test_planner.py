@@ -195,3 +195,25 @@ def test_lone_diagonal_gates_never_sit_on_lane_bits(built_lib, oracle, seed):
     init = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
     want = oracle.state(gl, params, init=init)
     assert np.abs(run_plan_windows(plan, n, params, init=init) - want).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,gates,seed,brick", [(13, 200, 41, False), (14, 400, 42, False), (16, 300, 43, False),
+                                                 (20, 440, 5, True), (18, 600, 44, False), (15, 60, 45, False),
+                                                 (22, 500, 46, False), (17, 300, 47, True)])
+def test_streaming_layouts_validate(built_lib, n, gates, seed, brick):
+    """Streaming kernel (tq_stream.cu): every multi-tile tensor-core pass gets TMA box orders whose dims reproduce the tile's
+    physical offsets, and every window's resolved slot offsets address distinct slots inside the box (validate_stream)."""
+    gl = brickwork_circuit(n, 21, gates - 21 * (n - 1), seed) if brick else synthetic_circuit(n, gates, seed)
+    masks = [(1 << q) | (1 << (q + 1)) for q in range(n - 1)]
+    passes = plan_dump(gl, 16, 12, 3, cover_masks=masks)
+    assert len(passes) > 1
+    streamed = [p for p in passes if p.get("stream")]
+    assert streamed, "no pass was given a streaming layout"
+    for p in streamed:
+        assert p["streamcheck"] == "ok", p["streamcheck"]
+        for lay in p["layouts"].values():
+            assert lay["box_of"][:3] == [0, 1, 2] and 1 <= lay["ops"] <= 32
+            assert lay["ops"] * lay["box_bytes"] == 16 << lay["live"]
+    # the expectation windows that follow gate windows read the store layout: the plan must still cover every mask
+    codes = [o[0] for p in passes for w in p["windows"] for o in w["ops"]]
+    assert codes.count(20) >= len(masks)   # one M_EXPC class (or more) per flip mask
