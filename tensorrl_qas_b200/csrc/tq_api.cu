@@ -43,8 +43,8 @@ struct DevPass {
     bool sparse_ok = false;  // the known-zero bookkeeping of run_plan matches what the planner assumed (support_in)
     uint64_t support_in = ~0ull;
     StreamLayout lin_dense, lin_sparse, lout;
-    const MmaWindowDev* swin_dense = nullptr;
-    const MmaWindowDev* swin_sparse = nullptr;
+    const StreamWindowDev* swin_dense = nullptr;
+    const StreamWindowDev* swin_sparse = nullptr;
 };
 
 struct Plan {
@@ -71,6 +71,7 @@ struct tq_context {
     bool direct_kernel = true;  // TQ_DIRECT_KERNEL: the streaming expectation-only passes of a plan in one persistent launch
     bool sparse_init = true;    // TQ_SPARSE_INIT: skip the known zeros of states grown from |0...0> (tensor-core passes)
     bool stream_kernel = true;  // TQ_STREAM: multi-tile tensor-core passes run on the persistent TMA kernel (tq_stream.cu)
+    bool stream_expect = false; // TQ_STREAM=2: the expectation-only passes as well (else expect_direct_kernel)
     int64_t stream_launches = 0;
     bool spin_wait = true;      // TQ_SPIN: poll the pinned result slots instead of cudaStreamSynchronize (latency path)
     bool zero_copy = true;      // TQ_ZERO_COPY: small host-buffer calls read angles / write energies in pinned host memory
@@ -286,6 +287,7 @@ int compile_plan(tq_handle h, int which) {
 
     opt.fuse = env_int("TQ_FUSE", 1) != 0;
     opt.mma = env_int("TQ_MMA", 1) != 0;
+    opt.dead_budget = env_int("TQ_DEAD_BUDGET", 5);
     CompiledCircuit cc = which == 1 ? plan_density(n, h->gates, opt, &perr)
                                     : plan_statevector(n, h->gates, opt, cover, &perr);
     if (!perr.empty()) return fail(h, TQ_EINVAL, perr);
@@ -346,13 +348,13 @@ int compile_plan(tq_handle h, int which) {
             for (const MmaWindow& w : p.mwindows) dev.push_back(resolve_window(w, p));
             offs[i].windows = append(dev.data(), dev.size() * sizeof(MmaWindowDev));
             if (p.stream) {
-                std::vector<MmaWindowDev> sd, ss;
+                std::vector<StreamWindowDev> sd, ss;
                 for (int wi = 0; wi < (int)p.mwindows.size(); ++wi) {
-                    sd.push_back(resolve_window_stream(p, wi, false));
-                    ss.push_back(resolve_window_stream(p, wi, true));
+                    sd.push_back(stream_window_dev(p, wi, false));
+                    ss.push_back(stream_window_dev(p, wi, true));
                 }
-                offs[i].swin_dense = append(sd.data(), sd.size() * sizeof(MmaWindowDev));
-                offs[i].swin_sparse = append(ss.data(), ss.size() * sizeof(MmaWindowDev));
+                offs[i].swin_dense = append(sd.data(), sd.size() * sizeof(StreamWindowDev));
+                offs[i].swin_sparse = append(ss.data(), ss.size() * sizeof(StreamWindowDev));
             }
         } else {
             offs[i].windows = append(p.windows.data(), p.windows.size() * sizeof(Window));
@@ -410,8 +412,8 @@ int compile_plan(tq_handle h, int which) {
             dp.lin_dense = passes[i].lin_dense;
             dp.lin_sparse = passes[i].lin_sparse;
             dp.lout = passes[i].lout;
-            dp.swin_dense = (const MmaWindowDev*)(base + offs[i].swin_dense);
-            dp.swin_sparse = (const MmaWindowDev*)(base + offs[i].swin_sparse);
+            dp.swin_dense = (const StreamWindowDev*)(base + offs[i].swin_dense);
+            dp.swin_sparse = (const StreamWindowDev*)(base + offs[i].swin_sparse);
         }
         for (const DevOp& d : passes[i].ops) {
             const std::vector<int>& loc = passes[i].local;
@@ -728,7 +730,8 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
             }
             // ---- streaming kernel (persistent CTAs, TMA tile I/O) for multi-tile tensor-core passes ----
             const bool sparse_in = pp.in_mask != ~0ull;
-            const bool use_stream = h->stream_kernel && dp.stream && pp.mwindows && !xchg && !fuse_prep && pp.src_mode != 0 &&
+            const bool use_stream = h->stream_kernel && (dp.gate_pass || h->stream_expect) && dp.stream && pp.mwindows && !xchg &&
+                                    !fuse_prep && pp.src_mode != 0 &&
                                     pp.n_groups == 0 && pp.exp_mode != 2 && (!sparse_in || dp.sparse_ok) &&
                                     ((uint64_t)bc << (plan.nbits + 1)) <= (1ull << 31);
             if (use_stream) {
@@ -741,8 +744,9 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 if (fits) {
                     StreamSub& S = sp.sub[sp.n_sub];
                     S.pp = pp;
-                    S.pp.mwindows = sparse_in ? dp.swin_sparse : dp.swin_dense;
+                    S.swindows = sparse_in ? dp.swin_sparse : dp.swin_dense;
                     S.pp.direct = 0;
+                    S.has_gates = (dp.gate_pass && !dp.no_ops) ? 1 : 0;
                     const StreamLayout& lin = sparse_in ? dp.lin_sparse : dp.lin_dense;
                     fill_tma(S.in, lin);
                     S.out.n_ops = 0;
@@ -953,6 +957,7 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->sparse_init = env_int("TQ_SPARSE_INIT", 1) != 0;
     h->direct_kernel = env_int("TQ_DIRECT_KERNEL", 1) != 0;
     h->stream_kernel = env_int("TQ_STREAM", 1) != 0;
+    h->stream_expect = env_int("TQ_STREAM", 1) >= 2;
     h->direct_ctas_per_sm = std::max(1, std::min(8, env_int("TQ_DIRECT_CTAS", 2)));
     h->n_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -1357,6 +1362,7 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
     std::string err;
     opt.fuse = env_int("TQ_FUSE", 1) != 0;
     opt.mma = env_int("TQ_MMA", 1) != 0;
+    opt.dead_budget = env_int("TQ_DEAD_BUDGET", 5);
     CompiledCircuit cc = which == 1 ? plan_density(n_qubits, gates, opt, &err)
                                     : plan_statevector(n_qubits, gates, opt, cover, &err);
     std::string out;

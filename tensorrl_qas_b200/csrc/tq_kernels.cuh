@@ -107,9 +107,11 @@ struct StreamTma {                    // one direction of one sub-pass (tq_plan.
     uint32_t op_goff[kStreamMaxOps];  // physical amplitude offset of operation i inside the tile
 };
 struct StreamSub {
-    PassParams pp;             // geometry, windows (resolve_window_stream), ops, eterms, mats, partial: as for the pass kernels
+    PassParams pp;             // geometry, ops, eterms, mats, partial: as for the pass kernels (its window pointers are unused)
+    const StreamWindowDev* swindows;   // the pass's windows resolved for the streaming layouts (stream_window_dev)
     StreamTma in, out;
     uint64_t in_elem_stride;   // amplitudes between consecutive elements of the source (0: one shared initial vector)
+    int has_gates;             // the sub-pass has gate windows (block matrices are staged per element)
 };
 struct alignas(64) StreamParams {
     CUtensorMap map_in[kStreamMaxSub];   // rank-5 views over doubles; dim 0 = 16 doubles whose coordinate is the tile's base

@@ -105,23 +105,26 @@ __device__ __forceinline__ void m_cx_out(Regs& a, bool pred) {
 }
 // expectation class on registers: every lane contributes the products of ITS component; the two lanes of a pair are
 // summed by the CTA-wide reduction.  Im(conj(w) v) needs the other component of v: one shuffle per register pair.
+// a product the compiler must leave where it is: the state registers do not change between the expectation ops of a
+// window, so every a[r] * a[r'] is loop-invariant there, and hoisting them all out of the op loop (31 flip patterns x 16
+// pairs) costs far more registers than a thread has
+__device__ __forceinline__ double mul_here(double x, double y) {
+    double p;
+    asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(p) : "d"(x), "d"(y));
+    return p;
+}
 template <int XR>
 __device__ __forceinline__ double m_expc(const Regs& a, const double* __restrict__ cA, const double* __restrict__ cB,
                                          bool im_lane) {
     double s[4] = {0.0, 0.0, 0.0, 0.0};   // four independent accumulation chains
-    double c[NR / 2];
-#pragma unroll
-    for (int i = 0; i < NR / 2; i += 2) {   // all sixteen coefficients up front (eight 16-byte shared-memory loads)
-        const double2 t = *reinterpret_cast<const double2*>(cA + i);
-        c[i] = t.x;
-        c[i + 1] = t.y;
-    }
     {
         int q = 0;
+        double2 c = make_double2(0.0, 0.0);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             if ((r ^ XR) > r) {
-                s[q & 3] = fma(c[q], a[r ^ XR] * a[r], s[q & 3]);
+                if ((q & 1) == 0) c = *reinterpret_cast<const double2*>(cA + q);   // coefficients two at a time
+                s[q & 3] = fma((q & 1) ? c.y : c.x, mul_here(a[r ^ XR], a[r]), s[q & 3]);
                 ++q;
             }
         }
@@ -132,7 +135,7 @@ __device__ __forceinline__ double m_expc(const Regs& a, const double* __restrict
         for (int r = 0; r < NR; ++r) {
             if ((r ^ XR) > r) {
                 const double vp = __shfl_xor_sync(kFull, a[r], 1);
-                const double im = im_lane ? -(a[r ^ XR] * vp) : a[r ^ XR] * vp;   // w.x v.y  |  -w.y v.x
+                const double im = im_lane ? -mul_here(a[r ^ XR], vp) : mul_here(a[r ^ XR], vp);   // w.x v.y  |  -w.y v.x
                 s[q & 3] = fma(-__ldg(cB + q), im, s[q & 3]);
                 ++q;
             }

@@ -212,6 +212,15 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
         uint64_t L = (nbits <= k) ? all : (bit(std::min(opt.low_bits, k)) - 1);
         uint64_t blocked_mix = 0, blocked_diag = 0;
         std::vector<int> mine, deferred;
+        // Tensor-core plans of a run from |0...0>: a window keeps six qubits on registers / QL and spreads the other six
+        // tile positions over lanes and warps.  Where those are qubits nothing has populated yet, most warps of a CTA idle
+        // (a brick chain growing into eight fresh qubits kept one warp of eight busy).  Once the populated part of the
+        // state spans many tiles, a pass therefore takes at most opt.dead_budget still-empty qubits (they fit its first
+        // window) and fills up with populated ones: more passes, but the early ones only stream the small populated part.
+        int dead_budget = 64;
+        if (mma && opt.dead_budget > 0 && nbits > k && support != ~0ull && __builtin_popcountll(support & all) >= k - 1 &&
+            __builtin_popcountll(L & ~support) <= opt.dead_budget)
+            dead_budget = std::max(opt.dead_budget, __builtin_popcountll(L & ~support) + 2);   // (any block still fits)
         for (int idx : remaining) {
             const AOp& a = ops[idx];
             // commutes with every deferred block iff on each shared bit both act diagonally
@@ -219,7 +228,9 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
             bool take = !clash;
             if (take) {
                 const uint64_t need = a.mix & ~L;
-                if (__builtin_popcountll(L) + __builtin_popcountll(need) <= k) L |= need;
+                if (__builtin_popcountll(L) + __builtin_popcountll(need) <= k &&
+                    __builtin_popcountll((L | need) & ~support) <= dead_budget)
+                    L |= need;
                 else take = false;
             }
             if (take) mine.push_back(idx);
@@ -233,6 +244,9 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
             for (uint64_t m : cover_masks)
                 if (__builtin_popcountll(L | m) <= k) L |= m;
         }
+        if (dead_budget < 64)   // populated qubits first
+            for (int q = 0; q < nbits && __builtin_popcountll(L) < k; ++q)
+                if ((support >> q) & 1ull) L |= bit(q);
         for (int q = 0; q < nbits && __builtin_popcountll(L) < k; ++q) L |= bit(q);
         Pass p;
         finish_pass(p, nbits, L);
@@ -1361,6 +1375,32 @@ MmaWindowDev resolve_window_stream(const Pass& p, int widx, bool sparse) {
             if (!((live >> w.wpos[i]) & 1)) d.dead_wbits |= (uint8_t)(1u << i);
     }
     return d;
+}
+
+StreamWindowDev stream_window_dev(const Pass& p, int widx, bool sparse) {
+    const MmaWindowDev d = resolve_window_stream(p, widx, sparse);
+    StreamWindowDev s{};
+    for (int r = 0; r < kMmaRegBits; ++r) { s.rofs[r] = (uint16_t)(d.rslot[r] << 4); s.rofs_out[r] = (uint16_t)(d.rslot_out[r] << 4); }
+    s.qofs = (uint16_t)(d.qslot << 4);
+    s.qofs_out = (uint16_t)(d.qslot_out << 4);
+    for (int i = 0; i < 3; ++i) {
+        s.gofs[i] = (uint16_t)(d.gslot[i] << 4);
+        s.wofs[i] = (uint16_t)(d.wslot[i] << 4);
+        s.gofs_out[i] = (uint16_t)(d.gslot_out[i] << 4);
+        s.wofs_out[i] = (uint16_t)(d.wslot_out[i] << 4);
+        s.gmask[i] = 1u << d.gphys[i];
+        s.wmask[i] = 1u << d.wphys[i];
+    }
+    s.qlmask = 1u << d.qlphys;
+    for (int r = 0; r < kMmaRegBits; ++r) s.rmask[r] = 1u << d.rphys[r];
+    s.op_begin = d.op_begin;
+    s.op_end = d.op_end;
+    s.flags = d.flags;
+    s.flags2 = d.flags2;
+    s.dead_wbits = d.dead_wbits;
+    s.dead_r = d.dead_r;
+    s.dead_l = d.dead_l;
+    return s;
 }
 
 std::string validate_stream(const Pass& p) {

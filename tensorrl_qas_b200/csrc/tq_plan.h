@@ -192,8 +192,23 @@ constexpr int kWinU4 = sizeof(MmaWindowDev) / 16;   // 16-byte units per header
 constexpr int kWin2StoreAll = 1;    // entry and exit layouts differ: every thread (idle warps too) writes its registers back
 constexpr int kWin2DeadEntry = 2;   // honour dead_r / dead_l / dead_wbits on entry (compact load layout)
 MmaWindowDev resolve_window(const MmaWindow& w, const struct Pass& p);
+// What the streaming kernel reads: byte offsets into the tile buffer (slot << 4) and the physical index bit of every
+// thread bit as a mask, so that a thread's layout costs a handful of three-input logic ops.
+struct StreamWindowDev {   // 112 bytes
+    uint16_t rofs[kMmaRegBits], rofs_out[kMmaRegBits];
+    uint16_t qofs, qofs_out;
+    uint16_t gofs[3], wofs[3];
+    uint16_t gofs_out[3], wofs_out[3];
+    uint32_t gmask[3], wmask[3], qlmask;   // 1 << physical qubit of lane bits 2..4, of the warp bits, of QL (on entry)
+    int32_t op_begin, op_end;
+    uint8_t flags, flags2, dead_wbits, dead_r, dead_l, pad[3];
+    uint32_t rmask[kMmaRegBits];           // 1 << physical qubit of the register bits (on entry)
+};
+static_assert(sizeof(StreamWindowDev) == 112, "StreamWindowDev layout");
+constexpr int kSWinU4 = sizeof(StreamWindowDev) / 16;
 // Streaming variant: window widx of a pass with p.stream set; sparse = the input has the known zeros of p.support_in
 MmaWindowDev resolve_window_stream(const struct Pass& p, int widx, bool sparse);
+StreamWindowDev stream_window_dev(const struct Pass& p, int widx, bool sparse);
 // Choose the layouts of a pass for the streaming kernel (sets p.stream; false = the pass stays on tile_pass_mma_kernel).
 // Gate passes: call after schedule_windows_mma and BEFORE append_expectation_windows_mma (the expectation windows then
 // pick their lanes for the store layout); expectation-only passes: call after their windows exist.
@@ -258,6 +273,8 @@ struct PlanOptions {
     bool trajectory = false;  // TQ_DEPOL* become per-element sampled Pauli gates (else skipped on the pure path)
     bool fuse = true;     // false: every gate is its own block (debugging / A-B comparisons)
     bool mma = true;      // pure-state passes with >= 2^9-amplitude tiles use DMMA windows
+    int dead_budget = 5;  // still-empty qubits a tensor-core pass may take once the populated state spans many tiles (pack();
+                          // 0 = no limit)
 };
 
 struct CompiledCircuit {

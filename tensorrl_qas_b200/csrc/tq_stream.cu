@@ -6,15 +6,18 @@
 //     no thread spends registers or issue slots on tile I/O;
 //   * a CTA walks a list of jobs (tile, sub-pass).  Job j is computed by group j % 2 in buffer j % 3, so while the two groups
 //     run their windows on two buffers the third one is in flight: the load of job j + 3 is issued as soon as job j has
-//     released its buffer (windows done, TMA store drained), about half a job ahead of its use;
+//     released its buffer (windows done, TMA store drained), about half a job ahead of its use.  The thread that issues
+//     the load also leaves the job's descriptor (tile base, element, flags) next to the barrier;
 //   * window headers / op words / expectation tables are staged once per CTA, block matrices once per (group, element);
 //   * the TMA engine writes a box in box order with the hardware 128-byte swizzle; the planner (plan_stream_layouts) picks
 //     the box order so that the first window's entry and the last gate window's exit are bank-conflict free in THAT
-//     layout, all exchanges in between use the kSwizzleVec layout -- the kernel only sees resolved slot offsets;
+//     layout, all exchanges in between use the kSwizzleVec layout -- the kernel only sees resolved byte offsets;
 //   * known zeros (states grown from |0...0>): only the populated sub-box of a tile is loaded (compact layout), registers
 //     and threads on unpopulated qubits start from 0.0 instead of a load.
 // Replaces what qulacs does at environments/VQAs/VQE_qulacs.py:83-85 for problems larger than one tile.
 #include <cuda.h>
+
+#include <type_traits>
 
 #include "tq_kernels.cuh"
 
@@ -28,6 +31,27 @@ constexpr int kGroups = 2;
 constexpr int kBufs = 3;
 constexpr int kTileBytes = 16 << kStreamTileBits;
 constexpr int kOpSlots = kStreamOpSlots, kWinSlots = kStreamWinSlots;
+
+struct JobDesc {   // written by the thread that issues the job's load, read by the group that computes the job
+    uint32_t tile_base;   // the tile's fixed (non-local) index bits
+    uint32_t elem;        // batch element
+    uint32_t tile;        // tile number inside the element (partial-sum slot)
+    uint32_t flags;       // bit 0: the whole tile is known zeros (nothing was loaded); bits 8..: sub-pass
+};
+
+struct SubInfo {   // per-sub-pass scalars, staged in shared memory: the loops index them with a run-time sub-pass number
+                   // (a run-time index into the kernel parameters would make ptxas copy them to local memory)
+    uint32_t n_nl;
+    uint8_t nonlocal[32];
+    uint32_t n_ops, box_bytes, tile_bytes;
+    uint32_t op_goff[kStreamMaxOps];
+    uint64_t in_elem_stride;
+    const EUnit* eterms;
+    double* partial;
+    int partial_ld, partial_off;
+    int n_gate_windows, n_windows;
+    int wbase, obase;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -55,24 +79,123 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tma_load(void* dst, const CUtensorMap* map, uint64_t* bar, int c0) {
+__device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0) {
     asm volatile(
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %4, %4, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(0)
+        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(0)
         : "memory");
 }
-__device__ __forceinline__ void tma_store(const CUtensorMap* map, const void* src, int c0) {
+__device__ __forceinline__ void tma_store(const CUtensorMap* map, uint32_t src, int c0) {
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %3, %3, %3}], [%1];" ::"l"(map),
-                 "r"(smem_u32(src)), "r"(c0), "r"(0)
+                 "r"(src), "r"(c0), "r"(0)
                  : "memory");
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void group_sync(int grp) {
-    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kGroupThreads) : "memory");
+template <int GRP>
+__device__ __forceinline__ void group_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(GRP + 1), "n"(kGroupThreads) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
+// real-coefficient expectation class (tq_mma_dev.cuh m_expc without the imaginary part): coefficients two at a time, so
+// that the register budget of the caller (32 doubles of state) is not exceeded
+template <int XR>
+__device__ __forceinline__ double s_expc(const Regs& a, const double2* __restrict__ cA) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};   // four independent accumulation chains
+    int q = 0;
+    double2 c = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        if ((r ^ XR) > r) {
+            if ((q & 1) == 0) c = cA[q >> 1];
+            s[q & 3] = fma((q & 1) ? c.y : c.x, mul_here(a[r ^ XR], a[r]), s[q & 3]);
+            ++q;
+        }
+    }
+    return (s[0] + s[1]) + (s[2] + s[3]);
+}
+__device__ __forceinline__ double exec_s_expc(const Regs& a, int xr, const double2* cA) {
+#define TQ_XC(V) case V: return s_expc<V>(a, cA);
+    switch (xr) {
+        TQ_XC(1) TQ_XC(2) TQ_XC(3) TQ_XC(4) TQ_XC(5) TQ_XC(6) TQ_XC(7) TQ_XC(8) TQ_XC(9) TQ_XC(10) TQ_XC(11)
+        TQ_XC(12) TQ_XC(13) TQ_XC(14) TQ_XC(15) TQ_XC(16) TQ_XC(17) TQ_XC(18) TQ_XC(19) TQ_XC(20) TQ_XC(21)
+        TQ_XC(22) TQ_XC(23) TQ_XC(24) TQ_XC(25) TQ_XC(26) TQ_XC(27) TQ_XC(28) TQ_XC(29) TQ_XC(30)
+    default: return s_expc<31>(a, cA);
+    }
+#undef TQ_XC
 }
 
+// ---- rare expectation ops, kept out of line and off the register file: they re-read the tile from shared memory --------
+// byte offset / physical index bits of register r of a window
+__device__ __forceinline__ uint32_t reg_ofs(const StreamWindowDev* hdr, int r) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < kMmaRegBits; ++i)
+        if ((r >> i) & 1) x ^= hdr->rofs[i];
+    return x;
+}
+__device__ __forceinline__ uint32_t reg_bits(const StreamWindowDev* hdr, int r) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < kMmaRegBits; ++i)
+        if ((r >> i) & 1) x |= hdr->rmask[i];
+    return x;
+}
+// M_EXPD: diagonal terms whose Z strings reach outside the window (tq_plan.h): head = 16 class counts over register bits
+// 0..3, terms = (Z mask without those four bits, weight) sorted by class
+__device__ __forceinline__ double slow_expd(uint32_t tile_u32, uint32_t base, const StreamWindowDev* hdr, uint32_t ctx,
+                                            const double2* head, const double2* __restrict__ terms) {
+    const unsigned short* cnt = reinterpret_cast<const unsigned short*>(head);
+    double total = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < NR; ++r) {
+        const double v = lds_f64(tile_u32 + (base ^ reg_ofs(hdr, r)));
+        const uint32_t idx = ctx | reg_bits(hdr, r);
+        double sgn = 0.0;
+        int t = 0;
+#pragma unroll 1
+        for (int zr = 0; zr < 16; ++zr) {
+            const uint32_t zin = reg_bits(hdr, zr);
+            const int c = cnt[zr];
+            for (int i = 0; i < c; ++i) {
+                const double2 term = __ldg(terms + t + i);
+                const uint32_t z = (uint32_t)__double_as_longlong(term.x) | zin;
+                sgn += (__popc(idx & z) & 1) ? -term.y : term.y;
+            }
+            t += c;
+        }
+        total = fma(v * v, sgn, total);
+    }
+    return total;
+}
+// M_EXPC with imaginary class coefficients (terms with an odd number of Y factors): the partner component of an amplitude
+// sits 8 bytes away in shared memory
+__device__ __forceinline__ double slow_expc_imag(uint32_t tile_u32, uint32_t base, const StreamWindowDev* hdr, int xr,
+                                                 const double* cA, const double* __restrict__ cB, bool im_lane) {
+    double sum = 0.0;
+    int q = 0;
+#pragma unroll 1
+    for (int r = 0; r < NR; ++r) {
+        if ((r ^ xr) < r) continue;
+        const double v = lds_f64(tile_u32 + (base ^ reg_ofs(hdr, r))), vp = lds_f64(tile_u32 + ((base ^ reg_ofs(hdr, r)) ^ 8u));
+        const double w = lds_f64(tile_u32 + (base ^ reg_ofs(hdr, r ^ xr)));
+        sum = fma(cA[q], w * v, sum);
+        const double im = im_lane ? -(w * vp) : w * vp;   // w.x v.y  |  -w.y v.x
+        sum = fma(-__ldg(cB + q), im, sum);
+        ++q;
+    }
+    return sum;
+}
+
+// MODE 0: gate pass, 1: gate pass with expectation windows, 2: expectation-only sub-passes
+template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __grid_constant__ StreamParams sp) {
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment: the hardware swizzle pattern is a function of the shared-memory address
@@ -80,59 +203,71 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     unsigned char* tiles = base;
     double2* s_mat_all = reinterpret_cast<double2*>(base + kBufs * kTileBytes);
     WinOp* s_wops = reinterpret_cast<WinOp*>(s_mat_all + kGroups * kOpSlots * kMatStride);
-    MmaWindowDev* s_win = reinterpret_cast<MmaWindowDev*>(s_wops + kOpSlots);
+    StreamWindowDev* s_win = reinterpret_cast<StreamWindowDev*>(s_wops + kOpSlots);
     double* s_red_all = reinterpret_cast<double*>(s_win + kWinSlots);          // kGroups x 2 x 8
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_red_all + kGroups * 16);   // kBufs (+1 pad)
-    int* s_wbase = reinterpret_cast<int*>(full_bar + kBufs + 1);               // kStreamMaxSub + 1
-    int* s_obase = s_wbase + kStreamMaxSub + 1;                                // kStreamMaxSub + 1
+    JobDesc* s_job = reinterpret_cast<JobDesc*>(full_bar + kBufs + 1);         // kBufs (+1 pad)
+    SubInfo* s_sub = reinterpret_cast<SubInfo*>(s_job + kBufs + 1);            // kStreamMaxSub
 
     const int tid = threadIdx.x;
-    const int grp = tid >> 8, gtid = tid & (kGroupThreads - 1);
-    const int lane = tid & 31, warp = gtid >> 5;
-    const int comp = lane & 1;
-    const bool l1 = (lane >> 1) & 1;
-    double2* s_mat = s_mat_all + grp * kOpSlots * kMatStride;
-    double* s_red = s_red_all + grp * 16;
-
-    // ---- stage every sub-pass once: window headers, op words, expectation tables ----
+    // ---- stage every sub-pass once: scalars, window headers, op words, expectation tables ----
     if (tid == 0) {
         int wb = 0, ob = 0;
-        for (int s = 0; s < sp.n_sub; ++s) {
-            s_wbase[s] = wb;
-            s_obase[s] = ob;
-            wb += sp.sub[s].pp.n_windows;
-            ob += sp.sub[s].pp.n_wops;
+#pragma unroll
+        for (int s = 0; s < kStreamMaxSub; ++s) {   // (static indices into the kernel parameters)
+            if (s < sp.n_sub) {
+                const StreamSub& S = sp.sub[s];
+                SubInfo& si = s_sub[s];
+                si.n_nl = (uint32_t)S.pp.n_nl;
+                for (int i = 0; i < 32; ++i) si.nonlocal[i] = S.pp.nonlocal[i];
+                si.n_ops = (uint32_t)S.in.n_ops;
+                si.box_bytes = S.in.box_bytes;
+                si.tile_bytes = S.in.tile_bytes;
+                for (int i = 0; i < kStreamMaxOps; ++i) si.op_goff[i] = S.in.op_goff[i];
+                si.in_elem_stride = S.in_elem_stride;
+                si.eterms = S.pp.eterms;
+                si.partial = S.pp.partial;
+                si.partial_ld = S.pp.partial_ld;
+                si.partial_off = S.pp.partial_off;
+                si.n_gate_windows = S.pp.n_gate_windows;
+                si.n_windows = S.pp.n_windows;
+                si.wbase = wb;
+                si.obase = ob;
+                wb += S.pp.n_windows;
+                ob += S.pp.n_wops;
+            }
         }
-        s_wbase[sp.n_sub] = wb;
-        s_obase[sp.n_sub] = ob;
         for (int i = 0; i < kBufs; ++i) mbar_init(full_bar + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
     __syncthreads();
-    for (int s = 0; s < sp.n_sub; ++s) {
+#pragma unroll
+    for (int s = 0; s < kStreamMaxSub; ++s) {
+        if (s >= sp.n_sub) break;
         const PassParams& p = sp.sub[s].pp;
-        for (int i = tid; i < kWinU4 * p.n_windows; i += kStreamThreads)
-            reinterpret_cast<uint4*>(s_win + s_wbase[s])[i] = __ldg(reinterpret_cast<const uint4*>(p.mwindows) + i);
+        const int wbase = s_sub[s].wbase, obase = s_sub[s].obase;
+        const uint4* wsrc = reinterpret_cast<const uint4*>(sp.sub[s].swindows);
+        for (int i = tid; i < kSWinU4 * p.n_windows; i += kStreamThreads)
+            reinterpret_cast<uint4*>(s_win + wbase)[i] = __ldg(wsrc + i);
         for (int i = tid; i < p.n_wops * kMatStride; i += kStreamThreads) {
             const int oi = i >> 4, e = i & 15;
             WinOp wo = p.wops[oi];
             const int code = wo.w0 & 0xff;
             if (e == 0) {
                 wo.w0 = (wo.w0 & ~0xffu) | (uint32_t)flat_code_mma(wo.w0);
-                s_wops[s_obase[s] + oi] = wo;
+                s_wops[obase + oi] = wo;
             }
             if (code >= M_EXPC && e < (code == M_EXPC ? 9 : code == M_EXPT ? 16 : 2)) {
                 const double2 v = reinterpret_cast<const double2*>(p.eterms)[(size_t)wo.t + e];
 #pragma unroll
-                for (int g = 0; g < kGroups; ++g) s_mat_all[(g * kOpSlots + s_obase[s] + oi) * kMatStride + e] = v;
+                for (int g = 0; g < kGroups; ++g) s_mat_all[(g * kOpSlots + obase + oi) * kMatStride + e] = v;
             }
         }
     }
     __syncthreads();
 
     // ---- this CTA's jobs ----
-    const int n_sub = sp.n_sub;
     const uint32_t n_cta = gridDim.x, cta = blockIdx.x;
     const uint32_t total_tiles = (uint32_t)sp.batch << sp.sub[0].pp.n_nl;
     uint32_t t_first, t_stride, n_jobs;
@@ -144,41 +279,58 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     } else {
         t_first = cta;
         t_stride = n_cta;
-        n_jobs = cta < total_tiles ? ((total_tiles - cta + n_cta - 1) / n_cta) * (uint32_t)n_sub : 0u;
+        n_jobs = cta < total_tiles ? ((total_tiles - cta + n_cta - 1) / n_cta) * (uint32_t)sp.n_sub : 0u;
     }
-    // job j -> (tile number t, sub-pass s); tile_base = the tile's fixed (non-local) index bits
-    auto job_tile = [&](uint32_t j, int& s) -> uint32_t {
-        if (n_sub == 1) { s = 0; return t_first + j * t_stride; }
-        s = (int)(j % (uint32_t)n_sub);
-        return t_first + (j / (uint32_t)n_sub) * t_stride;
-    };
-    auto tile_base_of = [&](const PassParams& p, uint32_t t) -> uint64_t {
-        const uint32_t tile = t & ((1u << p.n_nl) - 1u);
-        uint64_t tb = 0;
-        for (int i = 0; i < p.n_nl; ++i) tb |= (uint64_t)((tile >> i) & 1u) << p.nonlocal[i];
-        return tb;
-    };
-    // issued by ONE thread: the TMA loads of job j into buffer j % kBufs
+    // the two groups run the same code with their own barrier id, matrix staging area and reduction slots
+    auto run_group = [&](auto grp_tag, double2* s_mat, double* s_red) {
+        constexpr int GRP = decltype(grp_tag)::value;
+    const int gtid = threadIdx.x & (kGroupThreads - 1);
+    const int lane = gtid & 31, warp = gtid >> 5;
+    const uint32_t comp8 = (uint32_t)(lane & 1) << 3;
+    const bool l1 = (lane >> 1) & 1;
+    // all-ones masks of this thread's lane / warp bits
+    const uint32_t mq = 0u - (uint32_t)((lane >> 1) & 1), mg0 = 0u - (uint32_t)((lane >> 2) & 1),
+                   mg1 = 0u - (uint32_t)((lane >> 3) & 1), mg2 = 0u - (uint32_t)((lane >> 4) & 1),
+                   mw0 = 0u - (uint32_t)(warp & 1), mw1 = 0u - (uint32_t)((warp >> 1) & 1), mw2 = 0u - (uint32_t)((warp >> 2) & 1);
+    const int n_sub = sp.n_sub;
+    const uint32_t tiles_u32 = smem_u32(tiles);
+
+    // issued by ONE thread: descriptor + TMA loads of job j into buffer j % kBufs
     auto issue_load = [&](uint32_t j) {
-        int s;
-        const uint32_t t = job_tile(j, s);
-        const StreamSub& S = sp.sub[s];
-        const PassParams& p = S.pp;
-        const uint64_t tb = tile_base_of(p, t);
-        uint64_t* bar = full_bar + (j % kBufs);
-        if (p.in_mask != ~0ull && (tb & ~p.in_mask)) {   // the whole tile is known zeros: nothing to load
+        int s = 0;
+        uint32_t t = t_first + j * t_stride;
+        if (MODE == 2 && n_sub > 1) {
+            s = (int)(j % (uint32_t)n_sub);
+            t = t_first + (j / (uint32_t)n_sub) * t_stride;
+        }
+        const SubInfo& si = s_sub[s];
+        const uint32_t n_nl = si.n_nl;
+        const uint32_t tile = t & ((1u << n_nl) - 1u);
+        uint32_t tb = 0;
+        for (uint32_t i = 0; i < n_nl; ++i) tb |= ((tile >> i) & 1u) << si.nonlocal[i];
+        const uint32_t buf = j % kBufs;
+        uint64_t* bar = full_bar + buf;
+        const bool dead = MODE != 2 && sp.sub[0].pp.in_mask != ~0ull && ((uint64_t)tb & ~sp.sub[0].pp.in_mask);
+        uint4 jd;
+        jd.x = tb;
+        jd.y = t >> n_nl;
+        jd.z = tile;
+        jd.w = (dead ? 1u : 0u) | ((uint32_t)s << 8);
+        *reinterpret_cast<uint4*>(s_job + buf) = jd;
+        if (dead) {   // the whole tile is known zeros: nothing to load
             mbar_arrive(bar);
             return;
         }
-        const uint64_t amp0 = (uint64_t)(t >> p.n_nl) * S.in_elem_stride + tb;
-        unsigned char* dst = tiles + (j % kBufs) * kTileBytes;
-        mbar_expect_tx(bar, S.in.tile_bytes);
-        for (int i = 0; i < S.in.n_ops; ++i)
-            tma_load(dst + (size_t)i * S.in.box_bytes, &sp.map_in[s], bar, (int)(2u * (uint32_t)(amp0 + S.in.op_goff[i])));
+        const uint64_t amp0 = (uint64_t)jd.y * si.in_elem_stride + tb;
+        const uint32_t dst = tiles_u32 + buf * kTileBytes;
+        const CUtensorMap* map = s == 0 ? &sp.map_in[0] : s == 1 ? &sp.map_in[1] : s == 2 ? &sp.map_in[2] : &sp.map_in[3];
+        mbar_expect_tx(bar, si.tile_bytes);
+        for (uint32_t i = 0; i < si.n_ops; ++i)
+            tma_load(dst + i * si.box_bytes, map, bar, (int)(2u * (uint32_t)(amp0 + si.op_goff[i])));
     };
 
     if (gtid == 0) {
-        if (grp == 0) {
+        if (GRP == 0) {
             if (n_jobs > 0) issue_load(0);
             if (n_jobs > 2) issue_load(2);
         } else if (n_jobs > 1) issue_load(1);
@@ -186,31 +338,32 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
 
     // B-fragment coordinates of this lane: B[k = lane & 3][n = lane >> 2]; n = (QL', c', RX'), k = (QL, c)
     const int g8 = lane >> 2;
-    const int brow = (g8 >> 2) | ((g8 & 1) << 1);
-    const int bcol = (lane >> 1) & 1;
-    const bool bsame = ((g8 >> 1) & 1) == comp;
+    const int brow = (g8 >> 2) | ((g8 & 1) << 1), bcol = (lane >> 1) & 1;
+    const uint32_t bfrag = (uint32_t)((brow * 4 + bcol) * 16);   // byte offset of m[brow * 4 + bcol]
+    const bool bsame = ((g8 >> 1) & 1) == (lane & 1);
     const long long bneg = ((g8 >> 1) & 1) ? 0ll : (long long)(1ull << 63);
 
-    long long cur_elem = -1;
+    uint32_t cur_elem = 0xffffffffu;
     int flip = 0;
     bool load_pending = false;   // (thread gtid == 0) the buffer of this group's previous job still waits for its refill
     uint32_t pending_job = 0;
 
-    for (uint32_t j = grp; j < n_jobs; j += kGroups) {
-        int s;
-        const uint32_t t = job_tile(j, s);
-        const StreamSub& S = sp.sub[s];
-        const PassParams& p = S.pp;
-        const uint32_t b = t >> p.n_nl;
-        const uint32_t tile = t & ((1u << p.n_nl) - 1u);
-        const uint64_t tile_base = tile_base_of(p, t);
-        unsigned char* tile_ptr = tiles + (j % kBufs) * kTileBytes;
-        const bool tile_dead = p.in_mask != ~0ull && (tile_base & ~p.in_mask);
-        const int w0 = s_wbase[s], o0 = s_obase[s];
+#pragma unroll 1
+    for (uint32_t j = GRP; j < n_jobs; j += kGroups) {
+        const uint32_t buf = j % kBufs;
+        mbar_wait(full_bar + buf, (j / kBufs) & 1u);
+        const uint4 jd = *reinterpret_cast<const uint4*>(s_job + buf);
+        const uint32_t tile_base = jd.x, b = jd.y;
+        const bool tile_dead = MODE != 2 && (jd.w & 1u);
+        const int s = MODE == 2 ? (int)(jd.w >> 8) : 0;
+        const PassParams& p = sp.sub[0].pp;   // (gate passes have one sub-pass; the expectation code below goes through si)
+        const SubInfo& si = s_sub[s];
+        const uint32_t tile_u32 = tiles_u32 + buf * kTileBytes;
+        const int w0 = si.wbase, o0 = si.obase;
 
         // block matrices of this element (gate passes): once per (group, element)
-        if (p.n_gate_windows > 0 && p.n_mats > 0 && (long long)b != cur_elem) {
-            group_sync(grp);   // every thread of the group is done with the previous job's matrices
+        if (MODE != 2 && p.n_mats > 0 && b != cur_elem) {
+            group_sync<GRP>();   // every thread of the group is done with the previous job's matrices
             const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
             for (int i = gtid; i < p.n_wops * kMatStride; i += kGroupThreads) {
                 const int oi = i >> 4, e = i & 15;
@@ -230,194 +383,186 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                 const int dst = ((wo.w0 >> 24) & kMmaFlagSwapOut) ? (((((r & 1) << 1) | (r >> 1)) << 2) | c) : e;
                 s_mat[(o0 + oi) * kMatStride + dst] = v;
             }
-            cur_elem = (long long)b;
-            group_sync(grp);
+            cur_elem = b;
+            group_sync<GRP>();
         }
-
-        mbar_wait(full_bar + (j % kBufs), (j / kBufs) & 1u);
 
         Regs a;
         double acc = 0.0;
-        uint32_t slot_rest = 0;
-        uint64_t ctx = 0;
-        // entering window hdr: this thread's layout and its 32 doubles.  Returns false when the thread's warp idles through
-        // the window (its share of the tile is known zeros and stays so).
-        auto enter = [&](const MmaWindowDev* hdr) -> bool {
-            slot_rest = (((lane >> 2) & 1) ? hdr->gslot[0] : 0u) ^ (((lane >> 3) & 1) ? hdr->gslot[1] : 0u) ^
-                        (((lane >> 4) & 1) ? hdr->gslot[2] : 0u);
-            ctx = tile_base | ((uint64_t)((lane >> 2) & 1) << hdr->gphys[0]) | ((uint64_t)((lane >> 3) & 1) << hdr->gphys[1]) |
-                  ((uint64_t)((lane >> 4) & 1) << hdr->gphys[2]) | ((uint64_t)l1 << hdr->qlphys);
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                if ((warp >> i) & 1) {
-                    slot_rest ^= hdr->wslot[i];
-                    ctx |= 1ull << hdr->wphys[i];
-                }
-            const bool idle = p.use_dead && (warp & hdr->dead_wbits);
-            uint32_t dead_r = 0;
-            bool zero_all = tile_dead && !(hdr->flags & kWinFlagReadOnly);
-            if (hdr->flags2 & kWin2DeadEntry) {
-                dead_r = hdr->dead_r;
-                zero_all = zero_all || idle || (((lane >> 1) & 0xf) & hdr->dead_l);
-            }
-            if (idle && !zero_all) {   // (a dead tile's first window writes zeros everywhere: zero_all is already set)
-                if (!(hdr->flags2 & kWin2StoreAll)) return false;
-                zero_all = true;   // the layout changes at this window's exit: the zeros have to be written
-            }
-            if (zero_all) {
-#pragma unroll
-                for (int r = 0; r < NR; ++r) a[r] = 0.0;
-                return !idle;
-            }
-            // byte offset of register r's double: ((slot_t ^ xor of its bits' slots) << 4) | comp << 3, as three-input XORs
-            const uint32_t tt = ((slot_rest ^ (l1 ? hdr->qslot : 0u)) << 4) | ((uint32_t)comp << 3);
-            const uint32_t x0 = (uint32_t)hdr->rslot[0] << 4, x1 = (uint32_t)hdr->rslot[1] << 4, x2 = (uint32_t)hdr->rslot[2] << 4,
-                           x3 = (uint32_t)hdr->rslot[3] << 4, x4 = (uint32_t)hdr->rslot[4] << 4;
+        uint32_t ctx = 0, ebase = 0;
+        // entering window hdr: this thread's physical index bits (ctx) and its 32 doubles
+        auto enter = [&](const StreamWindowDev* hdr) {
+            // byte offset inside the tile buffer of this thread's part of the index (the register bits are XORed on top)
+            const uint32_t base = comp8 ^ (mq & hdr->qofs) ^ (mg0 & hdr->gofs[0]) ^ (mg1 & hdr->gofs[1]) ^
+                                  (mg2 & hdr->gofs[2]) ^ (mw0 & hdr->wofs[0]) ^ (mw1 & hdr->wofs[1]) ^ (mw2 & hdr->wofs[2]);
+            ctx = tile_base | (mq & hdr->qlmask) | (mg0 & hdr->gmask[0]) | (mg1 & hdr->gmask[1]) | (mg2 & hdr->gmask[2]) |
+                  (mw0 & hdr->wmask[0]) | (mw1 & hdr->wmask[1]) | (mw2 & hdr->wmask[2]);
+            ebase = base;
+            const uint32_t x0 = hdr->rofs[0], x1 = hdr->rofs[1], x2 = hdr->rofs[2], x3 = hdr->rofs[3], x4 = hdr->rofs[4];
             const uint32_t lo[4] = {0u, x0, x1, x0 ^ x1};
-            const uint32_t hi[8] = {tt, tt ^ x2, tt ^ x3, tt ^ x2 ^ x3, tt ^ x4, tt ^ x4 ^ x2, tt ^ x4 ^ x3, tt ^ x4 ^ x3 ^ x2};
-            if (dead_r == 0) {
+            const uint32_t hi[8] = {base, base ^ x2, base ^ x3, base ^ x2 ^ x3, base ^ x4, base ^ x4 ^ x2, base ^ x4 ^ x3,
+                                    base ^ x4 ^ x3 ^ x2};
 #pragma unroll
-                for (int r = 0; r < NR; ++r) a[r] = *reinterpret_cast<const double*>(tile_ptr + (hi[r >> 2] ^ lo[r & 3]));
-            } else {
-#pragma unroll
-                for (int r = 0; r < NR; ++r)
-                    a[r] = (r & dead_r) ? 0.0 : *reinterpret_cast<const double*>(tile_ptr + (hi[r >> 2] ^ lo[r & 3]));
-            }
-            return true;
+            for (int r = 0; r < NR; ++r) a[r] = lds_f64(tile_u32 + (hi[r >> 2] ^ lo[r & 3]));
         };
 
         // ---- gate windows ----
         bool first_gate = true;
-        for (int w = w0; w < w0 + p.n_gate_windows; ++w) {
-            const MmaWindowDev* hdr = s_win + w;
-            if (hdr->flags & kWinFlagReadOnly) continue;   // layout-only window (expectation-only pass)
-            const bool busy = enter(hdr);
-            group_sync(grp);   // everyone holds its entry data: the tile may be overwritten from here on
-            if (first_gate) {
-                first_gate = false;
-                // the refill of the buffer this group used last: its TMA store has had the time of a barrier to drain
-                if (gtid == 0 && load_pending) {
-                    tma_wait_read0();
-                    issue_load(pending_job);
-                    load_pending = false;
+        if (MODE != 2) {
+            for (int w = w0; w < w0 + p.n_gate_windows; ++w) {
+                const StreamWindowDev* hdr = s_win + w;
+                const uint32_t wflags = hdr->flags | ((uint32_t)hdr->flags2 << 8) | ((uint32_t)hdr->dead_wbits << 16);
+                if (wflags & kWinFlagReadOnly) continue;   // layout-only window
+                const bool store_all = ((wflags >> 8) & kWin2StoreAll) || tile_dead;
+                const bool idle = p.use_dead && (warp & (int)(wflags >> 16));
+                const bool busy = !idle;
+                if (busy || store_all) enter(hdr);   // (an idle warp that has to write zeros back still needs its layout)
+                if (tile_dead || (((wflags >> 8) & kWin2DeadEntry) != 0)) {
+                    // known zeros on entry: a dead tile, or register / lane / warp bits nothing has populated yet
+                    const uint32_t dead_r = tile_dead ? 31u : hdr->dead_r;
+                    const bool zero_all = tile_dead || idle || (((lane >> 1) & 0xf) & hdr->dead_l);
+#pragma unroll
+                    for (int r = 0; r < NR; ++r)
+                        if (zero_all || (r & dead_r)) a[r] = 0.0;
+                } else if (idle && store_all) {
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) a[r] = 0.0;
                 }
-            }
-            const int o_end = busy ? o0 + hdr->op_end : 0;
-            // op word and B fragment of op o (prefetched one op ahead, so the loads run under the previous block's DMMAs)
-            auto fetch = [&](int o, uint32_t& w0n_, double& b0, double& b1) {
-                w0n_ = s_wops[o].w0;
-                const double2* m = s_mat + o * kMatStride;
-                double2 u0 = m[brow * 4 + bcol], u1 = m[brow * 4 + bcol + 2];
-                if ((w0n_ & 0xff) == FM_SCAL) {
-                    const double2 d = ((ctx >> ((w0n_ >> 16) & 0xff)) & 1ull) ? m[3] : m[0];
-                    const double2 z = make_double2(0.0, 0.0);
-                    u0 = (brow == bcol) ? d : z;
-                    u1 = (brow == (bcol | 2)) ? d : z;
-                }
-                b0 = bsame ? u0.x : __longlong_as_double(__double_as_longlong(u0.y) ^ bneg);
-                b1 = bsame ? u1.x : __longlong_as_double(__double_as_longlong(u1.y) ^ bneg);
-            };
-            uint32_t w0n = 0;
-            double b0n = 0.0, b1n = 0.0;
-            int o = o0 + hdr->op_begin;
-            if (o < o_end) fetch(o, w0n, b0n, b1n);
-            for (; o < o_end; ++o) {
-                const uint32_t wcur = w0n;
-                const double b0 = b0n, b1 = b1n;
-                if (o + 1 < o_end) fetch(o + 1, w0n, b0n, b1n);
-                const int fc = wcur & 0xff;
-                const int qsel = (wcur >> 16) & 0xff;
-                if (fc <= FM_SCAL) {
-                    const uint32_t dead = p.use_dead ? ((wcur >> 25) & 0x1fu) : 0u;
-                    if (fc == FM_U2 + 1) m_u2<1>(a, b0, b1, dead);
-                    else if (fc == FM_U2 + 2) m_u2<2>(a, b0, b1, dead);
-                    else if (fc == FM_U2 + 3) m_u2<3>(a, b0, b1, dead);
-                    else if (fc == FM_U2 + 4) m_u2<4>(a, b0, b1, dead);
-                    else m_u2<0>(a, b0, b1, dead);
-                } else {
-                    switch (fc) {
-                    case FM_SWAP + 0: m_swapql<0>(a, l1); break;
-                    case FM_SWAP + 1: m_swapql<1>(a, l1); break;
-                    case FM_SWAP + 2: m_swapql<2>(a, l1); break;
-                    case FM_SWAP + 3: m_swapql<3>(a, l1); break;
-                    case FM_SWAP + 4: m_swapql<4>(a, l1); break;
-                    case FM_CXO + 0: m_cx_out<0>(a, (bool)((ctx >> qsel) & 1ull)); break;
-                    case FM_CXO + 1: m_cx_out<1>(a, (bool)((ctx >> qsel) & 1ull)); break;
-                    case FM_CXO + 2: m_cx_out<2>(a, (bool)((ctx >> qsel) & 1ull)); break;
-                    case FM_CXO + 3: m_cx_out<3>(a, (bool)((ctx >> qsel) & 1ull)); break;
-                    case FM_CXO + 4: m_cx_out<4>(a, (bool)((ctx >> qsel) & 1ull)); break;
-                    default: break;
+                group_sync<GRP>();   // everyone holds its entry data: the tile may be overwritten from here on
+                if (first_gate) {
+                    first_gate = false;
+                    // the refill of the buffer this group used last: its TMA store has had the time of a barrier to drain
+                    if (gtid == 0 && load_pending) {
+                        tma_wait_read0();
+                        issue_load(pending_job);
+                        load_pending = false;
                     }
                 }
-            }
-            if (busy || (hdr->flags2 & kWin2StoreAll) || tile_dead) {
-                uint32_t so = (((lane >> 2) & 1) ? hdr->gslot_out[0] : 0u) ^ (((lane >> 3) & 1) ? hdr->gslot_out[1] : 0u) ^
-                              (((lane >> 4) & 1) ? hdr->gslot_out[2] : 0u);
+                const int o_end = busy ? o0 + hdr->op_end : 0;
+                // op word and B fragment of op o (prefetched one op ahead, so the loads run under the previous block's DMMAs)
+                auto fetch = [&](int o, uint32_t& w0n_, double& b0, double& b1) {
+                    w0n_ = s_wops[o].w0;
+                    const double2* m = s_mat + o * kMatStride;
+                    double2 u0 = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(m) + bfrag);
+                    double2 u1 = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(m) + bfrag + 32);
+                    if ((w0n_ & 0xff) == FM_SCAL) {
+                        const double2 d = ((ctx >> ((w0n_ >> 16) & 0xff)) & 1u) ? m[3] : m[0];
+                        const double2 z = make_double2(0.0, 0.0);
+                        u0 = (brow == bcol) ? d : z;
+                        u1 = (brow == (bcol | 2)) ? d : z;
+                    }
+                    b0 = bsame ? u0.x : __longlong_as_double(__double_as_longlong(u0.y) ^ bneg);
+                    b1 = bsame ? u1.x : __longlong_as_double(__double_as_longlong(u1.y) ^ bneg);
+                };
+                uint32_t w0n = 0;
+                double b0n = 0.0, b1n = 0.0;
+                int o = o0 + hdr->op_begin;
+                if (o < o_end) fetch(o, w0n, b0n, b1n);
+                for (; o < o_end; ++o) {
+                    const uint32_t wcur = w0n;
+                    const double b0 = b0n, b1 = b1n;
+                    if (o + 1 < o_end) fetch(o + 1, w0n, b0n, b1n);
+                    const int fc = wcur & 0xff;
+                    const int qsel = (wcur >> 16) & 0xff;
+                    if (fc <= FM_SCAL) {
+                        const uint32_t dead = p.use_dead ? ((wcur >> 25) & 0x1fu) : 0u;
+                        if (fc == FM_U2 + 1) m_u2<1>(a, b0, b1, dead);
+                        else if (fc == FM_U2 + 2) m_u2<2>(a, b0, b1, dead);
+                        else if (fc == FM_U2 + 3) m_u2<3>(a, b0, b1, dead);
+                        else if (fc == FM_U2 + 4) m_u2<4>(a, b0, b1, dead);
+                        else m_u2<0>(a, b0, b1, dead);
+                    } else {
+                        const bool ctl = (ctx >> qsel) & 1u;
+                        switch (fc) {
+                        case FM_SWAP + 0: m_swapql<0>(a, l1); break;
+                        case FM_SWAP + 1: m_swapql<1>(a, l1); break;
+                        case FM_SWAP + 2: m_swapql<2>(a, l1); break;
+                        case FM_SWAP + 3: m_swapql<3>(a, l1); break;
+                        case FM_SWAP + 4: m_swapql<4>(a, l1); break;
+                        case FM_CXO + 0: m_cx_out<0>(a, ctl); break;
+                        case FM_CXO + 1: m_cx_out<1>(a, ctl); break;
+                        case FM_CXO + 2: m_cx_out<2>(a, ctl); break;
+                        case FM_CXO + 3: m_cx_out<3>(a, ctl); break;
+                        case FM_CXO + 4: m_cx_out<4>(a, ctl); break;
+                        default: break;
+                        }
+                    }
+                }
+                if (busy || store_all) {
+                    const uint32_t base = comp8 ^ (mq & hdr->qofs_out) ^ (mg0 & hdr->gofs_out[0]) ^ (mg1 & hdr->gofs_out[1]) ^
+                                          (mg2 & hdr->gofs_out[2]) ^ (mw0 & hdr->wofs_out[0]) ^ (mw1 & hdr->wofs_out[1]) ^
+                                          (mw2 & hdr->wofs_out[2]);
+                    const uint32_t x0 = hdr->rofs_out[0], x1 = hdr->rofs_out[1], x2 = hdr->rofs_out[2], x3 = hdr->rofs_out[3],
+                                   x4 = hdr->rofs_out[4];
+                    const uint32_t lo[4] = {0u, x0, x1, x0 ^ x1};
+                    const uint32_t hi[8] = {base, base ^ x2, base ^ x3, base ^ x2 ^ x3, base ^ x4, base ^ x4 ^ x2,
+                                            base ^ x4 ^ x3, base ^ x4 ^ x3 ^ x2};
 #pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    if ((warp >> i) & 1) so ^= hdr->wslot_out[i];
-                const uint32_t tt = ((so ^ (l1 ? hdr->qslot_out : 0u)) << 4) | ((uint32_t)comp << 3);
-                const uint32_t x0 = (uint32_t)hdr->rslot_out[0] << 4, x1 = (uint32_t)hdr->rslot_out[1] << 4,
-                               x2 = (uint32_t)hdr->rslot_out[2] << 4, x3 = (uint32_t)hdr->rslot_out[3] << 4,
-                               x4 = (uint32_t)hdr->rslot_out[4] << 4;
-                const uint32_t lo[4] = {0u, x0, x1, x0 ^ x1};
-                const uint32_t hi[8] = {tt, tt ^ x2, tt ^ x3, tt ^ x2 ^ x3, tt ^ x4, tt ^ x4 ^ x2, tt ^ x4 ^ x3, tt ^ x4 ^ x3 ^ x2};
-#pragma unroll
-                for (int r = 0; r < NR; ++r) *reinterpret_cast<double*>(tile_ptr + (hi[r >> 2] ^ lo[r & 3])) = a[r];
+                    for (int r = 0; r < NR; ++r) sts_f64(tile_u32 + (hi[r >> 2] ^ lo[r & 3]), a[r]);
+                }
+                fence_proxy_async();   // (the last window's writes are read by the TMA store)
+                group_sync<GRP>();     // the tile is complete in shared memory again
             }
-            fence_proxy_async();   // (the last window's writes are read by the TMA store)
-            group_sync(grp);       // the tile is complete in shared memory again
-        }
 
-        // ---- write back: the buffer holds the final tile in the store layout ----
-        if (S.out.n_ops > 0 && gtid == 0) {
-            const uint64_t amp0 = ((uint64_t)b << p.nbits) + tile_base;
-            for (int i = 0; i < S.out.n_ops; ++i)
-                tma_store(&sp.map_out, tile_ptr + (size_t)i * S.out.box_bytes, (int)(2u * (uint32_t)(amp0 + S.out.op_goff[i])));
-            tma_commit();
+            // ---- write back: the buffer holds the final tile in the store layout ----
+            const StreamSub& S = sp.sub[0];
+            if (S.out.n_ops > 0 && gtid == 0) {
+                const uint32_t amp0 = (b << p.nbits) + tile_base;
+                for (int i = 0; i < S.out.n_ops; ++i)
+                    tma_store(&sp.map_out, tile_u32 + (uint32_t)i * S.out.box_bytes, (int)(2u * (amp0 + S.out.op_goff[i])));
+                tma_commit();
+            }
         }
 
         // ---- expectation windows (read-only: no barriers between them) ----
-        if (p.exp_mode == 1) {
-            for (int w = w0 + p.n_gate_windows; w < w0 + p.n_windows; ++w) {
-                const MmaWindowDev* hdr = s_win + w;
+        if (MODE != 0) {
+#pragma unroll 1
+            for (int w = w0 + si.n_gate_windows; w < w0 + si.n_windows; ++w) {
+                const StreamWindowDev* hdr = s_win + w;
                 enter(hdr);
                 const int o_begin = o0 + hdr->op_begin, o_end = o0 + hdr->op_end;
                 if (hdr->flags & kWinFlagGenericDiag) {
                     for (int o = o_begin; o < o_end; ++o) {
                         const WinOp wo = s_wops[o];
                         const double2* m = s_mat + o * kMatStride;
-                        if ((wo.w0 & 0xff) == FM_EXPD) {
-                            const double2* terms = reinterpret_cast<const double2*>(p.eterms) + wo.t + 2;
-                            acc += m_expd_half<0>(a, ctx, m, terms);
-                            acc += m_expd_half<1>(a, ctx | (1ull << ((wo.w0 >> 16) & 0xff)), m, terms);
+                        if ((wo.w0 & 0xff) == FM_EXPD) {   // register bit 4 counts as a bit outside the window's classes
+                            acc += slow_expd(tile_u32, ebase, hdr, ctx, m, reinterpret_cast<const double2*>(si.eterms) + wo.t + 2);
                         } else if ((wo.w0 & 0xff) == FM_EXPT) {
-                            const double* D = reinterpret_cast<const double*>(m);
-                            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+                            double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                            for (int r = 0; r < NR; ++r) s4[r & 3] = fma(a[r] * a[r], D[r], s4[r & 3]);
-                            acc += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                            for (int r = 0; r < NR; r += 2) {
+                                const double2 D = m[r >> 1];
+                                s0 = fma(mul_here(a[r], a[r]), D.x, s0);
+                                s1 = fma(mul_here(a[r + 1], a[r + 1]), D.y, s1);
+                            }
+                            acc += s0 + s1;
                         }
                     }
                     continue;
                 }
+#pragma unroll 1
                 for (int o = o_begin; o < o_end; ++o) {
-                    const WinOp wo = s_wops[o];
+                    const uint32_t wo0 = s_wops[o].w0;
                     const double2* m = s_mat + o * kMatStride;
-                    if ((wo.w0 & 0xff) == FM_EXPC) {
-                        const double* cA = reinterpret_cast<const double*>(m + 1);
-                        const double* cB = ((wo.w0 >> 12) & 1)
-                                               ? reinterpret_cast<const double*>(reinterpret_cast<const double2*>(p.eterms) + wo.t + 9)
-                                               : nullptr;
-                        const double sum = exec_m_expc(a, (int)(wo.w0 >> 24), cA, cB, comp != 0);
-                        const uint64_t zphys = (uint64_t)__double_as_longlong(m[0].x);
-                        acc += (__popcll(ctx & zphys) & 1) ? -sum : sum;
-                    } else {   // FM_EXPT
-                        const double* D = reinterpret_cast<const double*>(m);
-                        double s4[4] = {0.0, 0.0, 0.0, 0.0};
+                    if ((wo0 & 0xff) == FM_EXPC) {
+                        double sum;
+                        if ((wo0 >> 12) & 1) {   // rare: imaginary class coefficients (terms with an odd number of Y factors)
+                            const double* cB = reinterpret_cast<const double*>(reinterpret_cast<const double2*>(si.eterms) + s_wops[o].t + 9);
+                            sum = slow_expc_imag(tile_u32, ebase, hdr, (int)(wo0 >> 24), reinterpret_cast<const double*>(m + 1), cB, (lane & 1) != 0);
+                        } else {
+                            sum = exec_s_expc(a, (int)(wo0 >> 24), m + 1);
+                        }
+                        const uint32_t zphys = (uint32_t)__double_as_longlong(m[0].x);
+                        acc += (__popc(ctx & zphys) & 1) ? -sum : sum;
+                    } else {   // FM_EXPT: diagonal terms inside the window, signed-weight table
+                        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                        for (int r = 0; r < NR; ++r) s4[r & 3] = fma(a[r] * a[r], D[r], s4[r & 3]);
-                        acc += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                        for (int r = 0; r < NR; r += 2) {
+                            const double2 D = m[r >> 1];
+                            s0 = fma(mul_here(a[r], a[r]), D.x, s0);
+                            s1 = fma(mul_here(a[r + 1], a[r + 1]), D.y, s1);
+                        }
+                        acc += s0 + s1;
                     }
                 }
             }
@@ -428,19 +573,18 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(kFull, acc, off);
             if (lane == 0) red[warp] = acc;
-            group_sync(grp);   // also: every thread of the group has finished reading the buffer
+            group_sync<GRP>();   // also: every thread of the group has finished reading the buffer
             if (gtid == 0) {
                 double tot = 0.0;
+#pragma unroll
                 for (int wv = 0; wv < kGroupThreads / 32; ++wv) tot += red[wv];
-                p.partial[(size_t)b * p.partial_ld + p.partial_off + tile] = tot;
+                si.partial[(size_t)b * si.partial_ld + si.partial_off + jd.z] = tot;
             }
-        } else if (p.n_gate_windows == 0 || first_gate) {
-            group_sync(grp);   // (a job without any barrier: keep the group together before its buffer is refilled)
         }
 
         // ---- refill this job's buffer with job j + kBufs ----
         if (gtid == 0 && j + kBufs < n_jobs) {
-            if (p.exp_mode == 1 || first_gate) {   // the group is past its last read of the buffer (barrier above)
+            if (MODE != 0) {   // the group is past its last read of the buffer (barrier above)
                 tma_wait_read0();
                 issue_load(j + kBufs);
             } else {   // defer: after the first barrier of this group's next job
@@ -450,23 +594,35 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
         }
     }
     if (gtid == 0) tma_wait_all0();
+    };
+    if (tid < kGroupThreads) run_group(std::integral_constant<int, 0>{}, s_mat_all, s_red_all);
+    else run_group(std::integral_constant<int, 1>{}, s_mat_all + kOpSlots * kMatStride, s_red_all + 16);
 }
 
 }  // namespace
 
-cudaError_t tile_stream_configure() {
-    return cudaFuncSetAttribute((const void*)tile_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)tile_stream_smem_bytes());
-}
-
 size_t tile_stream_smem_bytes() {
     return (size_t)kBufs * kTileBytes + (size_t)kGroups * kOpSlots * kMatStride * sizeof(double2) + kOpSlots * sizeof(WinOp) +
-           kWinSlots * sizeof(MmaWindowDev) + kGroups * 16 * sizeof(double) + (kBufs + 1) * sizeof(uint64_t) +
-           2 * (kStreamMaxSub + 1) * sizeof(int) + 1024 /* alignment slack */;
+           kWinSlots * sizeof(StreamWindowDev) + kGroups * 16 * sizeof(double) + (kBufs + 1) * sizeof(uint64_t) +
+           (kBufs + 1) * sizeof(JobDesc) + kStreamMaxSub * sizeof(SubInfo) + 1024 /* alignment slack */;
+}
+
+cudaError_t tile_stream_configure() {
+    const void* kernels[] = {(const void*)tile_stream_kernel<0>, (const void*)tile_stream_kernel<1>,
+                             (const void*)tile_stream_kernel<2>};
+    for (const void* k : kernels) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_stream_smem_bytes());
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 void launch_tile_stream(const StreamParams& sp, int n_ctas, cudaStream_t stream) {
-    tile_stream_kernel<<<n_ctas, kStreamThreads, tile_stream_smem_bytes(), stream>>>(sp);
+    const size_t smem = tile_stream_smem_bytes();
+    const bool gates = sp.sub[0].has_gates != 0;
+    if (!gates) tile_stream_kernel<2><<<n_ctas, kStreamThreads, smem, stream>>>(sp);
+    else if (sp.sub[0].pp.exp_mode == 1) tile_stream_kernel<1><<<n_ctas, kStreamThreads, smem, stream>>>(sp);
+    else tile_stream_kernel<0><<<n_ctas, kStreamThreads, smem, stream>>>(sp);
 }
 
 }  // namespace tq

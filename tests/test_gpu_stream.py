@@ -16,7 +16,7 @@ def heisenberg(n):
 
 
 def make_sim(n, gl, ham, monkeypatch, stream, init=None):
-    monkeypatch.setenv("TQ_STREAM", "1" if stream else "0")
+    monkeypatch.setenv("TQ_STREAM", "2" if stream else "0")   # 2: gate passes AND expectation-only passes
     monkeypatch.setenv("TQ_VALIDATE_PLAN", "1")
     sim = Simulator(n, 0)
     sim.set_pauli_hamiltonian(*ham)
@@ -93,7 +93,7 @@ def test_stream_untouched_qubits(built_lib, oracle, monkeypatch):
         gl.add_cnot(14, 5)
         gl.add_cnot(1, 0)
     ham = heisenberg(n)
-    p = np.zeros((2, 1))
+    p = parameter_batch(gl, 2)
     sim = make_sim(n, gl, ham, monkeypatch, True)
     got = sim.energies(p)
     st = sim.states(p[:1])[0]
