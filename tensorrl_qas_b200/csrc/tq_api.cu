@@ -71,7 +71,7 @@ struct tq_context {
     bool direct_kernel = true;  // TQ_DIRECT_KERNEL: the streaming expectation-only passes of a plan in one persistent launch
     bool sparse_init = true;    // TQ_SPARSE_INIT: skip the known zeros of states grown from |0...0> (tensor-core passes)
     bool stream_kernel = true;  // TQ_STREAM: multi-tile tensor-core passes run on the persistent TMA kernel (tq_stream.cu)
-    bool stream_expect = false; // TQ_STREAM=2: the expectation-only passes as well (else expect_direct_kernel)
+    bool stream_expect = true;  // TQ_STREAM=2 (default): the expectation-only passes as well; 1: those stay on expect_direct_kernel
     int64_t stream_launches = 0;
     bool spin_wait = true;      // TQ_SPIN: poll the pinned result slots instead of cudaStreamSynchronize (latency path)
     bool zero_copy = true;      // TQ_ZERO_COPY: small host-buffer calls read angles / write energies in pinned host memory
@@ -949,15 +949,15 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->n = n_qubits;
     h->device = device_id;
     h->opt.tile_bits = std::max(8, std::min(kMaxTileBits, env_int("TQ_TILE_BITS", 12)));  // kMaxTileBits = 12
-    h->opt.low_bits = std::max(0, std::min(h->opt.tile_bits - 4, env_int("TQ_LOW_BITS", 3)));
+    h->opt.low_bits = std::max(0, std::min(h->opt.tile_bits - 4, env_int("TQ_LOW_BITS", 4)));
     h->max_scratch = (size_t)std::max(64, env_int("TQ_MAX_SCRATCH_MB", 16384)) << 20;
     h->fuse_prep = env_int("TQ_FUSE_PREP", 1) != 0;
     h->zero_copy = env_int("TQ_ZERO_COPY", 1) != 0;
     h->spin_wait = env_int("TQ_SPIN", 1) != 0;
     h->sparse_init = env_int("TQ_SPARSE_INIT", 1) != 0;
     h->direct_kernel = env_int("TQ_DIRECT_KERNEL", 1) != 0;
-    h->stream_kernel = env_int("TQ_STREAM", 1) != 0;
-    h->stream_expect = env_int("TQ_STREAM", 1) >= 2;
+    h->stream_kernel = env_int("TQ_STREAM", 2) != 0;
+    h->stream_expect = env_int("TQ_STREAM", 2) >= 2;
     h->direct_ctas_per_sm = std::max(1, std::min(8, env_int("TQ_DIRECT_CTAS", 2)));
     h->n_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {

@@ -2,6 +2,9 @@
 // (tq_kernels.cu) and the streaming pass kernel (tq_stream.cu).  Include INSIDE `namespace tq { namespace {`.
 // A thread holds NR = 32 doubles: component c = lane & 1 (real / imaginary part) of the 32 amplitudes that differ in the
 // window's register qubits; lane bit 1 = QL, lane bits 2..4 and the warp index = untouched tile positions (tq_plan.h).
+#ifndef TQ_MMA_CHAINS
+#define TQ_MMA_CHAINS 2   // independent DMMA chains per warp inside a dense block (tq_stream.cu: 4)
+#endif
 constexpr int NR = 1 << kMmaRegBits;
 typedef double Regs[NR];
 constexpr unsigned kFull = 0xffffffffu;
@@ -22,6 +25,41 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 template <int X>
 __device__ __forceinline__ void m_u2(Regs& a, double b0, double b1, uint32_t dead) {
     if (dead == 0) {   // the common case: a straight run of 64 DMMAs
+#if TQ_MMA_CHAINS == 4
+        // four independent chains in flight (the DMMAs are volatile asm: they issue in program order, so the second
+        // stage of a register quad must not follow its first stage directly)
+        if (X == 0) {
+#pragma unroll
+            for (int p = 0; p < NR; p += 8) {
+                double t0, t1, u0, u1, v0, v1, w0, w1;
+                dmma884(t0, t1, a[p], b0, 0.0, 0.0);
+                dmma884(u0, u1, a[p + 2], b0, 0.0, 0.0);
+                dmma884(v0, v1, a[p + 4], b0, 0.0, 0.0);
+                dmma884(w0, w1, a[p + 6], b0, 0.0, 0.0);
+                dmma884(a[p], a[p + 1], a[p + 1], b1, t0, t1);
+                dmma884(a[p + 2], a[p + 3], a[p + 3], b1, u0, u1);
+                dmma884(a[p + 4], a[p + 5], a[p + 5], b1, v0, v1);
+                dmma884(a[p + 6], a[p + 7], a[p + 7], b1, w0, w1);
+            }
+        } else {
+#pragma unroll
+            for (int o = 0; o < NR / 4; o += 2) {
+                const int lo = o & ((1 << (X - 1)) - 1), hi = o >> (X - 1);
+                const int p00 = (hi << (X + 1)) | (lo << 1), p01 = p00 | 1, p10 = p00 | (1 << X), p11 = p10 | 1;
+                const int lo2 = (o + 1) & ((1 << (X - 1)) - 1), hi2 = (o + 1) >> (X - 1);
+                const int q00 = (hi2 << (X + 1)) | (lo2 << 1), q01 = q00 | 1, q10 = q00 | (1 << X), q11 = q10 | 1;
+                double t0, t1, u0, u1, v0, v1, w0, w1;
+                dmma884(t0, t1, a[p00], b0, 0.0, 0.0);
+                dmma884(u0, u1, a[p01], b0, 0.0, 0.0);
+                dmma884(v0, v1, a[q00], b0, 0.0, 0.0);
+                dmma884(w0, w1, a[q01], b0, 0.0, 0.0);
+                dmma884(a[p00], a[p01], a[p10], b1, t0, t1);
+                dmma884(a[p10], a[p11], a[p11], b1, u0, u1);
+                dmma884(a[q00], a[q01], a[q10], b1, v0, v1);
+                dmma884(a[q10], a[q11], a[q11], b1, w0, w1);
+            }
+        }
+#else
         if (X == 0) {
 #pragma unroll
             for (int p = 0; p < NR; p += 4) {   // two independent chains in flight
@@ -44,6 +82,7 @@ __device__ __forceinline__ void m_u2(Regs& a, double b0, double b1, uint32_t dea
                 dmma884(a[p10], a[p11], a[p11], b1, u0, u1);   // -> (bit X = 1; bit 0 = RX')
             }
         }
+#endif
         return;
     }
     // early in a run from |0...0>: skip the register pairs that are known zeros

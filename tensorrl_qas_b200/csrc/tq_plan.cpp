@@ -928,7 +928,19 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
                 p.eterms.push_back(head);
                 for (int i = 0; i < NR / 2; i += 2) { EUnit u; memcpy(&u.w[0], &ca[i], 8); memcpy(&u.w[1], &ca[i + 1], 8); p.eterms.push_back(u); }
                 for (int i = 0; i < NR / 2; i += 2) { EUnit u; memcpy(&u.w[0], &cb[i], 8); memcpy(&u.w[1], &cb[i + 1], 8); p.eterms.push_back(u); }
-                o.w0 = winop_pack(M_EXPC, 0, imag ? 1 : 0, 9, (int)xr);
+                // exchange class: two flipped register bits lo < hi and a coefficient only on the pairs whose lower
+                // member has bit lo set (01 <-> 10): the streaming kernel then skips the other half (rb2 bit 1)
+                bool anti = !imag && popc32(xr) == 2;
+                if (anti) {
+                    const int lo = __builtin_ctz(xr);
+                    int qq = 0;
+                    for (uint32_t r = 0; r < (uint32_t)NR; ++r) {
+                        if ((r ^ xr) < r) continue;
+                        if (!((r >> lo) & 1) && ca[qq] != 0.0) anti = false;
+                        ++qq;
+                    }
+                }
+                o.w0 = winop_pack(M_EXPC, 0, (imag ? 1 : 0) | (anti ? 2 : 0) | (key ? 4 : 0), 9, (int)xr);   // rb2 bit 2: outside mask != 0
                 ops.push_back(o);
             }
         }
@@ -1373,6 +1385,7 @@ MmaWindowDev resolve_window_stream(const Pass& p, int widx, bool sparse) {
         d.dead_wbits = 0;
         for (int i = 0; i < 3 && i < k - 9; ++i)
             if (!((live >> w.wpos[i]) & 1)) d.dead_wbits |= (uint8_t)(1u << i);
+        if (!(d.dead_r | d.dead_l | d.dead_wbits)) d.flags2 &= (uint8_t)~kWin2DeadEntry;   // nothing to zero
     }
     return d;
 }

@@ -24,6 +24,9 @@
 namespace tq {
 namespace {
 
+#ifndef TQ_MMA_CHAINS
+#define TQ_MMA_CHAINS 4
+#endif
 #include "tq_mma_dev.cuh"
 
 constexpr int kGroupThreads = 256;
@@ -104,18 +107,22 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 
-// real-coefficient expectation class (tq_mma_dev.cuh m_expc without the imaginary part): coefficients two at a time, so
-// that the register budget of the caller (32 doubles of state) is not exceeded
+// real-coefficient expectation class (tq_mma_dev.cuh m_expc without the imaginary part).  The sixteen coefficients are
+// fetched eight at a time, ahead of the products that use them.
 template <int XR>
 __device__ __forceinline__ double s_expc(const Regs& a, const double2* __restrict__ cA) {
     double s[4] = {0.0, 0.0, 0.0, 0.0};   // four independent accumulation chains
+    double2 c[4];
     int q = 0;
-    double2 c = make_double2(0.0, 0.0);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         if ((r ^ XR) > r) {
-            if ((q & 1) == 0) c = cA[q >> 1];
-            s[q & 3] = fma((q & 1) ? c.y : c.x, mul_here(a[r ^ XR], a[r]), s[q & 3]);
+            if ((q & 7) == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c[i] = cA[(q >> 1) + i];
+            }
+            const double2 cc = c[(q >> 1) & 3];
+            s[q & 3] = fma((q & 1) ? cc.y : cc.x, mul_here(a[r ^ XR], a[r]), s[q & 3]);
             ++q;
         }
     }
@@ -130,6 +137,48 @@ __device__ __forceinline__ double exec_s_expc(const Regs& a, int xr, const doubl
     default: return s_expc<31>(a, cA);
     }
 #undef TQ_XC
+}
+// "exchange" class: the flip mask has two register bits LO < HI and only the pairs that differ in them the other way
+// round (01 <-> 10) carry a coefficient -- XX + YY with equal weights (Heisenberg couplings, fermionic hopping terms): the
+// aligned pairs (00 <-> 11) cancel.  Eight products instead of sixteen; the coefficient table keeps its sixteen slots.
+template <int LO, int HI>
+__device__ __forceinline__ double s_expc_anti(const Regs& a, const double* __restrict__ cA) {
+    constexpr int XR = (1 << LO) | (1 << HI);
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    double c[8];
+    {
+        int q = 0, n = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if ((r ^ XR) > r) {
+                if ((r >> LO) & 1) c[n++] = cA[q];
+                ++q;
+            }
+        }
+    }
+    int n = 0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        if ((r ^ XR) > r && ((r >> LO) & 1)) {
+            s[n & 3] = fma(c[n], mul_here(a[r ^ XR], a[r]), s[n & 3]);
+            ++n;
+        }
+    }
+    return (s[0] + s[1]) + (s[2] + s[3]);
+}
+__device__ __forceinline__ double exec_s_expc_anti(const Regs& a, int xr, const double* cA) {
+    switch (xr) {
+    case 3: return s_expc_anti<0, 1>(a, cA);
+    case 5: return s_expc_anti<0, 2>(a, cA);
+    case 9: return s_expc_anti<0, 3>(a, cA);
+    case 17: return s_expc_anti<0, 4>(a, cA);
+    case 6: return s_expc_anti<1, 2>(a, cA);
+    case 10: return s_expc_anti<1, 3>(a, cA);
+    case 18: return s_expc_anti<1, 4>(a, cA);
+    case 12: return s_expc_anti<2, 3>(a, cA);
+    case 20: return s_expc_anti<2, 4>(a, cA);
+    default: return s_expc_anti<3, 4>(a, cA);
+    }
 }
 
 // ---- rare expectation ops, kept out of line and off the register file: they re-read the tile from shared memory --------
@@ -284,6 +333,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     // the two groups run the same code with their own barrier id, matrix staging area and reduction slots
     auto run_group = [&](auto grp_tag, double2* s_mat, double* s_red) {
         constexpr int GRP = decltype(grp_tag)::value;
+        double* s_red_cta = s_red_all;
     const int gtid = threadIdx.x & (kGroupThreads - 1);
     const int lane = gtid & 31, warp = gtid >> 5;
     const uint32_t comp8 = (uint32_t)(lane & 1) << 3;
@@ -332,8 +382,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     if (gtid == 0) {
         if (GRP == 0) {
             if (n_jobs > 0) issue_load(0);
+            if (MODE == 2 && n_jobs > 1) issue_load(1);
             if (n_jobs > 2) issue_load(2);
-        } else if (n_jobs > 1) issue_load(1);
+        } else if (MODE != 2 && n_jobs > 1) issue_load(1);
     }
 
     // B-fragment coordinates of this lane: B[k = lane & 3][n = lane >> 2]; n = (QL', c', RX'), k = (QL, c)
@@ -348,8 +399,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     bool load_pending = false;   // (thread gtid == 0) the buffer of this group's previous job still waits for its refill
     uint32_t pending_job = 0;
 
+    // MODE 2 (read-only windows): BOTH groups work on every job -- they share out its windows -- so that one buffer is
+    // being read while two are in flight (a tile of expectation work is short: one load in flight does not cover HBM's
+    // latency-bandwidth product); gate passes alternate jobs between the groups
 #pragma unroll 1
-    for (uint32_t j = GRP; j < n_jobs; j += kGroups) {
+    for (uint32_t j = (MODE == 2 ? 0 : GRP); j < n_jobs; j += (MODE == 2 ? 1 : kGroups)) {
         const uint32_t buf = j % kBufs;
         mbar_wait(full_bar + buf, (j / kBufs) & 1u);
         const uint4 jd = *reinterpret_cast<const uint4*>(s_job + buf);
@@ -518,6 +572,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
         if (MODE != 0) {
 #pragma unroll 1
             for (int w = w0 + si.n_gate_windows; w < w0 + si.n_windows; ++w) {
+                if (MODE == 2 && ((w + (int)j) & 1) != GRP) continue;   // the other group's window
                 const StreamWindowDev* hdr = s_win + w;
                 enter(hdr);
                 const int o_begin = o0 + hdr->op_begin, o_end = o0 + hdr->op_end;
@@ -549,11 +604,16 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                         if ((wo0 >> 12) & 1) {   // rare: imaginary class coefficients (terms with an odd number of Y factors)
                             const double* cB = reinterpret_cast<const double*>(reinterpret_cast<const double2*>(si.eterms) + s_wops[o].t + 9);
                             sum = slow_expc_imag(tile_u32, ebase, hdr, (int)(wo0 >> 24), reinterpret_cast<const double*>(m + 1), cB, (lane & 1) != 0);
+                        } else if ((wo0 >> 13) & 1) {   // exchange class: half of the pairs
+                            sum = exec_s_expc_anti(a, (int)(wo0 >> 24), reinterpret_cast<const double*>(m + 1));
                         } else {
                             sum = exec_s_expc(a, (int)(wo0 >> 24), m + 1);
                         }
-                        const uint32_t zphys = (uint32_t)__double_as_longlong(m[0].x);
-                        acc += (__popc(ctx & zphys) & 1) ? -sum : sum;
+                        if ((wo0 >> 14) & 1) {   // Z / Y factors outside the window: sign from the thread's index bits
+                            const uint32_t zphys = (uint32_t)__double_as_longlong(m[0].x);
+                            sum = (__popc(ctx & zphys) & 1) ? -sum : sum;
+                        }
+                        acc += sum;
                     } else {   // FM_EXPT: diagonal terms inside the window, signed-weight table
                         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
@@ -566,24 +626,40 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                     }
                 }
             }
-            // deterministic group sum (same tree as block_sum); two sets of slots alternate so that a fast warp cannot
+            // deterministic sum (same tree as block_sum); two sets of slots alternate so that a fast warp cannot
             // overwrite what thread 0 is still adding up
-            double* red = s_red + (flip ? 8 : 0);
-            flip ^= 1;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(kFull, acc, off);
-            if (lane == 0) red[warp] = acc;
-            group_sync<GRP>();   // also: every thread of the group has finished reading the buffer
-            if (gtid == 0) {
-                double tot = 0.0;
+            if (MODE == 2) {   // both groups contributed to this tile: one CTA-wide barrier per job
+                double* red = s_red_cta + (flip ? 16 : 0);
+                flip ^= 1;
+                if (lane == 0) red[GRP * 8 + warp] = acc;
+                asm volatile("bar.sync 0, %0;" ::"n"(kStreamThreads) : "memory");   // also: everyone has finished reading the buffer
+                // the tail of a job (sum, partial, refill) is serial work of one thread: a different warp takes it every job,
+                // so that no warp falls behind the others by more than one tail
+                if (lane == 0 && (uint32_t)(GRP * 8 + warp) == (j & 15u)) {
+                    if (j + kBufs < n_jobs) issue_load(j + kBufs);
+                    double tot = 0.0;
 #pragma unroll
-                for (int wv = 0; wv < kGroupThreads / 32; ++wv) tot += red[wv];
-                si.partial[(size_t)b * si.partial_ld + si.partial_off + jd.z] = tot;
+                    for (int wv = 0; wv < 2 * kGroupThreads / 32; ++wv) tot += red[wv];
+                    si.partial[(size_t)b * si.partial_ld + si.partial_off + jd.z] = tot;
+                }
+            } else {
+                double* red = s_red + (flip ? 8 : 0);
+                flip ^= 1;
+                if (lane == 0) red[warp] = acc;
+                group_sync<GRP>();   // also: every thread of the group has finished reading the buffer
+                if (gtid == 0) {
+                    double tot = 0.0;
+#pragma unroll
+                    for (int wv = 0; wv < kGroupThreads / 32; ++wv) tot += red[wv];
+                    si.partial[(size_t)b * si.partial_ld + si.partial_off + jd.z] = tot;
+                }
             }
         }
 
         // ---- refill this job's buffer with job j + kBufs ----
-        if (gtid == 0 && j + kBufs < n_jobs) {
+        if (MODE != 2 && gtid == 0 && j + kBufs < n_jobs) {
             if (MODE != 0) {   // the group is past its last read of the buffer (barrier above)
                 tma_wait_read0();
                 issue_load(j + kBufs);

@@ -117,3 +117,33 @@ def test_stream_bench_shape_matches_oracle_sample(built_lib, oracle, monkeypatch
     assert launches >= 3
     assert np.abs(got[:2] - oracle.energies(gl, p[:2], pauli=ham)).max() < 1e-10
     assert np.abs(got - off).max() < 1e-11
+
+
+def test_stream_random_pauli_sum(built_lib, oracle, monkeypatch):
+    """Random Pauli strings (odd numbers of Y, long Z strings, masks wider than a window): the rare expectation paths of
+    the streaming kernel (imaginary class coefficients, index-dependent signs) and its fall-backs against the oracle."""
+    n = 14
+    rng = np.random.default_rng(11)
+    x = np.zeros(40, dtype=np.uint64)
+    z = np.zeros(40, dtype=np.uint64)
+    for t in range(40):
+        weight = int(rng.integers(1, 5)) if t < 30 else int(rng.integers(6, 10))
+        for q in rng.choice(n, size=weight, replace=False):
+            kind = int(rng.integers(0, 3)) if t % 3 else 2      # every third string is a pure Z string
+            if kind in (0, 1):
+                x[t] |= np.uint64(1 << int(q))
+            if kind in (1, 2):
+                z[t] |= np.uint64(1 << int(q))
+    w = rng.normal(size=40)
+    ham = (x, z, w)
+    gl = synthetic_circuit(n, 160, 31)
+    p = parameter_batch(gl, 3)
+    want = oracle.energies(gl, p, pauli=ham)
+    sim = make_sim(n, gl, ham, monkeypatch, True)
+    got = sim.energies(p)
+    sim.close()
+    ref = make_sim(n, gl, ham, monkeypatch, False)
+    off = ref.energies(p)
+    ref.close()
+    assert np.abs(off - want).max() < 1e-10
+    assert np.abs(got - want).max() < 1e-10
