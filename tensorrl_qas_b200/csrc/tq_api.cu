@@ -730,8 +730,8 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
             }
             // ---- streaming kernel (persistent CTAs, TMA tile I/O) for multi-tile tensor-core passes ----
             const bool sparse_in = pp.in_mask != ~0ull;
-            const bool use_stream = h->stream_kernel && (dp.gate_pass || h->stream_expect) && dp.stream && pp.mwindows && !xchg &&
-                                    !fuse_prep && pp.src_mode != 0 &&
+            const bool use_stream = h->stream_kernel && (dp.gate_pass ? !dp.no_ops : (h->stream_expect && pp.exp_mode == 1)) &&
+                                    dp.stream && pp.mwindows && !xchg && !fuse_prep && pp.src_mode != 0 &&
                                     pp.n_groups == 0 && pp.exp_mode != 2 && (!sparse_in || dp.sparse_ok) &&
                                     ((uint64_t)bc << (plan.nbits + 1)) <= (1ull << 31);
             if (use_stream) {
