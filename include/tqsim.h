@@ -21,7 +21,10 @@
  * Threading: a handle is single-threaded; distinct handles may be driven from distinct host threads.
  * Streams: *_dev entry points enqueue on the caller's stream (a cudaStream_t passed as void*, NULL = default
  * stream) and return without synchronising; *_host entry points copy in, run and copy out, and return when
- * the result is in the caller's host buffer.
+ * the result is in the caller's host buffer.  A handle owns ONE set of scratch buffers (states, block matrices, partial
+ * sums): keep at most one stream in flight per handle -- enqueueing on a second stream (or mixing a caller stream with
+ * a *_host call) before the first has finished is a data race on that scratch.  The tq_set_* calls wait for the stream
+ * used last.
  * There is NO CPU fallback: without a CUDA device tq_create fails with TQ_ENODEV.
  */
 #ifndef TQSIM_H
@@ -76,7 +79,8 @@ int tq_set_pauli_hamiltonian(tq_handle h, int n_terms, const uint64_t* xmask, co
                              const double* coeff_re, const double* coeff_im);
 
 /* Hamiltonian as the dense 2^n x 2^n complex128 matrix the reference passes as `op`
- * (environments/VQAs/VQE_qulacs.py:84-85, E = Re(conj(psi).T @ op @ psi)); row-major, n_qubits <= 13.
+ * (environments/VQAs/VQE_qulacs.py:84-85, E = Re(conj(psi).T @ op @ psi)); row-major; n_qubits <= 12 (the state must be
+ * one tile; TQ_EINVAL otherwise -- larger registers take tq_set_pauli_hamiltonian).
  * The library keeps the non-zero entries and evaluates exactly that bilinear form over them. */
 int tq_set_dense_hamiltonian(tq_handle h, const double* h_matrix_host);
 

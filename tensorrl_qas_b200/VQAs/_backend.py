@@ -64,6 +64,13 @@ def noise_rng(module_rng):
     return getattr(_ctx, "rng", None) or module_rng
 
 
+def release_slots(tag):
+    """Close and forget the handles of one lock-step driver (slot keys (tag, worker)): its streams, pinned staging and device
+    scratch go back, and so do the references to its circuits and Hamiltonians."""
+    for key in [k for k in _sims if isinstance(k[2], tuple) and k[2][0] == tag]:
+        _sims.pop(key).sim.close()
+
+
 def reset_backends():
     """Drop all cached handles (tests)."""
     for s in _sims.values():

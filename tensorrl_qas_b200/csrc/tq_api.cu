@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -126,6 +127,15 @@ namespace {
 
 int fail(tq_handle h, int code, const std::string& msg) {
     if (h) h->err = msg;
+    return code;
+}
+
+int api_fail(tq_handle h, int code, const std::string& msg) noexcept {
+    try {
+        if (h) h->err = msg;
+        else g_create_error = msg;
+    } catch (...) {
+    }
     return code;
 }
 
@@ -640,6 +650,9 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
     const bool needs_buffer = states_out == nullptr && (total_passes > 1 || dm);
     int chunk = batch;
     if (needs_buffer) {
+        if (elem_bytes > h->max_scratch)
+            return fail(h, TQ_ENOMEM, "one state vector (" + std::to_string(elem_bytes >> 20) + " MiB) exceeds the scratch limit (" +
+                                          std::to_string(h->max_scratch >> 20) + " MiB, TQ_MAX_SCRATCH_MB)");
         const size_t cap_elems = std::max<size_t>(1, h->max_scratch / elem_bytes);
         chunk = (int)std::min<size_t>(batch, cap_elems);
         const int forced = env_int("TQ_CHUNK_ELEMS", 0);
@@ -912,12 +925,22 @@ int run_host(tq_handle h, int which, int batch, const double* params_host, int l
 
 }  // namespace
 
+// Exception barrier of the C ABI (include/tqsim.h: "nothing throws or aborts across the ABI"): the planner and the handle
+// use std::vector / std::string / new, so every entry point turns a C++ exception into an error code + message.
+#define TQ_API_TRY try {
+#define TQ_API_CATCH(hh)                                                                                  \
+    }                                                                                                     \
+    catch (const std::bad_alloc&) { return api_fail(hh, TQ_ENOMEM, "out of host memory"); }               \
+    catch (const std::exception& e_) { return api_fail(hh, TQ_EINVAL, std::string("internal error: ") + e_.what()); } \
+    catch (...) { return api_fail(hh, TQ_EINVAL, "internal error (unknown exception)"); }
+
 // =================================================================== C ABI ===================================
 extern "C" {
 
 int tq_version(void) { return TQ_VERSION; }
 
 int tq_create(int n_qubits, int device_id, tq_handle* out) {
+    TQ_API_TRY
     if (!out) return TQ_EINVAL;
     *out = nullptr;
     if (n_qubits < 1 || n_qubits > 30) { g_create_error = "n_qubits must be in [1, 30]"; return TQ_EINVAL; }
@@ -950,7 +973,7 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->device = device_id;
     h->opt.tile_bits = std::max(8, std::min(kMaxTileBits, env_int("TQ_TILE_BITS", 12)));  // kMaxTileBits = 12
     h->opt.low_bits = std::max(0, std::min(h->opt.tile_bits - 4, env_int("TQ_LOW_BITS", 4)));
-    h->max_scratch = (size_t)std::max(64, env_int("TQ_MAX_SCRATCH_MB", 16384)) << 20;
+    h->max_scratch = (size_t)std::max(1, env_int("TQ_MAX_SCRATCH_MB", 16384)) << 20;
     h->fuse_prep = env_int("TQ_FUSE_PREP", 1) != 0;
     h->zero_copy = env_int("TQ_ZERO_COPY", 1) != 0;
     h->spin_wait = env_int("TQ_SPIN", 1) != 0;
@@ -967,9 +990,11 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     }
     *out = h;
     return TQ_OK;
+    TQ_API_CATCH(nullptr)
 }
 
 int tq_destroy(tq_handle h) {
+    TQ_API_TRY
     if (!h) return TQ_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
@@ -986,12 +1011,14 @@ int tq_destroy(tq_handle h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return TQ_OK;
+    TQ_API_CATCH(nullptr)
 }
 
 const char* tq_last_error(tq_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int tq_set_pauli_hamiltonian(tq_handle h, int n_terms, const uint64_t* xmask, const uint64_t* zmask,
                              const double* coeff_re, const double* coeff_im) {
+    TQ_API_TRY
     if (!h) return TQ_EINVAL;
     if (n_terms < 0 || (n_terms > 0 && (!xmask || !zmask || !coeff_re))) return fail(h, TQ_EINVAL, "bad Pauli term arrays");
     const uint64_t valid = (h->n >= 64) ? ~0ull : ((1ull << h->n) - 1);
@@ -1019,12 +1046,18 @@ int tq_set_pauli_hamiltonian(tq_handle h, int n_terms, const uint64_t* xmask, co
     h->hent_uploaded = false;
     invalidate_plans(h);
     return TQ_OK;
+    TQ_API_CATCH(h)
 }
 
 int tq_set_dense_hamiltonian(tq_handle h, const double* h_matrix_host) {
+    TQ_API_TRY
     if (!h) return TQ_EINVAL;
     if (!h_matrix_host) return fail(h, TQ_EINVAL, "matrix is NULL");
-    if (h->n > 13) return fail(h, TQ_EINVAL, "dense Hamiltonian needs n_qubits <= 13");
+    // the dense bilinear form is evaluated where the whole state is one tile (pure path) -- say so here, not at the first
+    // evaluation
+    if (h->n > h->opt.tile_bits)
+        return fail(h, TQ_EINVAL, "dense Hamiltonian needs n_qubits <= " + std::to_string(h->opt.tile_bits) +
+                                      " (one tile, TQ_TILE_BITS); larger registers take a Pauli sum");
     entries_from_dense(h, h_matrix_host);
     h->have_dense = true;
     h->have_pauli = false;
@@ -1033,9 +1066,11 @@ int tq_set_dense_hamiltonian(tq_handle h, const double* h_matrix_host) {
     h->hent_uploaded = false;
     invalidate_plans(h);
     return TQ_OK;
+    TQ_API_CATCH(h)
 }
 
 int tq_set_init_state(tq_handle h, const double* psi) {
+    TQ_API_TRY
     if (!h) return TQ_EINVAL;
     TQ_CUDA(cudaSetDevice(h->device));
     if (h->last_stream) TQ_CUDA(cudaStreamSynchronize(h->last_stream));
@@ -1047,10 +1082,12 @@ int tq_set_init_state(tq_handle h, const double* psi) {
     TQ_CUDA(upload_sync(h, h->d_init, psi, dim * 16));
     h->have_init = true;
     return TQ_OK;
+    TQ_API_CATCH(h)
 }
 
 int tq_set_circuit(tq_handle h, int n_gates, const int32_t* kind, const int32_t* q0, const int32_t* q1,
                    const int32_t* param_idx, const double* fixed, int n_params) {
+    TQ_API_TRY
     if (!h) return TQ_EINVAL;
     if (n_gates < 0 || n_params < 0 || (n_gates > 0 && (!kind || !q0 || !q1 || !param_idx || !fixed)))
         return fail(h, TQ_EINVAL, "bad circuit arrays");
@@ -1075,22 +1112,28 @@ int tq_set_circuit(tq_handle h, int n_gates, const int32_t* kind, const int32_t*
     h->have_circuit = true;
     invalidate_plans(h);
     return TQ_OK;
+    TQ_API_CATCH(h)
 }
 
 int tq_energy_batch(tq_handle h, int batch, const double* params_dev, int ld_params, double* out_dev, void* stream) {
+    TQ_API_TRY
     if (!h || !out_dev) return TQ_EINVAL;
     TQ_CUDA(cudaSetDevice(h->device));
     return run_plan(h, 0, batch, params_dev, ld_params, nullptr, 0, out_dev, nullptr, (cudaStream_t)stream);
+    TQ_API_CATCH(h)
 }
 
 int tq_energy_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* out_host) {
+    TQ_API_TRY
     if (!h || !out_host) return TQ_EINVAL;
     return run_host(h, 0, batch, params_host, ld_params, nullptr, 0, out_host, nullptr, 0);
+    TQ_API_CATCH(h)
 }
 
 // One launch for n DIFFERENT problems (lock-step drivers: B environments, one cost evaluation each per COBYLA round).
 int tq_energy_multi_host(int n_problems, tq_handle* handles, const double* const* params_host,
                          const uint8_t* const* codes_host, double* out_host) {
+    TQ_API_TRY
     if (n_problems <= 0) return n_problems == 0 ? TQ_OK : TQ_EINVAL;
     if (!handles || !out_host || !handles[0]) return TQ_EINVAL;
     tq_handle m = handles[0];   // its stream and pinned staging buffer carry the call
@@ -1161,10 +1204,14 @@ int tq_energy_multi_host(int n_problems, tq_handle* handles, const double* const
         memcpy(&table[i], &pp, sizeof(PassParams));
         slots[i] = kPending;
         smem = std::max(smem, tile_pass_smem_bytes(pp.k_eff, pp.k, pp.lead));
-        threads = std::max(threads, dp.threads);
+        // one launch = one kernel variant and one block size for all problems (both follow from n_qubits and the
+        // TQ_MMA / TQ_TILE_BITS switches the handles were created under: refuse a table that disagrees)
+        if (i > 0 && (mma != (pp.mwindows != nullptr) || threads != dp.threads))
+            return fail(m, TQ_EINVAL, "tq_energy_multi_host: the problems do not share one kernel variant / block size");
+        threads = dp.threads;
         mma = pp.mwindows != nullptr;
-        h->last_stream = m->stream;
     }
+    for (int i = 0; i < n_problems; ++i) handles[i]->last_stream = m->stream;
     launch_tile_pass_table(table, n_problems, threads, smem, mma, m->stream);
     ++m->launches;
     rc = check_launch(m, "tile_pass_kernel (table launch)");
@@ -1179,52 +1226,69 @@ int tq_energy_multi_host(int n_problems, tq_handle* handles, const double* const
         }
     }
     if (!done) TQ_CUDA_H(m, cudaStreamSynchronize(m->stream));
+    // every result slot is written (a CTA's last act), so the launch has finished reading the handles' buffers: the
+    // other handles must not keep a reference to handles[0]'s stream, which may be destroyed before they are
+    for (int i = 1; i < n_problems; ++i) handles[i]->last_stream = nullptr;
     memcpy(out_host, hp + o_off, (size_t)n_problems * sizeof(double));
     return TQ_OK;
+    TQ_API_CATCH((handles && n_problems > 0 ? handles[0] : nullptr))
 }
 
 int tq_energy_traj_batch(tq_handle h, int batch, const double* params_dev, int ld_params, const uint8_t* codes_dev,
                          int ld_codes, double* out_dev, void* stream) {
+    TQ_API_TRY
     if (!h || !out_dev) return TQ_EINVAL;
     TQ_CUDA(cudaSetDevice(h->device));
     return run_plan(h, 2, batch, params_dev, ld_params, codes_dev, ld_codes, out_dev, nullptr, (cudaStream_t)stream);
+    TQ_API_CATCH(h)
 }
 
 int tq_energy_traj_batch_host(tq_handle h, int batch, const double* params_host, int ld_params,
                               const uint8_t* codes_host, int ld_codes, double* out_host) {
+    TQ_API_TRY
     if (!h || !out_host) return TQ_EINVAL;
     return run_host(h, 2, batch, params_host, ld_params, codes_host, ld_codes, out_host, nullptr, 0);
+    TQ_API_CATCH(h)
 }
 
 int tq_energy_dm_batch(tq_handle h, int batch, const double* params_dev, int ld_params, double* out_dev, void* stream) {
+    TQ_API_TRY
     if (!h || !out_dev) return TQ_EINVAL;
     if (h->n > 13) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
     TQ_CUDA(cudaSetDevice(h->device));
     return run_plan(h, 1, batch, params_dev, ld_params, nullptr, 0, out_dev, nullptr, (cudaStream_t)stream);
+    TQ_API_CATCH(h)
 }
 
 int tq_energy_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* out_host) {
+    TQ_API_TRY
     if (!h || !out_host) return TQ_EINVAL;
     if (h->n > 13) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
     return run_host(h, 1, batch, params_host, ld_params, nullptr, 0, out_host, nullptr, 0);
+    TQ_API_CATCH(h)
 }
 
 int tq_state_batch(tq_handle h, int batch, const double* params_dev, int ld_params, double* states_dev, void* stream) {
+    TQ_API_TRY
     if (!h || !states_dev) return TQ_EINVAL;
     TQ_CUDA(cudaSetDevice(h->device));
     return run_plan(h, 0, batch, params_dev, ld_params, nullptr, 0, nullptr, (double2*)states_dev, (cudaStream_t)stream);
+    TQ_API_CATCH(h)
 }
 
 int tq_evolve_states(tq_handle h, int batch, const double* params_dev, int ld_params, double* states_dev,
                      double* energies_dev, void* stream) {
+    TQ_API_TRY
     if (!h || !states_dev) return TQ_EINVAL;
     TQ_CUDA(cudaSetDevice(h->device));
     return run_plan(h, 0, batch, params_dev, ld_params, nullptr, 0, energies_dev, (double2*)states_dev,
                     (cudaStream_t)stream, /*from_states=*/true);
+    TQ_API_CATCH(h)
 }
 
 int tq_evolve_states_exchange(tq_handle h, const double* params_dev, int ld_params, double* shard_dev, int n_ranks,
                               int rank, const uint64_t* recv_ptrs, void* stream) {
+    TQ_API_TRY
     if (!h || !shard_dev || !recv_ptrs) return TQ_EINVAL;
     if (n_ranks < 2 || n_ranks > kMaxShardRanks || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks)
         return fail(h, TQ_EINVAL, "n_ranks must be 2, 4 or 8 and 0 <= rank < n_ranks");
@@ -1240,22 +1304,28 @@ int tq_evolve_states_exchange(tq_handle h, const double* params_dev, int ld_para
     TQ_CUDA(cudaSetDevice(h->device));
     return run_plan(h, 0, 1, params_dev, ld_params, nullptr, 0, nullptr, (double2*)shard_dev, (cudaStream_t)stream,
                     /*from_states=*/true, &x);
+    TQ_API_CATCH(h)
 }
 
 int tq_device_alloc(int device, uint64_t bytes, void** out) {
+    TQ_API_TRY
     if (!out || bytes == 0) return TQ_EINVAL;
     *out = nullptr;
     if (cudaSetDevice(device) != cudaSuccess) return TQ_ECUDA;
     return cudaMalloc(out, bytes) == cudaSuccess ? TQ_OK : TQ_ENOMEM;
+    TQ_API_CATCH(nullptr)
 }
 
 int tq_device_free(int device, void* p) {
+    TQ_API_TRY
     if (!p) return TQ_OK;
     if (cudaSetDevice(device) != cudaSuccess) return TQ_ECUDA;
     return cudaFree(p) == cudaSuccess ? TQ_OK : TQ_ECUDA;
+    TQ_API_CATCH(nullptr)
 }
 
 int tq_ipc_export(int device, void* base, unsigned char* handle64) {
+    TQ_API_TRY
     if (!base || !handle64) return TQ_EINVAL;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     if (cudaSetDevice(device) != cudaSuccess) return TQ_ECUDA;
@@ -1263,9 +1333,11 @@ int tq_ipc_export(int device, void* base, unsigned char* handle64) {
     if (cudaIpcGetMemHandle(&hd, base) != cudaSuccess) { cudaGetLastError(); return TQ_ECUDA; }
     memcpy(handle64, &hd, 64);
     return TQ_OK;
+    TQ_API_CATCH(nullptr)
 }
 
 int tq_ipc_open(int device, const unsigned char* handle64, void** out) {
+    TQ_API_TRY
     if (!handle64 || !out) return TQ_EINVAL;
     *out = nullptr;
     if (cudaSetDevice(device) != cudaSuccess) return TQ_ECUDA;
@@ -1273,26 +1345,34 @@ int tq_ipc_open(int device, const unsigned char* handle64, void** out) {
     memcpy(&hd, handle64, 64);
     if (cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return TQ_ECUDA; }
     return TQ_OK;
+    TQ_API_CATCH(nullptr)
 }
 
 int tq_ipc_close(int device, void* p) {
+    TQ_API_TRY
     if (!p) return TQ_OK;
     if (cudaSetDevice(device) != cudaSuccess) return TQ_ECUDA;
     return cudaIpcCloseMemHandle(p) == cudaSuccess ? TQ_OK : TQ_ECUDA;
+    TQ_API_CATCH(nullptr)
 }
 
 int tq_state_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* states_host) {
+    TQ_API_TRY
     if (!h || !states_host) return TQ_EINVAL;
     return run_host(h, 0, batch, params_host, ld_params, nullptr, 0, nullptr, states_host, (size_t)1 << h->n);
+    TQ_API_CATCH(h)
 }
 
 int tq_dm_batch_host(tq_handle h, int batch, const double* params_host, int ld_params, double* rho_host) {
+    TQ_API_TRY
     if (!h || !rho_host) return TQ_EINVAL;
     if (h->n > 13) return fail(h, TQ_EINVAL, "density-matrix path needs n_qubits <= 13");
     return run_host(h, 1, batch, params_host, ld_params, nullptr, 0, nullptr, rho_host, (size_t)1 << (2 * h->n));
+    TQ_API_CATCH(h)
 }
 
 int tq_plan_info(tq_handle h, int which, int64_t* info8) {
+    TQ_API_TRY
     if (!h || !info8 || which < 0 || which > 2) return TQ_EINVAL;
     TQ_CUDA(cudaSetDevice(h->device));
     int rc = compile_plan(h, which);
@@ -1309,9 +1389,11 @@ int tq_plan_info(tq_handle h, int which, int64_t* info8) {
     info8[6] = plan.n_unitary;
     info8[7] = plan.n_rot;
     return TQ_OK;
+    TQ_API_CATCH(h)
 }
 
 int tq_plan_counts(tq_handle h, int which, int64_t* counts8) {
+    TQ_API_TRY
     if (!h || !counts8 || which < 0 || which > 2) return TQ_EINVAL;
     TQ_CUDA(cudaSetDevice(h->device));
     int rc = compile_plan(h, which);
@@ -1337,6 +1419,7 @@ int tq_plan_counts(tq_handle h, int which, int64_t* counts8) {
     counts8[6] = (int64_t)(work + 0.5);
     counts8[7] = h->stream_launches;   // launches of the streaming kernel (persistent CTAs, TMA tile I/O) by this handle so far
     return TQ_OK;
+    TQ_API_CATCH(h)
 }
 
 int64_t tq_launch_count(tq_handle h) { return h ? h->launches : 0; }
@@ -1348,6 +1431,7 @@ int64_t tq_launch_count(tq_handle h) { return h ? h->launches : 0; }
 char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t* q0, const int32_t* q1,
                    const int32_t* param_idx, const double* fixed, int which, int tile_bits, int low_bits,
                    int n_cover, const uint64_t* cover_masks) {
+    try {
     std::vector<Gate> gates(n_gates);
     for (int g = 0; g < n_gates; ++g) gates[g] = Gate{kind[g], q0[g], q1[g], param_idx[g], fixed[g]};
     // which & 16: also assign a synthetic Hamiltonian (one XX + YY-like group per cover mask and a ZZ-like diagonal group) to
@@ -1449,8 +1533,14 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
         }
     }
     char* res = (char*)malloc(out.size() + 1);
-    memcpy(res, out.c_str(), out.size() + 1);
+    if (res) memcpy(res, out.c_str(), out.size() + 1);
     return res;
+    } catch (...) {   // (the ABI never throws: a failed dry run is reported as an ERROR line, or NULL without memory)
+        const char msg[] = "ERROR internal error in the planner dry run\n";
+        char* res = (char*)malloc(sizeof msg);
+        if (res) memcpy(res, msg, sizeof msg);
+        return res;
+    }
 }
 
 void tq_free(void* p) { free(p); }

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <new>
 #include <vector>
 
 #include "../../include/tqsim.h"
@@ -261,9 +262,11 @@ L550:
 
 struct tq_cobyla { Cobyla c; };
 
+// (exception barrier: nothing throws across the C ABI -- include/tqsim.h)
 extern "C" {
 
 int tq_cobyla_create(int n, const double* x0, double rhobeg, double rhoend, int maxfun, tq_cobyla_handle* out) {
+    try {
     if (!out) return TQ_EINVAL;
     *out = nullptr;
     if (n < 1 || !x0 || !(rhobeg > 0.0) || !(rhoend > 0.0) || rhoend > rhobeg || maxfun < 1) return TQ_EINVAL;
@@ -289,21 +292,39 @@ int tq_cobyla_create(int n, const double* x0, double rhobeg, double rhoend, int 
     next_eval(c);   // the first point is x0
     *out = h;
     return TQ_OK;
+    } catch (const std::bad_alloc&) {
+        return TQ_ENOMEM;
+    } catch (...) {
+        return TQ_EINVAL;
+    }
 }
 
 int tq_cobyla_destroy(tq_cobyla_handle h) {
+    try {
     delete h;
     return TQ_OK;
+    } catch (const std::bad_alloc&) {
+        return TQ_ENOMEM;
+    } catch (...) {
+        return TQ_EINVAL;
+    }
 }
 
 int tq_cobyla_ask(tq_cobyla_handle h, double* x_out) {
+    try {
     if (!h || !x_out) return TQ_EINVAL;
     if (!h->c.waiting) return 1;   // finished: nothing to evaluate
     std::copy(h->c.x.begin(), h->c.x.end(), x_out);
     return 0;
+    } catch (const std::bad_alloc&) {
+        return TQ_ENOMEM;
+    } catch (...) {
+        return TQ_EINVAL;
+    }
 }
 
 int tq_cobyla_tell(tq_cobyla_handle h, double f) {
+    try {
     if (!h) return TQ_EINVAL;
     Cobyla& c = h->c;
     if (!c.waiting) return TQ_ESTATE;
@@ -319,9 +340,15 @@ int tq_cobyla_tell(tq_cobyla_handle h, double f) {
         return 1;
     }
     return 0;
+    } catch (const std::bad_alloc&) {
+        return TQ_ENOMEM;
+    } catch (...) {
+        return TQ_EINVAL;
+    }
 }
 
 int tq_cobyla_result(tq_cobyla_handle h, double* x_out, double* f_out, int* nfev_out, int* status_out) {
+    try {
     if (!h) return TQ_EINVAL;
     const Cobyla& c = h->c;
     if (c.waiting) return TQ_ESTATE;
@@ -330,6 +357,11 @@ int tq_cobyla_result(tq_cobyla_handle h, double* x_out, double* f_out, int* nfev
     if (nfev_out) *nfev_out = c.nfvals;
     if (status_out) *status_out = c.status;
     return TQ_OK;
+    } catch (const std::bad_alloc&) {
+        return TQ_ENOMEM;
+    } catch (...) {
+        return TQ_EINVAL;
+    }
 }
 
 }  // extern "C"

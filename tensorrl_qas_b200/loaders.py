@@ -71,7 +71,12 @@ class _Reader:
 def load_qpy_circuit(path):
     """Parse the first circuit of a QPY v10-v14 file whose instructions are RX/RY/RZ/CX gates with float parameters."""
     with open(path, "rb") as f:
-        r = _Reader(f.read())
+        return load_qpy_bytes(f.read(), path)
+
+
+def load_qpy_bytes(data, path="<bytes>"):
+    """load_qpy_circuit on the file's contents (`path` only labels error messages)."""
+    r = _Reader(bytes(data))
     magic, version, _maj, _min, _pat, n_prog = r.unpack(_FILE_HEADER)
     if magic != b"QISKIT":
         raise ValueError(f"{path}: not a QPY file")

@@ -15,6 +15,7 @@ ask/tell COBYLA (`TQ_OPTIMIZER=native`, tensorrl_qas_b200/cobyla.py) a worker ha
 group (`LockstepGroup.optimise`): one thread hand-over per `step()`, all optimisers driven by one host loop, one launch per
 round -- 617 environment steps per second for 64 environments against 54-66 serial with scipy.
 """
+import itertools
 import threading
 
 import numpy as np
@@ -149,7 +150,8 @@ class LockstepGroup:
 def run_lockstep(tasks, seeds=None, evaluate_round=None, slot_prefix="lockstep"):
     """Run the callables `tasks` (one per environment) in worker threads whose energy evaluations are batched round by
     round.  seeds[i] (optional) seeds worker i's private noise generator.  Returns (results, group); an exception in any
-    worker is re-raised here after all workers have stopped."""
+    worker is re-raised here after all workers have stopped.  The workers' handles stay cached under `slot_prefix` for the
+    next call with the same prefix; `_backend.release_slots(slot_prefix)` drops them."""
     n = len(tasks)
     group = LockstepGroup(n, evaluate_round)
     results, errors = [None] * n, [None] * n
@@ -180,6 +182,9 @@ def run_lockstep(tasks, seeds=None, evaluate_round=None, slot_prefix="lockstep")
     return results, group
 
 
+_tags = itertools.count()
+
+
 class LockstepEnvs:
     """B environments advanced together: `reset_all()` and `step_all(actions)` mirror `CircuitEnv.reset()` / `.step()`
     element-wise.  Each environment keeps its own libtqsim handle (its circuit differs from the others')."""
@@ -189,7 +194,18 @@ class LockstepEnvs:
         self.seeds = seeds
         self._rngs = None if seeds is None else [np.random.default_rng(s) for s in seeds]
         self.last_group = None
-        self._tag = f"lockstep-{id(self)}"
+        self._tag = f"lockstep-{next(_tags)}"   # (not id(self): a recycled id would inherit a dead driver's handles)
+
+    def close(self):
+        """Release the per-environment libtqsim handles of this driver."""
+        _backend.release_slots(self._tag)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
     def _run(self, tasks):
         n = len(tasks)

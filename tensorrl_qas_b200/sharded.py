@@ -248,9 +248,14 @@ class TorchComm:
             return
         torch.cuda.synchronize(engine.device)
         self._dist.barrier(group=self.group)
-        for ptr in opened:
-            engine.lib.tq_ipc_close(engine.index, ctypes.c_void_p(ptr))
-        self._opened = []
+        try:
+            for ptr in opened:
+                engine.lib.tq_ipc_close(engine.index, ctypes.c_void_p(ptr))
+        finally:
+            self._opened = []
+            # second rendezvous: no rank may free its own (exported) shard buffers while a slower peer still has them
+            # mapped -- cudaFree of an allocation that is open in another process is undefined behaviour
+            self._dist.barrier(group=self.group)
 
 
 class LocalComm:
@@ -389,8 +394,10 @@ class ShardedSimulator:
                 step.close()
         self._program = self._copy_steps = None
         if self._xbufs is not None:
-            self.comm.release_exchange(self.engine)
-            self._xbufs = self._xtables = None
+            try:
+                self.comm.release_exchange(self.engine)   # (two barriers: unmap everywhere, THEN drop the own buffers)
+            finally:
+                self._xbufs = self._xtables = None
 
     def set_circuit(self, gl):
         if gl.n_qubits != self.n_qubits:

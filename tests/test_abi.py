@@ -51,3 +51,24 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_exception_barrier_on_cpu(built_lib):
+    """include/tqsim.h: nothing throws or aborts across the ABI.  Entry points that need no GPU are driven into C++
+    exceptions (std::length_error / std::bad_alloc from absurd sizes) and must come back with an error, not terminate."""
+    import ctypes
+    from tensorrl_qas_b200 import _lib
+    L = _lib.lib()
+    ip, dp = _lib.c_int_p, _lib.c_dbl_p
+    z = (ctypes.c_int32 * 1)(0)
+    f = (ctypes.c_double * 1)(0.0)
+    ptr = L.tq_plan_dump(4, -1, ctypes.cast(z, ip), ctypes.cast(z, ip), ctypes.cast(z, ip), ctypes.cast(z, ip),
+                         ctypes.cast(f, dp), 0, 12, 3, 0, None)
+    assert ptr
+    text = ctypes.string_at(ptr).decode()
+    L.tq_free(ptr)
+    assert text.startswith("ERROR")
+    h = ctypes.c_void_p()
+    x0 = (ctypes.c_double * 1)(0.0)
+    rc = L.tq_cobyla_create(2 ** 31 - 1, ctypes.cast(x0, dp), 1.0, 1e-4, 10, ctypes.byref(h))
+    assert rc in (-4, -1) and not h.value      # TQ_ENOMEM (or TQ_EINVAL): reported, not thrown

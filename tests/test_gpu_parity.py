@@ -390,3 +390,25 @@ def test_zero_skipping_from_the_all_zero_state(built_lib, oracle, monkeypatch):
         p = parameter_batch(gl, 3)
         assert np.abs(e1 - oracle.energies(gl, p, pauli=(x, z, w))).max() < TOL
         assert np.abs(s1 - oracle.state(gl, p[0])).max() < 1e-12
+
+
+def test_out_of_memory_is_an_error_code(built_lib, monkeypatch):
+    """TQ_ENOMEM with a message instead of an abort: a state larger than the scratch limit, and an impossible device
+    allocation (include/tqsim.h error model)."""
+    import ctypes
+    from tensorrl_qas_b200 import _lib
+    from tensorrl_qas_b200.simulator import TqError
+    monkeypatch.setenv("TQ_MAX_SCRATCH_MB", "8")
+    n = 20
+    paulis, w = loaders.heisenberg_terms(n)
+    x, z = loaders.pauli_masks(paulis, n)
+    gl = brickwork_circuit(n, 21, 41, 5)
+    sim = Simulator(n, 0)
+    sim.set_pauli_hamiltonian(x, z, w)
+    sim.set_circuit(gl)
+    with pytest.raises(TqError) as e:
+        sim.energies(parameter_batch(gl, 2))
+    assert e.value.code == -4 and "TQ_MAX_SCRATCH_MB" in str(e.value)
+    sim.close()
+    out = ctypes.c_void_p()
+    assert _lib.lib().tq_device_alloc(0, 1 << 46, ctypes.byref(out)) == -4 and not out.value
