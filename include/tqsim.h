@@ -203,6 +203,25 @@ int tq_plan_counts(tq_handle h, int which, int64_t* counts8);
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t tq_launch_count(tq_handle h);
 
+/* Per-launch device timing (bench.py's measured roofline; replaces profiler-derived constants).  While enabled, every
+ * kernel launch of the handle is bracketed by a CUDA-event pair on the launch stream.  tq_profile_read waits for the
+ * recorded launches, returns them in issue order and clears the list:
+ *   kind[i]         0 prep_matrices  1 tile_pass (FP64-pipe windows)  2 tile_pass_mma  3 tile_stream (gate pass)
+ *                   4 tile_stream (gate pass + expectation windows)  5 tile_stream (expectation-only sub-passes)
+ *                   6 expect_direct  7 reduce_partials  8 dm_expect  9 table launch (tq_energy_multi_host)
+ *   ms[i]           device time of the launch
+ *   model_bytes[i]  HBM bytes the compiled plan moves in it (populated part of the state in, whole tiles out)
+ *   alg_bytes[i]    bytes the reference's one-state-pass-per-gate model charges for the gates / Hamiltonian groups the
+ *                   launch covers (16 * 2^n * (2 G + M) per evaluation)
+ * Any output array may be NULL. */
+int tq_profile_enable(tq_handle h, int on);
+int tq_profile_read(tq_handle h, int max_records, int32_t* kind, float* ms, double* model_bytes, double* alg_bytes,
+                    int* n_out);
+
+/* Measured FP64 peak of the device in TFLOP/s: which = 0 mma.sync.m8n8k4.f64 (the tensor-core instruction of the fused
+ * dense blocks), 1 DFMA on the FP64 pipe.  Best of three timed runs of a register-resident kernel. */
+int tq_fp64_peak(int device, int which, double* tflops_out);
+
 /* Diagnostics -- planner dry run, needs no GPU: text dump ("PASS lead=.. local=a,b,.." / "OP op a b t flags fixed"
  * lines) of the tile passes the circuit compiler produces for a gate list.  which as in tq_plan_info (2 =
  * trajectory-noise plan); which | 16 additionally assigns a synthetic Hamiltonian built from cover_masks to the passes and

@@ -40,6 +40,8 @@ struct DevPass {
     bool gate_pass = true;
     bool no_ops = false;     // the single pass of a gate-free circuit: it only stages the state
     // streaming kernel (tq_stream.cu): layouts chosen by the planner, window headers resolved for them
+    int n_gates = 0;         // reference gates fused into this pass (SURVEY.md section 8d traffic model)
+    int n_exp_groups = 0;    // Hamiltonian flip-mask groups evaluated in this pass
     bool stream = false;
     bool sparse_ok = false;  // the known-zero bookkeeping of run_plan matches what the planner assumed (support_in)
     uint64_t support_in = ~0ull;
@@ -121,6 +123,11 @@ struct tq_context {
     size_t d_stage_cap = 0;
 
     int64_t launches = 0;
+
+    // optional per-launch timing (tq_profile_enable / tq_profile_read): a CUDA-event pair around every launch
+    struct ProfRec { int kind; cudaEvent_t e0, e1; double model_bytes, alg_bytes; };
+    bool profile = false;
+    std::vector<ProfRec> prof;
 };
 
 namespace {
@@ -416,6 +423,11 @@ int compile_plan(tq_handle h, int which) {
         dp.gate_pass = (int)i < n_gate_passes;
         dp.no_ops = passes[i].ops.empty();
         dp.direct = passes[i].direct;
+        for (const DevOp& d : passes[i].ops) {   // a block stands for the gates of its matrix program, anything else for one
+            const bool has_mat = d.op == OP_U2 || d.op == OP_U1 || d.op == OP_D1 || d.op == OP_D1_NL;
+            dp.n_gates += (has_mat && d.t >= 0 && d.t < (int)cc.mats.size()) ? std::max(1, cc.mats[d.t].end - cc.mats[d.t].begin) : 1;
+        }
+        dp.n_exp_groups = (int)groups_of_pass[i].size();
         if (passes[i].mma && passes[i].stream) {
             dp.stream = true;
             dp.support_in = passes[i].support_in;
@@ -612,6 +624,21 @@ void fill_tma(StreamTma& t, const StreamLayout& L) {
     for (int i = 0; i < L.n_ops; ++i) t.op_goff[i] = L.op_goff[i];
 }
 
+// per-launch timing records (kinds: see tq_profile_read in include/tqsim.h)
+enum { PK_PREP = 0, PK_TILE = 1, PK_TILE_MMA = 2, PK_STREAM_GATE = 3, PK_STREAM_GATE_EXP = 4, PK_STREAM_EXP = 5,
+       PK_DIRECT = 6, PK_REDUCE = 7, PK_DM_EXPECT = 8, PK_TABLE = 9 };
+void prof_begin(tq_handle h, cudaStream_t stream, int kind, double model_bytes, double alg_bytes) {
+    if (!h->profile) return;
+    tq_context::ProfRec r{kind, nullptr, nullptr, model_bytes, alg_bytes};
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, stream);
+    h->prof.push_back(r);
+}
+void prof_end(tq_handle h, cudaStream_t stream) {
+    if (!h->profile || h->prof.empty()) return;
+    cudaEventRecord(h->prof.back().e1, stream);
+}
+
 // Run the plan for `batch` elements: energies into `out` and / or final states into `states_out`.  from_states: the
 // elements start from the states already in `states_out` (device-resident, evolved in place) instead of the handle's
 // initial state.
@@ -675,8 +702,10 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
         // single-tile plans (one CTA per element): the pass kernel evaluates the block matrices itself -> one launch
         const bool fuse_prep = plan.n_mats > 0 && total_passes == 1 && plan.passes[0].proto.n_nl == 0 && h->fuse_prep;
         if (plan.n_mats > 0 && !fuse_prep) {
+            prof_begin(h, stream, PK_PREP, 0.0, 0.0);
             launch_prep_matrices(plan.d_descs, plan.d_prog, plan.n_mats, bc, params ? params + (size_t)b0 * ld : nullptr, ld,
                                  codes ? codes + (size_t)b0 * ldc : nullptr, ldc, h->d_mats, stream);
+            prof_end(h, stream);
             ++h->launches;
             rc = check_launch(h, "prep_matrices_kernel");
             if (rc) return rc;
@@ -687,6 +716,7 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
         std::unique_ptr<StreamParams> gstream(new StreamParams), estream(new StreamParams);
         memset(estream.get(), 0, sizeof(StreamParams));
         int estream_windows = 0, estream_ops = 0;
+        double estream_model = 0.0, estream_alg = 0.0, direct_model = 0.0, direct_alg = 0.0;
         for (int i = 0; i < total_passes; ++i) {
             const DevPass& dp = plan.passes[i];
             PassParams pp = dp.proto;
@@ -741,6 +771,21 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 pp.direct = (dp.direct && pp.src_mode == 2 && pp.exp_mode == 1 && pp.n_groups == 0 && !pp.dst &&
                              plan.nbits <= 27 /* 32-bit byte offsets inside an element */) ? 1 : 0;
             }
+            // bytes this launch has to move (plan model: live part of the state in, whole tiles out) and the bytes the
+            // reference's one-pass-per-gate model charges for the same work
+            double model_bytes = 0.0;
+            {
+                const double tile_bytes = 16.0 * (double)(1u << pp.k_eff);
+                const double tiles_run = (double)bc * (double)(1u << pp.n_nl);
+                double in_frac = 1.0;   // share of a tile that is read: only the populated positions of a run from |0...0>
+                if (pp.in_mask != ~0ull)
+                    for (int q = 0; q < pp.k; ++q)
+                        if (!((pp.in_mask >> pp.local[q]) & 1ull)) in_frac *= 0.5;
+                if (pp.src_mode == 2) model_bytes += tiles_run * tile_bytes * in_frac;
+                else if (pp.src_mode == 1) model_bytes += (double)elem_bytes;
+                if (pp.dst) model_bytes += tiles_run * tile_bytes;
+            }
+            const double alg_bytes = (double)bc * (double)elem_bytes * (2.0 * dp.n_gates + (pp.exp_mode ? dp.n_exp_groups : 0));
             // ---- streaming kernel (persistent CTAs, TMA tile I/O) for multi-tile tensor-core passes ----
             const bool sparse_in = pp.in_mask != ~0ull;
             const bool use_stream = h->stream_kernel && (dp.gate_pass ? !dp.no_ops : (h->stream_expect && pp.exp_mode == 1)) &&
@@ -775,6 +820,8 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                         fprintf(stderr, "[tqsim] streaming kernel disabled: %s\n", terr.c_str());
                         h->stream_kernel = false;
                     } else if (exp_only) {
+                        estream_model += model_bytes;
+                        estream_alg += alg_bytes;
                         ++sp.n_sub;
                         estream_windows += pp.n_windows;
                         estream_ops += pp.n_wops;
@@ -784,7 +831,9 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                         sp.batch = bc;
                         sp.contiguous = 1;
                         const long long tiles = (long long)bc << pp.n_nl;
+                        prof_begin(h, stream, pp.exp_mode == 1 ? PK_STREAM_GATE_EXP : PK_STREAM_GATE, model_bytes, alg_bytes);
                         launch_tile_stream(sp, (int)std::min<long long>(tiles, h->n_sms), stream);
+                        prof_end(h, stream);
                         ++h->launches;
                         ++h->stream_launches;
                         rc = check_launch(h, "tile_stream_kernel");
@@ -799,11 +848,15 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 // expectation-only pass that streams the state: a sub-pass of the one persistent launch below
                 direct_windows += pp.n_windows - pp.n_gate_windows;
                 direct_ops += pp.n_wops;
+                direct_model += model_bytes;
+                direct_alg += alg_bytes;
                 direct_threads = dp.threads;
                 direct.sub[direct.n_sub++] = pp;
                 continue;
             }
+            prof_begin(h, stream, pp.mwindows ? PK_TILE_MMA : PK_TILE, model_bytes, alg_bytes);
             launch_tile_pass(pp, bc, dp.threads, dm, stream);
+            prof_end(h, stream);
             ++h->launches;
             rc = check_launch(h, "tile_pass_kernel");
             if (rc) return rc;
@@ -812,7 +865,9 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
             estream->batch = bc;
             estream->contiguous = 0;
             const long long tiles = (long long)bc << estream->sub[0].pp.n_nl;
+            prof_begin(h, stream, PK_STREAM_EXP, estream_model, estream_alg);
             launch_tile_stream(*estream, (int)std::min<long long>(tiles, h->n_sms), stream);
+            prof_end(h, stream);
             ++h->launches;
             ++h->stream_launches;
             rc = check_launch(h, "tile_stream_kernel (expectation)");
@@ -821,20 +876,26 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
         if (direct.n_sub > 0) {
             direct.batch = bc;
             const long long tiles = (long long)bc << direct.sub[0].n_nl;
+            prof_begin(h, stream, PK_DIRECT, direct_model, direct_alg);
             launch_expect_direct(direct, (int)std::min<long long>(tiles, (long long)h->n_sms * h->direct_ctas_per_sm),
                                  direct_threads, stream);
+            prof_end(h, stream);
             ++h->launches;
             rc = check_launch(h, "expect_direct_kernel");
             if (rc) return rc;
         }
         if (want_energy) {
             if (dm) {
+                prof_begin(h, stream, PK_DM_EXPECT, (double)h->hent.size() * 16.0 * bc, (double)bc * (double)elem_bytes);
                 launch_dm_expect(buf, h->n, h->d_hent, (int)h->hent.size(), out + b0, bc, stream);
+                prof_end(h, stream);
                 ++h->launches;
                 rc = check_launch(h, "dm_expect_kernel");
                 if (rc) return rc;
             } else if (plan.slots > 1) {
+                prof_begin(h, stream, PK_REDUCE, (double)bc * plan.slots * 8.0, 0.0);
                 launch_reduce_partials(h->d_partial, plan.slots, plan.slots, out + b0, bc, stream);
+                prof_end(h, stream);
                 ++h->launches;
                 rc = check_launch(h, "reduce_partials_kernel");
                 if (rc) return rc;
@@ -1008,6 +1069,7 @@ int tq_destroy(tq_handle h) {
     if (h->d_mats) cudaFree(h->d_mats);
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->h_pin) cudaFreeHost(h->h_pin);
+    for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return TQ_OK;
@@ -1423,6 +1485,62 @@ int tq_plan_counts(tq_handle h, int which, int64_t* counts8) {
 }
 
 int64_t tq_launch_count(tq_handle h) { return h ? h->launches : 0; }
+
+int tq_profile_enable(tq_handle h, int on) {
+    TQ_API_TRY
+    if (!h) return TQ_EINVAL;
+    TQ_CUDA(cudaSetDevice(h->device));
+    for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    h->prof.clear();
+    h->profile = on != 0;
+    return TQ_OK;
+    TQ_API_CATCH(h)
+}
+
+int tq_profile_read(tq_handle h, int max_records, int32_t* kind, float* ms, double* model_bytes, double* alg_bytes,
+                    int* n_out) {
+    TQ_API_TRY
+    if (!h || !n_out || max_records < 0) return TQ_EINVAL;
+    TQ_CUDA(cudaSetDevice(h->device));
+    int n = 0;
+    for (auto& r : h->prof) {
+        TQ_CUDA(cudaEventSynchronize(r.e1));
+        float t = 0.f;
+        TQ_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        if (n < max_records) {
+            if (kind) kind[n] = r.kind;
+            if (ms) ms[n] = t;
+            if (model_bytes) model_bytes[n] = r.model_bytes;
+            if (alg_bytes) alg_bytes[n] = r.alg_bytes;
+            ++n;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    h->prof.clear();
+    *n_out = n;
+    return TQ_OK;
+    TQ_API_CATCH(h)
+}
+
+int tq_fp64_peak(int device, int which, double* tflops_out) {
+    TQ_API_TRY
+    if (!tflops_out || which < 0 || which > 1) return TQ_EINVAL;
+    tq_handle h = nullptr;
+    TQ_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TQ_CUDA(cudaGetDeviceProperties(&prop, device));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        float ms = 0.f;
+        const double flop = fp64_peak_run(which, prop.multiProcessorCount, &ms);
+        if (flop <= 0.0 || ms <= 0.f) return api_fail(nullptr, TQ_ECUDA, "fp64 peak kernel failed");
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);   // (first run: warm-up)
+    }
+    *tflops_out = best;
+    return TQ_OK;
+    TQ_API_CATCH(nullptr)
+}
 
 // --------------------------------------------------------------------------------------------------------------
 // Planner dry run (no GPU needed): text dump of the passes for a gate list, used by the CPU test-suite to check

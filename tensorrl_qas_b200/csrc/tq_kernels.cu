@@ -1247,7 +1247,60 @@ __global__ void __launch_bounds__(kMaxThreads) dm_expect_kernel(const double2* _
     if (threadIdx.x == 0) out[blockIdx.x] = total;
 }
 
+// ---- FP64 peak microbenchmark (bench.py's roofline denominator for the tensor-core work; MEASURED_PEAKS.json has none) ----
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int which, int iters, double* sink) {
+    const int lane = threadIdx.x & 31;
+    if (which == 0) {   // DMMA: 8 independent accumulator pairs per warp, b-operand fixed
+        double d[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) d[i] = 1e-3 * (lane + i);
+        const double a = 1.0 + 1e-9 * lane, b = 1.0 - 1e-9 * lane;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) dmma884(d[i], d[i + 1], a, b, d[i], d[i + 1]);
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += d[i];
+        if (s == 123.456) sink[0] = s;
+    } else {            // DFMA: 16 independent chains per thread
+        double d[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) d[i] = 1e-3 * (lane + i);
+        const double a = 1.0 - 1e-9, b = 1e-12 * lane;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) d[i] = fma(d[i], a, b);
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += d[i];
+        if (s == 123.456) sink[0] = s;
+    }
+}
+
 }  // namespace
+
+double fp64_peak_run(int which, int n_sms, float* ms_out) {
+    const int iters = 4096, blocks = n_sms * 4, threads = 256;
+    double* sink = nullptr;
+    if (cudaMalloc(&sink, 8) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(which, iters, sink);
+    cudaEventRecord(e1);
+    const cudaError_t err = cudaEventSynchronize(e1);
+    cudaEventElapsedTime(ms_out, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (err != cudaSuccess || cudaGetLastError() != cudaSuccess) return -1.0;
+    const double warps = (double)blocks * threads / 32.0;
+    // DMMA m8n8k4: 8 * 8 * 4 FMA = 512 flop per warp instruction; DFMA: 2 flop per lane
+    return which == 0 ? warps * iters * 8.0 * 512.0 : warps * 32.0 * iters * 16.0 * 2.0;
+}
 
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead) {
     const size_t n_hi = (size_t)1 << (k - lead);

@@ -125,6 +125,10 @@ size_t tile_stream_smem_bytes();
 cudaError_t tile_stream_configure();   // opt in to the dynamic shared memory
 void launch_tile_stream(const StreamParams& sp, int n_ctas, cudaStream_t stream);
 
+// FP64 peak of the device, measured (tq_fp64_peak): which = 0 mma.sync.m8n8k4.f64 chains as the pass kernels issue them,
+// 1 DFMA chains on the FP64 pipe.  Returns the flop executed and the kernel time.
+double fp64_peak_run(int which, int n_sms, float* ms_out);
+
 size_t tile_pass_smem_bytes(int k_eff, int k, int lead);
 cudaError_t tile_pass_configure();  // opt in to > 48 KiB dynamic shared memory
 void launch_tile_pass(const PassParams& p, int batch, int threads, bool density, cudaStream_t stream);

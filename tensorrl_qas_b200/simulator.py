@@ -222,6 +222,25 @@ class Simulator:
     def launch_count(self):
         return int(self._L.tq_launch_count(self._h))
 
+    PROFILE_KINDS = ("prep_matrices_kernel", "tile_pass_kernel", "tile_pass_mma_kernel", "tile_stream_kernel<gates>",
+                     "tile_stream_kernel<gates+expect>", "tile_stream_kernel<expect>", "expect_direct_kernel",
+                     "reduce_partials_kernel", "dm_expect_kernel", "tile_pass_kernel<table>")
+
+    def profile(self, on=True):
+        """Bracket every kernel launch of this handle with CUDA events (tq_profile_enable)."""
+        self._check(self._L.tq_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, max_records=4096):
+        """Launches recorded since profile(True) / the last read: list of dicts (kernel, ms, model_bytes, alg_bytes)."""
+        kind = (ctypes.c_int32 * max_records)()
+        ms = (ctypes.c_float * max_records)()
+        mb = (ctypes.c_double * max_records)()
+        ab = (ctypes.c_double * max_records)()
+        n = ctypes.c_int32(0)
+        self._check(self._L.tq_profile_read(self._h, max_records, kind, ms, mb, ab, ctypes.byref(n)))
+        return [{"kernel": self.PROFILE_KINDS[kind[i]], "ms": float(ms[i]), "model_bytes": float(mb[i]),
+                 "alg_bytes": float(ab[i])} for i in range(n.value)]
+
 
 def energies_multi(sims, params, codes=None):
     """One launch for len(sims) DIFFERENT problems (tq_energy_multi_host): sims[i] is a Simulator with its own circuit /
@@ -247,6 +266,15 @@ def energies_multi(sims, params, codes=None):
     if rc != 0:
         raise TqError(rc, L.tq_last_error(sims[0]._h).decode())
     return out
+
+
+def fp64_peak(device=0, which=0):
+    """Measured FP64 peak in TFLOP/s: which = 0 DMMA (mma.sync.m8n8k4.f64), 1 DFMA (tq_fp64_peak)."""
+    out = ctypes.c_double(0.0)
+    rc = _lib.lib().tq_fp64_peak(int(device), int(which), ctypes.byref(out))
+    if rc != 0:
+        raise TqError(rc, "tq_fp64_peak failed")
+    return float(out.value)
 
 
 def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=(), with_mats=False):

@@ -42,76 +42,81 @@ def _check_batch(sim_energies, oracle_energies, params, sample):
 
 
 def test_c1_four_qubit_dense_hamiltonian_latency_case(built_lib, oracle):
-    """C1: 4 qubits, dense 16x16 Hamiltonian (the shipped LiH-4q file is dense-only: a random Hermitian matrix with the
-    same structure here), loaded initial state from a 27-gate brickwork, 20 agent gates; B = 1 and B = 4096."""
-    n = 4
-    rng = np.random.default_rng(41)
-    A = rng.normal(size=(16, 16)) + 1j * rng.normal(size=(16, 16))
-    H = A + A.conj().T
-    init = oracle.state(synthetic_circuit(n, 27, 0), parameter_batch(synthetic_circuit(n, 27, 0), 1)[0])
-    gl = synthetic_circuit(n, 20, 1)
-    sim = Simulator(n)
-    sim.set_circuit(gl)
-    sim.set_init_state(init)
-    sim.set_dense_hamiltonian(H)
-    ref = lambda p: oracle.energies(gl, p, dense=H, init=init)  # noqa: E731
-    one = parameter_batch(gl, 1)
-    assert abs(sim.energies(one)[0] - ref(one)[0]) < TOL
-    _check_batch(sim.energies, ref, parameter_batch(gl, 4096), 32)
+    """C1 (bench_workloads.build("C1")): 4 qubits, the reference's shipped LiH-4q dense parity Hamiltonian
+    (tests/golden/lih_4q_parity.npz; it has no Pauli list: the trace projection gives 100 terms in 16 flip groups), loaded
+    initial state from a 27-gate brickwork, 20 agent gates; B = 1 and B = 4096."""
+    import bench_workloads
+    w = bench_workloads.build("C1")
+    assert w.dense.shape == (16, 16) and np.abs(w.dense - w.dense.conj().T).max() == 0 and w.groups == 16
+    # the shipped eigvals are those of the shipped matrix (complex64 precision)
+    assert abs(np.linalg.eigvalsh(w.dense).min() - w.eig_min) < 1e-6
+    # the loaded state (made with plain numpy in bench_workloads) is what the oracle gets for the same circuit
+    init_gl = synthetic_circuit(4, 27, 0)
+    assert np.abs(oracle.state(init_gl, parameter_batch(init_gl, 1)[0]) - w.init).max() < 1e-14
+    sim = w.bind(Simulator(w.n))
+    one = w.params(1)
+    assert abs(sim.energies(one)[0] - w.oracle_energies(one)[0]) < TOL
+    e = _check_batch(sim.energies, w.oracle_energies, w.params(4096), 32)
+    assert e.min() >= w.eig_min - 1e-6
     # the dense form through its Pauli decomposition (trace projection) agrees
-    x, z, c = loaders.dense_to_pauli(H)
+    x, z, c = loaders.dense_to_pauli(w.dense)
+    assert len(c) == 100
     sim.set_pauli_hamiltonian(x, z, c)
-    assert abs(sim.energies(one)[0] - ref(one)[0]) < TOL
+    assert abs(sim.energies(one)[0] - w.oracle_energies(one)[0]) < TOL
     sim.close()
 
 
 def test_c2_beh2_trainable_256_parameter_sets(built_lib, oracle):
     """C2: BeH2-6q (the shipped substitute for the non-existent LiH-6q), trainable-env circuit from the shipped QPY
     (mirrored, negated, float32 angles) + agent gates, P ~ 105, B = 256."""
-    c = Case("beh2_6q")
-    gl = _with_agent_gates(c.gatelist("in"), 20, 2)
-    H = c.dense(False)
-    sim = Simulator(c.n)
-    sim.set_circuit(gl)
-    sim.set_dense_hamiltonian(H)
-    e = _check_batch(sim.energies, lambda p: oracle.energies(gl, p, dense=H), parameter_batch(gl, 256), 24)
-    assert e.min() >= c.eig_min - 1e-9   # variational bound against the shipped eigvals
+    import bench_workloads
+    w = bench_workloads.build("C2")
+    sim = w.bind(Simulator(w.n))
+    e = _check_batch(sim.energies, w.oracle_energies, w.params(256), 24)
+    assert e.min() >= w.eig_min - 1e-9   # variational bound against the shipped eigvals
     sim.close()
 
 
 def test_c3_h2o_fixed_4096_cost_evaluations(built_lib, oracle):
     """C3: H2O-8q fixed env: TN state from the shipped QPY loaded, bit-reversed Hamiltonian, 20 agent gates, B = 4096."""
-    c = Case("h2o_8q")
-    gl = synthetic_circuit(c.n, 20, 3)
-    H = c.dense(True)
-    tn = c.g["notin_tn_state"]
-    sim = Simulator(c.n)
-    sim.set_circuit(gl)
-    sim.set_init_state(tn)
-    sim.set_dense_hamiltonian(H)
-    e = _check_batch(sim.energies, lambda p: oracle.energies(gl, p, dense=H, init=tn), parameter_batch(gl, 4096), 32)
-    assert e.min() >= c.eig_min - 1e-9
+    import bench_workloads
+    w = bench_workloads.build("C3")
+    sim = w.bind(Simulator(w.n))
+    e = _check_batch(sim.energies, w.oracle_energies, w.params(4096), 32)
+    assert e.min() >= w.eig_min - 1e-9
     sim.close()
 
 
 def test_c4_eight_qubit_depolarising_density_matrix(built_lib, oracle):
     """C4: environment_qulacs_noise semantics on H2O-8q: shipped QPY circuit (150 gates) + 40 agent gates, p1 = 0.01
     after every rotation, p2 = 0.05 after every CNOT, exact channels on rho (2^16 entries); B = 64."""
-    c = Case("h2o_8q")
-    gl = _noisy(_with_agent_gates(c.gatelist("in"), 40, 4))
-    assert gl.n_unitary >= 150
-    H = c.dense(False)
-    sim = Simulator(c.n)
-    sim.set_circuit(gl)
-    sim.set_dense_hamiltonian(H)
-    params = parameter_batch(gl, 64)
+    import bench_workloads
+    w = bench_workloads.build("C4")
+    gl = w.gl
+    assert gl.n_unitary >= 150 and w.mode == "dm"
+    sim = w.bind(Simulator(w.n))
+    params = w.params(64)
     e = sim.energies_dm(params)
     idx = [0, 21, 42, 63]
-    assert np.abs(e[idx] - oracle.dm_energies(gl, params[idx], dense=H)).max() < TOL
+    assert np.abs(e[idx] - w.oracle_energies(params[idx])).max() < TOL
     assert np.array_equal(sim.energies_dm(params[::-1].copy()), e[::-1])
     # a depolarised state sits above the noise-free energy of the same circuit and inside the spectrum
     clean = sim.energies(params)
-    assert np.all(e >= c.eig_min - 1e-9) and np.abs(e - clean).max() > 1e-3
+    assert np.all(e >= w.eig_min - 1e-9) and np.abs(e - clean).max() > 1e-3
+    sim.close()
+
+
+@pytest.mark.parametrize("name", ["C5L", "C5G"])
+def test_c5_companions(built_lib, oracle, name):
+    """C5's companions of the bench: a loaded dense initial state (known-zero skipping off) and 440 gates from the generic
+    generator (no brick structure); two elements against the oracle, batch independence on eight."""
+    import bench_workloads
+    w = bench_workloads.build(name)
+    sim = w.bind(Simulator(w.n))
+    params = w.params(8)
+    e = sim.energies(params)
+    assert np.abs(e[:2] - w.oracle_energies(params[:2])).max() < TOL
+    assert np.array_equal(sim.energies(params[::-1].copy()), e[::-1])
     sim.close()
 
 
