@@ -203,6 +203,14 @@ int tq_plan_counts(tq_handle h, int which, int64_t* counts8);
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t tq_launch_count(tq_handle h);
 
+/* Compiled plans are cached per handle, keyed on the gate list (kinds, qubits, parameter slots, fixed angles; angles bound
+ * through param_idx are run-time parameters and do not enter the key): tq_set_circuit with the circuit that is already
+ * bound is a no-op, a circuit seen before gets its plan back without recompilation (least recently used of
+ * TQ_PLAN_CACHE = 64 circuits evicted; setting a Hamiltonian drops the cache).  The reference rebuilds its circuit twice
+ * per environment step (environments/environment_qulacs.py:409-411, 423-425) and revisits the same structures episode
+ * after episode.  stats4: plans restored from the cache, circuits compiled afresh, no-op calls, circuits cached now. */
+int tq_plan_cache_stats(tq_handle h, int64_t* stats4);
+
 /* Per-launch device timing (bench.py's measured roofline; replaces profiler-derived constants).  While enabled, every
  * kernel launch of the handle is bracketed by a CUDA-event pair on the launch stream.  tq_profile_read waits for the
  * recorded launches, returns them in issue order and clears the list:

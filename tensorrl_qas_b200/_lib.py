@@ -66,6 +66,7 @@ SIGNATURES = {
     "tq_plan_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p]),
     "tq_plan_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p]),
     "tq_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "tq_plan_cache_stats": (ctypes.c_int, [ctypes.c_void_p, c_i64_p]),
     "tq_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "tq_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_int_p, ctypes.POINTER(ctypes.c_float), c_dbl_p,
                                        c_dbl_p, c_int_p]),

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <list>
 #include <map>
 #include <memory>
 #include <new>
@@ -106,6 +107,19 @@ struct tq_context {
     int n_params = 0, n_slots = 0;
     Plan plan_sv, plan_traj, plan_dm;
 
+    // compiled plans of circuits seen before (tq_set_circuit): an RL environment rebuilds its circuit twice per step and
+    // revisits the same structures episode after episode; angles are parameters, so a plan only depends on the gate list
+    struct CachedCircuit {
+        uint64_t hash = 0;
+        std::vector<Gate> gates;
+        int n_params = 0, n_slots = 0;
+        Plan plan_sv, plan_traj, plan_dm;
+    };
+    std::list<CachedCircuit> plan_cache;   // most recently used first
+    int plan_cache_cap = 64;               // TQ_PLAN_CACHE (0 = off)
+    uint64_t circuit_hash = 0;
+    int64_t cache_hits = 0, cache_misses = 0, cache_same = 0;
+
     // scratch
     double2* d_state = nullptr;
     size_t state_cap = 0;  // bytes
@@ -175,6 +189,43 @@ int env_int(const char* name, int dflt) {
 
 void invalidate_plans(tq_handle h) {
     h->plan_sv.valid = h->plan_traj.valid = h->plan_dm.valid = false;
+}
+
+void free_plan(Plan& p) {
+    if (p.arena) cudaFree(p.arena);
+    p = Plan();
+}
+
+// the Hamiltonian (or anything else the plans were compiled against) changed: nothing cached is valid any more
+void drop_plan_cache(tq_handle h) {
+    for (auto& c : h->plan_cache) { free_plan(c.plan_sv); free_plan(c.plan_traj); free_plan(c.plan_dm); }
+    h->plan_cache.clear();
+    invalidate_plans(h);
+}
+
+// a rotation bound to a parameter column takes its angle at evaluation time: `fixed` (its initial value in the callers'
+// gate lists) is not part of the compiled plan
+inline bool angle_is_parameter(const Gate& g) { return g.kind >= TQ_RX && g.kind <= TQ_RZ && g.pidx >= 0; }
+
+uint64_t hash_gates(const std::vector<Gate>& gates, int n_params) {
+    uint64_t x = 1469598103934665603ull ^ (uint64_t)n_params;   // FNV-1a over the gate records
+    for (const Gate& g : gates) {
+        uint64_t w[3];
+        w[0] = ((uint64_t)(uint32_t)g.kind << 32) | (uint32_t)g.q0;
+        w[1] = ((uint64_t)(uint32_t)g.q1 << 32) | (uint32_t)g.pidx;
+        w[2] = 0;
+        if (!angle_is_parameter(g)) memcpy(&w[2], &g.fixed, 8);
+        for (uint64_t v : w) { x ^= v; x *= 1099511628211ull; }
+    }
+    return x;
+}
+bool same_gates(const std::vector<Gate>& a, const std::vector<Gate>& b) {
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); ++i)
+        if (a[i].kind != b[i].kind || a[i].q0 != b[i].q0 || a[i].q1 != b[i].q1 || a[i].pidx != b[i].pidx ||
+            (!angle_is_parameter(a[i]) && memcmp(&a[i].fixed, &b[i].fixed, 8) != 0))
+            return false;
+    return true;
 }
 
 cudaError_t upload_sync(tq_handle h, void* dst, const void* src, size_t bytes) {
@@ -1041,6 +1092,7 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->sparse_init = env_int("TQ_SPARSE_INIT", 1) != 0;
     h->direct_kernel = env_int("TQ_DIRECT_KERNEL", 1) != 0;
     h->stream_kernel = env_int("TQ_STREAM", 2) != 0;
+    h->plan_cache_cap = std::max(0, std::min(1024, env_int("TQ_PLAN_CACHE", 64)));
     h->stream_expect = env_int("TQ_STREAM", 2) >= 2;
     h->direct_ctas_per_sm = std::max(1, std::min(8, env_int("TQ_DIRECT_CTAS", 2)));
     h->n_sms = prop.multiProcessorCount;
@@ -1061,6 +1113,9 @@ int tq_destroy(tq_handle h) {
     cudaDeviceSynchronize();
     for (Plan* p : {&h->plan_sv, &h->plan_traj, &h->plan_dm})
         if (p->arena) cudaFree(p->arena);
+    for (auto& c : h->plan_cache)
+        for (Plan* p : {&c.plan_sv, &c.plan_traj, &c.plan_dm})
+            if (p->arena) cudaFree(p->arena);
     if (h->d_hent) cudaFree(h->d_hent);
     if (h->d_init) cudaFree(h->d_init);
     if (h->d_init_rho) cudaFree(h->d_init_rho);
@@ -1106,7 +1161,7 @@ int tq_set_pauli_hamiltonian(tq_handle h, int n_terms, const uint64_t* xmask, co
     h->hent.clear();
     if (h->n <= 13) entries_from_pauli(h);
     h->hent_uploaded = false;
-    invalidate_plans(h);
+    drop_plan_cache(h);   // the plans (expectation windows, groups) were compiled against the old Hamiltonian
     return TQ_OK;
     TQ_API_CATCH(h)
 }
@@ -1126,7 +1181,7 @@ int tq_set_dense_hamiltonian(tq_handle h, const double* h_matrix_host) {
     h->groups.clear();
     h->px.clear();
     h->hent_uploaded = false;
-    invalidate_plans(h);
+    drop_plan_cache(h);   // the plans (expectation windows, groups) were compiled against the old Hamiltonian
     return TQ_OK;
     TQ_API_CATCH(h)
 }
@@ -1164,15 +1219,63 @@ int tq_set_circuit(tq_handle h, int n_gates, const int32_t* kind, const int32_t*
             if (!(fixed[g] >= 0.0 && fixed[g] <= 1.0)) return fail(h, TQ_EINVAL, "gate " + std::to_string(g) + ": probability outside [0, 1]");
         }
     }
+    const uint64_t hash = hash_gates(gates, n_params);
+    if (h->have_circuit && hash == h->circuit_hash && n_params == h->n_params && same_gates(gates, h->gates)) {
+        ++h->cache_same;   // the circuit that is already bound (the environments build it twice per step): nothing to do
+        return TQ_OK;
+    }
     std::string perr;
-    PlanOptions probe = h->opt;
-    (void)plan_statevector(h->n, gates, probe, {}, &perr);  // validates kinds / qubit ranges
-    if (!perr.empty()) return fail(h, TQ_EINVAL, perr);
+    if (!validate_gates(h->n, gates, &perr)) return fail(h, TQ_EINVAL, perr);
+    if (h->plan_cache_cap > 0) {
+        TQ_CUDA(cudaSetDevice(h->device));
+        // park the plans of the outgoing circuit (kernels still in flight keep reading their arenas: nothing is freed here)
+        if (h->have_circuit && (h->plan_sv.valid || h->plan_traj.valid || h->plan_dm.valid)) {
+            h->plan_cache.emplace_front();
+            tq_context::CachedCircuit& c = h->plan_cache.front();
+            c.hash = h->circuit_hash;
+            c.gates = h->gates;
+            c.n_params = h->n_params;
+            c.n_slots = h->n_slots;
+            c.plan_sv = h->plan_sv;
+            c.plan_traj = h->plan_traj;
+            c.plan_dm = h->plan_dm;
+            h->plan_sv = Plan();
+            h->plan_traj = Plan();
+            h->plan_dm = Plan();
+        } else {
+            invalidate_plans(h);
+        }
+        bool hit = false;
+        for (auto it = h->plan_cache.begin(); it != h->plan_cache.end(); ++it) {
+            if (it->hash != hash || it->n_params != n_params || !same_gates(it->gates, gates)) continue;
+            free_plan(h->plan_sv);
+            free_plan(h->plan_traj);
+            free_plan(h->plan_dm);
+            h->plan_sv = it->plan_sv;
+            h->plan_traj = it->plan_traj;
+            h->plan_dm = it->plan_dm;
+            h->plan_cache.erase(it);
+            hit = true;
+            break;
+        }
+        ++(hit ? h->cache_hits : h->cache_misses);
+        while ((int)h->plan_cache.size() > h->plan_cache_cap) {   // evict the least recently used circuit
+            if (h->last_stream) TQ_CUDA(cudaStreamSynchronize(h->last_stream));
+            tq_context::CachedCircuit& c = h->plan_cache.back();
+            free_plan(c.plan_sv);
+            free_plan(c.plan_traj);
+            free_plan(c.plan_dm);
+            h->plan_cache.pop_back();
+        }
+    } else {
+        invalidate_plans(h);
+        ++h->cache_misses;
+    }
     h->gates.swap(gates);
     h->n_params = n_params;
     h->n_slots = n_slots;
+    h->circuit_hash = hash;
     h->have_circuit = true;
-    invalidate_plans(h);
     return TQ_OK;
     TQ_API_CATCH(h)
 }
@@ -1485,6 +1588,17 @@ int tq_plan_counts(tq_handle h, int which, int64_t* counts8) {
 }
 
 int64_t tq_launch_count(tq_handle h) { return h ? h->launches : 0; }
+
+int tq_plan_cache_stats(tq_handle h, int64_t* stats4) {
+    TQ_API_TRY
+    if (!h || !stats4) return TQ_EINVAL;
+    stats4[0] = h->cache_hits;
+    stats4[1] = h->cache_misses;
+    stats4[2] = h->cache_same;
+    stats4[3] = (int64_t)h->plan_cache.size();
+    return TQ_OK;
+    TQ_API_CATCH(h)
+}
 
 int tq_profile_enable(tq_handle h, int on) {
     TQ_API_TRY

@@ -1502,6 +1502,8 @@ uint32_t mask_to_local(const Pass& p, uint64_t mask) {
     return out;
 }
 
+bool validate_gates(int n, const std::vector<Gate>& gates, std::string* err) { return validate(n, gates, err); }
+
 CompiledCircuit plan_statevector(int n, const std::vector<Gate>& gates, const PlanOptions& opt,
                                  const std::vector<uint64_t>& cover_masks, std::string* err) {
     CompiledCircuit cc;

@@ -286,6 +286,9 @@ struct CompiledCircuit {
     std::vector<MatGate> prog;
 };
 
+// Gate kinds / qubit ranges of a user circuit (what the plan_* entry points check first); false + message on error
+bool validate_gates(int n, const std::vector<Gate>& gates, std::string* err);
+
 // Pure-state plan over n qubits.  cover_masks: flip masks (physical bits) of the Hamiltonian groups the LAST pass
 // should try to keep local.
 CompiledCircuit plan_statevector(int n, const std::vector<Gate>& gates, const PlanOptions& opt,

@@ -222,6 +222,12 @@ class Simulator:
     def launch_count(self):
         return int(self._L.tq_launch_count(self._h))
 
+    def plan_cache_stats(self):
+        """Plan cache of tq_set_circuit: {'hits', 'misses', 'same', 'entries'} (tq_plan_cache_stats)."""
+        c = (ctypes.c_int64 * 4)()
+        self._check(self._L.tq_plan_cache_stats(self._h, c))
+        return dict(zip(("hits", "misses", "same", "entries"), [int(v) for v in c]))
+
     PROFILE_KINDS = ("prep_matrices_kernel", "tile_pass_kernel", "tile_pass_mma_kernel", "tile_stream_kernel<gates>",
                      "tile_stream_kernel<gates+expect>", "tile_stream_kernel<expect>", "expect_direct_kernel",
                      "reduce_partials_kernel", "dm_expect_kernel", "tile_pass_kernel<table>")

@@ -412,3 +412,42 @@ def test_out_of_memory_is_an_error_code(built_lib, monkeypatch):
     sim.close()
     out = ctypes.c_void_p()
     assert _lib.lib().tq_device_alloc(0, 1 << 46, ctypes.byref(out)) == -4 and not out.value
+
+
+def test_plan_cache_restores_plans_bit_for_bit(built_lib, oracle, monkeypatch):
+    """tq_set_circuit keeps compiled plans per gate list: re-binding the bound circuit is a no-op,
+    a circuit seen before comes back from the cache, and the energies are the ones of a fresh compilation, bit for bit."""
+    n = 8
+    c = Case("h2o_8q")
+    H = c.dense(False)
+    circuits = [synthetic_circuit(n, 30 + 3 * i, 70 + i) for i in range(5)]
+    params = [parameter_batch(g, 3) for g in circuits]
+    sim = Simulator(n, 0)
+    sim.set_dense_hamiltonian(H)
+    first = []
+    for g, p in zip(circuits, params):
+        sim.set_circuit(g)
+        sim.set_circuit(g)                      # what an environment step does: the same structure twice
+        first.append(sim.energies(p))
+    st = sim.plan_cache_stats()
+    assert st["same"] == 5 and st["misses"] == 5 and st["hits"] == 0
+    for i in (2, 0, 4, 1, 3):                   # revisit in another order: every plan comes from the cache
+        sim.set_circuit(circuits[i])
+        assert np.array_equal(sim.energies(params[i]), first[i])
+    st = sim.plan_cache_stats()
+    assert st["hits"] == 5 and st["misses"] == 5
+    for g, p, e in zip(circuits, params, first):
+        assert np.abs(e - oracle.energies(g, p, dense=H)).max() < 1e-10
+    sim.set_dense_hamiltonian(2.0 * H)          # a new Hamiltonian drops the cache
+    assert sim.plan_cache_stats()["entries"] == 0
+    sim.set_circuit(circuits[0])
+    assert np.abs(sim.energies(params[0]) - 2.0 * first[0]).max() < 1e-9
+    sim.close()
+    monkeypatch.setenv("TQ_PLAN_CACHE", "0")    # switched off: every new circuit is compiled
+    sim = Simulator(n, 0)
+    sim.set_dense_hamiltonian(H)
+    for i in (0, 1, 0):
+        sim.set_circuit(circuits[i])
+        assert np.array_equal(sim.energies(params[i]), first[i])
+    assert sim.plan_cache_stats()["hits"] == 0
+    sim.close()
