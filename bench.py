@@ -266,15 +266,21 @@ def main():
     which = 1 if w.mode == "dm" else 0
     info = sim.plan_info(which)
 
-    from tensorrl_qas_b200.sharding import gather_energies
+    from tensorrl_qas_b200.sharding import OverlappedGather, gather_energies
     p_dev = torch.from_numpy(params).to(dev)
     out = torch.empty(B, dtype=torch.float64, device=dev)
+    # the path's only collective: every rank receives all B * world energies.  It runs on a side stream under the next
+    # step's kernels (two result buffers alternate); sync_all() at the end of the timed region waits for all of them
+    gather = OverlappedGather(B, world, dev) if world > 1 else None
 
     def step():
-        sim.energies_dev(p_dev, out=out, mode=w.mode)
-        if world > 1:  # the path's only collective: every rank receives all B * world energies
-            return gather_energies(out, B * world)
-        return out
+        if gather is None:
+            sim.energies_dev(p_dev, out=out, mode=w.mode)
+            return out
+        buf = gather.local_buffer()
+        sim.energies_dev(p_dev, out=buf, mode=w.mode)
+        gather.submit()
+        return buf
 
     def host_step():
         e = sim.energies_dm(params) if w.mode == "dm" else sim.energies(params)
@@ -284,6 +290,8 @@ def main():
         return e, e
 
     def sync_all():
+        if gather is not None:
+            gather.wait()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -333,7 +341,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     e2e_value = evals / t_e2e
-    assert np.array_equal(e_host, out.cpu().numpy()), "host and device entry points disagree"
+    e_dev = (gather.local[(gather.i - 1) % 2] if gather is not None else out).cpu().numpy()
+    assert np.array_equal(e_host, e_dev), "host and device entry points disagree"
+    if gather is not None:   # the gathered vector holds every rank's slice in rank order
+        full = gather.wait().cpu().numpy()
+        assert np.array_equal(full[rank * B:(rank + 1) * B], e_dev), "all-gather misplaced this rank's energies"
 
     # ---------------- per-launch device times of a few more steps (CUDA events around every kernel launch) --------
     prof_steps = 3

@@ -54,3 +54,61 @@ def sharded_energies(evaluate, params, group=None):
     if dist.get_backend(group) == "nccl":
         t = t.cuda()
     return gather_energies(t, batch, group).cpu().numpy()
+
+
+class OverlappedGather:
+    """The path's only collective, off the critical path: the all-gather of step i runs on a side stream while the kernels
+    of step i + 1 are already executing (the energies alternate between two buffers, so the next step never overwrites
+    what is being gathered).  One rank per GPU, NCCL.
+
+        g = OverlappedGather(batch_per_rank, world, device)
+        for step in ...:
+            out = g.local_buffer()              # this step's energies go here (torch float64 [batch_per_rank])
+            sim.energies_dev(params, out=out)
+            g.submit()                          # returns at once
+        all_energies = g.wait()                 # [batch_per_rank * world] of the LAST step; earlier ones via g.result(k)
+    """
+
+    def __init__(self, batch_per_rank, world, device, group=None, depth=2):
+        import torch
+        self.torch = torch
+        self.group = group
+        self.device = device
+        self.side = torch.cuda.Stream(device=device)
+        self.local = [torch.empty(batch_per_rank, dtype=torch.float64, device=device) for _ in range(depth)]
+        self.full = [torch.empty(batch_per_rank * world, dtype=torch.float64, device=device) for _ in range(depth)]
+        self.done = [None] * depth
+        self.i = 0
+
+    def local_buffer(self):
+        k = self.i % len(self.local)
+        if self.done[k] is not None:   # the gather that last used this pair of buffers must be over before they are rewritten
+            self.torch.cuda.current_stream(self.device).wait_event(self.done[k])
+        return self.local[k]
+
+    def submit(self):
+        import torch.distributed as dist
+        torch = self.torch
+        k = self.i % len(self.local)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            dist.all_gather_into_tensor(self.full[k], self.local[k], group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[k] = ev
+        self.i += 1
+        return k
+
+    def result(self, k):
+        self.done[k].synchronize()
+        return self.full[k]
+
+    def wait(self):
+        """Block the current stream on every outstanding gather and return the last step's global vector."""
+        cur = self.torch.cuda.current_stream(self.device)
+        for ev in self.done:
+            if ev is not None:
+                cur.wait_event(ev)
+        return self.full[(self.i - 1) % len(self.full)] if self.i else None
