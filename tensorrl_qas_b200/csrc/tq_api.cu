@@ -77,6 +77,7 @@ struct tq_context {
     bool stream_kernel = true;  // TQ_STREAM: multi-tile tensor-core passes run on the persistent TMA kernel (tq_stream.cu)
     bool stream_expect = true;  // TQ_STREAM=2 (default): the expectation-only passes as well; 1: those stay on expect_direct_kernel
     int64_t stream_launches = 0;
+    int stream_stagger_ns = 0;  // TQ_STREAM_STAGGER_NS
     bool spin_wait = true;      // TQ_SPIN: poll the pinned result slots instead of cudaStreamSynchronize (latency path)
     bool zero_copy = true;      // TQ_ZERO_COPY: small host-buffer calls read angles / write energies in pinned host memory
     int n = 0, device = 0;
@@ -881,6 +882,7 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                         sp.n_sub = 1;
                         sp.batch = bc;
                         sp.contiguous = 1;
+                        sp.stagger_ns = h->stream_stagger_ns;
                         const long long tiles = (long long)bc << pp.n_nl;
                         prof_begin(h, stream, pp.exp_mode == 1 ? PK_STREAM_GATE_EXP : PK_STREAM_GATE, model_bytes, alg_bytes);
                         launch_tile_stream(sp, (int)std::min<long long>(tiles, h->n_sms), stream);
@@ -1092,6 +1094,7 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->sparse_init = env_int("TQ_SPARSE_INIT", 1) != 0;
     h->direct_kernel = env_int("TQ_DIRECT_KERNEL", 1) != 0;
     h->stream_kernel = env_int("TQ_STREAM", 2) != 0;
+    h->stream_stagger_ns = std::max(0, std::min(100000, env_int("TQ_STREAM_STAGGER_NS", 0)));
     h->plan_cache_cap = std::max(0, std::min(1024, env_int("TQ_PLAN_CACHE", 64)));
     h->stream_expect = env_int("TQ_STREAM", 2) >= 2;
     h->direct_ctas_per_sm = std::max(1, std::min(8, env_int("TQ_DIRECT_CTAS", 2)));

@@ -118,6 +118,7 @@ struct alignas(64) StreamParams {
     CUtensorMap map_out;                 // gate passes (n_sub == 1) that write the tile back
     StreamSub sub[kStreamMaxSub];
     int n_sub, batch;
+    int stagger_ns;   // gate passes: the second group starts this much later, so that the groups' DMMA phases interleave
     int contiguous;   // 1: CTA c takes a contiguous range of tiles (gate passes: block matrices are staged once per element);
                       // 0: tiles c, c + grid, ... element-major (expectation sub-passes find the element in L2)
 };

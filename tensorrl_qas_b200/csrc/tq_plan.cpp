@@ -1531,7 +1531,9 @@ std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const Pla
     assignment->assign(todo.size(), -1);
     size_t left = todo.size();
     while (left > 0) {
-        uint64_t L = (n <= k) ? all : (bit(std::min(opt.low_bits, k)) - 1);
+        // expectation-only passes only READ the state: 128-byte runs (three low qubits) stream as fast as longer ones, and
+        // every tile position spent on a low qubit is one flip mask less per pass (one more pass over the state)
+        uint64_t L = (n <= k) ? all : (bit(std::min(std::min(opt.low_bits, 3), k)) - 1);
         const int me = int(passes.size());
         bool progressed = false;
         for (size_t i = 0; i < todo.size(); ++i) {

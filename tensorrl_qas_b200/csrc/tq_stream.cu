@@ -394,6 +394,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     const bool bsame = ((g8 >> 1) & 1) == (lane & 1);
     const long long bneg = ((g8 >> 1) & 1) ? 0ll : (long long)(1ull << 63);
 
+    if (MODE != 2 && GRP == 1 && sp.stagger_ns > 0) {   // (see StreamParams::stagger_ns)
+        for (int left = sp.stagger_ns; left > 0; left -= 1000) __nanosleep(1000);
+    }
     uint32_t cur_elem = 0xffffffffu;
     int flip = 0;
     bool load_pending = false;   // (thread gtid == 0) the buffer of this group's previous job still waits for its refill

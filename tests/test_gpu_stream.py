@@ -104,9 +104,10 @@ def test_stream_untouched_qubits(built_lib, oracle, monkeypatch):
 
 def test_stream_bench_shape_matches_oracle_sample(built_lib, oracle, monkeypatch):
     """The bench workload (C5, 20 qubits): two elements against the oracle, the whole batch against the kernel switched off."""
-    import bench
-    gl, ham, parameter_batch_ = bench.workload()
-    p = parameter_batch_(gl, 8)
+    import bench_workloads
+    w = bench_workloads.build("C5")
+    gl, ham = w.gl, w.pauli
+    p = w.params(8)
     sim = make_sim(20, gl, ham, monkeypatch, True)
     got = sim.energies(p)
     launches = sim.plan_counts()["stream_launches"]
