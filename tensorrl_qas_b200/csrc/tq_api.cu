@@ -41,6 +41,7 @@ struct DevPass {
     bool gate_pass = true;
     bool no_ops = false;     // the single pass of a gate-free circuit: it only stages the state
     // streaming kernel (tq_stream.cu): layouts chosen by the planner, window headers resolved for them
+    int partial_off_wide = 0;   // partial-sum offset of this pass in the wide layout (Plan::slots_wide)
     int n_gates = 0;         // reference gates fused into this pass (SURVEY.md section 8d traffic model)
     int n_exp_groups = 0;    // Hamiltonian flip-mask groups evaluated in this pass
     bool stream = false;
@@ -57,6 +58,7 @@ struct Plan {
     std::vector<DevPass> passes;  // gate passes first, then expectation-only passes
     int n_gate_passes = 0;
     int slots = 0;        // partial sums per element
+    int slots_wide = 0;   // the same when the streamed expectation-only passes keep one slot per (tile, warp)
     int n_unitary = 0, n_rot = 0;
     int64_t counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // see tq_plan_counts
     void* arena = nullptr;  // device blob holding windows / ops / groups / terms of all passes + matrix programs
@@ -463,6 +465,7 @@ int compile_plan(tq_handle h, int which) {
     plan.nbits = nbits;
     plan.n_gate_passes = n_gate_passes;
     plan.slots = 0;
+    plan.slots_wide = 0;
     const unsigned char* base = (const unsigned char*)plan.arena;
     plan.n_mats = (int)cc.mats.size();
     plan.d_descs = (const MatDesc*)(base + off_descs);
@@ -541,6 +544,9 @@ int compile_plan(tq_handle h, int which) {
             if (dp.proto.exp_mode) {
                 dp.proto.partial_off = plan.slots;
                 plan.slots += dp.n_tiles;
+                // the streaming kernel's expectation-only passes run without any barrier: one slot per (tile, warp)
+                dp.partial_off_wide = plan.slots_wide;
+                plan.slots_wide += dp.n_tiles * ((!dp.gate_pass && passes[i].stream) ? kStreamWarpSlots : 1);
             }
         }
         if (tile_pass_smem_bytes(dp.proto.k_eff, dp.proto.k, dp.proto.lead) > 100 * 1024)
@@ -740,7 +746,10 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
         if (rc) return rc;
     }
     chunk = std::min(chunk, (int)(0x7fffffffu >> std::max(0, plan.nbits - h->opt.tile_bits)) / 2);  // grid.x limit
-    if (want_energy && !dm && plan.slots > 1) { rc = ensure_partial(h, (size_t)chunk * plan.slots); if (rc) return rc; }
+    // partial-sum layout of this call: wide when the expectation-only passes go to the streaming kernel
+    const bool wide = h->stream_kernel && h->stream_expect && !xchg && plan.slots_wide > plan.slots;
+    const int n_slots = wide ? plan.slots_wide : plan.slots;
+    if (want_energy && !dm && n_slots > 1) { rc = ensure_partial(h, (size_t)chunk * n_slots); if (rc) return rc; }
     rc = grow(h, (void**)&h->d_mats, &h->mats_cap, std::max<size_t>(16, (size_t)chunk * plan.n_mats * kMatStride * 16));
     if (rc) return rc;
 
@@ -800,8 +809,8 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
             if (!want_energy || dm) pp.exp_mode = 0;
             if (pp.exp_mode == 2) { pp.hent = h->d_hent; pp.n_hent = (int)h->hent.size(); }
             if (pp.exp_mode) {
-                if (plan.slots == 1) { pp.partial = out + b0; pp.partial_ld = 1; pp.partial_off = 0; }
-                else { pp.partial = h->d_partial; pp.partial_ld = plan.slots; }
+                if (n_slots == 1) { pp.partial = out + b0; pp.partial_ld = 1; pp.partial_off = 0; }
+                else { pp.partial = h->d_partial; pp.partial_ld = n_slots; if (wide) pp.partial_off = dp.partial_off_wide; }
             }
             pp.in_mask = ~0ull;
             pp.use_dead = (pp.mwindows && track_support) ? 1 : 0;
@@ -895,6 +904,11 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                     }
                 }
             }
+            if (wide && !dp.gate_pass && dp.stream && pp.exp_mode == 1 && n_slots > 1) {
+                // (wide layout, but this pass stays on the per-tile kernels: they fill one slot per tile, the rest is zero)
+                TQ_CUDA(cudaMemset2DAsync(h->d_partial + pp.partial_off, (size_t)n_slots * sizeof(double), 0,
+                                          (size_t)dp.n_tiles * kStreamWarpSlots * sizeof(double), (size_t)bc, stream));
+            }
             if (pp.direct && h->direct_kernel && direct.n_sub < kMaxDirectSub &&
                 direct_windows + (pp.n_windows - pp.n_gate_windows) <= kDirectWinSlots &&
                 direct_ops + pp.n_wops <= kDirectOpSlots) {
@@ -945,9 +959,9 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 ++h->launches;
                 rc = check_launch(h, "dm_expect_kernel");
                 if (rc) return rc;
-            } else if (plan.slots > 1) {
-                prof_begin(h, stream, PK_REDUCE, (double)bc * plan.slots * 8.0, 0.0);
-                launch_reduce_partials(h->d_partial, plan.slots, plan.slots, out + b0, bc, stream);
+            } else if (n_slots > 1) {
+                prof_begin(h, stream, PK_REDUCE, (double)bc * n_slots * 8.0, 0.0);
+                launch_reduce_partials(h->d_partial, n_slots, n_slots, out + b0, bc, stream);
                 prof_end(h, stream);
                 ++h->launches;
                 rc = check_launch(h, "reduce_partials_kernel");

@@ -100,6 +100,7 @@ void launch_expect_direct(const DirectParams& dp, int n_ctas, int threads, cudaS
 // ---- streaming pass kernel (tq_stream.cu): persistent CTAs, tiles moved by TMA --------------------------------------
 constexpr int kStreamMaxSub = 4;      // sub-passes per launch (expectation-only passes share one launch)
 constexpr int kStreamThreads = 512;   // two groups of 256 threads, one tile each
+constexpr int kStreamWarpSlots = kStreamThreads / 32;   // partial-sum slots per tile of an expectation-only sub-pass (one per warp)
 struct StreamTma {                    // one direction of one sub-pass (tq_plan.h StreamLayout, resolved)
     int n_ops;                        // TMA operations per tile; 0 = direction unused
     uint32_t box_bytes;               // bytes per operation = distance of the operations' shared-memory destinations

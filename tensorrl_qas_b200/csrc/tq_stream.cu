@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_red_all + kGroups * 16);   // kBufs (+1 pad)
     JobDesc* s_job = reinterpret_cast<JobDesc*>(full_bar + kBufs + 1);         // kBufs (+1 pad)
     SubInfo* s_sub = reinterpret_cast<SubInfo*>(s_job + kBufs + 1);            // kStreamMaxSub
+    int* s_done = reinterpret_cast<int*>(s_sub + kStreamMaxSub);               // kBufs (+1 pad): warps done with a buffer (MODE 2)
 
     const int tid = threadIdx.x;
     // ---- stage every sub-pass once: scalars, window headers, op words, expectation tables ----
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
             }
         }
         for (int i = 0; i < kBufs; ++i) mbar_init(full_bar + i, 1);
+        for (int i = 0; i < kBufs + 1; ++i) s_done[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
@@ -633,20 +635,20 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
             // overwrite what thread 0 is still adding up
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(kFull, acc, off);
-            if (MODE == 2) {   // both groups contributed to this tile: one CTA-wide barrier per job
-                double* red = s_red_cta + (flip ? 16 : 0);
-                flip ^= 1;
-                if (lane == 0) red[GRP * 8 + warp] = acc;
-                asm volatile("bar.sync 0, %0;" ::"n"(kStreamThreads) : "memory");   // also: everyone has finished reading the buffer
-                // the tail of a job (sum, partial, refill) is serial work of one thread: a different warp takes it every job,
-                // so that no warp falls behind the others by more than one tail
-                if (lane == 0 && (uint32_t)(GRP * 8 + warp) == (j & 15u)) {
-                    if (j + kBufs < n_jobs) issue_load(j + kBufs);
-                    double tot = 0.0;
-#pragma unroll
-                    for (int wv = 0; wv < 2 * kGroupThreads / 32; ++wv) tot += red[wv];
-                    si.partial[(size_t)b * si.partial_ld + si.partial_off + jd.z] = tot;
+            if (MODE == 2) {
+                // no barrier at all: every warp leaves its own partial sum (sixteen slots per tile; reduce_partials_kernel
+                // adds them in slot order, so the result does not depend on timing), and the warp that finishes a tile
+                // last refills its buffer.  Warps drift apart by at most the three buffers.
+                if (lane == 0) {
+                    si.partial[(size_t)b * si.partial_ld + si.partial_off + (size_t)jd.z * 16 + (GRP * 8 + warp)] = acc;
+                    __threadfence_block();
+                    if (atomicAdd(&s_done[buf], 1) == 2 * (kGroupThreads / 32) - 1) {
+                        s_done[buf] = 0;
+                        __threadfence_block();
+                        if (j + kBufs < n_jobs) issue_load(j + kBufs);
+                    }
                 }
+                __syncwarp();
             } else {
                 double* red = s_red + (flip ? 8 : 0);
                 flip ^= 1;
@@ -683,7 +685,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
 size_t tile_stream_smem_bytes() {
     return (size_t)kBufs * kTileBytes + (size_t)kGroups * kOpSlots * kMatStride * sizeof(double2) + kOpSlots * sizeof(WinOp) +
            kWinSlots * sizeof(StreamWindowDev) + kGroups * 16 * sizeof(double) + (kBufs + 1) * sizeof(uint64_t) +
-           (kBufs + 1) * sizeof(JobDesc) + kStreamMaxSub * sizeof(SubInfo) + 1024 /* alignment slack */;
+           (kBufs + 1) * sizeof(JobDesc) + kStreamMaxSub * sizeof(SubInfo) + (kBufs + 1) * sizeof(int) +
+           1024 /* alignment slack */;
 }
 
 cudaError_t tile_stream_configure() {
