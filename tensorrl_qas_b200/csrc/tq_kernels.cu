@@ -1220,16 +1220,18 @@ __global__ void __launch_bounds__(128) prep_matrices_kernel(const MatDesc* __res
     eval_block_matrix(descs[mi], prog, params, (size_t)b, ld_params, codes, ld_codes, mats + (size_t)idx * kMatStride);
 }
 
-__global__ void reduce_partials_kernel(const double* __restrict__ partial, int ld, int n, double* __restrict__ out,
-                                       int batch) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= batch) return;
-    const double* row = partial + (size_t)warp * ld;
+// out[b] = sum of row b of `partial` (n entries, row stride ld): one CTA per element, fixed summation order (thread t adds
+// entries t, t + 256, ... in order, then the same shuffle tree / warp order as block_sum): re-runs are bit-identical
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partial, int ld, int n,
+                                                               double* __restrict__ out, int batch) {
+    __shared__ double s_red[32];
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    const double* row = partial + (size_t)b * ld;
     double v = 0.0;
-    for (int i = lane; i < n; i += 32) v += row[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) out[warp] = v;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += row[i];
+    const double total = block_sum(v, s_red, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) out[b] = total;
 }
 
 __global__ void __launch_bounds__(kMaxThreads) dm_expect_kernel(const double2* __restrict__ rho, int n,
@@ -1348,9 +1350,7 @@ void launch_prep_matrices(const MatDesc* descs, const MatGate* prog, int n_mats,
 }
 
 void launch_reduce_partials(const double* partial, int ld, int n, double* out, int batch, cudaStream_t stream) {
-    const int threads = 128, warps_per_block = threads / 32;
-    reduce_partials_kernel<<<(batch + warps_per_block - 1) / warps_per_block, threads, 0, stream>>>(partial, ld, n, out,
-                                                                                                  batch);
+    reduce_partials_kernel<<<batch, n >= 1024 ? 256 : 64, 0, stream>>>(partial, ld, n, out, batch);
 }
 
 void launch_dm_expect(const double2* rho, int n, const HEntry* hent, int n_hent, double* out, int batch,
