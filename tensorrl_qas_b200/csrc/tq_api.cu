@@ -359,6 +359,7 @@ int compile_plan(tq_handle h, int which) {
     opt.fuse = env_int("TQ_FUSE", 1) != 0;
     opt.mma = env_int("TQ_MMA", 1) != 0;
     opt.dead_budget = env_int("TQ_DEAD_BUDGET", 5);
+    opt.early_expect = env_int("TQ_EARLY_EXPECT", 1) != 0;
     CompiledCircuit cc = which == 1 ? plan_density(n, h->gates, opt, &perr)
                                     : plan_statevector(n, h->gates, opt, cover, &perr);
     if (!perr.empty()) return fail(h, TQ_EINVAL, perr);
@@ -822,6 +823,9 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                     int kept = 0;
                     for (int q = 0; q < pp.n_nl; ++q)
                         if ((support >> pp.nonlocal[q]) & 1ull) pp.nonlocal[kept++] = pp.nonlocal[q];
+                    if (kept < pp.n_nl && pp.exp_mode && n_slots > 1)   // (early-evaluated groups: the skipped tiles add zero)
+                        TQ_CUDA(cudaMemset2DAsync(h->d_partial + pp.partial_off, (size_t)n_slots * sizeof(double), 0,
+                                                  (size_t)dp.n_tiles * sizeof(double), (size_t)bc, stream));
                     pp.n_nl = kept;
                 }
             }
@@ -1696,11 +1700,13 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
     opt.fuse = env_int("TQ_FUSE", 1) != 0;
     opt.mma = env_int("TQ_MMA", 1) != 0;
     opt.dead_budget = env_int("TQ_DEAD_BUDGET", 5);
+    opt.early_expect = env_int("TQ_EARLY_EXPECT", 1) != 0;
     CompiledCircuit cc = which == 1 ? plan_density(n_qubits, gates, opt, &err)
                                     : plan_statevector(n_qubits, gates, opt, cover, &err);
     std::string out;
     char line[256];
     if (!err.empty()) out = "ERROR " + err + "\n";
+    ExpPlan ep;
     if (with_stream && err.empty() && which != 1 && !cc.passes.empty() && n_qubits > tile_bits) {
         std::vector<ExpGroupIn> groups;
         ExpGroupIn diag;
@@ -1714,7 +1720,7 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
             diag.terms.push_back(ExpTermIn{m, 0.25, 0.0});
         }
         if (!diag.terms.empty()) groups.push_back(diag);
-        ExpPlan ep = attach_expectation(cc.passes, groups, opt, n_qubits, true, true);
+        ep = attach_expectation(cc.passes, groups, opt, n_qubits, true, true);
         if (!ep.err.empty()) out += "ERROR " + ep.err + "\n";
     }
     for (const MatDesc& md : cc.mats) {
@@ -1725,10 +1731,16 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
             out += line;
         }
     }
-    for (const Pass& p : cc.passes) {
+    for (size_t pi = 0; pi < cc.passes.size(); ++pi) {
+        const Pass& p = cc.passes[pi];
         out += "PASS lead=" + std::to_string(p.lead) + " local=";
         for (size_t i = 0; i < p.local.size(); ++i) out += (i ? "," : "") + std::to_string(p.local[i]);
         out += " support=" + std::to_string((unsigned long long)p.support_in) + "\n";
+        if (pi < ep.groups_of_pass.size()) {   // Hamiltonian groups evaluated in this pass (indices into the cover masks)
+            out += "EXPGROUPS";
+            for (int g : ep.groups_of_pass[pi]) out += " " + std::to_string(g);
+            out += "\n";
+        }
         if (with_stream) {
             auto lay = [&](const char* name, const StreamLayout& L) {
                 std::string t = std::string("STREAM ") + name + " live=" + std::to_string(L.n_live) + " ops=" + std::to_string(L.n_ops) +

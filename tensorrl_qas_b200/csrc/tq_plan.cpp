@@ -2,6 +2,7 @@
 #include "tq_plan.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "../../include/tqsim.h"
@@ -198,6 +199,49 @@ void finish_pass(Pass& p, int nbits, uint64_t lmask) {
     while (p.lead < (int)p.local.size() && p.local[p.lead] == p.lead) ++p.lead;
 }
 
+// physical qubits the gates of a pass act on (any action: a diagonal gate does not commute with a flip of its qubit)
+uint64_t pass_touched(const Pass& p) {
+    uint64_t m = 0;
+    for (const DevOp& d : p.ops) {
+        switch (d.op) {
+        case OP_U2: case OP_CNOT: m |= bit(p.local[d.a]) | bit(p.local[d.b]); break;
+        case OP_U1: case OP_D1: m |= bit(p.local[d.a]); break;
+        case OP_D1_NL: m |= bit(d.a); break;
+        case OP_CNOT_NL: m |= bit(d.a) | bit(p.local[d.b]); break;
+        default: m = ~0ull; break;   // density-matrix channels: no early evaluation
+        }
+    }
+    return m;
+}
+
+// Light cone (attach_expectation): flip masks `todo` that are not local to the last gate pass; early[t] >= 0: the gate pass
+// after which group t may be evaluated instead of on the final state.  Decides which of them are (moved[t] = 1): all that
+// it takes to save expectation-only passes over the state, and no more (the gate passes are the compute-bound ones).
+// Returns the number of expectation-only passes left.
+size_t choose_early(int n, const PlanOptions& opt, const std::vector<uint64_t>& todo, const std::vector<int>& early,
+                    std::vector<char>& moved) {
+    moved.assign(todo.size(), 0);
+    auto n_cover = [&]() {
+        std::vector<uint64_t> rest;
+        for (size_t t = 0; t < todo.size(); ++t)
+            if (!moved[t]) rest.push_back(todo[t]);
+        std::vector<int> a;
+        return cover_sets(n, rest, opt, &a).size();
+    };
+    const size_t c0 = n_cover();
+    bool any = false;
+    for (size_t t = 0; t < todo.size(); ++t) { moved[t] = early[t] >= 0; any = any || moved[t]; }
+    if (!any) return c0;
+    const size_t c1 = n_cover();
+    if (c1 >= c0) { moved.assign(todo.size(), 0); return c0; }
+    for (size_t t = 0; t < todo.size(); ++t) {   // hand back whatever the remaining passes hold anyway
+        if (!moved[t]) continue;
+        moved[t] = 0;
+        if (n_cover() != c1) moved[t] = 1;
+    }
+    return c1;
+}
+
 // greedy packing of blocks into passes
 std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions& opt,
                        const std::vector<uint64_t>& cover_masks, bool mma) {
@@ -240,9 +284,64 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
                 blocked_diag |= a.diag;
             }
         }
-        if (deferred.empty()) {
-            for (uint64_t m : cover_masks)
-                if (__builtin_popcountll(L | m) <= k) L |= m;
+        if (deferred.empty() && !cover_masks.empty()) {
+            // Last gate pass: spend its free tile positions on Hamiltonian flip masks (groups evaluated right here).  Which
+            // ones decides how many expectation-only passes over the state follow: greedy fills from every start in the
+            // mask list are compared, with the groups an earlier pass can take (light cone, choose_early) accounted for.
+            const size_t M = cover_masks.size();
+            const uint64_t L0 = L;
+            std::vector<int> early(M, -1);
+            std::vector<double> share(passes.size(), 1.0);   // populated share of the state after pass i
+            const bool search = nbits > k && M <= 64;
+            if (search && mma && opt.early_expect && !passes.empty()) {
+                uint64_t after = 0;
+                for (int idx : mine) after |= ops[idx].mix | ops[idx].diag;
+                std::vector<uint64_t> after_of(passes.size());
+                for (int i = (int)passes.size() - 1; i >= 0; --i) {
+                    after_of[i] = after;
+                    after |= pass_touched(passes[i]);
+                    const uint64_t sup_out = (i + 1 < (int)passes.size()) ? passes[i + 1].support_in : support;
+                    share[i] = std::ldexp(1.0, __builtin_popcountll(sup_out & all) - nbits);
+                }
+                for (size_t m = 0; m < M; ++m)
+                    for (size_t i = 0; i < passes.size() && early[m] < 0; ++i)
+                        if (passes[i].mma && !passes[i].ops.empty() && mask_is_local(passes[i], cover_masks[m]) &&
+                            !(cover_masks[m] & after_of[i]))
+                            early[m] = (int)i;
+            }
+            auto fill = [&](size_t start, bool late_first) {
+                uint64_t X = L0;
+                for (int phase = 0; phase < (late_first ? 2 : 1); ++phase)
+                    for (size_t c = 0; c < M; ++c) {
+                        const size_t m = (start + c) % M;
+                        if (late_first && (phase == 0) != (early[m] < 0)) continue;
+                        if (__builtin_popcountll(X | cover_masks[m]) <= k) X |= cover_masks[m];
+                    }
+                return X;
+            };
+            auto cost = [&](uint64_t X) {
+                std::vector<uint64_t> todo;
+                std::vector<int> e;
+                for (size_t m = 0; m < M; ++m)
+                    if (cover_masks[m] & ~X) { todo.push_back(cover_masks[m]); e.push_back(early[m]); }
+                std::vector<char> moved;
+                double c = (double)choose_early(nbits, opt, todo, e, moved);
+                for (size_t t = 0; t < todo.size(); ++t)
+                    if (moved[t]) c += 0.125 * share[e[t]];   // (a window more in a gate pass over that share of the state)
+                return c - 1e-3 * (double)(M - todo.size());
+            };
+            uint64_t best = fill(0, false);
+            if (search) {
+                double best_cost = cost(best);
+                for (int lf = 0; lf < 2; ++lf)
+                    for (size_t st = 0; st < M; ++st) {
+                        const uint64_t X = fill(st, lf != 0);
+                        if (X == best) continue;
+                        const double c = cost(X);
+                        if (c < best_cost - 1e-9) { best = X; best_cost = c; }
+                    }
+            }
+            L = best;
         }
         if (dead_budget < 64)   // populated qubits first
             for (int q = 0; q < nbits && __builtin_popcountll(L) < k; ++q)
@@ -1147,6 +1246,11 @@ ExpPlan attach_expectation(std::vector<Pass>& passes, const std::vector<ExpGroup
     ExpPlan ep;
     ep.n_gate_passes = (int)passes.size();
     ep.groups_of_pass.assign(passes.size(), {});
+    int diag_group = -1;                                   // the group of the diagonal terms (flip mask 0)
+    for (size_t g = 0; g < groups.size(); ++g)
+        if (groups[g].x == 0) diag_group = (int)g;
+    std::vector<char> diag_taken(diag_group >= 0 ? groups[diag_group].terms.size() : 0, 0);
+    std::vector<std::vector<ExpTermIn>> early_diag(passes.size());   // diagonal terms that go with the early groups
     if (!groups.empty()) {
         std::vector<uint64_t> todo;
         std::vector<int> todo_group;
@@ -1160,6 +1264,48 @@ ExpPlan attach_expectation(std::vector<Pass>& passes, const std::vector<ExpGroup
                 ep.groups_of_pass[ep.n_gate_passes - 1].push_back((int)g);
             else { todo.push_back(groups[g].x); todo_group.push_back((int)g); }
         }
+        // Light cone: a group whose qubits no later gate touches has the same expectation value right after an EARLIER
+        // gate pass (the later gates commute with it), so it may be evaluated there if its flips are local to that pass.
+        // Used only where it saves a whole expectation-only pass over the state -- the gate passes are the compute-bound
+        // ones -- and then for as few groups as that takes.
+        if (in_pass && opt.early_expect && !todo.empty() && ep.n_gate_passes > 1) {
+            std::vector<uint64_t> after(ep.n_gate_passes, 0);   // qubits touched by the gates of the passes after i
+            for (int i = ep.n_gate_passes - 2; i >= 0; --i) after[i] = after[i + 1] | pass_touched(passes[i + 1]);
+            std::vector<int> early(todo.size(), -1);
+            bool any = false;
+            for (size_t t = 0; t < todo.size(); ++t) {
+                uint64_t supp = todo[t];
+                for (const ExpTermIn& in : groups[todo_group[t]].terms) supp |= in.z;
+                for (int i = 0; i + 1 < ep.n_gate_passes && early[t] < 0; ++i)   // earliest: the fewest populated tiles
+                    if (passes[i].mma && !passes[i].ops.empty() && mask_is_local(passes[i], todo[t]) && !(supp & after[i]))
+                        early[t] = i;
+                any = any || early[t] >= 0;
+            }
+            if (any) {
+                std::vector<char> moved;
+                choose_early(n, opt, todo, early, moved);
+                if (std::find(moved.begin(), moved.end(), (char)1) != moved.end()) {
+                    std::vector<uint64_t> todo2;
+                    std::vector<int> group2;
+                    for (size_t t = 0; t < todo.size(); ++t) {
+                        if (!moved[t]) { todo2.push_back(todo[t]); group2.push_back(todo_group[t]); continue; }
+                        ep.groups_of_pass[early[t]].push_back(todo_group[t]);
+                        // the diagonal terms on the same qubits (ZZ next to XX + YY) would otherwise find no window that
+                        // holds them on the final state: they share the group's light cone and its window
+                        if (diag_group >= 0)
+                            for (size_t d = 0; d < diag_taken.size(); ++d) {
+                                const ExpTermIn& in = groups[diag_group].terms[d];
+                                if (!diag_taken[d] && in.z != 0 && (in.z & ~todo[t]) == 0) {
+                                    diag_taken[d] = 1;
+                                    early_diag[early[t]].push_back(in);
+                                }
+                            }
+                    }
+                    todo.swap(todo2);
+                    todo_group.swap(group2);
+                }
+            }
+        }
         if (!todo.empty()) {
             std::vector<int> assign;
             std::vector<Pass> extra = plan_cover(n, todo, opt, &assign);
@@ -1172,6 +1318,7 @@ ExpPlan attach_expectation(std::vector<Pass>& passes, const std::vector<ExpGroup
         }
     }
     ep.wide_of_pass.assign(passes.size(), {});
+    early_diag.resize(passes.size());
     std::vector<ExpTermIn> diag_pool;   // diagonal terms still to be evaluated (tensor-core passes share them)
     size_t last_eval_pass = 0;
     for (size_t i = 0; i < passes.size(); ++i)
@@ -1181,7 +1328,15 @@ ExpPlan attach_expectation(std::vector<Pass>& passes, const std::vector<ExpGroup
         // streaming kernel: the layouts are fixed before the expectation windows pick their lane qubits
         if (stream && p.mma) plan_stream_layouts(p, n);
         std::vector<ExpGroupIn> gin;
-        for (int g : ep.groups_of_pass[i]) gin.push_back(groups[g]);
+        for (int g : ep.groups_of_pass[i]) {
+            gin.push_back(groups[g]);
+            if (g == diag_group) {
+                gin.back().terms.clear();
+                for (size_t d = 0; d < diag_taken.size(); ++d)
+                    if (!diag_taken[d]) gin.back().terms.push_back(groups[g].terms[d]);
+            }
+        }
+        for (const ExpTermIn& in : early_diag[i]) diag_pool.push_back(in);
         std::vector<int> wide;
         if (!gin.empty()) {
             if (p.mma) append_expectation_windows_mma(p, gin, &wide, &diag_pool, i == last_eval_pass);
@@ -1523,9 +1678,9 @@ CompiledCircuit plan_density(int n, const std::vector<Gate>& gates, const PlanOp
     return cc;
 }
 
-std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const PlanOptions& opt,
-                             std::vector<int>* assignment) {
-    std::vector<Pass> passes;
+std::vector<uint64_t> cover_sets(int n, const std::vector<uint64_t>& todo, const PlanOptions& opt,
+                                 std::vector<int>* assignment) {
+    std::vector<uint64_t> sets;
     const int k = std::min(opt.tile_bits, n);
     const uint64_t all = bit(n) - 1;
     assignment->assign(todo.size(), -1);
@@ -1534,7 +1689,7 @@ std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const Pla
         // expectation-only passes only READ the state: 128-byte runs (three low qubits) stream as fast as longer ones, and
         // every tile position spent on a low qubit is one flip mask less per pass (one more pass over the state)
         uint64_t L = (n <= k) ? all : (bit(std::min(std::min(opt.low_bits, 3), k)) - 1);
-        const int me = int(passes.size());
+        const int me = int(sets.size());
         bool progressed = false;
         for (size_t i = 0; i < todo.size(); ++i) {
             if ((*assignment)[i] >= 0) continue;
@@ -1546,13 +1701,24 @@ std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const Pla
             }
         }
         for (int q = 0; q < n && __builtin_popcountll(L) < k; ++q) L |= bit(q);
+        sets.push_back(L);
+        if (!progressed) break;  // a mask wider than the tile: caller reports the error
+    }
+    return sets;
+}
+
+std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const PlanOptions& opt,
+                             std::vector<int>* assignment) {
+    std::vector<Pass> passes;
+    const int k = std::min(opt.tile_bits, n);
+    for (uint64_t L : cover_sets(n, todo, opt, assignment)) {
         Pass p;
         finish_pass(p, n, L);
         if (opt.mma && (int)p.local.size() >= kMmaMinTileBits) schedule_windows_mma(p);
         else schedule_windows(p);
         passes.push_back(std::move(p));
-        if (!progressed) break;  // a mask wider than the tile: caller reports the error
     }
+    (void)k;
     return passes;
 }
 

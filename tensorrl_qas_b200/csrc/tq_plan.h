@@ -278,6 +278,8 @@ struct PlanOptions {
     bool mma = true;      // pure-state passes with >= 2^9-amplitude tiles use DMMA windows
     int dead_budget = 5;  // still-empty qubits a tensor-core pass may take once the populated state spans many tiles (pack();
                           // 0 = no limit)
+    bool early_expect = true;   // Hamiltonian groups that no later gate touches may be evaluated in an earlier gate pass
+                                // when that saves an expectation-only pass (attach_expectation)
 };
 
 struct CompiledCircuit {
@@ -301,6 +303,9 @@ CompiledCircuit plan_density(int n, const std::vector<Gate>& gates, const PlanOp
 // Expectation-only passes that cover the flip masks `todo` (those not local in the last gate pass).
 std::vector<Pass> plan_cover(int n, const std::vector<uint64_t>& todo, const PlanOptions& opt,
                              std::vector<int>* assignment);
+// the local-qubit sets plan_cover would use (one per pass), without building the passes
+std::vector<uint64_t> cover_sets(int n, const std::vector<uint64_t>& todo, const PlanOptions& opt,
+                                 std::vector<int>* assignment);
 
 void schedule_windows(Pass& p);
 void schedule_windows_mma(Pass& p);   // needs >= kMmaMinTileBits local qubits, no density-matrix ops

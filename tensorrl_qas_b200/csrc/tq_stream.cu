@@ -640,7 +640,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                 // adds them in slot order, so the result does not depend on timing), and the warp that finishes a tile
                 // last refills its buffer.  Warps drift apart by at most the three buffers.
                 if (lane == 0) {
-                    si.partial[(size_t)b * si.partial_ld + si.partial_off + (size_t)jd.z * 16 + (GRP * 8 + warp)] = acc;
+                    // (slot by the parity class of the windows this group took in this job, not by the group: the sum
+                    // of a tile must not depend on where its job fell in this CTA's list)
+                    si.partial[(size_t)b * si.partial_ld + si.partial_off + (size_t)jd.z * 16 + ((((uint32_t)GRP + j) & 1u) * 8 + warp)] = acc;
                     __threadfence_block();
                     if (atomicAdd(&s_done[buf], 1) == 2 * (kGroupThreads / 32) - 1) {
                         s_done[buf] = 0;
@@ -665,10 +667,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
 
         // ---- refill this job's buffer with job j + kBufs ----
         if (MODE != 2 && gtid == 0 && j + kBufs < n_jobs) {
-            if (MODE != 0) {   // the group is past its last read of the buffer (barrier above)
+            if (MODE != 0 && si.n_windows - si.n_gate_windows >= 2) {
+                // several expectation windows later the TMA store has long read the buffer, and the group is past its own
+                // last read of it (the barrier of the reduction above): refill right away
                 tma_wait_read0();
                 issue_load(j + kBufs);
-            } else {   // defer: after the first barrier of this group's next job
+            } else {   // defer: after the first barrier of this group's next job (the store gets that time to drain)
                 load_pending = true;
                 pending_job = j + kBufs;
             }

@@ -311,6 +311,8 @@ def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=(), w
             local = [int(v) for v in tok[2].split("=")[1].split(",") if v != ""]
             support = int(tok[3].split("=")[1]) if len(tok) > 3 else (1 << 64) - 1
             passes.append({"lead": lead, "local": local, "support": support, "ops": [], "windows": []})
+        elif tok[0] == "EXPGROUPS":   # (which | 16) Hamiltonian groups evaluated in this pass: indices into cover_masks,
+            passes[-1]["exp_groups"] = [int(v) for v in tok[1:]]   # len(cover_masks) = the diagonal group
         elif tok[0] == "STREAMABLE":
             passes[-1]["stream"] = tok[1] == "1"
         elif tok[0] == "STREAM":

@@ -148,3 +148,32 @@ def test_stream_random_pauli_sum(built_lib, oracle, monkeypatch):
     ref.close()
     assert np.abs(off - want).max() < 1e-10
     assert np.abs(got - want).max() < 1e-10
+
+
+@pytest.mark.parametrize("n,gates,seed,brick", [(17, 0, 4, True), (17, 60, 7, False), (18, 5, 0, True), (18, 41, 1, True),
+                                                 (18, 30, 3, False), (18, 100, 3, False), (18, 100, 0, False)])
+def test_early_expectation_matches_oracle(built_lib, oracle, monkeypatch, n, gates, seed, brick):
+    """Light-cone assignment (tq_plan.cpp attach_expectation): Hamiltonian groups that no later gate touches are evaluated
+    in an earlier gate pass when that saves an expectation-only pass.  Every case here has such groups (checked on the
+    plan); the energies must agree with the oracle and with the plan that evaluates everything on the final state."""
+    from tensorrl_qas_b200.simulator import plan_dump
+    gl = brickwork_circuit(n, 21, gates, seed) if brick else synthetic_circuit(n, gates, seed)
+    masks = [(1 << q) | (1 << (q + 1)) for q in range(n - 1)]
+    plan = plan_dump(gl, 16, 12, 4, cover_masks=masks)
+    last_gate_pass = max(i for i, p in enumerate(plan) if p["ops"])
+    assert any(p.get("exp_groups") for p in plan[:last_gate_pass]), "case does not exercise early evaluation"
+    ham = heisenberg(n)
+    p = parameter_batch(gl, 3)
+    want = oracle.energies(gl, p, pauli=ham)
+    for stream in (True, False):
+        sim = make_sim(n, gl, ham, monkeypatch, stream)
+        got = sim.energies(p)
+        again = sim.energies(p)
+        sim.close()
+        assert np.abs(got - want).max() < 1e-10, (stream, np.abs(got - want).max())
+        assert np.array_equal(got, again)
+    monkeypatch.setenv("TQ_EARLY_EXPECT", "0")
+    sim = make_sim(n, gl, ham, monkeypatch, True)
+    late = sim.energies(p)
+    sim.close()
+    assert np.abs(late - want).max() < 1e-10

@@ -217,3 +217,49 @@ def test_streaming_layouts_validate(built_lib, n, gates, seed, brick):
     # the expectation windows that follow gate windows read the store layout: the plan must still cover every mask
     codes = [o[0] for p in passes for w in p["windows"] for o in w["ops"]]
     assert codes.count(20) >= len(masks)   # one M_EXPC class (or more) per flip mask
+
+
+def _touched(p):
+    """physical qubits the gate ops of a dumped pass act on (OP_* of tq_plan.h: a / b are tile positions unless *_NL)"""
+    loc, m = p["local"], 0
+    for op, a, b, *_r in p["ops"]:
+        if op in (0, 4):
+            m |= (1 << loc[a]) | (1 << loc[b])
+        elif op in (1, 2):
+            m |= 1 << loc[a]
+        elif op == 3:
+            m |= 1 << a
+        elif op == 5:
+            m |= (1 << a) | (1 << loc[b])
+    return m
+
+
+@pytest.mark.parametrize("n,extra,seed,brick", [(20, 41, 5, True), (18, 5, 0, True), (18, 41, 1, True), (17, 60, 7, False),
+                                                 (18, 100, 3, False), (16, 300, 43, False), (22, 500, 46, False)])
+def test_early_expectation_light_cone(built_lib, monkeypatch, n, extra, seed, brick):
+    """attach_expectation: every Hamiltonian group is evaluated exactly once; a group evaluated before the last gate pass has
+    its flips local there and no later gate touches its qubits; the headline shape (20 qubits, brickwork) needs ONE
+    expectation-only pass instead of two."""
+    gl = brickwork_circuit(n, 21, extra, seed) if brick else synthetic_circuit(n, extra, seed)
+    masks = [(1 << q) | (1 << (q + 1)) for q in range(n - 1)]
+    plan = plan_dump(gl, 16, 12, 4, cover_masks=masks)
+    seen = sorted(g for p in plan for g in p.get("exp_groups", []))
+    assert seen == list(range(len(masks) + 1))   # (+1: the diagonal group)
+    gate_passes = [i for i, p in enumerate(plan) if p["ops"]]
+    last = gate_passes[-1]
+    for i in gate_passes[:-1]:
+        after = 0
+        for j in gate_passes:
+            if j > i:
+                after |= _touched(plan[j])
+        local = sum(1 << q for q in plan[i]["local"])
+        for g in plan[i].get("exp_groups", []):
+            assert g < len(masks), "the diagonal group belongs to the final state"
+            assert masks[g] & ~local == 0 and masks[g] & after == 0
+    n_exp_only = len(plan) - (last + 1)
+    monkeypatch.setenv("TQ_EARLY_EXPECT", "0")
+    late = plan_dump(gl, 16, 12, 4, cover_masks=masks)
+    assert all(not p.get("exp_groups") for p in late[:last])
+    assert n_exp_only <= len(late) - (last + 1)
+    if (n, extra, seed, brick) == (20, 41, 5, True):
+        assert (n_exp_only, len(late) - (last + 1)) == (1, 2)
