@@ -57,6 +57,7 @@ struct Plan {
     int nbits = 0;
     std::vector<DevPass> passes;  // gate passes first, then expectation-only passes
     int n_gate_passes = 0;
+    bool last_store_needed = true;   // (ExpPlan) false: the expectation-only passes may read the last gate pass's input
     int slots = 0;        // partial sums per element
     int slots_wide = 0;   // the same when the streamed expectation-only passes keep one slot per (tile, warp)
     int n_unitary = 0, n_rot = 0;
@@ -360,6 +361,7 @@ int compile_plan(tq_handle h, int which) {
     opt.mma = env_int("TQ_MMA", 1) != 0;
     opt.dead_budget = env_int("TQ_DEAD_BUDGET", 5);
     opt.early_expect = env_int("TQ_EARLY_EXPECT", 1) != 0;
+    opt.skip_last_store = env_int("TQ_SKIP_LAST_STORE", 1) != 0;
     CompiledCircuit cc = which == 1 ? plan_density(n, h->gates, opt, &perr)
                                     : plan_statevector(n, h->gates, opt, cover, &perr);
     if (!perr.empty()) return fail(h, TQ_EINVAL, perr);
@@ -465,6 +467,7 @@ int compile_plan(tq_handle h, int which) {
     plan.passes.clear();
     plan.nbits = nbits;
     plan.n_gate_passes = n_gate_passes;
+    plan.last_store_needed = ep.last_store_needed;
     plan.slots = 0;
     plan.slots_wide = 0;
     const unsigned char* base = (const unsigned char*)plan.arena;
@@ -757,6 +760,8 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
     h->last_stream = stream;
     // qubits that can be 1 so far: a run that starts from |0...0> (no loaded state) only populates what its gates touch
     const bool track_support = h->sparse_init && !h->have_init && !dm && !from_states;
+    const bool skip_last_store = !plan.last_store_needed && want_energy && !states_out && !dm && !xchg && !from_states &&
+                                 total_passes > plan.n_gate_passes && plan.n_gate_passes >= 2;
     for (int b0 = 0; b0 < batch; b0 += chunk) {
         uint64_t support = track_support ? 0ull : ~0ull;
         const int bc = std::min(chunk, batch - b0);
@@ -798,6 +803,9 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
             } else { pp.src_mode = 2; pp.src = buf; }
             const bool is_last = (i == total_passes - 1);
             pp.dst = (states_out || dm || !is_last) && dp.gate_pass ? buf : nullptr;
+            // light cone: nothing the expectation-only passes evaluate is touched by the gates of the last gate pass, so
+            // they read its INPUT (the scratch buffer as the previous pass left it) and it writes nothing back
+            if (skip_last_store && i == plan.n_gate_passes - 1) pp.dst = nullptr;
             if (from_states && dp.no_ops && !xchg) pp.dst = nullptr;   // gate-free circuit: the states stay as they are
             if (xchg && i == plan.n_gate_passes - 1) {
                 if (!pp.mwindows) return fail(h, TQ_EINVAL, "the exchange write-back needs tensor-core passes (shards of >= 2^9 amplitudes, TQ_MMA=1)");
@@ -819,7 +827,8 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 pp.in_mask = support;
                 // every pass but the last gate pass may skip the tiles that are entirely zero (a non-local qubit set
                 // that nothing has populated yet): the next pass knows not to read them
-                if (i + 1 < plan.n_gate_passes) {
+                // (unless the expectation-only passes read this pass's output: they take every tile)
+                if (i + 1 < plan.n_gate_passes && !(skip_last_store && i + 2 == plan.n_gate_passes)) {
                     int kept = 0;
                     for (int q = 0; q < pp.n_nl; ++q)
                         if ((support >> pp.nonlocal[q]) & 1ull) pp.nonlocal[kept++] = pp.nonlocal[q];
@@ -1701,6 +1710,7 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
     opt.mma = env_int("TQ_MMA", 1) != 0;
     opt.dead_budget = env_int("TQ_DEAD_BUDGET", 5);
     opt.early_expect = env_int("TQ_EARLY_EXPECT", 1) != 0;
+    opt.skip_last_store = env_int("TQ_SKIP_LAST_STORE", 1) != 0;
     CompiledCircuit cc = which == 1 ? plan_density(n_qubits, gates, opt, &err)
                                     : plan_statevector(n_qubits, gates, opt, cover, &err);
     std::string out;
@@ -1731,6 +1741,7 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
             out += line;
         }
     }
+    if (with_stream) out += std::string("LASTSTORE ") + (ep.last_store_needed ? "1" : "0") + "\n";
     for (size_t pi = 0; pi < cc.passes.size(); ++pi) {
         const Pass& p = cc.passes[pi];
         out += "PASS lead=" + std::to_string(p.lead) + " local=";

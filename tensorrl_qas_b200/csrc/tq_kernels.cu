@@ -1209,15 +1209,75 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) expect_direct_kern
     }
 }
 
-// one thread per (batch element, fused block)
+// Four threads per (batch element, fused block): thread c carries column c of the block's 4x4 matrix.  A gate mixes ROWS, so
+// the columns never meet and each one sees exactly the arithmetic of eval_block_matrix (same results, bit for bit); the next
+// gate's descriptor and angle are fetched while the current one is applied (the loop is a chain of dependent loads otherwise).
 __global__ void __launch_bounds__(128) prep_matrices_kernel(const MatDesc* __restrict__ descs, const MatGate* __restrict__ prog,
                                                             int n_mats, int batch, const double* __restrict__ params,
                                                             int ld_params, const uint8_t* __restrict__ codes,
                                                             int ld_codes, double2* __restrict__ mats) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, col = threadIdx.x & 3;
     if (idx >= n_mats * batch) return;
     const int b = idx / n_mats, mi = idx - b * n_mats;
-    eval_block_matrix(descs[mi], prog, params, (size_t)b, ld_params, codes, ld_codes, mats + (size_t)idx * kMatStride);
+    const MatDesc md = descs[mi];
+    double2 M[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) M[r] = make_double2(r == col ? 1.0 : 0.0, 0.0);
+    auto angle_of = [&](const MatGate& g) {
+        return (g.kind <= MG_RZ && g.pidx >= 0) ? params[(size_t)b * ld_params + g.pidx] : g.fixed;
+    };
+    MatGate g{};
+    double theta = 0.0;
+    if (md.begin < md.end) { g = prog[md.begin]; theta = angle_of(g); }
+    for (int gi = md.begin; gi < md.end; ++gi) {
+        const MatGate cur = g;
+        const double th = theta;
+        if (gi + 1 < md.end) { g = prog[gi + 1]; theta = angle_of(g); }
+        int kind = cur.kind;
+        if (kind == MG_CX) {  // control = lq: swap the two rows with the control bit set
+            const int ra = cur.lq == 0 ? 1 : 2;
+            const double2 t = M[ra]; M[ra] = M[3]; M[3] = t;
+            continue;
+        }
+        if (kind == MG_PAULI_SLOT) {
+            const int code = (codes[(size_t)b * ld_codes + cur.pidx] >> (int)cur.fixed) & 3;
+            if (code == 0) continue;
+            kind = MG_X + code - 1;
+        }
+        double2 g00 = make_double2(0.0, 0.0), g01 = g00, g10 = g00, g11 = g00;
+        if (kind <= MG_RZ) {
+            double sn, cs;
+            sincos(0.5 * th, &sn, &cs);
+            if (kind == MG_RX) { g00.x = cs; g01.y = sn; g10.y = sn; g11.x = cs; }
+            else if (kind == MG_RY) { g00.x = cs; g01.x = sn; g10.x = -sn; g11.x = cs; }
+            else { g00.x = cs; g00.y = sn; g11.x = cs; g11.y = -sn; }
+        } else if (kind == MG_X) { g01.x = 1.0; g10.x = 1.0; }
+        else if (kind == MG_Y) { g01.y = -1.0; g10.y = 1.0; }
+        else { g00.x = 1.0; g11.x = -1.0; }
+        if (cur.lq == 0) {
+#pragma unroll
+            for (int r = 0; r < 4; r += 2) {
+                const double2 x0 = M[r], x1 = M[r + 1];
+                M[r] = cfma(g01, x1, cmul(g00, x0));
+                M[r + 1] = cfma(g11, x1, cmul(g10, x0));
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double2 x0 = M[r], x1 = M[r + 2];
+                M[r] = cfma(g01, x1, cmul(g00, x0));
+                M[r + 2] = cfma(g11, x1, cmul(g10, x0));
+            }
+        }
+    }
+    double2* out = mats + (size_t)idx * kMatStride;
+    if (md.nq == 2) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) out[r * 4 + col] = M[r];
+    } else if (col < 2) {  // one-qubit block: the 2x2 matrix in entries 0..3
+        out[col] = M[0];
+        out[2 + col] = M[1];
+    }
 }
 
 // out[b] = sum of row b of `partial` (n entries, row stride ld): one CTA per element, fixed summation order (thread t adds
@@ -1345,7 +1405,7 @@ void launch_prep_matrices(const MatDesc* descs, const MatGate* prog, int n_mats,
                           int ld_params, const uint8_t* codes, int ld_codes, double2* mats, cudaStream_t stream) {
     const int total = n_mats * batch;
     if (total <= 0) return;
-    prep_matrices_kernel<<<(total + 127) / 128, 128, 0, stream>>>(descs, prog, n_mats, batch, params, ld_params, codes,
+    prep_matrices_kernel<<<(total * 4 + 127) / 128, 128, 0, stream>>>(descs, prog, n_mats, batch, params, ld_params, codes,
                                                                    ld_codes, mats);
 }
 

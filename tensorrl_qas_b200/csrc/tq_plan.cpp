@@ -293,9 +293,10 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
             std::vector<int> early(M, -1);
             std::vector<double> share(passes.size(), 1.0);   // populated share of the state after pass i
             const bool search = nbits > k && M <= 64;
+            uint64_t touched_here = 0;                       // qubits the gates of this (last) pass act on
+            for (int idx : mine) touched_here |= ops[idx].mix | ops[idx].diag;
             if (search && mma && opt.early_expect && !passes.empty()) {
-                uint64_t after = 0;
-                for (int idx : mine) after |= ops[idx].mix | ops[idx].diag;
+                uint64_t after = touched_here;
                 std::vector<uint64_t> after_of(passes.size());
                 for (int i = (int)passes.size() - 1; i >= 0; --i) {
                     after_of[i] = after;
@@ -309,12 +310,21 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
                             !(cover_masks[m] & after_of[i]))
                             early[m] = (int)i;
             }
-            auto fill = [&](size_t start, bool late_first) {
+            // priority classes of a fill: 0 = the mask list as it is; 1 = first the groups no earlier pass can take;
+            // 2 = before those, the groups this pass's own gates touch (with all of them evaluated here, the groups left
+            // to the expectation-only passes have the same value before and after this pass: it need not write the
+            // state back -- ExpPlan::last_store_needed)
+            auto cls = [&](size_t m, int variant) {
+                if (variant == 0) return 0;
+                if (variant == 2 && (cover_masks[m] & touched_here)) return 0;
+                return early[m] < 0 ? 1 : 2;
+            };
+            auto fill = [&](size_t start, int variant) {
                 uint64_t X = L0;
-                for (int phase = 0; phase < (late_first ? 2 : 1); ++phase)
+                for (int phase = 0; phase < (variant ? 3 : 1); ++phase)
                     for (size_t c = 0; c < M; ++c) {
                         const size_t m = (start + c) % M;
-                        if (late_first && (phase == 0) != (early[m] < 0)) continue;
+                        if (cls(m, variant) != phase) continue;
                         if (__builtin_popcountll(X | cover_masks[m]) <= k) X |= cover_masks[m];
                     }
                 return X;
@@ -322,20 +332,27 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
             auto cost = [&](uint64_t X) {
                 std::vector<uint64_t> todo;
                 std::vector<int> e;
+                bool no_store = opt.skip_last_store && !passes.empty();
                 for (size_t m = 0; m < M; ++m)
-                    if (cover_masks[m] & ~X) { todo.push_back(cover_masks[m]); e.push_back(early[m]); }
+                    if (cover_masks[m] & ~X) {
+                        todo.push_back(cover_masks[m]);
+                        e.push_back(early[m]);
+                        no_store = no_store && !(cover_masks[m] & touched_here);
+                    }
                 std::vector<char> moved;
-                double c = (double)choose_early(nbits, opt, todo, e, moved);
+                const size_t n_exp = choose_early(nbits, opt, todo, e, moved);
+                double c = (double)n_exp;
                 for (size_t t = 0; t < todo.size(); ++t)
                     if (moved[t]) c += 0.125 * share[e[t]];   // (a window more in a gate pass over that share of the state)
+                if (no_store && n_exp > 0) c -= 0.4;          // (one write of the state less)
                 return c - 1e-3 * (double)(M - todo.size());
             };
-            uint64_t best = fill(0, false);
+            uint64_t best = fill(0, 0);
             if (search) {
                 double best_cost = cost(best);
-                for (int lf = 0; lf < 2; ++lf)
+                for (int variant = 0; variant < 3; ++variant)
                     for (size_t st = 0; st < M; ++st) {
-                        const uint64_t X = fill(st, lf != 0);
+                        const uint64_t X = fill(st, variant);
                         if (X == best) continue;
                         const double c = cost(X);
                         if (c < best_cost - 1e-9) { best = X; best_cost = c; }
@@ -1317,6 +1334,16 @@ ExpPlan attach_expectation(std::vector<Pass>& passes, const std::vector<ExpGroup
             for (Pass& p : extra) passes.push_back(std::move(p));
         }
     }
+    // Does the last gate pass have to write the state back for the expectation-only passes?  Not if its gates touch none
+    // of the groups (and, below, none of the diagonal terms) evaluated there: those have the same value on its input.
+    const uint64_t touched_last = ep.n_gate_passes > 0 ? pass_touched(passes[ep.n_gate_passes - 1]) : ~0ull;
+    ep.last_store_needed = !opt.skip_last_store || ep.n_gate_passes < 2 || (int)passes.size() == ep.n_gate_passes;
+    for (size_t i = (size_t)ep.n_gate_passes; i < passes.size(); ++i)
+        for (int g : ep.groups_of_pass[i]) {
+            uint64_t supp = groups[g].x;
+            for (const ExpTermIn& in : groups[g].terms) supp |= in.z;
+            if (supp & touched_last) ep.last_store_needed = true;
+        }
     ep.wide_of_pass.assign(passes.size(), {});
     early_diag.resize(passes.size());
     std::vector<ExpTermIn> diag_pool;   // diagonal terms still to be evaluated (tensor-core passes share them)
@@ -1343,6 +1370,9 @@ ExpPlan attach_expectation(std::vector<Pass>& passes, const std::vector<ExpGroup
             else append_expectation_windows(p, gin, &wide);
         }
         for (int wi : wide) ep.wide_of_pass[i].push_back(ep.groups_of_pass[i][wi]);
+        if ((int)i == ep.n_gate_passes - 1)   // what is left of the diagonal terms goes to the passes after this one
+            for (const ExpTermIn& in : diag_pool)
+                if (in.z & touched_last) ep.last_store_needed = true;
         if (p.stream && (!wide.empty() || (int)p.wops.size() > kStreamOpSlots || (int)p.mwindows.size() > kStreamWinSlots))
             p.stream = false;   // (the windows picked their lanes for the streaming layout: a few more bank conflicts)
     }

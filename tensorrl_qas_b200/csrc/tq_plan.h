@@ -278,6 +278,8 @@ struct PlanOptions {
     bool mma = true;      // pure-state passes with >= 2^9-amplitude tiles use DMMA windows
     int dead_budget = 5;  // still-empty qubits a tensor-core pass may take once the populated state spans many tiles (pack();
                           // 0 = no limit)
+    bool skip_last_store = true;   // the last gate pass may leave the state unwritten when the expectation-only passes read
+                                   // groups its gates do not touch (ExpPlan::last_store_needed)
     bool early_expect = true;   // Hamiltonian groups that no later gate touches may be evaluated in an earlier gate pass
                                 // when that saves an expectation-only pass (attach_expectation)
 };
@@ -324,6 +326,8 @@ struct ExpPlan {
     int n_gate_passes = 0;
     std::vector<std::vector<int>> groups_of_pass;   // indices into `groups`
     std::vector<std::vector<int>> wide_of_pass;     // of those, the groups left to the shared-memory fallback
+    bool last_store_needed = true;   // false: the expectation-only passes may read the INPUT of the last gate pass (no
+                                     // gate of that pass touches a qubit of their groups: light cone)
     std::string err;
 };
 ExpPlan attach_expectation(std::vector<Pass>& passes, const std::vector<ExpGroupIn>& groups, const PlanOptions& opt, int n,

@@ -298,11 +298,14 @@ def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=(), w
     L.tq_free(ptr)
     passes = []
     mats = []
+    last_store = True
     for line in text.splitlines():
         tok = line.split()
         if tok[0] == "ERROR":
             raise ValueError(line[6:])
-        if tok[0] == "MAT":
+        if tok[0] == "LASTSTORE":   # (which | 16) does the last gate pass write the state back for the expectation-only passes
+            last_store = tok[1] == "1"
+        elif tok[0] == "MAT":
             mats.append({"nq": int(tok[1]), "diag": int(tok[2]), "gates": []})
         elif tok[0] == "MG":  # (kind, lq, pidx, fixed)
             mats[-1]["gates"].append((int(tok[1]), int(tok[2]), int(tok[3]), float(tok[4])))
@@ -337,4 +340,6 @@ def plan_dump(gl: GateList, which=0, tile_bits=12, low_bits=4, cover_masks=(), w
                                           "flags": int(kv["flags"]), "dead": int(kv.get("dead", 0)), "ops": []})
         elif tok[0] == "WOP":  # (code, rb, rb2, qsel, flags, t, fixed)
             passes[-1]["windows"][-1]["ops"].append(tuple(int(v) for v in tok[1:7]) + (float(tok[7]),))
+    for p in passes:
+        p["last_store_needed"] = last_store
     return {"passes": passes, "mats": mats} if with_mats else passes

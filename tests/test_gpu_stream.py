@@ -151,7 +151,8 @@ def test_stream_random_pauli_sum(built_lib, oracle, monkeypatch):
 
 
 @pytest.mark.parametrize("n,gates,seed,brick", [(17, 0, 4, True), (17, 60, 7, False), (18, 5, 0, True), (18, 41, 1, True),
-                                                 (18, 30, 3, False), (18, 100, 3, False), (18, 100, 0, False)])
+                                                 (18, 30, 3, False), (18, 200, 4, False), (18, 100, 0, False), (18, 41, 3, True),
+                                                 (18, 200, 5, False)])
 def test_early_expectation_matches_oracle(built_lib, oracle, monkeypatch, n, gates, seed, brick):
     """Light-cone assignment (tq_plan.cpp attach_expectation): Hamiltonian groups that no later gate touches are evaluated
     in an earlier gate pass when that saves an expectation-only pass.  Every case here has such groups (checked on the
@@ -177,3 +178,40 @@ def test_early_expectation_matches_oracle(built_lib, oracle, monkeypatch, n, gat
     late = sim.energies(p)
     sim.close()
     assert np.abs(late - want).max() < 1e-10
+
+
+@pytest.mark.parametrize("n,gates,seed,brick", [(16, 60, 5, False), (16, 30, 6, False), (17, 41, 0, True), (18, 41, 3, True),
+                                                 (18, 200, 5, False), (17, 200, 6, False), (18, 30, 1, False)])
+def test_skip_last_store_matches_oracle(built_lib, oracle, monkeypatch, n, gates, seed, brick):
+    """When no gate of the last gate pass touches a group evaluated in the expectation-only passes, that pass writes nothing
+    back and they read its input (ExpPlan::last_store_needed, tq_plan.h).  Every case here has such a plan; energies against
+    the oracle, against the plan that stores, and through tq_evolve_states (which does store: the states are its output)."""
+    import torch
+    from tensorrl_qas_b200.simulator import plan_dump
+    gl = brickwork_circuit(n, 21, gates, seed) if brick else synthetic_circuit(n, gates, seed)
+    masks = [(1 << q) | (1 << (q + 1)) for q in range(n - 1)]
+    plan = plan_dump(gl, 16, 12, 4, cover_masks=masks)
+    assert not plan[0]["last_store_needed"], "case does not exercise the skipped write-back"
+    ham = heisenberg(n)
+    p = parameter_batch(gl, 3)
+    want = oracle.energies(gl, p, pauli=ham)
+    for stream in (True, False):
+        sim = make_sim(n, gl, ham, monkeypatch, stream)
+        got = sim.energies(p)
+        again = sim.energies(p)
+        # the same circuit applied to |0...0> states in place: the final states come back, the energies agree
+        st = torch.zeros((3, 1 << n), dtype=torch.complex128, device="cuda")
+        st[:, 0] = 1.0
+        e_ev = sim.evolve_states(st, torch.as_tensor(p, device="cuda").contiguous(), energies=True)
+        torch.cuda.synchronize()
+        psi = sim.states(p)
+        sim.close()
+        assert np.abs(got - want).max() < 1e-10, (stream, np.abs(got - want).max())
+        assert np.array_equal(got, again)
+        assert np.abs(e_ev.cpu().numpy() - want).max() < 1e-10
+        assert np.abs(st.cpu().numpy() - psi).max() < 1e-12
+    monkeypatch.setenv("TQ_SKIP_LAST_STORE", "0")
+    sim = make_sim(n, gl, ham, monkeypatch, True)
+    stored = sim.energies(p)
+    sim.close()
+    assert np.abs(stored - want).max() < 1e-10

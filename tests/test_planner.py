@@ -235,7 +235,7 @@ def _touched(p):
 
 
 @pytest.mark.parametrize("n,extra,seed,brick", [(20, 41, 5, True), (18, 5, 0, True), (18, 41, 1, True), (17, 60, 7, False),
-                                                 (18, 100, 3, False), (16, 300, 43, False), (22, 500, 46, False)])
+                                                 (18, 200, 5, False), (16, 300, 43, False), (22, 500, 46, False)])
 def test_early_expectation_light_cone(built_lib, monkeypatch, n, extra, seed, brick):
     """attach_expectation: every Hamiltonian group is evaluated exactly once; a group evaluated before the last gate pass has
     its flips local there and no later gate touches its qubits; the headline shape (20 qubits, brickwork) needs ONE
@@ -257,6 +257,14 @@ def test_early_expectation_light_cone(built_lib, monkeypatch, n, extra, seed, br
             assert g < len(masks), "the diagonal group belongs to the final state"
             assert masks[g] & ~local == 0 and masks[g] & after == 0
     n_exp_only = len(plan) - (last + 1)
+    # the last gate pass leaves the state unwritten only if none of its gates touches a group evaluated after it
+    if not plan[0]["last_store_needed"]:
+        assert n_exp_only > 0 and len(gate_passes) >= 2
+        for p in plan[last + 1:]:
+            for g in p["exp_groups"]:
+                assert g < len(masks) and masks[g] & _touched(plan[last]) == 0
+    if (n, extra, seed, brick) == (20, 41, 5, True):
+        assert not plan[0]["last_store_needed"]
     monkeypatch.setenv("TQ_EARLY_EXPECT", "0")
     late = plan_dump(gl, 16, 12, 4, cover_masks=masks)
     assert all(not p.get("exp_groups") for p in late[:last])
