@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     JobDesc* s_job = reinterpret_cast<JobDesc*>(full_bar + kBufs + 1);         // kBufs (+1 pad)
     SubInfo* s_sub = reinterpret_cast<SubInfo*>(s_job + kBufs + 1);            // kStreamMaxSub
     int* s_done = reinterpret_cast<int*>(s_sub + kStreamMaxSub);               // kBufs (+1 pad): warps done with a buffer (MODE 2)
+    int* s_token = s_done + kBufs + 1;   // [0]: the tensor-pipe token (StreamParams::dmma_token), [1 + g]: warps of group g done
 
     const int tid = threadIdx.x;
     // ---- stage every sub-pass once: scalars, window headers, op words, expectation tables ----
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
             }
         }
         for (int i = 0; i < kBufs; ++i) mbar_init(full_bar + i, 1);
-        for (int i = 0; i < kBufs + 1; ++i) s_done[i] = 0;
+        for (int i = 0; i < kBufs + 1 + 4; ++i) s_done[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
@@ -487,6 +488,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
 #pragma unroll
                     for (int r = 0; r < NR; ++r) a[r] = 0.0;
                 }
+                // Tensor-pipe token: the group's thread 0 takes it before the barrier, so the block chains of the two
+                // groups never run at the same time.  Sharing the pipe slows both down together and they then leave their
+                // DMMA phases -- and sit in their load / store / barrier phases -- together, with the pipe idle; with the
+                // token one group's chains run under the other's window entry and exit.
+                if (sp.dmma_token && gtid == 0) {
+                    while (atomicCAS(s_token, 0, 1) != 0) __nanosleep(40);
+                }
                 group_sync<GRP>();   // everyone holds its entry data: the tile may be overwritten from here on
                 if (first_gate) {
                     first_gate = false;
@@ -545,6 +553,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                         case FM_CXO + 4: m_cx_out<4>(a, ctl); break;
                         default: break;
                         }
+                    }
+                }
+                if (sp.dmma_token) {   // the last warp out of the op loop hands the token on
+                    __syncwarp();
+                    if (lane == 0 && atomicAdd(s_token + 1 + GRP, 1) == kGroupThreads / 32 - 1) {
+                        s_token[1 + GRP] = 0;
+                        __threadfence_block();
+                        atomicExch(s_token, 0);
                     }
                 }
                 if (busy || store_all) {
@@ -685,7 +701,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
 size_t tile_stream_smem_bytes() {
     return (size_t)kBufs * kTileBytes + (size_t)kGroups * kOpSlots * kMatStride * sizeof(double2) + kOpSlots * sizeof(WinOp) +
            kWinSlots * sizeof(StreamWindowDev) + kGroups * 16 * sizeof(double) + (kBufs + 1) * sizeof(uint64_t) +
-           (kBufs + 1) * sizeof(JobDesc) + kStreamMaxSub * sizeof(SubInfo) + (kBufs + 1) * sizeof(int) +
+           (kBufs + 1) * sizeof(JobDesc) + kStreamMaxSub * sizeof(SubInfo) + (kBufs + 1 + 4) * sizeof(int) +
            1024 /* alignment slack */;
 }
 
