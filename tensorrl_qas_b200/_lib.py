@@ -5,7 +5,8 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtqsim.so")
+# (TQ_LIB_PATH: A/B of alternative in-tree builds during kernel work; the default is the library build() makes)
+LIB_PATH = os.environ.get("TQ_LIB_PATH") or os.path.join(_HERE, "libtqsim.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["tq_api.cu", "tq_kernels.cu", "tq_stream.cu", "tq_plan.cpp", "tq_cobyla.cpp"]
 NVCC_FLAGS = [

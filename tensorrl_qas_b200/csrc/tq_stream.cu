@@ -96,9 +96,13 @@ __device__ __forceinline__ void tma_store(const CUtensorMap* map, uint32_t src, 
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-template <int GRP>
-__device__ __forceinline__ void group_sync() {
-    asm volatile("bar.sync %0, %1;" ::"n"(GRP + 1), "n"(kGroupThreads) : "memory");
+template <int V>
+struct GroupConst {   // a group index known at compile time (the expectation-only kernel)
+    __device__ constexpr operator int() const { return V; }
+};
+// named barrier of one group (id 1 or 2)
+__device__ __forceinline__ void group_sync(int grp) {
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
 }
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double v;
@@ -259,6 +263,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     SubInfo* s_sub = reinterpret_cast<SubInfo*>(s_job + kBufs + 1);            // kStreamMaxSub
     int* s_done = reinterpret_cast<int*>(s_sub + kStreamMaxSub);               // kBufs (+1 pad): warps done with a buffer (MODE 2)
     int* s_token = s_done + kBufs + 1;   // [0]: the tensor-pipe token (StreamParams::dmma_token), [1 + g]: warps of group g done
+    double* s_zero = reinterpret_cast<double*>(s_token + 4);   // 0.0: what a register with known-zero contents is loaded from
 
     const int tid = threadIdx.x;
     // ---- stage every sub-pass once: scalars, window headers, op words, expectation tables ----
@@ -290,6 +295,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
         }
         for (int i = 0; i < kBufs; ++i) mbar_init(full_bar + i, 1);
         for (int i = 0; i < kBufs + 1 + 4; ++i) s_done[i] = 0;
+        s_zero[0] = 0.0;
+        s_zero[1] = 0.0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
@@ -334,9 +341,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
         n_jobs = cta < total_tiles ? ((total_tiles - cta + n_cta - 1) / n_cta) * (uint32_t)sp.n_sub : 0u;
     }
     // the two groups run the same code with their own barrier id, matrix staging area and reduction slots
-    auto run_group = [&](auto grp_tag, double2* s_mat, double* s_red) {
-        constexpr int GRP = decltype(grp_tag)::value;
-        double* s_red_cta = s_red_all;
+    // Gate passes: ONE copy of the code for both groups (the group index is a run-time value; two instantiations doubled
+    // the kernel to ~180 KB of SASS and the instruction-cache misses showed up as `no_instructions` stalls: 0.865 -> 0.838 ms
+    // on the 20-qubit bench shape's dense gate pass).  The small expectation-only kernel keeps one instantiation per group.
+    auto run_group = [&](auto grp_tag) {
+    const int GRP = grp_tag;
+    double2* const s_mat = s_mat_all + GRP * (kOpSlots * kMatStride);
+    double* const s_red = s_red_all + GRP * 16;
     const int gtid = threadIdx.x & (kGroupThreads - 1);
     const int lane = gtid & 31, warp = gtid >> 5;
     const uint32_t comp8 = (uint32_t)(lane & 1) << 3;
@@ -347,6 +358,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                    mw0 = 0u - (uint32_t)(warp & 1), mw1 = 0u - (uint32_t)((warp >> 1) & 1), mw2 = 0u - (uint32_t)((warp >> 2) & 1);
     const int n_sub = sp.n_sub;
     const uint32_t tiles_u32 = smem_u32(tiles);
+    const uint32_t zero_u32 = smem_u32(s_zero);
 
     // issued by ONE thread: descriptor + TMA loads of job j into buffer j % kBufs
     auto issue_load = [&](uint32_t j) {
@@ -395,7 +407,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     const int brow = (g8 >> 2) | ((g8 & 1) << 1), bcol = (lane >> 1) & 1;
     const uint32_t bfrag = (uint32_t)((brow * 4 + bcol) * 16);   // byte offset of m[brow * 4 + bcol]
     const bool bsame = ((g8 >> 1) & 1) == (lane & 1);
-    const long long bneg = ((g8 >> 1) & 1) ? 0ll : (long long)(1ull << 63);
+    const uint32_t bpart = bfrag + (bsame ? 0u : 8u);
+    const int bsign = (bsame || ((g8 >> 1) & 1)) ? 0 : (int)0x80000000u;
 
     if (MODE != 2 && GRP == 1 && sp.stagger_ns > 0) {   // (see StreamParams::stagger_ns)
         for (int left = sp.stagger_ns; left > 0; left -= 1000) __nanosleep(1000);
@@ -423,7 +436,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
 
         // block matrices of this element (gate passes): once per (group, element)
         if (MODE != 2 && p.n_mats > 0 && b != cur_elem) {
-            group_sync<GRP>();   // every thread of the group is done with the previous job's matrices
+            group_sync(GRP);   // every thread of the group is done with the previous job's matrices
             const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
             for (int i = gtid; i < p.n_wops * kMatStride; i += kGroupThreads) {
                 const int oi = i >> 4, e = i & 15;
@@ -444,7 +457,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                 s_mat[(o0 + oi) * kMatStride + dst] = v;
             }
             cur_elem = b;
-            group_sync<GRP>();
+            group_sync(GRP);
         }
 
         Regs a;
@@ -465,6 +478,23 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
 #pragma unroll
             for (int r = 0; r < NR; ++r) a[r] = lds_f64(tile_u32 + (hi[r >> 2] ^ lo[r & 3]));
         };
+        // the same for a window with known zeros on entry (a dead tile, or register / lane / warp bits nothing has
+        // populated yet): those registers are read from a zero in shared memory -- one address select per register
+        // instead of a 64-bit select after the load (and a dead tile's buffer, which nothing was loaded into, is not read)
+        auto enter_zeros = [&](const StreamWindowDev* hdr, uint32_t dead_r, bool zero_all) {
+            const uint32_t base = comp8 ^ (mq & hdr->qofs) ^ (mg0 & hdr->gofs[0]) ^ (mg1 & hdr->gofs[1]) ^
+                                  (mg2 & hdr->gofs[2]) ^ (mw0 & hdr->wofs[0]) ^ (mw1 & hdr->wofs[1]) ^ (mw2 & hdr->wofs[2]);
+            ctx = tile_base | (mq & hdr->qlmask) | (mg0 & hdr->gmask[0]) | (mg1 & hdr->gmask[1]) | (mg2 & hdr->gmask[2]) |
+                  (mw0 & hdr->wmask[0]) | (mw1 & hdr->wmask[1]) | (mw2 & hdr->wmask[2]);
+            ebase = base;
+            const uint32_t x0 = hdr->rofs[0], x1 = hdr->rofs[1], x2 = hdr->rofs[2], x3 = hdr->rofs[3], x4 = hdr->rofs[4];
+            const uint32_t lo[4] = {0u, x0, x1, x0 ^ x1};
+            const uint32_t hi[8] = {base, base ^ x2, base ^ x3, base ^ x2 ^ x3, base ^ x4, base ^ x4 ^ x2, base ^ x4 ^ x3,
+                                    base ^ x4 ^ x3 ^ x2};
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+                a[r] = lds_f64((zero_all || (r & dead_r)) ? zero_u32 : tile_u32 + (hi[r >> 2] ^ lo[r & 3]));
+        };
 
         // ---- gate windows ----
         bool first_gate = true;
@@ -476,17 +506,16 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                 const bool store_all = ((wflags >> 8) & kWin2StoreAll) || tile_dead;
                 const bool idle = p.use_dead && (warp & (int)(wflags >> 16));
                 const bool busy = !idle;
-                if (busy || store_all) enter(hdr);   // (an idle warp that has to write zeros back still needs its layout)
+                // (an idle warp that has to write zeros back still needs its layout)
                 if (tile_dead || (((wflags >> 8) & kWin2DeadEntry) != 0)) {
                     // known zeros on entry: a dead tile, or register / lane / warp bits nothing has populated yet
                     const uint32_t dead_r = tile_dead ? 31u : hdr->dead_r;
                     const bool zero_all = tile_dead || idle || (((lane >> 1) & 0xf) & hdr->dead_l);
-#pragma unroll
-                    for (int r = 0; r < NR; ++r)
-                        if (zero_all || (r & dead_r)) a[r] = 0.0;
+                    if (busy || store_all) enter_zeros(hdr, dead_r, zero_all);
                 } else if (idle && store_all) {
-#pragma unroll
-                    for (int r = 0; r < NR; ++r) a[r] = 0.0;
+                    enter_zeros(hdr, 31u, true);
+                } else if (busy) {
+                    enter(hdr);
                 }
                 // Tensor-pipe token: the group's thread 0 takes it before the barrier, so the block chains of the two
                 // groups never run at the same time.  Sharing the pipe slows both down together and they then leave their
@@ -495,7 +524,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                 if (sp.dmma_token && gtid == 0) {
                     while (atomicCAS(s_token, 0, 1) != 0) __nanosleep(40);
                 }
-                group_sync<GRP>();   // everyone holds its entry data: the tile may be overwritten from here on
+                group_sync(GRP);   // everyone holds its entry data: the tile may be overwritten from here on
                 if (first_gate) {
                     first_gate = false;
                     // the refill of the buffer this group used last: its TMA store has had the time of a barrier to drain
@@ -506,40 +535,40 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                     }
                 }
                 const int o_end = busy ? o0 + hdr->op_end : 0;
-                // op word and B fragment of op o (prefetched one op ahead, so the loads run under the previous block's DMMAs)
-                auto fetch = [&](int o, uint32_t& w0n_, double& b0, double& b1) {
-                    w0n_ = s_wops[o].w0;
-                    const double2* m = s_mat + o * kMatStride;
-                    double2 u0 = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(m) + bfrag);
-                    double2 u1 = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(m) + bfrag + 32);
-                    if ((w0n_ & 0xff) == FM_SCAL) {
-                        const double2 d = ((ctx >> ((w0n_ >> 16) & 0xff)) & 1u) ? m[3] : m[0];
-                        const double2 z = make_double2(0.0, 0.0);
-                        u0 = (brow == bcol) ? d : z;
-                        u1 = (brow == (bcol | 2)) ? d : z;
-                    }
-                    b0 = bsame ? u0.x : __longlong_as_double(__double_as_longlong(u0.y) ^ bneg);
-                    b1 = bsame ? u1.x : __longlong_as_double(__double_as_longlong(u1.y) ^ bneg);
-                };
-                uint32_t w0n = 0;
-                double b0n = 0.0, b1n = 0.0;
-                int o = o0 + hdr->op_begin;
-                if (o < o_end) fetch(o, w0n, b0n, b1n);
-                for (; o < o_end; ++o) {
-                    const uint32_t wcur = w0n;
-                    const double b0 = b0n, b1 = b1n;
-                    if (o + 1 < o_end) fetch(o + 1, w0n, b0n, b1n);
+                // Op word and B fragment are fetched where they are used.  (A one-op-ahead prefetch -- the loads issued under
+                // the previous block's DMMAs -- cost five register moves per op and register pressure: 0.818 -> 0.787 ms for
+                // the dense gate pass of the 20-qubit bench shape without it.)  A lane's two B entries are the real or the
+                // imaginary part (bpart) of m[brow * 4 + bcol (+ 2)], the imaginary part negated for half of the lanes
+                // (bsign): two 8-byte loads, no selects (two 16-byte loads + selects before: 0.657 -> 0.608 ms on the last
+                // gate pass).
+                for (int o = o0 + hdr->op_begin; o < o_end; ++o) {
+                    const uint32_t wcur = s_wops[o].w0;
                     const int fc = wcur & 0xff;
-                    const int qsel = (wcur >> 16) & 0xff;
                     if (fc <= FM_SCAL) {
+                        const double2* m = s_mat + o * kMatStride;
+                        double b0, b1;
+                        if (fc == FM_SCAL) {   // a diagonal block picked by one of the thread's index bits
+                            const double2 d = ((ctx >> ((wcur >> 16) & 0xff)) & 1u) ? m[3] : m[0];
+                            const double dd = bsame ? d.x : d.y;
+                            b0 = (brow == bcol) ? dd : 0.0;
+                            b1 = (brow == (bcol | 2)) ? dd : 0.0;
+                        } else {
+                            const uint32_t ma = smem_u32(m) + bpart;
+                            b0 = lds_f64(ma);
+                            b1 = lds_f64(ma + 32);
+                        }
+                        b0 = __hiloint2double(__double2hiint(b0) ^ bsign, __double2loint(b0));
+                        b1 = __hiloint2double(__double2hiint(b1) ^ bsign, __double2loint(b1));
                         const uint32_t dead = p.use_dead ? ((wcur >> 25) & 0x1fu) : 0u;
-                        if (fc == FM_U2 + 1) m_u2<1>(a, b0, b1, dead);
-                        else if (fc == FM_U2 + 2) m_u2<2>(a, b0, b1, dead);
-                        else if (fc == FM_U2 + 3) m_u2<3>(a, b0, b1, dead);
-                        else if (fc == FM_U2 + 4) m_u2<4>(a, b0, b1, dead);
-                        else m_u2<0>(a, b0, b1, dead);
+                        switch (fc) {
+                        case FM_U2 + 1: m_u2<1>(a, b0, b1, dead); break;
+                        case FM_U2 + 2: m_u2<2>(a, b0, b1, dead); break;
+                        case FM_U2 + 3: m_u2<3>(a, b0, b1, dead); break;
+                        case FM_U2 + 4: m_u2<4>(a, b0, b1, dead); break;
+                        default: m_u2<0>(a, b0, b1, dead); break;
+                        }
                     } else {
-                        const bool ctl = (ctx >> qsel) & 1u;
+                        const bool ctl = (ctx >> ((wcur >> 16) & 0xff)) & 1u;
                         switch (fc) {
                         case FM_SWAP + 0: m_swapql<0>(a, l1); break;
                         case FM_SWAP + 1: m_swapql<1>(a, l1); break;
@@ -576,7 +605,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                     for (int r = 0; r < NR; ++r) sts_f64(tile_u32 + (hi[r >> 2] ^ lo[r & 3]), a[r]);
                 }
                 fence_proxy_async();   // (the last window's writes are read by the TMA store)
-                group_sync<GRP>();     // the tile is complete in shared memory again
+                group_sync(GRP);     // the tile is complete in shared memory again
             }
 
             // ---- write back: the buffer holds the final tile in the store layout ----
@@ -671,7 +700,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                 double* red = s_red + (flip ? 8 : 0);
                 flip ^= 1;
                 if (lane == 0) red[warp] = acc;
-                group_sync<GRP>();   // also: every thread of the group has finished reading the buffer
+                group_sync(GRP);   // also: every thread of the group has finished reading the buffer
                 if (gtid == 0) {
                     double tot = 0.0;
 #pragma unroll
@@ -692,8 +721,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     }
     if (gtid == 0) tma_wait_all0();
     };
-    if (tid < kGroupThreads) run_group(std::integral_constant<int, 0>{}, s_mat_all, s_red_all);
-    else run_group(std::integral_constant<int, 1>{}, s_mat_all + kOpSlots * kMatStride, s_red_all + 16);
+    if constexpr (MODE == 2) {
+        if (tid < kGroupThreads) run_group(GroupConst<0>{});
+        else run_group(GroupConst<1>{});
+    } else {
+        run_group(tid >= kGroupThreads ? 1 : 0);
+    }
 }
 
 }  // namespace
@@ -701,7 +734,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
 size_t tile_stream_smem_bytes() {
     return (size_t)kBufs * kTileBytes + (size_t)kGroups * kOpSlots * kMatStride * sizeof(double2) + kOpSlots * sizeof(WinOp) +
            kWinSlots * sizeof(StreamWindowDev) + kGroups * 16 * sizeof(double) + (kBufs + 1) * sizeof(uint64_t) +
-           (kBufs + 1) * sizeof(JobDesc) + kStreamMaxSub * sizeof(SubInfo) + (kBufs + 1 + 4) * sizeof(int) +
+           (kBufs + 1) * sizeof(JobDesc) + kStreamMaxSub * sizeof(SubInfo) + (kBufs + 1 + 4) * sizeof(int) + 2 * sizeof(double) +
            1024 /* alignment slack */;
 }
 
