@@ -81,7 +81,7 @@ struct tq_context {
     bool stream_expect = true;  // TQ_STREAM=2 (default): the expectation-only passes as well; 1: those stay on expect_direct_kernel
     int64_t stream_launches = 0;
     int stream_stagger_ns = 0;  // TQ_STREAM_STAGGER_NS
-    int stream_token = 0;       // TQ_STREAM_TOKEN: the groups of a CTA take turns on the tensor pipe (StreamParams::dmma_token)
+    int stream_chain = 1;       // TQ_STREAM_CHAIN: fused expectation windows for nearest-neighbour chains (StreamParams::chain_windows)
     bool spin_wait = true;      // TQ_SPIN: poll the pinned result slots instead of cudaStreamSynchronize (latency path)
     bool zero_copy = true;      // TQ_ZERO_COPY: small host-buffer calls read angles / write energies in pinned host memory
     int n = 0, device = 0;
@@ -906,6 +906,7 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                         sp.batch = bc;
                         sp.contiguous = 1;
                         sp.stagger_ns = h->stream_stagger_ns;
+                        sp.chain_windows = h->stream_chain;
                         const long long tiles = (long long)bc << pp.n_nl;
                         prof_begin(h, stream, pp.exp_mode == 1 ? PK_STREAM_GATE_EXP : PK_STREAM_GATE, model_bytes, alg_bytes);
                         launch_tile_stream(sp, (int)std::min<long long>(tiles, h->n_sms), stream);
@@ -947,6 +948,7 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
             estream->contiguous = 0;
             const long long tiles = (long long)bc << estream->sub[0].pp.n_nl;
             prof_begin(h, stream, PK_STREAM_EXP, estream_model, estream_alg);
+            estream->chain_windows = h->stream_chain;
             launch_tile_stream(*estream, (int)std::min<long long>(tiles, h->n_sms), stream);
             prof_end(h, stream);
             ++h->launches;
@@ -1123,7 +1125,7 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->direct_kernel = env_int("TQ_DIRECT_KERNEL", 1) != 0;
     h->stream_kernel = env_int("TQ_STREAM", 2) != 0;
     h->stream_stagger_ns = std::max(0, std::min(100000, env_int("TQ_STREAM_STAGGER_NS", 0)));
-    h->stream_token = env_int("TQ_STREAM_TOKEN", 0) != 0 ? 1 : 0;
+    h->stream_chain = env_int("TQ_STREAM_CHAIN", 1) != 0 ? 1 : 0;
     h->plan_cache_cap = std::max(0, std::min(1024, env_int("TQ_PLAN_CACHE", 64)));
     h->stream_expect = env_int("TQ_STREAM", 2) >= 2;
     h->direct_ctas_per_sm = std::max(1, std::min(8, env_int("TQ_DIRECT_CTAS", 2)));

@@ -120,7 +120,7 @@ struct alignas(64) StreamParams {
     StreamSub sub[kStreamMaxSub];
     int n_sub, batch;
     int stagger_ns;   // gate passes: the second group starts this much later, so that the groups' DMMA phases interleave
-    int dmma_token;   // gate passes: the two groups take turns on the tensor pipe (one token per CTA; tq_stream.cu)
+    int chain_windows;   // expectation windows of nearest-neighbour chains run as one fused routine (TQ_STREAM_CHAIN, default 1)
     int contiguous;   // 1: CTA c takes a contiguous range of tiles (gate passes: block matrices are staged once per element);
                       // 0: tiles c, c + grid, ... element-major (expectation sub-passes find the element in L2)
 };

@@ -1056,7 +1056,23 @@ void append_expectation_windows_mma(Pass& p, const std::vector<ExpGroupIn>& grou
                         ++qq;
                     }
                 }
-                o.w0 = winop_pack(M_EXPC, 0, (imag ? 1 : 0) | (anti ? 2 : 0) | (key ? 4 : 0), 9, (int)xr);   // rb2 bit 2: outside mask != 0
+                // ... and all of them the same coefficient (a bare XX + YY coupling): one multiplication for the class (rb2 bit 3)
+                bool uniform = anti;
+                if (anti) {
+                    const int lo = __builtin_ctz(xr);
+                    int qq = 0;
+                    double c0 = 0.0;
+                    bool first = true;
+                    for (uint32_t r = 0; r < (uint32_t)NR; ++r) {
+                        if ((r ^ xr) < r) continue;
+                        if ((r >> lo) & 1) {
+                            if (first) { c0 = ca[qq]; first = false; }
+                            else if (ca[qq] != c0) uniform = false;
+                        }
+                        ++qq;
+                    }
+                }
+                o.w0 = winop_pack(M_EXPC, 0, (imag ? 1 : 0) | (anti ? 2 : 0) | (key ? 4 : 0) | (uniform ? 8 : 0), 9, (int)xr);   // rb2 bit 2: outside mask != 0
                 ops.push_back(o);
             }
         }

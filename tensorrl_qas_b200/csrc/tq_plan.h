@@ -149,7 +149,8 @@ enum : int32_t {    // WinOp codes of DMMA windows; rb / rb2 are 4-bit fields, q
     M_EXPC = 20,    // expectation class: flags = flip mask over the register bits (!= 0), rb2 bit 0 = has imaginary
                     // coefficients, rb2 bit 1 = "exchange class" (two flipped bits, only the 01 <-> 10 pairs carry a
                     // coefficient: the streaming kernel evaluates half of the pairs), rb2 bit 2 = the class has Z / Y
-                    // factors outside the window (unit 0 != 0).
+                    // factors outside the window (unit 0 != 0), rb2 bit 3 = exchange class whose eight coefficients are
+                    // equal (a bare XX + YY coupling): the streaming kernel sums the products first.
                     // Data at eterms[t]: unit 0 = Z/Y mask outside the window; units 1..8 = cA[16]
                     // (one per register pair r < r ^ flip); units 9..16 = cB[16]
     M_EXPD = 21,    // diagonal terms with Z bits outside the window: classes over register bits 0..3 (units 0..1 at

@@ -170,6 +170,39 @@ __device__ __forceinline__ double s_expc_anti(const Regs& a, const double* __res
     }
     return (s[0] + s[1]) + (s[2] + s[3]);
 }
+// ... with one coefficient for all eight pairs (a bare XX + YY coupling): the products are summed first
+template <int LO, int HI>
+__device__ __forceinline__ double s_expc_anti_uniform(const Regs& a, const double* __restrict__ cA) {
+    constexpr int XR = (1 << LO) | (1 << HI);
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    int n = 0, q = 0, q0 = -1;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        if ((r ^ XR) > r) {
+            if ((r >> LO) & 1) {
+                if (q0 < 0) q0 = q;
+                s[n & 3] = n < 4 ? mul_here(a[r ^ XR], a[r]) : fma(a[r ^ XR], a[r], s[n & 3]);
+                ++n;
+            }
+            ++q;
+        }
+    }
+    return cA[q0] * ((s[0] + s[1]) + (s[2] + s[3]));
+}
+__device__ __forceinline__ double exec_s_expc_anti_uniform(const Regs& a, int xr, const double* cA) {
+    switch (xr) {
+    case 3: return s_expc_anti_uniform<0, 1>(a, cA);
+    case 5: return s_expc_anti_uniform<0, 2>(a, cA);
+    case 9: return s_expc_anti_uniform<0, 3>(a, cA);
+    case 17: return s_expc_anti_uniform<0, 4>(a, cA);
+    case 6: return s_expc_anti_uniform<1, 2>(a, cA);
+    case 10: return s_expc_anti_uniform<1, 3>(a, cA);
+    case 18: return s_expc_anti_uniform<1, 4>(a, cA);
+    case 12: return s_expc_anti_uniform<2, 3>(a, cA);
+    case 20: return s_expc_anti_uniform<2, 4>(a, cA);
+    default: return s_expc_anti_uniform<3, 4>(a, cA);
+    }
+}
 __device__ __forceinline__ double exec_s_expc_anti(const Regs& a, int xr, const double* cA) {
     switch (xr) {
     case 3: return s_expc_anti<0, 1>(a, cA);
@@ -247,6 +280,50 @@ __device__ __forceinline__ double slow_expc_imag(uint32_t tile_u32, uint32_t bas
     return sum;
 }
 
+// ---- "chain" windows --------------------------------------------------------------------------------------------------
+// The expectation window of a nearest-neighbour Hamiltonian (Heisenberg / XXZ couplings, hopping terms) on five consecutive
+// qubits: one diagonal table and up to four exchange classes with one coefficient each on the adjacent register-bit pairs
+// (0,1) .. (3,4).  Recognised when the ops are staged (no planner involvement) and evaluated as ONE straight-line routine --
+// no op dispatch, no coefficient tables beyond the diagonal one, every product independent of the others: per window ~100
+// FP64 instructions + 16 table loads instead of five dispatched ops (~50 non-FP64 instructions each around theirs).
+struct ChainWindow {
+    double c[4];      // coefficient of the pair (k, k + 1), 0.0 = no such class in the window
+    int32_t diag_op;  // op slot of the diagonal table (M_EXPT), -1 = none
+    int32_t chain;    // 1 = the window is evaluated by chain_window()
+};
+__device__ __forceinline__ double chain_window(const Regs& a, const ChainWindow& cw, const double2* __restrict__ s_mat) {
+    double e0 = 0.0, e1 = 0.0;
+    if (cw.diag_op >= 0) {
+        const double2* D = s_mat + cw.diag_op * kMatStride;
+#pragma unroll
+        for (int r = 0; r < NR; r += 2) {
+            const double2 d = D[r >> 1];
+            e0 = fma(a[r] * a[r], d.x, e0);
+            e1 = fma(a[r + 1] * a[r + 1], d.y, e1);
+        }
+    }
+    double t[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int XR = 3 << k;
+        int n = 0;
+        t[k][0] = 0.0;
+        t[k][1] = 0.0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if (((r >> k) & 3) == 1) {   // bit k set, bit k + 1 clear: the lower member of a 01 <-> 10 pair
+                t[k][n & 1] = n < 2 ? a[r ^ XR] * a[r] : fma(a[r ^ XR], a[r], t[k][n & 1]);
+                ++n;
+            }
+        }
+    }
+    e0 = fma(cw.c[0], t[0][0] + t[0][1], e0);
+    e1 = fma(cw.c[1], t[1][0] + t[1][1], e1);
+    e0 = fma(cw.c[2], t[2][0] + t[2][1], e0);
+    e1 = fma(cw.c[3], t[3][0] + t[3][1], e1);
+    return e0 + e1;
+}
+
 // MODE 0: gate pass, 1: gate pass with expectation windows, 2: expectation-only sub-passes
 template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __grid_constant__ StreamParams sp) {
@@ -262,8 +339,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     JobDesc* s_job = reinterpret_cast<JobDesc*>(full_bar + kBufs + 1);         // kBufs (+1 pad)
     SubInfo* s_sub = reinterpret_cast<SubInfo*>(s_job + kBufs + 1);            // kStreamMaxSub
     int* s_done = reinterpret_cast<int*>(s_sub + kStreamMaxSub);               // kBufs (+1 pad): warps done with a buffer (MODE 2)
-    int* s_token = s_done + kBufs + 1;   // [0]: the tensor-pipe token (StreamParams::dmma_token), [1 + g]: warps of group g done
+    int* s_token = s_done + kBufs + 1;   // (four spare words: a tensor-pipe token that made the groups take turns lived here --
+                                         // 0.863 -> 0.869 ms on the dense gate pass, i.e. the pipe is not what they fight over)
     double* s_zero = reinterpret_cast<double*>(s_token + 4);   // 0.0: what a register with known-zero contents is loaded from
+    ChainWindow* s_chain = reinterpret_cast<ChainWindow*>(s_zero + 2);   // kWinSlots
 
     const int tid = threadIdx.x;
     // ---- stage every sub-pass once: scalars, window headers, op words, expectation tables ----
@@ -325,6 +404,44 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
         }
     }
     __syncthreads();
+    // chain windows (see chain_window): one thread per expectation window looks at the staged ops
+    if (MODE != 0) {
+#pragma unroll
+        for (int sb = 0; sb < kStreamMaxSub; ++sb) {
+            if (sb >= sp.n_sub) break;
+            const int wb = s_sub[sb].wbase, ob = s_sub[sb].obase;
+            const int nw = s_sub[sb].n_windows, ng = s_sub[sb].n_gate_windows;
+            if (tid >= ng && tid < nw) {
+                const StreamWindowDev* hdr = s_win + wb + tid;
+                ChainWindow cw;
+                cw.c[0] = cw.c[1] = cw.c[2] = cw.c[3] = 0.0;
+                cw.diag_op = -1;
+                bool ok = !(hdr->flags & kWinFlagGenericDiag) && hdr->op_end > hdr->op_begin;
+                uint32_t seen = 0;
+                for (int o = ob + hdr->op_begin; ok && o < ob + hdr->op_end; ++o) {
+                    const uint32_t w0 = s_wops[o].w0;
+                    const int fc = w0 & 0xff;
+                    if (fc == FM_EXPT) {
+                        ok = cw.diag_op < 0;
+                        cw.diag_op = o;
+                    } else if (fc == FM_EXPC) {
+                        const uint32_t xr = w0 >> 24, rb2 = (w0 >> 12) & 0xf;   // exchange class, one coefficient, nothing outside
+                        const int k = xr == 3 ? 0 : xr == 6 ? 1 : xr == 12 ? 2 : xr == 24 ? 3 : -1;
+                        ok = rb2 == 10 && k >= 0 && !((seen >> k) & 1);
+                        if (ok) {
+                            seen |= 1u << k;
+                            cw.c[k] = reinterpret_cast<const double*>(s_mat_all + o * kMatStride + 1)[1 << k];
+                        }
+                    } else {
+                        ok = false;
+                    }
+                }
+                cw.chain = ok && sp.chain_windows ? 1 : 0;
+                s_chain[wb + tid] = cw;
+            }
+        }
+        __syncthreads();
+    }
 
     // ---- this CTA's jobs ----
     const uint32_t n_cta = gridDim.x, cta = blockIdx.x;
@@ -349,7 +466,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     double2* const s_mat = s_mat_all + GRP * (kOpSlots * kMatStride);
     double* const s_red = s_red_all + GRP * 16;
     const int gtid = threadIdx.x & (kGroupThreads - 1);
-    const int lane = gtid & 31, warp = gtid >> 5;
+    const int lane = gtid & 31, warp = __shfl_sync(0xffffffffu, gtid >> 5, 0);
     const uint32_t comp8 = (uint32_t)(lane & 1) << 3;
     const bool l1 = (lane >> 1) & 1;
     // all-ones masks of this thread's lane / warp bits
@@ -358,7 +475,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                    mw0 = 0u - (uint32_t)(warp & 1), mw1 = 0u - (uint32_t)((warp >> 1) & 1), mw2 = 0u - (uint32_t)((warp >> 2) & 1);
     const int n_sub = sp.n_sub;
     const uint32_t tiles_u32 = smem_u32(tiles);
-    const uint32_t zero_u32 = smem_u32(s_zero);
+    const uint32_t zero_rel = (uint32_t)(reinterpret_cast<unsigned char*>(s_zero) - tiles);   // (relative to the buffers)
 
     // issued by ONE thread: descriptor + TMA loads of job j into buffer j % kBufs
     auto issue_load = [&](uint32_t j) {
@@ -432,6 +549,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
         const PassParams& p = sp.sub[0].pp;   // (gate passes have one sub-pass; the expectation code below goes through si)
         const SubInfo& si = s_sub[s];
         const uint32_t tile_u32 = tiles_u32 + buf * kTileBytes;
+        // The buffer's offset is folded into the thread's XOR offset (its bits lie above the 64 KiB a tile spans), so a
+        // tile access is [thread offset + the uniform base of the buffers]: no add per access.
+        const uint32_t jbase = comp8 | (buf * (uint32_t)kTileBytes);
         const int w0 = si.wbase, o0 = si.obase;
 
         // block matrices of this element (gate passes): once per (group, element)
@@ -466,7 +586,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
         // entering window hdr: this thread's physical index bits (ctx) and its 32 doubles
         auto enter = [&](const StreamWindowDev* hdr) {
             // byte offset inside the tile buffer of this thread's part of the index (the register bits are XORed on top)
-            const uint32_t base = comp8 ^ (mq & hdr->qofs) ^ (mg0 & hdr->gofs[0]) ^ (mg1 & hdr->gofs[1]) ^
+            const uint32_t base = jbase ^ (mq & hdr->qofs) ^ (mg0 & hdr->gofs[0]) ^ (mg1 & hdr->gofs[1]) ^
                                   (mg2 & hdr->gofs[2]) ^ (mw0 & hdr->wofs[0]) ^ (mw1 & hdr->wofs[1]) ^ (mw2 & hdr->wofs[2]);
             ctx = tile_base | (mq & hdr->qlmask) | (mg0 & hdr->gmask[0]) | (mg1 & hdr->gmask[1]) | (mg2 & hdr->gmask[2]) |
                   (mw0 & hdr->wmask[0]) | (mw1 & hdr->wmask[1]) | (mw2 & hdr->wmask[2]);
@@ -476,13 +596,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
             const uint32_t hi[8] = {base, base ^ x2, base ^ x3, base ^ x2 ^ x3, base ^ x4, base ^ x4 ^ x2, base ^ x4 ^ x3,
                                     base ^ x4 ^ x3 ^ x2};
 #pragma unroll
-            for (int r = 0; r < NR; ++r) a[r] = lds_f64(tile_u32 + (hi[r >> 2] ^ lo[r & 3]));
+            for (int r = 0; r < NR; ++r) a[r] = *reinterpret_cast<const double*>(tiles + (hi[r >> 2] ^ lo[r & 3]));
         };
         // the same for a window with known zeros on entry (a dead tile, or register / lane / warp bits nothing has
         // populated yet): those registers are read from a zero in shared memory -- one address select per register
         // instead of a 64-bit select after the load (and a dead tile's buffer, which nothing was loaded into, is not read)
         auto enter_zeros = [&](const StreamWindowDev* hdr, uint32_t dead_r, bool zero_all) {
-            const uint32_t base = comp8 ^ (mq & hdr->qofs) ^ (mg0 & hdr->gofs[0]) ^ (mg1 & hdr->gofs[1]) ^
+            const uint32_t base = jbase ^ (mq & hdr->qofs) ^ (mg0 & hdr->gofs[0]) ^ (mg1 & hdr->gofs[1]) ^
                                   (mg2 & hdr->gofs[2]) ^ (mw0 & hdr->wofs[0]) ^ (mw1 & hdr->wofs[1]) ^ (mw2 & hdr->wofs[2]);
             ctx = tile_base | (mq & hdr->qlmask) | (mg0 & hdr->gmask[0]) | (mg1 & hdr->gmask[1]) | (mg2 & hdr->gmask[2]) |
                   (mw0 & hdr->wmask[0]) | (mw1 & hdr->wmask[1]) | (mw2 & hdr->wmask[2]);
@@ -493,7 +613,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                                     base ^ x4 ^ x3 ^ x2};
 #pragma unroll
             for (int r = 0; r < NR; ++r)
-                a[r] = lds_f64((zero_all || (r & dead_r)) ? zero_u32 : tile_u32 + (hi[r >> 2] ^ lo[r & 3]));
+                a[r] = *reinterpret_cast<const double*>(tiles + ((zero_all || (r & dead_r)) ? zero_rel : (hi[r >> 2] ^ lo[r & 3])));
         };
 
         // ---- gate windows ----
@@ -516,13 +636,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                     enter_zeros(hdr, 31u, true);
                 } else if (busy) {
                     enter(hdr);
-                }
-                // Tensor-pipe token: the group's thread 0 takes it before the barrier, so the block chains of the two
-                // groups never run at the same time.  Sharing the pipe slows both down together and they then leave their
-                // DMMA phases -- and sit in their load / store / barrier phases -- together, with the pipe idle; with the
-                // token one group's chains run under the other's window entry and exit.
-                if (sp.dmma_token && gtid == 0) {
-                    while (atomicCAS(s_token, 0, 1) != 0) __nanosleep(40);
                 }
                 group_sync(GRP);   // everyone holds its entry data: the tile may be overwritten from here on
                 if (first_gate) {
@@ -584,16 +697,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                         }
                     }
                 }
-                if (sp.dmma_token) {   // the last warp out of the op loop hands the token on
-                    __syncwarp();
-                    if (lane == 0 && atomicAdd(s_token + 1 + GRP, 1) == kGroupThreads / 32 - 1) {
-                        s_token[1 + GRP] = 0;
-                        __threadfence_block();
-                        atomicExch(s_token, 0);
-                    }
-                }
                 if (busy || store_all) {
-                    const uint32_t base = comp8 ^ (mq & hdr->qofs_out) ^ (mg0 & hdr->gofs_out[0]) ^ (mg1 & hdr->gofs_out[1]) ^
+                    const uint32_t base = jbase ^ (mq & hdr->qofs_out) ^ (mg0 & hdr->gofs_out[0]) ^ (mg1 & hdr->gofs_out[1]) ^
                                           (mg2 & hdr->gofs_out[2]) ^ (mw0 & hdr->wofs_out[0]) ^ (mw1 & hdr->wofs_out[1]) ^
                                           (mw2 & hdr->wofs_out[2]);
                     const uint32_t x0 = hdr->rofs_out[0], x1 = hdr->rofs_out[1], x2 = hdr->rofs_out[2], x3 = hdr->rofs_out[3],
@@ -602,7 +707,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                     const uint32_t hi[8] = {base, base ^ x2, base ^ x3, base ^ x2 ^ x3, base ^ x4, base ^ x4 ^ x2,
                                             base ^ x4 ^ x3, base ^ x4 ^ x3 ^ x2};
 #pragma unroll
-                    for (int r = 0; r < NR; ++r) sts_f64(tile_u32 + (hi[r >> 2] ^ lo[r & 3]), a[r]);
+                    for (int r = 0; r < NR; ++r) *reinterpret_cast<double*>(tiles + (hi[r >> 2] ^ lo[r & 3])) = a[r];
                 }
                 fence_proxy_async();   // (the last window's writes are read by the TMA store)
                 group_sync(GRP);     // the tile is complete in shared memory again
@@ -625,13 +730,17 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                 if (MODE == 2 && ((w + (int)j) & 1) != GRP) continue;   // the other group's window
                 const StreamWindowDev* hdr = s_win + w;
                 enter(hdr);
+                if (s_chain[w].chain) {
+                    acc += chain_window(a, s_chain[w], s_mat);
+                    continue;
+                }
                 const int o_begin = o0 + hdr->op_begin, o_end = o0 + hdr->op_end;
                 if (hdr->flags & kWinFlagGenericDiag) {
                     for (int o = o_begin; o < o_end; ++o) {
                         const WinOp wo = s_wops[o];
                         const double2* m = s_mat + o * kMatStride;
                         if ((wo.w0 & 0xff) == FM_EXPD) {   // register bit 4 counts as a bit outside the window's classes
-                            acc += slow_expd(tile_u32, ebase, hdr, ctx, m, reinterpret_cast<const double2*>(si.eterms) + wo.t + 2);
+                            acc += slow_expd(tiles_u32, ebase, hdr, ctx, m, reinterpret_cast<const double2*>(si.eterms) + wo.t + 2);
                         } else if ((wo.w0 & 0xff) == FM_EXPT) {
                             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
@@ -653,7 +762,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                         double sum;
                         if ((wo0 >> 12) & 1) {   // rare: imaginary class coefficients (terms with an odd number of Y factors)
                             const double* cB = reinterpret_cast<const double*>(reinterpret_cast<const double2*>(si.eterms) + s_wops[o].t + 9);
-                            sum = slow_expc_imag(tile_u32, ebase, hdr, (int)(wo0 >> 24), reinterpret_cast<const double*>(m + 1), cB, (lane & 1) != 0);
+                            sum = slow_expc_imag(tiles_u32, ebase, hdr, (int)(wo0 >> 24), reinterpret_cast<const double*>(m + 1), cB, (lane & 1) != 0);
+                        } else if ((wo0 >> 15) & 1) {   // exchange class with one coefficient
+                            sum = exec_s_expc_anti_uniform(a, (int)(wo0 >> 24), reinterpret_cast<const double*>(m + 1));
                         } else if ((wo0 >> 13) & 1) {   // exchange class: half of the pairs
                             sum = exec_s_expc_anti(a, (int)(wo0 >> 24), reinterpret_cast<const double*>(m + 1));
                         } else {
@@ -725,7 +836,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
         if (tid < kGroupThreads) run_group(GroupConst<0>{});
         else run_group(GroupConst<1>{});
     } else {
-        run_group(tid >= kGroupThreads ? 1 : 0);
+        run_group(__shfl_sync(0xffffffffu, tid >= kGroupThreads ? 1 : 0, 0));
     }
 }
 
@@ -735,7 +846,7 @@ size_t tile_stream_smem_bytes() {
     return (size_t)kBufs * kTileBytes + (size_t)kGroups * kOpSlots * kMatStride * sizeof(double2) + kOpSlots * sizeof(WinOp) +
            kWinSlots * sizeof(StreamWindowDev) + kGroups * 16 * sizeof(double) + (kBufs + 1) * sizeof(uint64_t) +
            (kBufs + 1) * sizeof(JobDesc) + kStreamMaxSub * sizeof(SubInfo) + (kBufs + 1 + 4) * sizeof(int) + 2 * sizeof(double) +
-           1024 /* alignment slack */;
+           kWinSlots * sizeof(ChainWindow) + 1024 /* alignment slack */;
 }
 
 cudaError_t tile_stream_configure() {

@@ -215,3 +215,50 @@ def test_skip_last_store_matches_oracle(built_lib, oracle, monkeypatch, n, gates
     stored = sim.energies(p)
     sim.close()
     assert np.abs(stored - want).max() < 1e-10
+
+
+def chain_hamiltonian(n, kind, seed=0):
+    """Nearest-neighbour chains: 'xxz' = J (XX + YY) + D ZZ with one J per bond (exchange classes with one coefficient),
+    'xyz' = independent weights on XX and YY (not an exchange class: the generic ops), 'gaps' = every third bond missing,
+    'field' = Heisenberg bonds + a Z field (diagonal terms on single qubits)."""
+    rng = np.random.default_rng(seed)
+    paulis, w = [], []
+    for q in range(n - 1):
+        if kind == "gaps" and q % 3 == 2:
+            continue
+        j, d = rng.normal(), rng.normal()
+        jy = rng.normal() if kind == "xyz" else j
+        for s, c in (("XX", j), ("YY", jy), ("ZZ", d)):
+            paulis.append("I" * q + s + "I" * (n - q - 2))
+            w.append(c)
+    if kind == "field":
+        for q in range(n):
+            paulis.append("I" * q + "Z" + "I" * (n - q - 1))
+            w.append(rng.normal())
+    x, z = loaders.pauli_masks(paulis, n)
+    return x, z, np.asarray(w)
+
+
+@pytest.mark.parametrize("n,kind,brick,seed", [(14, "xxz", False, 1), (16, "xxz", True, 2), (15, "gaps", False, 3),
+                                                (14, "xyz", False, 4), (15, "field", True, 5)])
+def test_chain_windows_match_generic_ops_and_oracle(built_lib, oracle, monkeypatch, n, kind, brick, seed):
+    """Expectation windows of nearest-neighbour chains run as one fused routine (tq_stream.cu, chain_window); it must agree
+    with the dispatched ops (TQ_STREAM_CHAIN=0) and with the oracle, for per-bond couplings, missing bonds, XX != YY (which
+    must stay on the generic ops) and extra single-qubit diagonal terms."""
+    gl = brickwork_circuit(n, 21, 40, seed) if brick else synthetic_circuit(n, 150, seed)
+    ham = chain_hamiltonian(n, kind, seed)
+    p = parameter_batch(gl, 3)
+    want = oracle.energies(gl, p, pauli=ham)
+    sim = make_sim(n, gl, ham, monkeypatch, True)
+    got = sim.energies(p)
+    again = sim.energies(p)
+    assert sim.plan_counts()["stream_launches"] > 0
+    sim.close()
+    monkeypatch.setenv("TQ_STREAM_CHAIN", "0")
+    ref = make_sim(n, gl, ham, monkeypatch, True)
+    generic = ref.energies(p)
+    ref.close()
+    assert np.abs(generic - want).max() < 1e-10
+    assert np.abs(got - want).max() < 1e-10
+    assert np.abs(got - generic).max() < 1e-11
+    assert np.array_equal(got, again)
