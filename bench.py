@@ -385,12 +385,19 @@ def main():
     for i in range(per_step):   # launch i of a step, averaged over the profiled steps
         rs = [recs[s * per_step + i] for s in range(prof_steps)]
         kernels.append({"kernel": rs[0]["kernel"], "ms": float(np.mean([r["ms"] for r in rs])),
-                        "model_bytes": rs[0]["model_bytes"], "alg_bytes": rs[0]["alg_bytes"]})
+                        "model_bytes": rs[0]["model_bytes"], "alg_bytes": rs[0]["alg_bytes"],
+                        "dmma_flops": rs[0].get("dmma_flops", 0.0)})
     step_ms_prof = sum(k["ms"] for k in kernels) or 1e-9
+    dmma_peak = fp64_peak(local_rank, 0)
+    dfma_peak = fp64_peak(local_rank, 1)
     for k in kernels:
         k["share_of_step"] = k["ms"] / step_ms_prof
         k["model_gbs"] = k["model_bytes"] / (k["ms"] * 1e-3) / 1e9
         k["frac_of_hbm_peak_model"] = k["model_gbs"] / peak
+        # FP64 tensor-core work of the launch against the DMMA peak measured in this run: with the HBM fraction beside
+        # it, this says which roof the launch is under
+        k["dmma_tflops"] = k["dmma_flops"] / (k["ms"] * 1e-3) / 1e12
+        k["frac_of_fp64_tensor_peak"] = k["dmma_tflops"] / dmma_peak if dmma_peak else None
     dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
     bytes_eval = w.algorithmic_bytes_per_eval()
     per_gpu_evals_s = B * args.steps / (ms * 1e-3)
@@ -405,8 +412,6 @@ def main():
         if tj.get("batch") == B and tj.get("workload") == w.name and tj.get("launch_sequence") == sig:
             traffic = tj.get("dram_bytes_per_step")
     counts = sim.plan_counts(which)
-    dmma_peak = fp64_peak(local_rank, 0)
-    dfma_peak = fp64_peak(local_rank, 1)
     tile_amps = 1 << info["tile_bits"]
     dmma_flop_eval = 2.0 * 16.0 * counts["tensor_core_block_tiles"] * tile_amps
     dmma_tflops = dmma_flop_eval * per_gpu_evals_s / 1e12
@@ -424,7 +429,12 @@ def main():
                     "`measured` is: the bytes the compiled plan really moves (populated part of the state in, whole tiles "
                     "out) over the same time, against the measured copy bandwidth",
             "measured": {"share_of_step": dom["share_of_step"], "model_bytes_per_launch": dom["model_bytes"],
-                         "model_gbs": dom["model_gbs"], "frac_of_peak_model": dom["frac_of_hbm_peak_model"]},
+                         "model_gbs": dom["model_gbs"], "frac_of_peak_model": dom["frac_of_hbm_peak_model"],
+                         "dmma_tflops": dom["dmma_tflops"], "frac_of_fp64_tensor_peak": dom["frac_of_fp64_tensor_peak"],
+                         "binding_roof": ("fp64 tensor pipe" if (dom["frac_of_fp64_tensor_peak"] or 0.0) >
+                                          dom["frac_of_hbm_peak_model"] else "hbm"),
+                         "frac_of_binding_roof": max(dom["frac_of_fp64_tensor_peak"] or 0.0,
+                                                     dom["frac_of_hbm_peak_model"])},
             "step": {"ms_profiled": step_ms_prof, "algorithmic_bytes_per_eval": bytes_eval,
                      "algorithmic_gbs": bytes_eval * per_gpu_evals_s / 1e9,
                      "frac_algorithmic": bytes_eval * per_gpu_evals_s / 1e9 / peak,

@@ -225,6 +225,9 @@ int tq_plan_cache_stats(tq_handle h, int64_t* stats4);
 int tq_profile_enable(tq_handle h, int on);
 int tq_profile_read(tq_handle h, int max_records, int32_t* kind, float* ms, double* model_bytes, double* alg_bytes,
                     int* n_out);
+/* FP64 tensor-core work (flops: 2 x 16 FMA per amplitude and fused dense block, known zeros left out) of the records the
+ * last tq_profile_read handed out, same order -- what bench.py divides by the launch time for the tensor-pipe roofline. */
+int tq_profile_read_flops(tq_handle h, int max_records, double* dmma_flops, int* n_out);
 
 /* Measured FP64 peak of the device in TFLOP/s: which = 0 mma.sync.m8n8k4.f64 (the tensor-core instruction of the fused
  * dense blocks), 1 DFMA on the FP64 pipe.  Best of three timed runs of a register-resident kernel. */

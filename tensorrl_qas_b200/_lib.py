@@ -71,6 +71,7 @@ SIGNATURES = {
     "tq_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "tq_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_int_p, ctypes.POINTER(ctypes.c_float), c_dbl_p,
                                        c_dbl_p, c_int_p]),
+    "tq_profile_read_flops": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_dbl_p, c_int_p]),
     "tq_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_dbl_p]),
     "tq_plan_dump": (ctypes.c_void_p, [ctypes.c_int, ctypes.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_u64_p]),

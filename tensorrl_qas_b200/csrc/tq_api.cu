@@ -81,6 +81,7 @@ struct tq_context {
     bool stream_expect = true;  // TQ_STREAM=2 (default): the expectation-only passes as well; 1: those stay on expect_direct_kernel
     int64_t stream_launches = 0;
     int stream_stagger_ns = 0;  // TQ_STREAM_STAGGER_NS
+    int stream_one_group = 0;   // TQ_STREAM_ONE_GROUP (diagnostic)
     int stream_chain = 1;       // TQ_STREAM_CHAIN: fused expectation windows for nearest-neighbour chains (StreamParams::chain_windows)
     bool spin_wait = true;      // TQ_SPIN: poll the pinned result slots instead of cudaStreamSynchronize (latency path)
     bool zero_copy = true;      // TQ_ZERO_COPY: small host-buffer calls read angles / write energies in pinned host memory
@@ -144,9 +145,10 @@ struct tq_context {
     int64_t launches = 0;
 
     // optional per-launch timing (tq_profile_enable / tq_profile_read): a CUDA-event pair around every launch
-    struct ProfRec { int kind; cudaEvent_t e0, e1; double model_bytes, alg_bytes; };
+    struct ProfRec { int kind; cudaEvent_t e0, e1; double model_bytes, alg_bytes, dmma_flops; };
     bool profile = false;
     std::vector<ProfRec> prof;
+    std::vector<double> prof_flops;   // FP64 tensor-core flops of the records handed out by the last tq_profile_read
 };
 
 namespace {
@@ -690,9 +692,9 @@ void fill_tma(StreamTma& t, const StreamLayout& L) {
 // per-launch timing records (kinds: see tq_profile_read in include/tqsim.h)
 enum { PK_PREP = 0, PK_TILE = 1, PK_TILE_MMA = 2, PK_STREAM_GATE = 3, PK_STREAM_GATE_EXP = 4, PK_STREAM_EXP = 5,
        PK_DIRECT = 6, PK_REDUCE = 7, PK_DM_EXPECT = 8, PK_TABLE = 9 };
-void prof_begin(tq_handle h, cudaStream_t stream, int kind, double model_bytes, double alg_bytes) {
+void prof_begin(tq_handle h, cudaStream_t stream, int kind, double model_bytes, double alg_bytes, double dmma_flops = 0.0) {
     if (!h->profile) return;
-    tq_context::ProfRec r{kind, nullptr, nullptr, model_bytes, alg_bytes};
+    tq_context::ProfRec r{kind, nullptr, nullptr, model_bytes, alg_bytes, dmma_flops};
     if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
     cudaEventRecord(r.e0, stream);
     h->prof.push_back(r);
@@ -861,6 +863,11 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 if (pp.dst) model_bytes += tiles_run * tile_bytes;
             }
             const double alg_bytes = (double)bc * (double)elem_bytes * (2.0 * dp.n_gates + (pp.exp_mode ? dp.n_exp_groups : 0));
+            // FP64 tensor-core work of this launch: 16 FMA per amplitude and dense block, known zeros left out (the
+            // accounting of tq_plan_counts, per pass)
+            const double dmma_flops = !pp.mwindows || !dp.gate_pass ? 0.0 :
+                2.0 * 16.0 * (double)bc * (double)(1u << pp.k_eff) * (double)(1u << pp.n_nl) *
+                ((pp.in_mask != ~0ull || track_support) ? dp.live_blocks : (double)dp.n_blocks);
             // ---- streaming kernel (persistent CTAs, TMA tile I/O) for multi-tile tensor-core passes ----
             const bool sparse_in = pp.in_mask != ~0ull;
             const bool use_stream = h->stream_kernel && (dp.gate_pass ? !dp.no_ops : (h->stream_expect && pp.exp_mode == 1)) &&
@@ -907,8 +914,9 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                         sp.contiguous = 1;
                         sp.stagger_ns = h->stream_stagger_ns;
                         sp.chain_windows = h->stream_chain;
+                        sp.one_group = h->stream_one_group;
                         const long long tiles = (long long)bc << pp.n_nl;
-                        prof_begin(h, stream, pp.exp_mode == 1 ? PK_STREAM_GATE_EXP : PK_STREAM_GATE, model_bytes, alg_bytes);
+                        prof_begin(h, stream, pp.exp_mode == 1 ? PK_STREAM_GATE_EXP : PK_STREAM_GATE, model_bytes, alg_bytes, dmma_flops);
                         launch_tile_stream(sp, (int)std::min<long long>(tiles, h->n_sms), stream);
                         prof_end(h, stream);
                         ++h->launches;
@@ -936,7 +944,7 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 direct.sub[direct.n_sub++] = pp;
                 continue;
             }
-            prof_begin(h, stream, pp.mwindows ? PK_TILE_MMA : PK_TILE, model_bytes, alg_bytes);
+            prof_begin(h, stream, pp.mwindows ? PK_TILE_MMA : PK_TILE, model_bytes, alg_bytes, dmma_flops);
             launch_tile_pass(pp, bc, dp.threads, dm, stream);
             prof_end(h, stream);
             ++h->launches;
@@ -1126,6 +1134,7 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->stream_kernel = env_int("TQ_STREAM", 2) != 0;
     h->stream_stagger_ns = std::max(0, std::min(100000, env_int("TQ_STREAM_STAGGER_NS", 0)));
     h->stream_chain = env_int("TQ_STREAM_CHAIN", 1) != 0 ? 1 : 0;
+    h->stream_one_group = env_int("TQ_STREAM_ONE_GROUP", 0) != 0 ? 1 : 0;
     h->plan_cache_cap = std::max(0, std::min(1024, env_int("TQ_PLAN_CACHE", 64)));
     h->stream_expect = env_int("TQ_STREAM", 2) >= 2;
     h->direct_ctas_per_sm = std::max(1, std::min(8, env_int("TQ_DIRECT_CTAS", 2)));
@@ -1639,6 +1648,7 @@ int tq_profile_enable(tq_handle h, int on) {
     if (!h) return TQ_EINVAL;
     TQ_CUDA(cudaSetDevice(h->device));
     for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    h->prof_flops.clear();
     h->prof.clear();
     h->profile = on != 0;
     return TQ_OK;
@@ -1665,7 +1675,23 @@ int tq_profile_read(tq_handle h, int max_records, int32_t* kind, float* ms, doub
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
     }
+    h->prof_flops.clear();
+    for (int i = 0; i < n; ++i) h->prof_flops.push_back(h->prof[i].dmma_flops);
     h->prof.clear();
+    *n_out = n;
+    return TQ_OK;
+    TQ_API_CATCH(h)
+}
+
+int tq_profile_read_flops(tq_handle h, int max_records, double* dmma_flops, int* n_out) {
+    TQ_API_TRY
+    if (!h || !n_out || max_records < 0) return TQ_EINVAL;
+    int n = 0;
+    for (double f : h->prof_flops) {
+        if (n >= max_records) break;
+        if (dmma_flops) dmma_flops[n] = f;
+        ++n;
+    }
     *n_out = n;
     return TQ_OK;
     TQ_API_CATCH(h)

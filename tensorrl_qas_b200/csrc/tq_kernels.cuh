@@ -120,6 +120,7 @@ struct alignas(64) StreamParams {
     StreamSub sub[kStreamMaxSub];
     int n_sub, batch;
     int stagger_ns;   // gate passes: the second group starts this much later, so that the groups' DMMA phases interleave
+    int one_group;    // diagnostic (TQ_STREAM_ONE_GROUP): gate passes run on one group of 256 threads per CTA
     int chain_windows;   // expectation windows of nearest-neighbour chains run as one fused routine (TQ_STREAM_CHAIN, default 1)
     int contiguous;   // 1: CTA c takes a contiguous range of tiles (gate passes: block matrices are staged once per element);
                       // 0: tiles c, c + grid, ... element-major (expectation sub-passes find the element in L2)

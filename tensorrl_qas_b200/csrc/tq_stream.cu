@@ -511,10 +511,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
             tma_load(dst + i * si.box_bytes, map, bar, (int)(2u * (uint32_t)(amp0 + si.op_goff[i])));
     };
 
+    // (diagnostic, StreamParams::one_group: gate passes run on group 0 alone -- what a job costs without a partner)
+    const bool solo = MODE != 2 && sp.one_group;
+    if (solo && GRP == 1) return;
     if (gtid == 0) {
         if (GRP == 0) {
             if (n_jobs > 0) issue_load(0);
-            if (MODE == 2 && n_jobs > 1) issue_load(1);
+            if ((MODE == 2 || solo) && n_jobs > 1) issue_load(1);
             if (n_jobs > 2) issue_load(2);
         } else if (MODE != 2 && n_jobs > 1) issue_load(1);
     }
@@ -539,7 +542,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     // being read while two are in flight (a tile of expectation work is short: one load in flight does not cover HBM's
     // latency-bandwidth product); gate passes alternate jobs between the groups
 #pragma unroll 1
-    for (uint32_t j = (MODE == 2 ? 0 : GRP); j < n_jobs; j += (MODE == 2 ? 1 : kGroups)) {
+    for (uint32_t j = (MODE == 2 || solo ? 0 : GRP); j < n_jobs; j += (MODE == 2 || solo ? 1 : kGroups)) {
         const uint32_t buf = j % kBufs;
         mbar_wait(full_bar + buf, (j / kBufs) & 1u);
         const uint4 jd = *reinterpret_cast<const uint4*>(s_job + buf);

@@ -237,15 +237,18 @@ class Simulator:
         self._check(self._L.tq_profile_enable(self._h, 1 if on else 0))
 
     def profile_read(self, max_records=4096):
-        """Launches recorded since profile(True) / the last read: list of dicts (kernel, ms, model_bytes, alg_bytes)."""
+        """Launches recorded since profile(True) / the last read: list of dicts (kernel, ms, model_bytes, alg_bytes, dmma_flops)."""
         kind = (ctypes.c_int32 * max_records)()
         ms = (ctypes.c_float * max_records)()
         mb = (ctypes.c_double * max_records)()
         ab = (ctypes.c_double * max_records)()
         n = ctypes.c_int32(0)
         self._check(self._L.tq_profile_read(self._h, max_records, kind, ms, mb, ab, ctypes.byref(n)))
+        fl = (ctypes.c_double * max_records)()
+        nf = ctypes.c_int32(0)
+        self._check(self._L.tq_profile_read_flops(self._h, max_records, fl, ctypes.byref(nf)))
         return [{"kernel": self.PROFILE_KINDS[kind[i]], "ms": float(ms[i]), "model_bytes": float(mb[i]),
-                 "alg_bytes": float(ab[i])} for i in range(n.value)]
+                 "alg_bytes": float(ab[i]), "dmma_flops": float(fl[i]) if i < nf.value else 0.0} for i in range(n.value)]
 
 
 def energies_multi(sims, params, codes=None):
