@@ -112,3 +112,36 @@ class OverlappedGather:
             if ev is not None:
                 cur.wait_event(ev)
         return self.full[(self.i - 1) % len(self.full)] if self.i else None
+
+
+class HostBatchGather:
+    """Host buffers in, every rank's energies out, one synchronisation per call: this rank's angle rows go from pinned host
+    memory to the device, the evaluation and the all-gather run on the device (same stream), the gathered [batch_per_rank *
+    world] vector comes back into pinned host memory.  (The plain host entry point followed by `gather_energies` costs a
+    device->host->device round trip of the local energies and a second synchronisation before the collective.)
+
+        g = HostBatchGather(sim, batch_per_rank, n_params, world, device)
+        all_energies = g(params_host)            # numpy [batch_per_rank * world], valid until the next call
+    """
+
+    def __init__(self, sim, batch_per_rank, ld, world, device, group=None, mode="pure"):
+        import torch
+        self.torch, self.sim, self.group, self.device, self.mode = torch, sim, group, device, mode
+        self.p_pin = torch.empty((batch_per_rank, ld), dtype=torch.float64).pin_memory()
+        self.p_dev = torch.empty((batch_per_rank, ld), dtype=torch.float64, device=device)
+        self.e_loc = torch.empty(batch_per_rank, dtype=torch.float64, device=device)
+        self.e_all = torch.empty(batch_per_rank * world, dtype=torch.float64, device=device)
+        self.e_pin = torch.empty(batch_per_rank * world, dtype=torch.float64).pin_memory()
+        self.h2d_bytes = self.p_pin.numel() * 8
+        self.d2h_bytes = self.e_pin.numel() * 8
+
+    def __call__(self, params):
+        import torch.distributed as dist
+        torch = self.torch
+        self.p_pin.copy_(torch.from_numpy(np.ascontiguousarray(params, dtype=np.float64)))
+        self.p_dev.copy_(self.p_pin, non_blocking=True)
+        self.sim.energies_dev(self.p_dev, out=self.e_loc, mode=self.mode)
+        dist.all_gather_into_tensor(self.e_all, self.e_loc, group=self.group)
+        self.e_pin.copy_(self.e_all, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.e_pin.numpy()

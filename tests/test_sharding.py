@@ -2,6 +2,7 @@
 for the per-GPU simulator) and all-gather the energies."""
 import os
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -80,3 +81,23 @@ def test_single_process_passthrough(oracle):
     p = parameter_batch(gl, 3)
     out = sharded_energies(lambda q: np.arange(len(q), dtype=np.float64), p)
     assert np.array_equal(out, [0.0, 1.0, 2.0])
+
+
+@pytest.mark.gpu
+def test_nccl_gather_drivers_on_the_gpus_of_the_box(built_lib):
+    """OverlappedGather and HostBatchGather (the N > 1 legs of bench.py) on real NCCL: one rank per visible GPU, at most
+    two (a one-GPU box runs a single-rank communicator -- same code path, collective included)."""
+    import socket
+    import subprocess
+    import torch
+    nproc = min(2, torch.cuda.device_count())
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "nccl_gather_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert f"GATHER_OK {nproc}" in res.stdout
