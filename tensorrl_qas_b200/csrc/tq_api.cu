@@ -9,6 +9,7 @@
 #include <list>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -1132,6 +1133,20 @@ int tq_create(int n_qubits, int device_id, tq_handle* out) {
     h->sparse_init = env_int("TQ_SPARSE_INIT", 1) != 0;
     h->direct_kernel = env_int("TQ_DIRECT_KERNEL", 1) != 0;
     h->stream_kernel = env_int("TQ_STREAM", 2) != 0;
+    if (h->stream_kernel) {   // (probed once per device; see kTilesBase in tq_stream.cu)
+        static std::mutex probe_mutex;
+        static int probed[64] = {};   // 0 = not yet, 1 = ok, 2 = the assumption does not hold
+        std::lock_guard<std::mutex> lock(probe_mutex);
+        int& state = probed[device_id & 63];
+        if (state == 0) {
+            cudaError_t pe = cudaSuccess;
+            state = tile_stream_base_ok(&pe) ? 1 : 2;
+            if (state == 2)
+                fprintf(stderr, "[tqsim] streaming kernel disabled: dynamic shared memory does not start at the assumed offset (%s)\n",
+                        pe == cudaSuccess ? "probe answered differently" : cudaGetErrorString(pe));
+        }
+        if (state == 2) h->stream_kernel = false;
+    }
     h->stream_stagger_ns = std::max(0, std::min(100000, env_int("TQ_STREAM_STAGGER_NS", 0)));
     h->stream_chain = env_int("TQ_STREAM_CHAIN", 1) != 0 ? 1 : 0;
     h->stream_one_group = env_int("TQ_STREAM_ONE_GROUP", 0) != 0 ? 1 : 0;

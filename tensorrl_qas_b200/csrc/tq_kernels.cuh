@@ -127,6 +127,7 @@ struct alignas(64) StreamParams {
 };
 size_t tile_stream_smem_bytes();
 cudaError_t tile_stream_configure();   // opt in to the dynamic shared memory
+bool tile_stream_base_ok(cudaError_t* err);   // the shared-memory layout the streaming kernel assumes holds on this device
 void launch_tile_stream(const StreamParams& sp, int n_ctas, cudaStream_t stream);
 
 // FP64 peak of the device, measured (tq_fp64_peak): which = 0 mma.sync.m8n8k4.f64 chains as the pass kernels issue them,

@@ -104,6 +104,21 @@ struct GroupConst {   // a group index known at compile time (the expectation-on
 __device__ __forceinline__ void group_sync(int grp) {
     asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
 }
+// Where the tile buffers start in the CTA's shared-memory window: the kernels use no static shared memory, so the dynamic
+// part begins right after the 1 KiB the system reserves -- 1024-aligned as the TMA swizzle needs.  Knowing the address at
+// compile time lets a tile access be `[thread's XOR offset + immediate]`: the offsets of a window are XOR combinations (bank
+// swizzle), so without it every access pays an add on top of its XOR (6.6 % of the last gate pass's instructions).  The
+// assumption is checked twice: tile_stream_base_ok() probes it from the host before the kernel is ever used (a different
+// answer keeps the library on the per-tile kernels), and every launch traps if it does not hold.
+constexpr uint32_t kTilesBase = 0x400;
+__device__ __forceinline__ double lds_tile(uint32_t rel) {   // rel: byte offset from the first tile buffer
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(rel), "n"(kTilesBase));
+    return v;
+}
+__device__ __forceinline__ void sts_tile(uint32_t rel, double v) {
+    asm volatile("st.shared.f64 [%0+%2], %1;" ::"r"(rel), "d"(v), "n"(kTilesBase) : "memory");
+}
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -292,14 +307,16 @@ struct ChainWindow {
     int32_t chain;    // 1 = the window is evaluated by chain_window()
 };
 __device__ __forceinline__ double chain_window(const Regs& a, const ChainWindow& cw, const double2* __restrict__ s_mat) {
-    double e0 = 0.0, e1 = 0.0;
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;   // (four accumulation chains: a dependent DFMA every eight issue slots)
     if (cw.diag_op >= 0) {
         const double2* D = s_mat + cw.diag_op * kMatStride;
 #pragma unroll
-        for (int r = 0; r < NR; r += 2) {
-            const double2 d = D[r >> 1];
+        for (int r = 0; r < NR; r += 4) {
+            const double2 d = D[r >> 1], f = D[(r >> 1) + 1];
             e0 = fma(a[r] * a[r], d.x, e0);
             e1 = fma(a[r + 1] * a[r + 1], d.y, e1);
+            e2 = fma(a[r + 2] * a[r + 2], f.x, e2);
+            e3 = fma(a[r + 3] * a[r + 3], f.y, e3);
         }
     }
     double t[4][2];
@@ -319,9 +336,9 @@ __device__ __forceinline__ double chain_window(const Regs& a, const ChainWindow&
     }
     e0 = fma(cw.c[0], t[0][0] + t[0][1], e0);
     e1 = fma(cw.c[1], t[1][0] + t[1][1], e1);
-    e0 = fma(cw.c[2], t[2][0] + t[2][1], e0);
-    e1 = fma(cw.c[3], t[3][0] + t[3][1], e1);
-    return e0 + e1;
+    e2 = fma(cw.c[2], t[2][0] + t[2][1], e2);
+    e3 = fma(cw.c[3], t[3][0] + t[3][1], e3);
+    return (e0 + e1) + (e2 + e3);
 }
 
 // MODE 0: gate pass, 1: gate pass with expectation windows, 2: expectation-only sub-passes
@@ -331,6 +348,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
     // 1024-byte alignment: the hardware swizzle pattern is a function of the shared-memory address
     unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char* tiles = base;
+    if (smem_u32(tiles) != kTilesBase) __trap();   // (see kTilesBase; tile_stream_base_ok() has checked this from the host)
     double2* s_mat_all = reinterpret_cast<double2*>(base + kBufs * kTileBytes);
     WinOp* s_wops = reinterpret_cast<WinOp*>(s_mat_all + kGroups * kOpSlots * kMatStride);
     StreamWindowDev* s_win = reinterpret_cast<StreamWindowDev*>(s_wops + kOpSlots);
@@ -599,7 +617,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
             const uint32_t hi[8] = {base, base ^ x2, base ^ x3, base ^ x2 ^ x3, base ^ x4, base ^ x4 ^ x2, base ^ x4 ^ x3,
                                     base ^ x4 ^ x3 ^ x2};
 #pragma unroll
-            for (int r = 0; r < NR; ++r) a[r] = *reinterpret_cast<const double*>(tiles + (hi[r >> 2] ^ lo[r & 3]));
+            for (int r = 0; r < NR; ++r) a[r] = lds_tile(hi[r >> 2] ^ lo[r & 3]);
         };
         // the same for a window with known zeros on entry (a dead tile, or register / lane / warp bits nothing has
         // populated yet): those registers are read from a zero in shared memory -- one address select per register
@@ -616,7 +634,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                                     base ^ x4 ^ x3 ^ x2};
 #pragma unroll
             for (int r = 0; r < NR; ++r)
-                a[r] = *reinterpret_cast<const double*>(tiles + ((zero_all || (r & dead_r)) ? zero_rel : (hi[r >> 2] ^ lo[r & 3])));
+                a[r] = lds_tile((zero_all || (r & dead_r)) ? zero_rel : (hi[r >> 2] ^ lo[r & 3]));
         };
 
         // ---- gate windows ----
@@ -710,9 +728,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) tile_stream_kernel(const __
                     const uint32_t hi[8] = {base, base ^ x2, base ^ x3, base ^ x2 ^ x3, base ^ x4, base ^ x4 ^ x2,
                                             base ^ x4 ^ x3, base ^ x4 ^ x3 ^ x2};
 #pragma unroll
-                    for (int r = 0; r < NR; ++r) *reinterpret_cast<double*>(tiles + (hi[r >> 2] ^ lo[r & 3])) = a[r];
+                    for (int r = 0; r < NR; ++r) sts_tile(hi[r >> 2] ^ lo[r & 3], a[r]);
                 }
-                fence_proxy_async();   // (the last window's writes are read by the TMA store)
+                fence_proxy_async();   // (the last window's writes are read by the TMA store; fencing only there, behind a
+                                       // test for "last executed gate window of a pass that writes back", measured slower)
                 group_sync(GRP);     // the tile is complete in shared memory again
             }
 
@@ -850,6 +869,29 @@ size_t tile_stream_smem_bytes() {
            kWinSlots * sizeof(StreamWindowDev) + kGroups * 16 * sizeof(double) + (kBufs + 1) * sizeof(uint64_t) +
            (kBufs + 1) * sizeof(JobDesc) + kStreamMaxSub * sizeof(SubInfo) + (kBufs + 1 + 4) * sizeof(int) + 2 * sizeof(double) +
            kWinSlots * sizeof(ChainWindow) + 1024 /* alignment slack */;
+}
+
+namespace {
+__global__ void tile_stream_base_probe(uint32_t* out) {
+    extern __shared__ unsigned char smem_probe[];
+    unsigned char* base = smem_probe + ((1024u - (smem_u32(smem_probe) & 1023u)) & 1023u);
+    if (threadIdx.x == 0) *out = smem_u32(base);
+}
+}  // namespace
+
+// true when the dynamic shared memory of a kernel without static shared memory starts where the streaming kernel assumes
+// (kTilesBase).  One probe launch with the streaming kernel's shared-memory size; the caller caches the answer per device.
+bool tile_stream_base_ok(cudaError_t* err) {
+    *err = cudaFuncSetAttribute((const void*)tile_stream_base_probe, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)tile_stream_smem_bytes());
+    if (*err != cudaSuccess) return false;
+    uint32_t* d = nullptr;
+    uint32_t hval = 0;
+    if ((*err = cudaMalloc(&d, sizeof(uint32_t))) != cudaSuccess) return false;
+    tile_stream_base_probe<<<1, 32, tile_stream_smem_bytes()>>>(d);
+    *err = cudaMemcpy(&hval, d, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return *err == cudaSuccess && hval == kTilesBase;
 }
 
 cudaError_t tile_stream_configure() {
