@@ -271,3 +271,23 @@ def test_early_expectation_light_cone(built_lib, monkeypatch, n, extra, seed, br
     assert n_exp_only <= len(late) - (last + 1)
     if (n, extra, seed, brick) == (20, 41, 5, True):
         assert (n_exp_only, len(late) - (last + 1)) == (1, 2)
+
+
+def test_exchange_classes_of_a_bond_carry_the_one_coefficient_flag(built_lib):
+    """A bare XX + YY coupling on a bond is an 'exchange class' (rb2 bit 1: only the 01 <-> 10 pairs carry a coefficient)
+    whose eight coefficients are equal (rb2 bit 3) -- what the streaming kernel's fused chain windows key on (tq_stream.cu).
+    The flip masks of a nearest-neighbour chain sit on adjacent register-bit pairs of their window."""
+    n = 16
+    gl = brickwork_circuit(n, 21, 20, 3)
+    masks = [(1 << q) | (1 << (q + 1)) for q in range(n - 1)]
+    passes = plan_dump(gl, 16, 12, 4, cover_masks=masks)
+    seen = 0
+    for p in passes:
+        for w in p["windows"]:
+            for code, rb, rb2, qsel, flags, t, fixed in w["ops"]:
+                if code != 20:          # M_EXPC
+                    continue
+                seen += 1
+                assert rb2 & 2 and rb2 & 8 and not rb2 & 1, (rb2, flags)
+                assert flags in (3, 6, 12, 24), flags
+    assert seen == n - 1
