@@ -66,6 +66,7 @@ struct Plan {
     void* arena = nullptr;  // device blob holding windows / ops / groups / terms of all passes + matrix programs
     size_t arena_cap = 0;
     int n_mats = 0;
+    int n_prog = 0;       // gates of the matrix programs (d_prog)
     const MatDesc* d_descs = nullptr;
     const MatGate* d_prog = nullptr;
 };
@@ -476,6 +477,7 @@ int compile_plan(tq_handle h, int which) {
     plan.slots_wide = 0;
     const unsigned char* base = (const unsigned char*)plan.arena;
     plan.n_mats = (int)cc.mats.size();
+    plan.n_prog = (int)cc.prog.size();
     plan.d_descs = (const MatDesc*)(base + off_descs);
     plan.d_prog = (const MatGate*)(base + off_prog);
     for (size_t i = 0; i < passes.size(); ++i) {
@@ -796,6 +798,7 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 pp.fused_prep = 1;
                 pp.descs = plan.d_descs;
                 pp.prog = plan.d_prog;
+                pp.n_prog = plan.n_prog;
                 pp.params = params ? params + (size_t)b0 * ld : nullptr;
                 pp.ld_params = ld;
                 pp.codes = codes ? codes + (size_t)b0 * ldc : nullptr;
@@ -1416,6 +1419,7 @@ int tq_energy_multi_host(int n_problems, tq_handle* handles, const double* const
         pp.fused_prep = plan.n_mats > 0 ? 1 : 0;
         pp.descs = plan.d_descs;
         pp.prog = plan.d_prog;
+        pp.n_prog = plan.n_prog;
         pp.ld_params = std::max(h->n_params, 1);
         pp.params = (const double*)(hp + pcur);
         if (h->n_params > 0 && params_host && params_host[i]) memcpy(hp + pcur, params_host[i], (size_t)h->n_params * sizeof(double));

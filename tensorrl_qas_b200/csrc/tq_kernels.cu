@@ -372,6 +372,114 @@ __device__ __forceinline__ void eval_block_matrix(const MatDesc md, const MatGat
     }
 }
 
+// One COLUMN of a block matrix (a gate mixes rows, so the four columns never meet and each sees exactly the arithmetic of
+// eval_block_matrix: same results, bit for bit), with the program and the sin / cos of its rotations already in shared memory.
+__device__ __forceinline__ void eval_block_column_staged(const MatDesc md, const MatGate* s_prog, const double2* s_sc,
+                                                         const uint8_t* __restrict__ codes, int col,
+                                                         double2* __restrict__ out) {
+    double2 M[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) M[r] = make_double2(r == col ? 1.0 : 0.0, 0.0);
+    for (int gi = md.begin; gi < md.end; ++gi) {
+        const MatGate g = s_prog[gi];
+        int kind = g.kind;
+        if (kind == MG_CX) {
+            const int ra = g.lq == 0 ? 1 : 2;
+            const double2 t = M[ra]; M[ra] = M[3]; M[3] = t;
+            continue;
+        }
+        if (kind == MG_PAULI_SLOT) {
+            const int code = (codes[g.pidx] >> (int)g.fixed) & 3;
+            if (code == 0) continue;
+            kind = MG_X + code - 1;
+        }
+        double2 g00 = make_double2(0.0, 0.0), g01 = g00, g10 = g00, g11 = g00;
+        if (kind <= MG_RZ) {
+            const double sn = s_sc[gi].x, cs = s_sc[gi].y;
+            if (kind == MG_RX) { g00.x = cs; g01.y = sn; g10.y = sn; g11.x = cs; }
+            else if (kind == MG_RY) { g00.x = cs; g01.x = sn; g10.x = -sn; g11.x = cs; }
+            else { g00.x = cs; g00.y = sn; g11.x = cs; g11.y = -sn; }
+        } else if (kind == MG_X) { g01.x = 1.0; g10.x = 1.0; }
+        else if (kind == MG_Y) { g01.y = -1.0; g10.y = 1.0; }
+        else { g00.x = 1.0; g11.x = -1.0; }
+        if (g.lq == 0) {
+#pragma unroll
+            for (int r = 0; r < 4; r += 2) {
+                const double2 x0 = M[r], x1 = M[r + 1];
+                M[r] = cfma(g01, x1, cmul(g00, x0));
+                M[r + 1] = cfma(g11, x1, cmul(g10, x0));
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double2 x0 = M[r], x1 = M[r + 2];
+                M[r] = cfma(g01, x1, cmul(g00, x0));
+                M[r + 2] = cfma(g11, x1, cmul(g10, x0));
+            }
+        }
+    }
+    if (md.nq == 2) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) out[r * 4 + col] = M[r];
+    } else if (col < 2) {  // one-qubit block: the 2x2 matrix in entries 0..3
+        out[col] = M[0];
+        out[2 + col] = M[1];
+    }
+}
+
+// Single-tile plans fold prep_matrices_kernel into the pass: the CTA of element b evaluates its block matrices itself.  This
+// is the latency path (one COBYLA cost evaluation per call: the reference's own loop), and what it costs is a chain of
+// dependent memory accesses, not arithmetic -- so: the element's angles (they may live in pinned HOST memory), the matrix
+// program and the block descriptors come in with coalesced sweeps, every rotation's sin / cos is evaluated by its own thread,
+// and four threads share a block (one column each).  One thread per block reading the program gate by gate from global
+// memory, with a sincos per gate in the chain, was 22.5 / 54 / 38 us of kernel time for the 4 / 6 / 8-qubit bench shapes at
+// B = 1 (ncu).  `scratch`: kOpSlots * kMatStride double2 of shared memory that nothing else uses yet.
+__device__ __forceinline__ void fused_prep(const PassParams& p, uint32_t b, int tid, int nthreads, double2* scratch,
+                                           double2* __restrict__ out_mats) {
+    const double* par = p.params ? p.params + (size_t)b * p.ld_params : nullptr;
+    const uint8_t* cod = p.codes ? p.codes + (size_t)b * p.ld_codes : nullptr;
+    const size_t cap = (size_t)kOpSlots * kMatStride * sizeof(double2);
+    const size_t off_prog = (size_t)p.ld_params * sizeof(double);
+    const size_t off_sc = (off_prog + (size_t)p.n_prog * sizeof(MatGate) + 15) & ~(size_t)15;
+    const size_t need = off_sc + (size_t)p.n_prog * sizeof(double2);
+    if (p.n_prog > 0 && need <= cap) {
+        unsigned char* raw = reinterpret_cast<unsigned char*>(scratch);
+        double* s_par = reinterpret_cast<double*>(raw);
+        MatGate* s_prog = reinterpret_cast<MatGate*>(raw + off_prog);
+        double2* s_sc = reinterpret_cast<double2*>(raw + off_sc);
+        if (par)
+            for (int i = tid; i < p.ld_params; i += nthreads) s_par[i] = par[i];
+        {   // the program as 8-byte words (24-byte gates)
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.prog);
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_prog);
+            for (int i = tid; i < p.n_prog * 3; i += nthreads) dst[i] = __ldg(src + i);
+        }
+        __syncthreads();
+        for (int gi = tid; gi < p.n_prog; gi += nthreads) {
+            const MatGate g = s_prog[gi];
+            if (g.kind <= MG_RZ) {
+                const double theta = g.pidx >= 0 ? s_par[g.pidx] : g.fixed;
+                double sn, cs;
+                sincos(0.5 * theta, &sn, &cs);
+                s_sc[gi] = make_double2(sn, cs);
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < 4 * p.n_mats; idx += nthreads)
+            eval_block_column_staged(p.descs[idx >> 2], s_prog, s_sc, cod, idx & 3, out_mats + (size_t)(idx >> 2) * kMatStride);
+    } else {
+        if (par && (size_t)p.ld_params * sizeof(double) <= cap) {
+            double* s_par = reinterpret_cast<double*>(scratch);
+            for (int i = tid; i < p.ld_params; i += nthreads) s_par[i] = par[i];
+            __syncthreads();
+            par = s_par;
+        }
+        for (int mi = tid; mi < p.n_mats; mi += nthreads)
+            eval_block_matrix(p.descs[mi], p.prog, par, 0, p.ld_params, cod, p.ld_codes, out_mats + (size_t)mi * kMatStride);
+    }
+    __syncthreads();
+}
+
 #define TQ_SEL4(i, v0, v1, v2, v3, OP) ((((i) & 1) ? (v0) : 0u) OP (((i) & 2) ? (v1) : 0u) OP (((i) & 4) ? (v2) : 0u) OP (((i) & 8) ? (v3) : 0u))
 #define TQ_SLOT(r) (slot_t ^ TQ_SEL4(r, ws0, ws1, ws2, ws3, ^))
 #define TQ_IO_SLOT(i) (io_slot ^ TQ_SEL4(i, iw0, iw1, iw2, iw3, ^))
@@ -446,21 +554,8 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
     const uint64_t elem_off = (uint64_t)b << p.nbits;
 
     const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
-    if (p.fused_prep) {   // single-tile plans: this CTA is the only one of its element and evaluates its block matrices itself
-        // the element's angles first, in one coalesced sweep (they may live in pinned HOST memory on the latency path)
-        const double* par = p.params ? p.params + (size_t)b * p.ld_params : nullptr;
-        const uint8_t* cod = p.codes ? p.codes + (size_t)b * p.ld_codes : nullptr;
-        if (par && p.ld_params <= kOpSlots * kMatStride * 2) {
-            double* s_par = reinterpret_cast<double*>(s_mat);
-            for (int i = tid; i < p.ld_params; i += nthreads) s_par[i] = par[i];
-            __syncthreads();
-            par = s_par;
-        }
-        for (int mi = tid; mi < p.n_mats; mi += nthreads)
-            eval_block_matrix(p.descs[mi], p.prog, par, 0, p.ld_params, cod, p.ld_codes,
-                              const_cast<double2*>(my_mats) + (size_t)mi * kMatStride);
-        __syncthreads();
-    }
+    if (p.fused_prep)   // single-tile plans: this CTA is the only one of its element and evaluates its block matrices itself
+        fused_prep(p, b, tid, nthreads, s_mat, const_cast<double2*>(my_mats));
     const bool active = tid < (tile_amps >> kRegBits);
     const int n_tbits = p.k_eff - kRegBits;
     const int n_run = (!DM && p.exp_mode == 1) ? p.n_windows : p.n_gate_windows;
@@ -731,21 +826,8 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_mma_kern
     const uint32_t ig0 = p.io_stride[0], ig1 = p.io_stride[1], ig2 = p.io_stride[2], ig3 = p.io_stride[3];
     const uint64_t elem_off = (uint64_t)b << p.nbits;
     const double2* my_mats = p.mats + (size_t)b * p.n_mats * kMatStride;
-    if (p.fused_prep) {   // single-tile plans: this CTA is the only one of its element and evaluates its block matrices itself
-        // the element's angles first, in one coalesced sweep (they may live in pinned HOST memory on the latency path)
-        const double* par = p.params ? p.params + (size_t)b * p.ld_params : nullptr;
-        const uint8_t* cod = p.codes ? p.codes + (size_t)b * p.ld_codes : nullptr;
-        if (par && p.ld_params <= kOpSlots * kMatStride * 2) {
-            double* s_par = reinterpret_cast<double*>(s_mat);
-            for (int i = tid; i < p.ld_params; i += nthreads) s_par[i] = par[i];
-            __syncthreads();
-            par = s_par;
-        }
-        for (int mi = tid; mi < p.n_mats; mi += nthreads)
-            eval_block_matrix(p.descs[mi], p.prog, par, 0, p.ld_params, cod, p.ld_codes,
-                              const_cast<double2*>(my_mats) + (size_t)mi * kMatStride);
-        __syncthreads();
-    }
+    if (p.fused_prep)   // single-tile plans: this CTA is the only one of its element and evaluates its block matrices itself
+        fused_prep(p, b, tid, nthreads, s_mat, const_cast<double2*>(my_mats));
     const int n_run = (p.exp_mode == 1) ? p.n_windows : p.n_gate_windows;
 
     // B-fragment coordinates of this lane: B[k = lane & 3][n = lane >> 2]; n = (QL', c', RX'), k = (QL, c)

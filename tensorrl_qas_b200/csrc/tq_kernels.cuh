@@ -56,6 +56,7 @@ struct PassParams {
     int fused_prep;
     const MatDesc* descs;
     const MatGate* prog;
+    int n_prog;                     // gates in `prog` (0 = unknown: the program is read from global memory gate by gate)
     const double* params;
     const uint8_t* codes;
     int ld_params, ld_codes;
