@@ -948,8 +948,20 @@ int run_plan(tq_handle h, int which, int batch, const double* params, int ld, co
                 direct.sub[direct.n_sub++] = pp;
                 continue;
             }
+            // Latency path (a handful of single-tile evaluations, e.g. one COBYLA cost evaluation per call): what the call
+            // waits for is the CTA's staging work -- angles, matrix program, block matrices, Hamiltonian entries -- and a
+            // tile below 2^9 amplitudes runs on ONE warp (16 amplitudes per thread).  Four warps share that work out (the
+            // extra threads idle in the register windows and leave the energy sum to the plan's own threads, so the bits do
+            // not depend on the launch shape); phase clocks at B = 1 on the 4 / 6 / 8-qubit bench shapes: block matrices
+            // 8.5 / 29 / 7.8 k cycles, tile + op staging 3.5 / 8.1 / 3.7 k cycles with one warp.  Large batches keep one warp
+            // per CTA: there the SMs are full and idle threads would only take registers.
+            int threads = dp.threads;
+            if (fuse_prep && !pp.mwindows && !dm && bc <= 2 * h->n_sms && threads < 128) {
+                pp.arith_threads = threads;   // (the energy is still accumulated in the plan's order: same bits as any other launch)
+                threads = 128;
+            }
             prof_begin(h, stream, pp.mwindows ? PK_TILE_MMA : PK_TILE, model_bytes, alg_bytes, dmma_flops);
-            launch_tile_pass(pp, bc, dp.threads, dm, stream);
+            launch_tile_pass(pp, bc, threads, dm, stream);
             prof_end(h, stream);
             ++h->launches;
             rc = check_launch(h, "tile_pass_kernel");

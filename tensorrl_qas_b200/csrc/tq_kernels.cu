@@ -522,6 +522,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
     uint32_t* hi_off = reinterpret_cast<uint32_t*>(s_win + 3 * kWinSlots);     // 2^(k - lead) entries
 
     const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int nar = (p.arith_threads > 0 && p.arith_threads < nthreads) ? p.arith_threads : nthreads;   // (see PassParams)
     const uint32_t ntiles = 1u << p.n_nl;
     const uint32_t tile = cta & (ntiles - 1u);
     const uint32_t b = cta >> p.n_nl;
@@ -744,7 +745,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
                     __syncthreads();
                     for (int i = tid; i < nt; i += nthreads) s_terms[i] = p.terms[t0 + i];
                     __syncthreads();
-                    for (int j = tid; j < valid_amps; j += nthreads) {
+                    for (int j = tid < nar ? tid : valid_amps; j < valid_amps; j += nar) {
                         const uint32_t sj = swz(j);
                         const double2 v = amp[sj], bq = amp[sj ^ xs];
                         const double px = bq.x * v.x + bq.y * v.y;  // conj(psi[j ^ x]) * psi[j]
@@ -761,7 +762,10 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
                 }
             }
         } else {
-            for (int e = tid; e < p.n_hent; e += nthreads) {
+            // (with extra staging warps -- PassParams::arith_threads -- the entries are still summed by the plan's own threads
+            // in the plan's order: sharing them out over four warps needs a summation order defined over 128 virtual
+            // threads for EVERY launch shape, and that cost the batched 8-qubit shape 18 % when it was tried)
+            for (int e = tid < nar ? tid : p.n_hent; e < p.n_hent; e += nar) {
                 const HEntry h = p.hent[e];
                 const double2 ar = amp[swz(h.r)], ac = amp[swz(h.c)];
                 const double px = ar.x * ac.x + ar.y * ac.y;  // conj(psi_r) * psi_c
@@ -769,7 +773,7 @@ __global__ void __launch_bounds__(kMaxThreads, TQ_MIN_BLOCKS) tile_pass_kernel(c
                 acc += h.re * px - h.im * py;
             }
         }
-        const double total = block_sum(acc, s_red, tid, nthreads);
+        const double total = block_sum(acc, s_red, tid, nar);
         if (tid == 0) p.partial[(size_t)b * p.partial_ld + p.partial_off + tile] = total;
     }
 }

@@ -57,6 +57,9 @@ struct PassParams {
     const MatDesc* descs;
     const MatGate* prog;
     int n_prog;                     // gates in `prog` (0 = unknown: the program is read from global memory gate by gate)
+    int arith_threads;              // > 0: the CTA was launched with MORE threads than the plan's (latency path: the extra
+                                    // warps only help with staging); the energy is accumulated by the first arith_threads
+                                    // threads in the plan's own order, so the result does not depend on the launch shape
     const double* params;
     const uint8_t* codes;
     int ld_params, ld_codes;
