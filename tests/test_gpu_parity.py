@@ -451,3 +451,42 @@ def test_plan_cache_restores_plans_bit_for_bit(built_lib, oracle, monkeypatch):
         assert np.array_equal(sim.energies(params[i]), first[i])
     assert sim.plan_cache_stats()["hits"] == 0
     sim.close()
+
+
+@pytest.mark.parametrize("n,dense", [(4, True), (6, True), (8, True), (7, False)])
+def test_launch_shape_does_not_change_the_bits(built_lib, oracle, monkeypatch, n, dense):
+    """One evaluation per call (the latency path: block matrices evaluated inside the pass, four warps staging), a batch that
+    fills the device (one warp per CTA) and the separate prep kernel (TQ_FUSE_PREP=0) must give the SAME bits for the same
+    parameter set: COBYLA trajectories depend on it (serial calls, batched calls and lock-step launches are interchangeable)."""
+    gl = synthetic_circuit(n, 60, 40 + n)
+    rng = np.random.default_rng(n)
+    p = parameter_batch(gl, 700)          # > 2 CTAs per SM: the batched launch shape
+    if dense:
+        h = rng.normal(size=(1 << n, 1 << n)) + 1j * rng.normal(size=(1 << n, 1 << n))
+        h = h + h.conj().T
+        kw = dict(dense=h)
+    else:
+        kw = dict(pauli=random_pauli_sum(n, 12, 3))
+
+    def run(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        sim = Simulator(n, 0)
+        sim.set_circuit(gl)
+        if dense:
+            sim.set_dense_hamiltonian(h)
+        else:
+            sim.set_pauli_hamiltonian(*kw["pauli"])
+        batched = sim.energies(p)
+        serial = np.array([sim.energies(p[i:i + 1])[0] for i in (0, 1, 350, 699)])
+        sim.close()
+        for k in env:
+            monkeypatch.delenv(k)
+        return batched, serial
+
+    batched, serial = run({})
+    unfused, serial_unfused = run({"TQ_FUSE_PREP": "0"})
+    assert np.abs(batched - oracle.energies(gl, p, **kw)).max() < TOL
+    assert np.array_equal(serial, batched[[0, 1, 350, 699]])
+    assert np.array_equal(unfused, batched)
+    assert np.array_equal(serial_unfused, serial)
