@@ -367,6 +367,7 @@ int compile_plan(tq_handle h, int which) {
     opt.dead_budget = env_int("TQ_DEAD_BUDGET", 5);
     opt.early_expect = env_int("TQ_EARLY_EXPECT", 1) != 0;
     opt.skip_last_store = env_int("TQ_SKIP_LAST_STORE", 1) != 0;
+    opt.pack_search = env_int("TQ_PACK_SEARCH", 0) != 0;
     CompiledCircuit cc = which == 1 ? plan_density(n, h->gates, opt, &perr)
                                     : plan_statevector(n, h->gates, opt, cover, &perr);
     if (!perr.empty()) return fail(h, TQ_EINVAL, perr);
@@ -1772,6 +1773,7 @@ char* tq_plan_dump(int n_qubits, int n_gates, const int32_t* kind, const int32_t
     opt.dead_budget = env_int("TQ_DEAD_BUDGET", 5);
     opt.early_expect = env_int("TQ_EARLY_EXPECT", 1) != 0;
     opt.skip_last_store = env_int("TQ_SKIP_LAST_STORE", 1) != 0;
+    opt.pack_search = env_int("TQ_PACK_SEARCH", 0) != 0;
     CompiledCircuit cc = which == 1 ? plan_density(n_qubits, gates, opt, &err)
                                     : plan_statevector(n_qubits, gates, opt, cover, &err);
     std::string out;

@@ -284,6 +284,55 @@ std::vector<Pass> pack(int nbits, const std::vector<AOp>& ops, const PlanOptions
                 blocked_diag |= a.diag;
             }
         }
+        // Optional search (PlanOptions::pack_search): the first-fit set above is whatever the earliest blocks happened to need.
+        // With a FIXED set X of local qubits a pass executes the blocks whose mixing qubits lie in X and that commute with
+        // everything deferred before them -- count(X), one scan.  Grow X from the forced low bits by the single qubit or the
+        // pair that raises the count most (pairs: a two-qubit block needs both), then keep the better of the two choices.
+        if (opt.pack_search && mma && nbits > k && !deferred.empty() && (support & all) == all) {
+            auto scan = [&](uint64_t X, std::vector<int>* take, std::vector<int>* defer) {
+                uint64_t bm = 0, bd = 0;
+                int cnt = 0;
+                for (int idx : remaining) {
+                    const AOp& a = ops[idx];
+                    const bool clash = (a.mix & (bm | bd)) || (a.diag & bm);
+                    if (!clash && !(a.mix & ~X)) {
+                        ++cnt;
+                        if (take) take->push_back(idx);
+                    } else {
+                        bm |= a.mix;
+                        bd |= a.diag;
+                        if (defer) defer->push_back(idx);
+                    }
+                }
+                return cnt;
+            };
+            uint64_t X = bit(std::min(opt.low_bits, k)) - 1;
+            while (__builtin_popcountll(X) < k) {
+                int best_cnt = -1;
+                uint64_t best_add = 0;
+                const int room = k - __builtin_popcountll(X);
+                for (int q0 = 0; q0 < nbits; ++q0) {
+                    if ((X >> q0) & 1ull) continue;
+                    const int c1 = scan(X | bit(q0), nullptr, nullptr);
+                    if (c1 > best_cnt) { best_cnt = c1; best_add = bit(q0); }
+                    if (room < 2) continue;
+                    for (int q1 = q0 + 1; q1 < nbits; ++q1) {
+                        if ((X >> q1) & 1ull) continue;
+                        const int c2 = scan(X | bit(q0) | bit(q1), nullptr, nullptr);
+                        // (a pair has to beat the best single qubit by more than it could gain with its second slot later)
+                        if (c2 > best_cnt + 1) { best_cnt = c2; best_add = bit(q0) | bit(q1); }
+                    }
+                }
+                X |= best_add;
+            }
+            std::vector<int> take, defer;
+            const int cnt = scan(X, &take, &defer);
+            if (cnt > (int)mine.size()) {
+                mine.swap(take);
+                deferred.swap(defer);
+                L = X;
+            }
+        }
         if (deferred.empty() && !cover_masks.empty()) {
             // Last gate pass: spend its free tile positions on Hamiltonian flip masks (groups evaluated right here).  Which
             // ones decides how many expectation-only passes over the state follow: greedy fills from every start in the

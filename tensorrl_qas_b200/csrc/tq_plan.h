@@ -283,6 +283,10 @@ struct PlanOptions {
                                    // groups its gates do not touch (ExpPlan::last_store_needed)
     bool early_expect = true;   // Hamiltonian groups that no later gate touches may be evaluated in an earlier gate pass
                                 // when that saves an expectation-only pass (attach_expectation)
+    bool pack_search = false;   // TQ_PACK_SEARCH=1: besides the first-fit choice of a pass's local qubits, try a set grown qubit
+                                // (pair) by qubit (pair) for the number of blocks it lets the pass execute, and keep whichever
+                                // executes more -- only once every qubit is populated (generic circuits; brick chains that
+                                // grow out of |0...0> keep their plans).  Off by default: measured on plans only so far.
 };
 
 struct CompiledCircuit {

@@ -291,3 +291,23 @@ def test_exchange_classes_of_a_bond_carry_the_one_coefficient_flag(built_lib):
                 assert rb2 & 2 and rb2 & 8 and not rb2 & 1, (rb2, flags)
                 assert flags in (3, 6, 12, 24), flags
     assert seen == n - 1
+
+
+@pytest.mark.parametrize("n,tile_bits,low_bits,seed,gates", [(13, 10, 3, 31, 400), (14, 10, 3, 32, 500), (15, 11, 4, 33, 450),
+                                                              (16, 12, 4, 34, 300)])
+def test_pack_search_plans_equal_the_gate_list_and_need_no_more_passes(built_lib, oracle, monkeypatch, n, tile_bits, low_bits,
+                                                                       seed, gates):
+    """TQ_PACK_SEARCH=1 (opt-in): a pass's local qubits are also grown qubit (pair) by qubit (pair) for the number of blocks
+    they let it execute; the plan must still be the circuit (numpy execution of the emitted windows against the oracle) and
+    must not need more passes than the first-fit plan."""
+    gl = synthetic_circuit(n, gates, seed)
+    params = parameter_batch(gl, 1)[0]
+    base = plan_dump(gl, 0, tile_bits, low_bits, with_mats=True)
+    monkeypatch.setenv("TQ_PACK_SEARCH", "1")
+    plan = plan_dump(gl, 0, tile_bits, low_bits, with_mats=True)
+    check_invariants(plan, n, tile_bits, low_bits)
+    assert sum(len(m["gates"]) for m in plan["mats"]) == len(gl)
+    want = oracle.state(gl, params)
+    assert np.abs(run_plan(plan, n, params) - want).max() < 1e-12
+    assert np.abs(run_plan_windows(plan, n, params) - want).max() < 1e-12
+    assert len(plan["passes"]) <= len(base["passes"])
